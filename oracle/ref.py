@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
+
+ctypes front-end of ``oracle/_ref/libccake_ref.so``: the UNMODIFIED CCAKE
+reference classes compiled against the shim headers in ``oracle/shim`` (see
+``oracle/Makefile`` and ``oracle/ref_driver.cpp``).  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference``
+legs may import this module.
+
+Member blocks follow ``CabanaParticle`` (reference ``include/particle.h:54-100``) and
+the enums of ``include/hydrodynamic_info.h:166-309``,
+``include/thermodynamic_info.h:35-71`` and ``include/densities.h:24-33``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libccake_ref.so")
+
+# particle_info::particle_data (include/particle.h:79-103): name -> (index, per-particle shape)
+MEMBERS = {
+    "hydro_space_matrix": (0, (25, 3, 3)),
+    "hydro_vector": (1, (20, 3)),
+    "hydro_diffusion_aux_matrix": (2, (2, 3, 9)),
+    "hydro_scalar": (3, (43,)),
+    "hydro_shear_aux_vector": (4, (4, 2, 3)),
+    "hydro_shear_aux_matrix": (5, (3, 2, 9)),
+    "thermo": (6, (31,)),
+    "hydro_spacetime_matrix": (7, (2, 4, 4)),
+    "hydro_diffusion": (8, (1, 3, 4)),
+    "input": (9, (5,)),
+    "smoothed": (10, (5,)),
+    "extensive": (11, (5,)),
+    "d_dt_extensive": (12, (5,)),
+    "sph_mass": (13, (5,)),
+    "position": (14, (3,)),
+    "efcheck": (15, ()),
+    "contribution_to_total_E": (16, ()),
+    "contribution_to_total_dEz": (17, ()),
+    "contribution_to_total_Ez": (18, ()),
+}
+
+HYDRO_SCALAR = ["t", "causality", "bulk", "extensive_bulk", "a", "rho_Q_ext", "rho_S_ext", "rho_B_ext", "tau_Pi",
+                "tau_pi", "zeta_Pi", "sigma_lab", "sigma", "gamma", "theta", "delta_PiPi", "delta_pipi",
+                "lambda_Pipi", "phi1", "phi3", "phi6", "phi7", "eta_pi", "tau_pipi", "lambda_piPi", "tmunu_trace",
+                "div_u", "d_extensive_bulk_dt", "F_extensive_bulk", "F_shv_nabla_u", "F_extensive_entropy",
+                "shv_nabla_u", "j0_ext", "shear_knudsen", "bulk_knudsen", "inverse_reynolds_shear",
+                "inverse_reynolds_bulk", "knudsen_diffusion_B", "knudsen_diffusion_S", "knudsen_diffusion_Q",
+                "inverse_reynolds_diffusion_B", "inverse_reynolds_diffusion_S", "inverse_reynolds_diffusion_Q"]
+HYDRO_VECTOR = ["v", "u", "gradP", "gradE", "gradBulk", "divshear", "gradshear", "div_qa", "grad_qa",
+                "M_extensive_bulk", "M_shv_nabla_u", "M_extensive_entropy", "R_extensive_entropy",
+                "R_extensive_bulk", "F_u", "F_extensive_N", "F_0i_shear", "j_ext", "du_dt", "F_q0_a"]
+HYDRO_SPACE_MATRIX = ["gradV", "grad_alpha_a", "M_u", "M_extensive_N", "R_extensive_N", "R_u", "R_0i_shear",
+                      "M_0i_shear", "tau_q", "kappa_q", "delta_qq", "l_qpi", "l_qPi", "tau_qpi", "tau_qPi",
+                      "lambda_qq", "lambda_qpi", "lambda_qPi", "phi_4", "phi_5", "M_q0_j_a", "R_q0_a_b",
+                      "F_extensive_diffusion_ib", "d_extensive_q_dt", "extensive_diffusion"]
+HYDRO_SPACETIME_MATRIX = ["shv", "sigma_tensor"]
+HYDRO_SHEAR_AUX_VECTOR = ["F_extensive_shear", "F_sigma_tensor", "extensive_shv", "d_extensive_shv_dt"]
+HYDRO_SHEAR_AUX_MATRIX = ["M_extensive_shear", "M_sigma_tensor", "R_extensive_shear"]
+THERMO = ["T", "muB", "muS", "muQ", "e", "s", "rhoB", "rhoS", "rhoQ", "p", "cs2", "w", "dwds", "dwdB", "dwdS",
+          "dwdQ", "dalpha_Bds", "dalpha_BdB", "dalpha_BdS", "dalpha_BdQ", "dalpha_Sds", "dalpha_SdB",
+          "dalpha_SdS", "dalpha_SdQ", "dalpha_Qds", "dalpha_QdB", "dalpha_QdS", "dalpha_QdQ", "chiBB", "chiBB0",
+          "eos_type_is_table"]
+DENSITIES = ["s", "e", "rhoB", "rhoS", "rhoQ"]
+
+_SUB = {
+    "hydro_scalar": HYDRO_SCALAR, "hydro_vector": HYDRO_VECTOR, "hydro_space_matrix": HYDRO_SPACE_MATRIX,
+    "hydro_spacetime_matrix": HYDRO_SPACETIME_MATRIX, "hydro_shear_aux_vector": HYDRO_SHEAR_AUX_VECTOR,
+    "hydro_shear_aux_matrix": HYDRO_SHEAR_AUX_MATRIX, "thermo": THERMO, "input": DENSITIES, "smoothed": DENSITIES,
+    "extensive": DENSITIES, "d_dt_extensive": DENSITIES, "sph_mass": DENSITIES,
+}
+
+PHASES = {"neighbour_list": 1, "gamma_velocity": 2, "smooth_fields": 3, "thermodynamics": 4, "reset_pi_tensor": 5,
+          "regulate_diffusion": 6, "viscosities": 8, "smooth_gradients": 9, "time_derivatives": 10}
+
+
+def available() -> bool:
+    return os.path.exists(LIB_PATH)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        dp, ip, lp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_long)
+        L.ccake_ref_create.restype = C.c_void_p
+        L.ccake_ref_create.argtypes = [C.c_char_p]
+        L.ccake_ref_destroy.argtypes = [C.c_void_p]
+        L.ccake_ref_add_particles.argtypes = [C.c_void_p, C.c_long] + [dp] * 8
+        for f in ("initialize", "get_time_derivatives"):
+            getattr(L, "ccake_ref_" + f).argtypes = [C.c_void_p]
+        L.ccake_ref_phase.argtypes = [C.c_void_p, C.c_int]
+        L.ccake_ref_allocate_raw.argtypes = [C.c_void_p, C.c_long]
+        L.ccake_ref_advance.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ccake_ref_n.restype = C.c_long
+        L.ccake_ref_n.argtypes = [C.c_void_p]
+        L.ccake_ref_time.restype = C.c_double
+        L.ccake_ref_time.argtypes = [C.c_void_p]
+        L.ccake_ref_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.ccake_ref_member_doubles.restype = C.c_long
+        L.ccake_ref_member_doubles.argtypes = [C.c_void_p, C.c_int]
+        L.ccake_ref_get_member.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ccake_ref_set_member.argtypes = [C.c_void_p, C.c_int, dp]
+        L.ccake_ref_get_ints.argtypes = [C.c_void_p, C.c_int, ip]
+        L.ccake_ref_set_ints.argtypes = [C.c_void_p, C.c_int, ip]
+        L.ccake_ref_neighbours.restype = C.c_long
+        L.ccake_ref_neighbours.argtypes = [C.c_void_p, lp, ip, ip, ip]
+        L.ccake_ref_totals.argtypes = [C.c_void_p, dp]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class RefSim:
+    """One reference simulation (SystemState + SPHWorkstation) built from a settings dict."""
+
+    def __init__(self, settings: dict):
+        kv = "\n".join(f"{k}={_fmt(v)}" for k, v in settings.items())
+        self.h = lib().ccake_ref_create(kv.encode())
+        if not self.h:
+            raise ValueError("ccake_ref_create rejected the settings")
+        self.settings = dict(settings)
+
+    def close(self):
+        if self.h:
+            lib().ccake_ref_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_particles(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        n = r.shape[0]
+        r3 = np.zeros((n, 3))
+        r3[:, : r.shape[1]] = r
+        z = np.zeros(n)
+        u3 = np.zeros((n, 3))
+        if u is not None:
+            u = np.asarray(u, dtype=np.float64)
+            u3[:, : u.shape[1]] = u
+        arrs = [r3, np.ascontiguousarray(e_or_s, dtype=np.float64)]
+        for a in (rhoB, rhoS, rhoQ):
+            arrs.append(z if a is None else np.ascontiguousarray(a, dtype=np.float64))
+        arrs.append(u3)
+        arrs.append(z if bulk is None else np.ascontiguousarray(bulk, dtype=np.float64))
+        arrs.append(np.zeros((n, 6)) if shv6 is None else np.ascontiguousarray(shv6, dtype=np.float64))
+        lib().ccake_ref_add_particles(self.h, n, *[_dp(a) for a in arrs])
+
+    def initialize(self):
+        lib().ccake_ref_initialize(self.h)
+
+    def allocate_raw(self, n):
+        """n blank particles; inject state with set_member/put, then run phases."""
+        lib().ccake_ref_allocate_raw(self.h, int(n))
+
+    def phase(self, name_or_id):
+        k = PHASES[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
+        if lib().ccake_ref_phase(self.h, k):
+            raise ValueError(f"unknown phase {name_or_id}")
+
+    def get_time_derivatives(self):
+        lib().ccake_ref_get_time_derivatives(self.h)
+
+    def advance(self, dt, rk_order=2):
+        lib().ccake_ref_advance(self.h, float(dt), int(rk_order))
+
+    @property
+    def n(self):
+        return lib().ccake_ref_n(self.h)
+
+    @property
+    def t(self):
+        return lib().ccake_ref_time(self.h)
+
+    @t.setter
+    def t(self, v):
+        lib().ccake_ref_set_time(self.h, float(v))
+
+    def member(self, name):
+        idx, shape = MEMBERS[name]
+        out = np.empty((self.n,) + shape, dtype=np.float64)
+        assert out.size == lib().ccake_ref_member_doubles(self.h, idx), name
+        lib().ccake_ref_get_member(self.h, idx, _dp(out))
+        return out
+
+    def set_member(self, name, arr):
+        idx, shape = MEMBERS[name]
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape((self.n,) + shape)
+        lib().ccake_ref_set_member(self.h, idx, _dp(a))
+
+    def get(self, member, field):
+        """e.g. get('hydro_scalar', 'sigma_lab') -> (n,), get('hydro_vector', 'gradP') -> (n,3)."""
+        return self.member(member)[:, _SUB[member].index(field)]
+
+    def put(self, member, field, values):
+        a = self.member(member)
+        a[:, _SUB[member].index(field)] = values
+        self.set_member(member, a)
+
+    def ints(self, which):
+        k = {"id": 0, "btrack": 1, "freeze": 2}[which]
+        out = np.empty(self.n, dtype=np.int32)
+        lib().ccake_ref_get_ints(self.h, k, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
+    def set_ints(self, which, vals):
+        k = {"id": 0, "btrack": 1, "freeze": 2}[which]
+        a = np.ascontiguousarray(vals, dtype=np.int32)
+        lib().ccake_ref_set_ints(self.h, k, a.ctypes.data_as(C.POINTER(C.c_int)))
+
+    def neighbours(self):
+        """CSR neighbour list of the last rebuild: (offsets[n+1], idx[nnz], cell_of[n], ncell[3])."""
+        n = self.n
+        nnz = lib().ccake_ref_neighbours(self.h, None, None, None, None)
+        off = np.empty(n + 1, dtype=np.int64)
+        idx = np.empty(max(nnz, 0), dtype=np.int32)
+        cell = np.empty(n, dtype=np.int32)
+        nc = np.empty(3, dtype=np.int32)
+        ip = C.POINTER(C.c_int)
+        lib().ccake_ref_neighbours(self.h, off.ctypes.data_as(C.POINTER(C.c_long)), idx.ctypes.data_as(ip),
+                                   cell.ctypes.data_as(ip), nc.ctypes.data_as(ip))
+        return off, idx, cell, nc
+
+    def totals(self):
+        out = np.zeros(6)
+        lib().ccake_ref_totals(self.h, _dp(out))
+        return dict(zip(["S", "B", "Sq", "Q", "E", "Ez"], out))
+
+
+def _fmt(v):
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, float):
+        return repr(v)
+    return str(v)

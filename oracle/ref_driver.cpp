@@ -1,0 +1,291 @@
+// TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
+//
+// C-ABI driver around the UNMODIFIED CCAKE reference classes
+// (SystemState<D>, SPHWorkstation<D,TEOM>, Evolver<D>, EquationOfState),
+// compiled from /root/reference against oracle/shim/ into
+// oracle/_ref/libccake_ref.so by oracle/Makefile. It replaces only the parts of
+// BSQHydro that do file I/O: particles arrive as arrays instead of a text file
+// (same fields and unit conversions as BSQHydro::read_ccake,
+// src/BSQHydro.cpp:207-425) and the initialisation sequence is the one of
+// BSQHydro::initialize_hydrodynamics (src/BSQHydro.cpp:569-611).
+//
+// State is read back member-block by member-block (the CabanaParticle member
+// order of include/particle.h:54-100), so tests can compare any intermediate of
+// the pipeline with the CUDA path.
+#include <cstring>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <string>
+
+#include "sph_workstation.h"
+#include "system_state.h"
+#include "settings.h"
+
+using namespace ccake;
+
+namespace {
+
+struct RefBase {
+  virtual ~RefBase() {}
+  virtual int add_particles(long n, const double* r, const double* e_or_s, const double* rhoB, const double* rhoS,
+                            const double* rhoQ, const double* u, const double* bulk, const double* shv6) = 0;
+  virtual int initialize() = 0;
+  virtual int allocate_raw(long n) = 0;
+  virtual int phase(int which) = 0;
+  virtual int get_time_derivatives() = 0;
+  virtual int advance(double dt, int rk) = 0;
+  virtual long n() = 0;
+  virtual double time() = 0;
+  virtual void set_time(double t) = 0;
+  virtual long member_doubles(int m) = 0;
+  virtual int get_member(int m, double* out) = 0;
+  virtual int set_member(int m, const double* in) = 0;
+  virtual int get_ints(int which, int* out) = 0;
+  virtual int set_ints(int which, const int* in) = 0;
+  virtual long neighbours(long* offsets, int* idx, int* cell_of, int* ncell) = 0;
+  virtual int totals(double* out) = 0;
+};
+
+template <unsigned int D, template <unsigned int> class TEOM>
+struct Ref : RefBase {
+  std::shared_ptr<Settings> st;
+  std::shared_ptr<SystemState<D>> sys;
+  std::shared_ptr<SPHWorkstation<D, TEOM>> ws;
+
+  explicit Ref(std::shared_ptr<Settings> s) : st(s) {
+    sys = std::make_shared<SystemState<D>>(st);
+    ws = std::make_shared<SPHWorkstation<D, TEOM>>(st, sys);
+  }
+
+  // Mirrors the per-row work of BSQHydro::read_ccake (src/BSQHydro.cpp:262-403).
+  int add_particles(long n, const double* r, const double* e_or_s, const double* rhoB, const double* rhoS,
+                    const double* rhoQ, const double* u, const double* bulk, const double* shv6) override {
+    const double hc = constants::hbarc_GeVfm;
+    for (long i = 0; i < n; ++i) {
+      Particle<D> p;
+      for (unsigned d = 0; d < D; ++d) { p.r(d) = r[3 * i + d]; p.hydro.u(d) = u[3 * i + d]; }
+      const double pixx = shv6[6 * i + 0] / hc, pixy = shv6[6 * i + 1] / hc, pixeta = shv6[6 * i + 2] / hc,
+                   piyy = shv6[6 * i + 3] / hc, piyeta = shv6[6 * i + 4] / hc, pietaeta = shv6[6 * i + 5] / hc;
+      p.hydro.shv(1, 1) = pixx; p.hydro.shv(1, 2) = pixy; p.hydro.shv(1, 3) = pixeta;
+      p.hydro.shv(2, 1) = pixy; p.hydro.shv(3, 1) = pixeta; p.hydro.shv(2, 2) = piyy;
+      p.hydro.shv(2, 3) = piyeta; p.hydro.shv(3, 2) = piyeta; p.hydro.shv(3, 3) = pietaeta;
+      double e = 0.0;
+      if (st->input_as_entropy) p.input.s = e_or_s[i];
+      else { e = e_or_s[i] / hc; p.input.e = e; }
+      p.input.rhoB = st->baryon_charge_enabled ? rhoB[i] : 0.0;
+      p.input.rhoS = st->strange_charge_enabled ? rhoS[i] : 0.0;
+      p.input.rhoQ = st->electric_charge_enabled ? rhoQ[i] : 0.0;
+      p.hydro.bulk = bulk[i] / hc;
+      for (int c = 0; c < 3; ++c) for (int m = 0; m < 4; ++m) p.hydro.diffusion(c, m) = 0.0;
+      if (st->input_as_entropy) {
+        const double C = 3.0 * pow(M_PI, 2.) / 90.0;
+        const double e_check = (3. * C) * pow(1. / (4. * C), 4. / 3.) * pow(e_or_s[i], 4. / 3.);
+        if (e_check > st->e_cutoff / hc) sys->add_particle(p);
+      } else if (e > st->e_cutoff / hc) sys->add_particle(p);
+    }
+    return 0;
+  }
+
+  // BSQHydro::initialize_hydrodynamics (src/BSQHydro.cpp:569-611), sources/jets off.
+  int initialize() override {
+    ws->initialize();
+    ws->process_initial_conditions();
+    sys->allocate_cabana_particles();
+    sys->initialize_linklist();
+    ws->initialize_entropy_and_charge_densities();
+    ws->setup_freeze_out();
+    ws->calculate_gamma_and_velocities();
+    ws->initial_smoothing();
+    return 0;
+  }
+
+  // Blank particles with ids 0..n-1, for tests that inject state member by member
+  // (the reference's own unit tests work this way, unit_tests/smoothing_test.cpp:22-57).
+  int allocate_raw(long n) override {
+    ws->initialize();
+    for (long i = 0; i < n; ++i) { Particle<D> p; p.ID = (int)i; p.hydro.ID = (int)i; sys->add_particle(p); }
+    sys->n_particles = (int)n;
+    sys->allocate_cabana_particles();
+    return 0;
+  }
+
+  // One phase of SPHWorkstation::get_time_derivatives (src/sph_workstation.cpp:1543-1583).
+  int phase(int which) override {
+    const double t = sys->t, t2 = t * t;
+    switch (which) {
+      case 1: sys->reset_neighbour_list(); break;
+      case 2: ws->calculate_gamma_and_velocities(); break;
+      case 3: ws->smooth_all_particle_fields(t2); break;
+      case 4: ws->update_all_particle_thermodynamics(); break;
+      case 5: ws->reset_pi_tensor(t2); break;
+      case 6: ws->regulate_diffusion(); break;
+      case 8: ws->update_all_particle_viscosities(); break;
+      case 9: ws->smooth_all_particle_gradients(t2); break;
+      case 10: TEOM<D>::evaluate_time_derivatives(sys, st); break;
+      default: return 1;
+    }
+    return 0;
+  }
+  int get_time_derivatives() override { ws->get_time_derivatives(st->dt); return 0; }
+  int advance(double dt, int rk) override { ws->advance_timestep(dt, rk); return 0; }
+  long n() override { return (long)sys->cabana_particles.size(); }
+  double time() override { return sys->t; }
+  void set_time(double t) override { sys->t = t; }
+
+  long member_doubles(int m) override { return (long)((*sys->cabana_particles.buf)[m].size() / sizeof(double)); }
+  int get_member(int m, double* out) override {
+    auto& b = (*sys->cabana_particles.buf)[m];
+    std::memcpy(out, b.data(), b.size());
+    return 0;
+  }
+  int set_member(int m, const double* in) override {
+    auto& b = (*sys->cabana_particles.buf)[m];
+    std::memcpy(b.data(), in, b.size());
+    return 0;
+  }
+  int get_ints(int which, int* out) override {  // 0 id, 1 btrack, 2 freeze
+    auto& b = (*sys->cabana_particles.buf)[particle_info::id + which];
+    std::memcpy(out, b.data(), b.size());
+    return 0;
+  }
+  int set_ints(int which, const int* in) override {
+    auto& b = (*sys->cabana_particles.buf)[particle_info::id + which];
+    std::memcpy(b.data(), in, b.size());
+    return 0;
+  }
+  long neighbours(long* offsets, int* idx, int* cell_of, int* ncell) override {
+    auto& l = sys->neighbour_list;
+    if (!l.offsets) return -1;
+    const long np = n();
+    if (offsets) std::memcpy(offsets, l.offsets->data(), sizeof(long) * (np + 1));
+    if (idx) std::memcpy(idx, l.neighbors->data(), sizeof(int) * l.neighbors->size());
+    if (cell_of) std::memcpy(cell_of, l.cell_of->data(), sizeof(int) * np);
+    if (ncell) for (int d = 0; d < 3; ++d) ncell[d] = l.ncell[d];
+    return (long)l.neighbors->size();
+  }
+  // S, B, S, Q, E, Ez  (src/system_state.cpp:739-885)
+  int totals(double* out) override {
+    sys->conservation_entropy(false);
+    sys->conservation_BSQ(false);
+    sys->conservation_energy(false, sys->t);
+    out[0] = sys->S; out[1] = sys->Btotal; out[2] = sys->Stotal; out[3] = sys->Qtotal; out[4] = sys->E; out[5] = sys->Ez;
+    return 0;
+  }
+};
+
+bool to_bool(const std::string& v) { return v == "1" || v == "true" || v == "True"; }
+
+// key=value lines -> Settings, named after the Settings members (include/settings.h).
+std::shared_ptr<Settings> parse_settings(const char* kv) {
+  auto s = std::make_shared<Settings>();
+  // defaults the YAML reader would apply (include/defaults.h), restricted to the hot path
+  s->IC_type = "ccake"; s->coordinate_system = "hyperbolic"; s->kernel_type = "cubic_spline";
+  s->eos_type = "conformal"; s->online_inverter_enabled = true; s->particlization_enabled = false;
+  s->Freeze_Out_Temperature = 150.0; s->etaMode = "constant"; s->shearRelaxMode = "default";
+  s->zetaMode = "constant"; s->bulkRelaxMode = "default"; s->diffusionMode = "disabled";
+  s->diffusionRelaxMode = "constant_over_T"; s->delta_pipi_mode = "default"; s->tau_pipi_mode = "default";
+  s->lambda_piPi_mode = "default"; s->phi6_mode = "default"; s->phi7_mode = "default";
+  s->delta_PiPi_mode = "default"; s->lambda_Pipi_mode = "default"; s->phi1_mode = "default"; s->phi3_mode = "default";
+  s->source_type = "disabled"; s->jets_type = "disabled"; s->print_conservation_status = false;
+  s->buffer_event = false; s->modulate_zeta_with_tanh = false; s->rk_order = 2;
+  std::istringstream in(kv);
+  std::string line;
+  while (std::getline(in, line)) {
+    const auto eq = line.find('=');
+    if (eq == std::string::npos) continue;
+    const std::string k = line.substr(0, eq), v = line.substr(eq + 1);
+    if (k == "dim") s->dim = std::stoi(v);
+    else if (k == "coordinate_system") s->coordinate_system = v;
+    else if (k == "t0") s->t0 = std::stod(v);
+    else if (k == "dt") s->dt = std::stod(v);
+    else if (k == "hT") s->hT = std::stod(v);
+    else if (k == "hEta") s->hEta = std::stod(v);
+    else if (k == "rk_order") s->rk_order = std::stoi(v);
+    else if (k == "factorized_kernel") s->factorized_kernel = to_bool(v);
+    else if (k == "e_cutoff") s->e_cutoff = std::stod(v);
+    else if (k == "input_as_entropy") s->input_as_entropy = to_bool(v);
+    else if (k == "stepx") s->stepx = std::stod(v);
+    else if (k == "stepy") s->stepy = std::stod(v);
+    else if (k == "stepEta") s->stepEta = std::stod(v);
+    else if (k == "xmin") s->xmin = std::stod(v);
+    else if (k == "ymin") s->ymin = std::stod(v);
+    else if (k == "etamin") s->etamin = std::stod(v);
+    else if (k == "max_tau") s->max_tau = std::stod(v);
+    else if (k == "eos_type") s->eos_type = v;
+    else if (k == "eos_path") s->eos_path = v;
+    else if (k == "normalize_by_T") s->normalize_by_T = to_bool(v);
+    else if (k == "Freeze_Out_Temperature") s->Freeze_Out_Temperature = std::stod(v);
+    else if (k == "baryon_charge_enabled") s->baryon_charge_enabled = to_bool(v);
+    else if (k == "strange_charge_enabled") s->strange_charge_enabled = to_bool(v);
+    else if (k == "electric_charge_enabled") s->electric_charge_enabled = to_bool(v);
+    else if (k == "etaMode") s->etaMode = v;
+    else if (k == "constant_eta_over_s") s->constant_eta_over_s = std::stod(v);
+    else if (k == "shearRelaxMode") s->shearRelaxMode = v;
+    else if (k == "use_vorticity") s->use_vorticity = to_bool(v);
+    else if (k == "delta_pipi_mode") s->delta_pipi_mode = v;
+    else if (k == "tau_pipi_mode") s->tau_pipi_mode = v;
+    else if (k == "lambda_piPi_mode") s->lambda_piPi_mode = v;
+    else if (k == "phi6_mode") s->phi6_mode = v;
+    else if (k == "phi7_mode") s->phi7_mode = v;
+    else if (k == "input_initial_shear") s->input_initial_shear = to_bool(v);
+    else if (k == "zetaMode") s->zetaMode = v;
+    else if (k == "constant_zeta_over_s") s->constant_zeta_over_s = std::stod(v);
+    else if (k == "cs2_dependent_zeta_A") s->cs2_dependent_zeta_A = std::stod(v);
+    else if (k == "cs2_dependent_zeta_p") s->cs2_dependent_zeta_p = std::stod(v);
+    else if (k == "bulk_from_trace") s->bulk_from_trace = to_bool(v);
+    else if (k == "bulkRelaxMode") s->bulkRelaxMode = v;
+    else if (k == "modulate_zeta_with_tanh") s->modulate_zeta_with_tanh = to_bool(v);
+    else if (k == "delta_PiPi_mode") s->delta_PiPi_mode = v;
+    else if (k == "lambda_Pipi_mode") s->lambda_Pipi_mode = v;
+    else if (k == "phi1_mode") s->phi1_mode = v;
+    else if (k == "phi3_mode") s->phi3_mode = v;
+    else if (k == "diffusionMode") s->diffusionMode = v;
+    else if (k == "diffusionRelaxMode") s->diffusionRelaxMode = v;
+    else if (k == "print_conservation_status") s->print_conservation_status = to_bool(v);
+    else if (k == "prohibit_unstable_cs2") s->prohibit_unstable_cs2 = to_bool(v);
+    else if (k == "prohibit_acausal_cs2") s->prohibit_acausal_cs2 = to_bool(v);
+    else if (k.rfind("kappa_", 0) == 0 && k.size() == 8) s->constant_kappa_over_T2[k[6] - '0'][k[7] - '0'] = std::stod(v);
+    else { std::fprintf(stderr, "ccake_ref: unknown setting '%s'\n", k.c_str()); return nullptr; }
+  }
+  s->check_consistency();
+  return s;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* ccake_ref_create(const char* kv) {
+  auto s = parse_settings(kv);
+  if (!s) return nullptr;
+  const bool cart = (s->coordinate_system == "cartesian");
+  if (s->dim == 2) return cart ? (RefBase*)new Ref<2, EoM_cartesian>(s) : (RefBase*)new Ref<2, EoM_default>(s);
+  if (s->dim == 3) return cart ? (RefBase*)new Ref<3, EoM_cartesian>(s) : (RefBase*)new Ref<3, EoM_default>(s);
+  return nullptr;
+}
+void ccake_ref_destroy(void* h) { delete static_cast<RefBase*>(h); }
+int ccake_ref_add_particles(void* h, long n, const double* r, const double* e_or_s, const double* rhoB,
+                            const double* rhoS, const double* rhoQ, const double* u, const double* bulk,
+                            const double* shv6) {
+  return static_cast<RefBase*>(h)->add_particles(n, r, e_or_s, rhoB, rhoS, rhoQ, u, bulk, shv6);
+}
+int ccake_ref_initialize(void* h) { return static_cast<RefBase*>(h)->initialize(); }
+int ccake_ref_allocate_raw(void* h, long n) { return static_cast<RefBase*>(h)->allocate_raw(n); }
+int ccake_ref_phase(void* h, int which) { return static_cast<RefBase*>(h)->phase(which); }
+int ccake_ref_get_time_derivatives(void* h) { return static_cast<RefBase*>(h)->get_time_derivatives(); }
+int ccake_ref_advance(void* h, double dt, int rk) { return static_cast<RefBase*>(h)->advance(dt, rk); }
+long ccake_ref_n(void* h) { return static_cast<RefBase*>(h)->n(); }
+double ccake_ref_time(void* h) { return static_cast<RefBase*>(h)->time(); }
+void ccake_ref_set_time(void* h, double t) { static_cast<RefBase*>(h)->set_time(t); }
+long ccake_ref_member_doubles(void* h, int m) { return static_cast<RefBase*>(h)->member_doubles(m); }
+int ccake_ref_get_member(void* h, int m, double* out) { return static_cast<RefBase*>(h)->get_member(m, out); }
+int ccake_ref_set_member(void* h, int m, const double* in) { return static_cast<RefBase*>(h)->set_member(m, in); }
+int ccake_ref_get_ints(void* h, int which, int* out) { return static_cast<RefBase*>(h)->get_ints(which, out); }
+int ccake_ref_set_ints(void* h, int which, const int* in) { return static_cast<RefBase*>(h)->set_ints(which, in); }
+long ccake_ref_neighbours(void* h, long* offsets, int* idx, int* cell_of, int* ncell) {
+  return static_cast<RefBase*>(h)->neighbours(offsets, idx, cell_of, ncell);
+}
+int ccake_ref_totals(void* h, double* out) { return static_cast<RefBase*>(h)->totals(out); }
+
+}  // extern "C"

@@ -1,0 +1,2 @@
+// TEST INFRASTRUCTURE ONLY (oracle): forwards to the GSL stand-in.
+#include "gsl_shim.h"
