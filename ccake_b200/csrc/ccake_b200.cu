@@ -1,0 +1,713 @@
+// C ABI of the B200-native CCAKE hot path (include/ccake_b200.h): context, device
+// memory, phase orchestration. One translation unit; the kernels live in
+// cells.cuh (phase 01), gather.cuh (03, 09) and local.cuh (02, 04, 05, 08, 10 + RK).
+//
+// There is deliberately NO host fallback: every entry point that computes launches
+// CUDA kernels on the context's stream and returns CCB_ERR_CUDA if no device is usable.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cells.cuh"
+#include "gather.cuh"
+#include "local.cuh"
+
+using namespace ccb;
+
+namespace {
+enum { PH_NEIGHBOUR = 0, PH_GAMMA, PH_SMOOTH_FIELDS, PH_THERMO, PH_LOCAL, PH_SMOOTH_GRAD, PH_TIME_DERIV, PH_OTHER, PH_COUNT };
+}
+
+struct ccb_ctx {
+  ccb_config cfg;
+  int D = 2;
+  bool milne = true;
+  cudaStream_t stream = nullptr;
+  int64_t n = 0, cap = 0;
+  double t = 0.0;
+  DeviceView dv;
+  CellGrid grid;
+  // allocations
+  double* slab = nullptr;       // all public columns
+  double* y0_slab = nullptr;    // snapshot of evolved columns
+  double* alt_slab = nullptr;   // ping-pong target of the permutation (persistent + y0 columns)
+  double* alt[CCB_F_COUNT];
+  double* alt_y0[CCB_F_COUNT];
+  int32_t* ints = nullptr;      // id, btrack, freeze, eos_id + alternates (8 columns)
+  int32_t* alt_int[4];
+  uint32_t *key_a = nullptr, *key_b = nullptr, *idx_a = nullptr, *idx_b = nullptr, *hist = nullptr, *cell_count = nullptr,
+           *scan_sums = nullptr;
+  int64_t ncells_alloc = 0, hist_alloc = 0, sums_alloc = 0;
+  double* rec = nullptr;        // gather records
+  int32_t* tasks = nullptr;
+  int32_t* d_small = nullptr;   // [0] ntasks, [1..2] err
+  double* d_stage = nullptr;    // staging for id-ordered transfers (16 columns) and reductions
+  double* init_tmp = nullptr;
+  double* d_reduce = nullptr;   // per-block partials of ccb_reduce
+  bool cells_valid = false;
+  bool have_state = false;
+  std::string err;
+  int64_t launches = 0;
+  // phase timing (CCAKE_PROFILE analogue)
+  bool profiling = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double phase_ms[PH_COUNT];
+  int64_t phase_calls[PH_COUNT];
+  KernelNorm kD, k2, k1;
+  double efcheck = 0.0;
+};
+
+namespace {
+
+#define CUDA_OK(call)                                                                 \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      return CCB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+#define LAUNCH(kernel, grid, block, ...)                                              \
+  do {                                                                                \
+    kernel<<<(grid), (block), 0, ctx->stream>>>(__VA_ARGS__);                         \
+    ctx->launches++;                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      ctx->err = std::string(#kernel) + ": " + cudaGetErrorString(e__);               \
+      return CCB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int field_offset(int field) {
+  int o = 0;
+  for (int f = 0; f < field; ++f) o += kFieldWidth[f];
+  return o;
+}
+int total_width() { return field_offset(CCB_F_COUNT); }
+
+struct PhaseTimer {
+  ccb_ctx* ctx; int ph;
+  PhaseTimer(ccb_ctx* c, int p) : ctx(c), ph(p) { if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream); }
+  ~PhaseTimer() {
+    if (!ctx->profiling) return;
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaEventSynchronize(ctx->ev1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->phase_ms[ph] += ms;
+    ctx->phase_calls[ph]++;
+  }
+};
+
+// The neighbour grid of the reference (src/system_state.cpp:651-700 + Cabana's Cartesian grid).
+void setup_grid(ccb_ctx* ctx) {
+  const ccb_config& c = ctx->cfg;
+  double min_pos[3] = {c.xmin, c.ymin, c.etamin};
+  const double h = c.hT;
+  for (int d = 0; d < 3; ++d) min_pos[d] *= 2.;
+  if (c.coordinate_system == CCB_COORD_CARTESIAN)
+    for (int d = 0; d < 3; ++d) min_pos[d] *= 3.;
+  const double radius = 2 * h;
+  for (int d = ctx->D; d < 3; ++d) min_pos[d] = -h;
+  CellGrid& g = ctx->grid;
+  g.ncells = 1;
+  for (int d = 0; d < 3; ++d) {
+    const double max_pos = -min_pos[d];
+    const double delta = 1. * radius;
+    int nc = (int)std::floor((max_pos - min_pos[d]) * (1.0 / delta));
+    if (nc < 1) nc = 1;
+    const double dx = (max_pos - min_pos[d]) / nc;
+    g.min[d] = min_pos[d];
+    g.rdx[d] = 1.0 / dx;
+    g.nc[d] = nc;
+    g.ncells *= nc;
+  }
+}
+
+int free_particles(ccb_ctx* ctx) {
+  cudaFree(ctx->slab); cudaFree(ctx->y0_slab); cudaFree(ctx->alt_slab); cudaFree(ctx->ints);
+  cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
+  cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
+  ctx->slab = ctx->y0_slab = ctx->alt_slab = nullptr; ctx->ints = nullptr;
+  ctx->key_a = ctx->key_b = ctx->idx_a = ctx->idx_b = ctx->hist = nullptr;
+  ctx->rec = nullptr; ctx->tasks = nullptr; ctx->d_stage = nullptr; ctx->init_tmp = nullptr;
+  return CCB_OK;
+}
+
+__global__ void iota_kernel(int32_t* id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) id[i] = (int32_t)i;
+}
+__global__ void fill_kernel(double* p, double v, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+int allocate_particles(ccb_ctx* ctx, int64_t n) {
+  free_particles(ctx);
+  ctx->n = n;
+  ctx->cap = ((n + 63) / 64) * 64;
+  if (ctx->cap == 0) ctx->cap = 64;
+  const int64_t cap = ctx->cap;
+  const int W = total_width();
+  int wy0 = 0, wp = 0;
+  for (int k = 0; k < kNumEvolvedFields; ++k) wy0 += kFieldWidth[kEvolvedFields[k]];
+  for (int f = 0; f < kNumPersistentFields; ++f) wp += kFieldWidth[f];
+  CUDA_OK(cudaMalloc(&ctx->slab, sizeof(double) * W * cap));
+  CUDA_OK(cudaMalloc(&ctx->y0_slab, sizeof(double) * wy0 * cap));
+  CUDA_OK(cudaMalloc(&ctx->alt_slab, sizeof(double) * (wp + wy0) * cap));
+  CUDA_OK(cudaMalloc(&ctx->ints, sizeof(int32_t) * 8 * cap));
+  CUDA_OK(cudaMemsetAsync(ctx->slab, 0, sizeof(double) * W * cap, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(ctx->y0_slab, 0, sizeof(double) * wy0 * cap, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(ctx->alt_slab, 0, sizeof(double) * (wp + wy0) * cap, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(ctx->ints, 0, sizeof(int32_t) * 8 * cap, ctx->stream));
+  DeviceView& dv = ctx->dv;
+  dv.n = n; dv.cap = cap;
+  int oy = 0, oa = 0;
+  for (int f = 0; f < CCB_F_COUNT; ++f) {
+    dv.f[f] = ctx->slab + (int64_t)field_offset(f) * cap;
+    dv.y0[f] = nullptr; ctx->alt[f] = nullptr; ctx->alt_y0[f] = nullptr;
+    if (f < kNumPersistentFields) { ctx->alt[f] = ctx->alt_slab + (int64_t)oa * cap; oa += kFieldWidth[f]; }
+  }
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    dv.y0[f] = ctx->y0_slab + (int64_t)oy * cap; oy += kFieldWidth[f];
+    ctx->alt_y0[f] = ctx->alt_slab + (int64_t)oa * cap; oa += kFieldWidth[f];
+  }
+  dv.id = ctx->ints; dv.btrack = ctx->ints + cap; dv.freeze = ctx->ints + 2 * cap; dv.eos_id = ctx->ints + 3 * cap;
+  for (int k = 0; k < 4; ++k) ctx->alt_int[k] = ctx->ints + (4 + k) * cap;
+  CUDA_OK(cudaMalloc(&ctx->key_a, sizeof(uint32_t) * cap)); CUDA_OK(cudaMalloc(&ctx->key_b, sizeof(uint32_t) * cap));
+  CUDA_OK(cudaMalloc(&ctx->idx_a, sizeof(uint32_t) * cap)); CUDA_OK(cudaMalloc(&ctx->idx_b, sizeof(uint32_t) * cap));
+  ctx->hist_alloc = 256 * cdiv(cap, kSortTile);
+  CUDA_OK(cudaMalloc(&ctx->hist, sizeof(uint32_t) * ctx->hist_alloc));
+  CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G1 * cap));
+  CUDA_OK(cudaMalloc(&ctx->tasks, sizeof(int32_t) * cap));
+  CUDA_OK(cudaMalloc(&ctx->d_stage, sizeof(double) * 16 * cap));
+  dv.key = ctx->key_a;
+  dv.cell_start = ctx->cell_count;
+  dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
+  dv.tasks = ctx->tasks; dv.ntasks = ctx->d_small; dv.err = ctx->d_small + 1;
+  const int64_t need_sums = cdiv(std::max<int64_t>(ctx->hist_alloc, ctx->grid.ncells + 1), kScanTile) + 1;
+  if (need_sums > ctx->sums_alloc) {
+    cudaFree(ctx->scan_sums);
+    CUDA_OK(cudaMalloc(&ctx->scan_sums, sizeof(uint32_t) * need_sums));
+    ctx->sums_alloc = need_sums;
+  }
+  if (n > 0) LAUNCH(iota_kernel, cdiv(n, 256), 256, dv.id, n);
+  ctx->cells_valid = false;
+  ctx->have_state = true;
+  return CCB_OK;
+}
+
+int exclusive_scan(ccb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int write_total) {
+  const int64_t nb = cdiv(n, kScanTile);
+  LAUNCH(scan_block_sums, nb, kScanThreads, in, ctx->scan_sums, n);
+  LAUNCH(scan_sums_inplace, 1, 1024, ctx->scan_sums, nb);
+  LAUNCH(scan_apply, nb, kScanThreads, in, out, ctx->scan_sums, n, write_total);
+  return CCB_OK;
+}
+
+int check_ready(ccb_ctx* ctx, bool need_cells) {
+  if (!ctx) return CCB_ERR_INVALID;
+  if (!ctx->have_state || ctx->n <= 0) { ctx->err = "no particles: call ccb_allocate or ccb_upload_ic first"; return CCB_ERR_STATE; }
+  if (need_cells && !ctx->cells_valid) { ctx->err = "cell list not built: call ccb_build_cells first"; return CCB_ERR_STATE; }
+  return CCB_OK;
+}
+
+StageParams make_stage(ccb_ctx* ctx, double h_stage, int do_update) {
+  return make_stage_params(ctx->cfg, ctx->t, h_stage, do_update);
+}
+
+GatherParams make_gather(ccb_ctx* ctx) {
+  GatherParams gp;
+  gp.kD = ctx->kD; gp.k2 = ctx->k2; gp.k1 = ctx->k1;
+  const double radius = 2 * ctx->cfg.hT;
+  gp.rsqr = radius * radius;
+  gp.t = ctx->t;
+  gp.milne = ctx->milne ? 1 : 0;
+  return gp;
+}
+
+constexpr int kGatherThreads = 128;
+constexpr int kReduceBlocks = 296;
+int gather_grid(ccb_ctx* ctx) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device);
+  return sms * 8;
+}
+
+// ---- phase implementations ------------------------------------------------------
+int do_build_cells(ccb_ctx* ctx) {
+  PhaseTimer pt(ctx, PH_NEIGHBOUR);
+  const int64_t n = ctx->n;
+  DeviceView& dv = ctx->dv;
+  const CellGrid& g = ctx->grid;
+  if (g.ncells + 1 > ctx->ncells_alloc) {
+    cudaFree(ctx->cell_count);
+    CUDA_OK(cudaMalloc(&ctx->cell_count, sizeof(uint32_t) * (g.ncells + 2)));
+    ctx->ncells_alloc = g.ncells + 1;
+  }
+  dv.cell_start = ctx->cell_count;
+  CUDA_OK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(uint32_t) * (g.ncells + 1), ctx->stream));
+  LAUNCH(cell_key_kernel, cdiv(n, 256), 256, dv, g, ctx->key_a, ctx->idx_a, ctx->cell_count);
+  int rc = exclusive_scan(ctx, ctx->cell_count, ctx->cell_count, g.ncells, 1);
+  if (rc) return rc;
+  // LSD radix sort over the significant bits of the key
+  int bits = 1;
+  while (((int64_t)1 << bits) < g.ncells) ++bits;
+  const int nblocks = (int)cdiv(n, kSortTile);
+  uint32_t *kin = ctx->key_a, *kout = ctx->key_b, *iin = ctx->idx_a, *iout = ctx->idx_b;
+  for (int shift = 0; shift < bits; shift += 8) {
+    LAUNCH(radix_hist, nblocks, kSortThreads, kin, ctx->hist, n, shift, nblocks);
+    rc = exclusive_scan(ctx, ctx->hist, ctx->hist, (int64_t)256 * nblocks, 0);
+    if (rc) return rc;
+    LAUNCH(radix_scatter, nblocks, kSortThreads, kin, iin, kout, iout, ctx->hist, n, shift, nblocks);
+    std::swap(kin, kout); std::swap(iin, iout);
+  }
+  // gather every persistent column (and the RK snapshot) through the permutation
+  PermuteList pl;
+  pl.ncols = 0; pl.nints = 0;
+  for (int f = 0; f < kNumPersistentFields; ++f) {
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = dv.f[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt[f] + (int64_t)c * dv.cap; pl.ncols++; }
+  }
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = dv.y0[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_y0[f] + (int64_t)c * dv.cap; pl.ncols++; }
+  }
+  int32_t* icur[4] = {dv.id, dv.btrack, dv.freeze, dv.eos_id};
+  for (int k = 0; k < 4; ++k) { pl.isrc[k] = icur[k]; pl.idst[k] = ctx->alt_int[k]; pl.nints++; }
+  LAUNCH(permute_columns, cdiv(n, 256), 256, pl, iin, n);
+  for (int f = 0; f < kNumPersistentFields; ++f) {
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    std::swap(dv.f[f], ctx->alt[f]);
+  }
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    std::swap(dv.y0[f], ctx->alt_y0[f]);
+  }
+  std::swap(dv.id, ctx->alt_int[0]); std::swap(dv.btrack, ctx->alt_int[1]); std::swap(dv.freeze, ctx->alt_int[2]);
+  std::swap(dv.eos_id, ctx->alt_int[3]);
+  dv.key = kin;  // sorted keys
+  if (kin != ctx->key_a) { std::swap(ctx->key_a, ctx->key_b); std::swap(ctx->idx_a, ctx->idx_b); }
+  // work list of the gathers
+  CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t), ctx->stream));
+  LAUNCH(build_tasks, cdiv(n, 256), 256, dv.key, dv.cell_start, dv.tasks, dv.ntasks, n);
+  ctx->cells_valid = true;
+  return CCB_OK;
+}
+
+template <int D, bool MILNE> int launch_prologue(ccb_ctx* ctx) {
+  LAUNCH((prologue_kernel<D, MILNE>), cdiv(ctx->n, 256), 256, ctx->dv, ctx->t);
+  return CCB_OK;
+}
+int do_prologue(ccb_ctx* ctx) {
+  PhaseTimer pt(ctx, PH_GAMMA);
+  if (ctx->D == 2) return ctx->milne ? launch_prologue<2, true>(ctx) : launch_prologue<2, false>(ctx);
+  return ctx->milne ? launch_prologue<3, true>(ctx) : launch_prologue<3, false>(ctx);
+}
+
+int do_gather_fields(ccb_ctx* ctx) {
+  PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
+  const GatherParams gp = make_gather(ctx);
+  const int grid = gather_grid(ctx);
+  const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
+  if (ctx->D == 2) LAUNCH((gather_fields_kernel<2, false>), grid, kGatherThreads, ctx->dv, ctx->grid, gp);
+  else if (fact) LAUNCH((gather_fields_kernel<3, true>), grid, kGatherThreads, ctx->dv, ctx->grid, gp);
+  else LAUNCH((gather_fields_kernel<3, false>), grid, kGatherThreads, ctx->dv, ctx->grid, gp);
+  return CCB_OK;
+}
+
+template <int D, bool MILNE> int launch_eos_local(ccb_ctx* ctx, const StageParams& sp) {
+  LAUNCH((eos_local_kernel<D, MILNE>), cdiv(ctx->n, 128), 128, ctx->dv, sp);
+  return CCB_OK;
+}
+int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
+  PhaseTimer pt(ctx, do_eos ? PH_THERMO : PH_LOCAL);
+  StageParams sp = make_stage(ctx, 0.0, 0);
+  sp.do_eos = do_eos; sp.do_local = do_local;
+  if (ctx->D == 2) return ctx->milne ? launch_eos_local<2, true>(ctx, sp) : launch_eos_local<2, false>(ctx, sp);
+  return ctx->milne ? launch_eos_local<3, true>(ctx, sp) : launch_eos_local<3, false>(ctx, sp);
+}
+
+template <int D> int launch_gather_grad(ccb_ctx* ctx, const GatherParams& gp, bool shear, bool diff, bool fact) {
+  const int grid = gather_grid(ctx);
+#define CCB_GG(S, F, X) LAUNCH((gather_gradients_kernel<D, S, F, X>), grid, kGatherThreads, ctx->dv, ctx->grid, gp)
+  if (fact) {
+    if (shear) { if (diff) CCB_GG(true, true, (D == 3)); else CCB_GG(true, false, (D == 3)); }
+    else { if (diff) CCB_GG(false, true, (D == 3)); else CCB_GG(false, false, (D == 3)); }
+  } else {
+    if (shear) { if (diff) CCB_GG(true, true, false); else CCB_GG(true, false, false); }
+    else { if (diff) CCB_GG(false, true, false); else CCB_GG(false, false, false); }
+  }
+#undef CCB_GG
+  return CCB_OK;
+}
+int do_gather_gradients(ccb_ctx* ctx) {
+  PhaseTimer pt(ctx, PH_SMOOTH_GRAD);
+  const GatherParams gp = make_gather(ctx);
+  const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
+  const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
+  return ctx->D == 2 ? launch_gather_grad<2>(ctx, gp, sh, df, false) : launch_gather_grad<3>(ctx, gp, sh, df, fact);
+}
+
+template <int D, bool MILNE> int launch_eom(ccb_ctx* ctx, const StageParams& sp) {
+  LAUNCH((eom_rk_kernel<D, MILNE>), cdiv(ctx->n, 128), 128, ctx->dv, sp);
+  return CCB_OK;
+}
+int do_eom(ccb_ctx* ctx, double h_stage, int do_update) {
+  PhaseTimer pt(ctx, PH_TIME_DERIV);
+  const StageParams sp = make_stage(ctx, h_stage, do_update);
+  if (ctx->D == 2) return ctx->milne ? launch_eom<2, true>(ctx, sp) : launch_eom<2, false>(ctx, sp);
+  return ctx->milne ? launch_eom<3, true>(ctx, sp) : launch_eom<3, false>(ctx, sp);
+}
+
+int derivative_evaluation(ccb_ctx* ctx, double h_stage, int do_update) {
+  int rc;
+  if ((rc = do_build_cells(ctx))) return rc;
+  if ((rc = do_prologue(ctx))) return rc;
+  if ((rc = do_gather_fields(ctx))) return rc;
+  if ((rc = do_eos_local(ctx, 1, 1))) return rc;
+  if ((rc = do_gather_gradients(ctx))) return rc;
+  return do_eom(ctx, h_stage, do_update);
+}
+
+int snapshot_y0(ccb_ctx* ctx) {
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    CUDA_OK(cudaMemcpyAsync(ctx->dv.y0[f], ctx->dv.f[f], sizeof(double) * kFieldWidth[f] * ctx->cap, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return CCB_OK;
+}
+
+int surface_device_error(ccb_ctx* ctx) {
+  int32_t e[2] = {0, 0};
+  CUDA_OK(cudaMemcpyAsync(e, ctx->d_small + 1, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (e[0] != 0) {
+    const char* what = e[0] == CCB_ERR_NEG_ENTROPY ? "negative entropy density" : e[0] == CCB_ERR_EOS_NO_ROOT ? "EoS: no solution found" : "device error";
+    ctx->err = std::string(what) + " (first offending particle id " + std::to_string(e[1]) + ")";
+    CUDA_OK(cudaMemsetAsync(ctx->d_small + 1, 0, 2 * sizeof(int32_t), ctx->stream));
+    return e[0];
+  }
+  return CCB_OK;
+}
+
+// ---- initialisation kernels (BSQHydro::initialize_hydrodynamics on the device) ---
+// tmp columns (current order): 0 e_or_s, 1 rhoB, 2 rhoS, 3 rhoQ, 4 bulk, 5..9 shv (xx,xy,xeta,yy,yeta)
+template <int D, bool MILNE>
+__global__ void init_particles_kernel(DeviceView dv, StageParams sp, const double* __restrict__ tmp, int input_as_entropy,
+                                      int input_initial_shear, int bulk_from_trace, double efcheck) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  const int64_t cap = dv.cap;
+  const double hc = kHbarcGeVfm;
+  const double rhoB = tmp[1 * cap + i], rhoS = tmp[2 * cap + i], rhoQ = tmp[3 * cap + i];
+  double T, muB, muS, muQ;
+  bool ok;
+  double e_in = 0., s_in = 0.;
+  // SPHWorkstation::initialize_entropy_and_charge_densities, src/sph_workstation.cpp:253-375
+  if (input_as_entropy) { s_in = tmp[i]; ok = conformal_invert_s(sp.conf, s_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
+  else { e_in = tmp[i] / hc; ok = conformal_invert_e(sp.conf, e_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
+  if (!ok) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
+  double r[TH_N];
+  conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
+  Thermo th;
+  thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+  if (input_as_entropy) e_in = th.e; else s_in = th.s;
+  store_thermo(dv, i, th);
+  dv.freeze[i] = (e_in > efcheck && dv.freeze[i] != 4) ? 0 : 4;
+  const double sigma = dv.f[CCB_F_SIGMA][i];
+  col(dv.f[CCB_F_EXTENSIVE], cap, 0, i) = s_in / sigma;
+  col(dv.f[CCB_F_EXTENSIVE], cap, 1, i) = rhoB / sigma;
+  col(dv.f[CCB_F_EXTENSIVE], cap, 2, i) = rhoS / sigma;
+  col(dv.f[CCB_F_EXTENSIVE], cap, 3, i) = rhoQ / sigma;
+  if (s_in < 0.0) dv.freeze[i] = 4;
+  // calculate_extensive_shv / set_bulk_Pi / set_diffusion, src/sph_workstation.cpp:1350-1460
+#pragma unroll
+  for (int c = 0; c < 5; ++c) col(dv.f[CCB_F_EXTENSIVE_SHV], cap, c, i) = input_initial_shear ? (tmp[(5 + c) * cap + i] / hc) / sigma : 0.0;
+  dv.f[CCB_F_EXTENSIVE_BULK][i] = bulk_from_trace ? (tmp[4 * cap + i] / hc - th.p) / sigma : 0.0;
+}
+
+template <int D, bool MILNE> int launch_init(ccb_ctx* ctx, const StageParams& sp) {
+  LAUNCH((init_particles_kernel<D, MILNE>), cdiv(ctx->n, 128), 128, ctx->dv, sp, ctx->init_tmp, ctx->cfg.input_as_entropy,
+         ctx->cfg.input_initial_shear, ctx->cfg.bulk_from_trace, ctx->efcheck);
+  return CCB_OK;
+}
+
+int upload_id_ordered(ccb_ctx* ctx, const double* host, double* dst_col) {
+  // host (id order) -> staging -> current order
+  CUDA_OK(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(gather_by_id, cdiv(ctx->n, 256), 256, ctx->d_stage, dst_col, ctx->dv.id, ctx->n);
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return CCB_OK;
+}
+
+}  // namespace
+
+// =================================================================================
+extern "C" {
+
+int ccb_field_width(int field) { return (field >= 0 && field < CCB_F_COUNT) ? kFieldWidth[field] : -1; }
+
+int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
+  if (!out || !cfg) return CCB_ERR_INVALID;
+  *out = nullptr;
+  ccb_ctx* ctx = new ccb_ctx();
+  ctx->cfg = *cfg;
+  *out = ctx;  // handed back even on failure so that ccb_last_error works
+  if (cfg->dim != 2 && cfg->dim != 3) { ctx->err = "dim must be 2 or 3"; return CCB_ERR_INVALID; }
+  if (cfg->rk_order != 2) { ctx->err = "rk_order must be 2"; return CCB_ERR_INVALID; }
+  if (cfg->eos_type != CCB_EOS_CONFORMAL) { ctx->err = "eos_type: only the conformal EoS is available in this build"; return CCB_ERR_INVALID; }
+  if (!(cfg->hT > 0.0)) { ctx->err = "hT must be positive"; return CCB_ERR_INVALID; }
+  ctx->D = cfg->dim;
+  ctx->milne = cfg->coordinate_system == CCB_COORD_HYPERBOLIC;
+  ctx->t = cfg->t0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
+  CUDA_OK(cudaSetDevice(cfg->device));
+  CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&ctx->ev0));
+  CUDA_OK(cudaEventCreate(&ctx->ev1));
+  CUDA_OK(cudaMalloc(&ctx->d_small, sizeof(int32_t) * 8));
+  CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t) * 8, ctx->stream));
+  CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
+  for (int p = 0; p < PH_COUNT; ++p) { ctx->phase_ms[p] = 0.; ctx->phase_calls[p] = 0; }
+  setup_grid(ctx);
+  if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
+  ctx->kD = make_kernel_norm(ctx->D, cfg->hT);
+  ctx->k2 = make_kernel_norm(2, cfg->hT);
+  ctx->k1 = make_kernel_norm(1, cfg->hEta > 0 ? cfg->hEta : cfg->hT);
+  // efcheck = e(T_FO, mu = 0): SPHWorkstation::initialize, src/sph_workstation.cpp:66-81
+  {
+    const double T = cfg->freeze_out_temperature_MeV / kHbarcMeVfm;
+    ConformalParams cp{cfg->conformal_c, cfg->conformal_T0, cfg->conformal_muB0, cfg->conformal_muS0, cfg->conformal_muQ0};
+    double r[TH_N];
+    conformal_full_thermo(cp, T, 0., 0., 0., r);
+    ctx->efcheck = r[TH_E];
+  }
+  return CCB_OK;
+}
+
+int ccb_destroy(ccb_ctx* ctx) {
+  if (!ctx) return CCB_ERR_INVALID;
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  free_particles(ctx);
+  cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return CCB_OK;
+}
+
+const char* ccb_last_error(ccb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t ccb_n(ccb_ctx* ctx) { return ctx ? ctx->n : -1; }
+double ccb_time(ccb_ctx* ctx) { return ctx ? ctx->t : 0.0; }
+int ccb_set_time(ccb_ctx* ctx, double t) { if (!ctx) return CCB_ERR_INVALID; ctx->t = t; return CCB_OK; }
+int64_t ccb_kernel_launches(ccb_ctx* ctx) { return ctx ? ctx->launches : -1; }
+void* ccb_stream(ccb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int ccb_grid_shape(ccb_ctx* ctx, int32_t nc[3]) { if (!ctx) return CCB_ERR_INVALID; for (int d = 0; d < 3; ++d) nc[d] = ctx->grid.nc[d]; return CCB_OK; }
+
+int ccb_profile_enable(ccb_ctx* ctx, int on) {
+  if (!ctx) return CCB_ERR_INVALID;
+  ctx->profiling = on != 0;
+  for (int p = 0; p < PH_COUNT; ++p) { ctx->phase_ms[p] = 0.; ctx->phase_calls[p] = 0; }
+  return CCB_OK;
+}
+int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls) {
+  if (!ctx || phase < 0 || phase >= PH_COUNT) return CCB_ERR_INVALID;
+  if (ms) *ms = ctx->phase_ms[phase];
+  if (calls) *calls = ctx->phase_calls[phase];
+  return CCB_OK;
+}
+
+int ccb_allocate(ccb_ctx* ctx, int64_t n) {
+  if (!ctx || n <= 0) return CCB_ERR_INVALID;
+  int rc = allocate_particles(ctx, n);
+  if (rc) return rc;
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return CCB_OK;
+}
+
+int ccb_set_field(ccb_ctx* ctx, int field, const double* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
+  const int w = kFieldWidth[field];
+  std::vector<double> colbuf(ctx->n);
+  for (int c = 0; c < w; ++c) {
+    for (int64_t i = 0; i < ctx->n; ++i) colbuf[i] = host[i * w + c];
+    if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->dv.f[field] + (int64_t)c * ctx->cap))) return rc;
+  }
+  if (field == CCB_F_POSITION) ctx->cells_valid = false;
+  return CCB_OK;
+}
+
+int ccb_get_field(ccb_ctx* ctx, int field, double* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
+  const int w = kFieldWidth[field];
+  std::vector<double> buf((size_t)ctx->n * w);
+  for (int c = 0; c < w; ++c)
+    LAUNCH(scatter_by_id, cdiv(ctx->n, 256), 256, ctx->dv.f[field] + (int64_t)c * ctx->cap, ctx->d_stage + (int64_t)c * ctx->cap, ctx->dv.id, ctx->n);
+  for (int c = 0; c < w; ++c)
+    CUDA_OK(cudaMemcpyAsync(buf.data() + (size_t)c * ctx->n, ctx->d_stage + (int64_t)c * ctx->cap, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < w; ++c)
+    for (int64_t i = 0; i < ctx->n; ++i) host[i * w + c] = buf[(size_t)c * ctx->n + i];
+  return CCB_OK;
+}
+
+int ccb_set_int_field(ccb_ctx* ctx, int field, const int32_t* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < CCB_I_BTRACK || field > CCB_I_FREEZE || !host) return CCB_ERR_INVALID;
+  int32_t* dst = field == CCB_I_BTRACK ? ctx->dv.btrack : ctx->dv.freeze;
+  int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
+  CUDA_OK(cudaMemcpyAsync(stage, host, sizeof(int32_t) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(gather_int_by_id, cdiv(ctx->n, 256), 256, stage, dst, ctx->dv.id, ctx->n);
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return CCB_OK;
+}
+
+int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
+  const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
+                                                                                                                      : reinterpret_cast<const int32_t*>(ctx->dv.key);
+  if (field == CCB_I_CELL && !ctx->cells_valid) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
+  int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
+  LAUNCH(scatter_int_by_id, cdiv(ctx->n, 256), 256, src, stage, ctx->dv.id, ctx->n);
+  CUDA_OK(cudaMemcpyAsync(host, stage, sizeof(int32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return CCB_OK;
+}
+
+int ccb_device_field(ccb_ctx* ctx, int field, int component, double** dptr) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < 0 || field >= CCB_F_COUNT || component < 0 || component >= kFieldWidth[field] || !dptr) return CCB_ERR_INVALID;
+  *dptr = ctx->dv.f[field] + (int64_t)component * ctx->cap;
+  return CCB_OK;
+}
+
+int ccb_build_cells(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : do_build_cells(ctx); }
+int ccb_smooth_fields(ccb_ctx* ctx) {
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if ((rc = do_prologue(ctx))) return rc;
+  return do_gather_fields(ctx);
+}
+int ccb_update_thermodynamics(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : do_eos_local(ctx, 1, 0); }
+int ccb_local_update(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : do_eos_local(ctx, 0, 1); }
+int ccb_smooth_gradients(ccb_ctx* ctx) { int rc = check_ready(ctx, true); return rc ? rc : do_gather_gradients(ctx); }
+int ccb_time_derivatives(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : do_eom(ctx, 0.0, 0); }
+int ccb_get_time_derivatives(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : derivative_evaluation(ctx, 0.0, 0); }
+
+int ccb_step(ccb_ctx* ctx, double dt) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  // Evolver::advance_timestep_rk2 (src/evolver.cpp:494-507): midpoint rule
+  if ((rc = snapshot_y0(ctx))) return rc;
+  const double t0 = ctx->t;
+  if ((rc = derivative_evaluation(ctx, 0.5 * dt, 1))) return rc;
+  ctx->t = t0 + 0.5 * dt;
+  if ((rc = derivative_evaluation(ctx, dt, 1))) return rc;
+  ctx->t = t0 + dt;
+  return CCB_OK;
+}
+
+int ccb_synchronize(ccb_ctx* ctx) {
+  if (!ctx) return CCB_ERR_INVALID;
+  return surface_device_error(ctx);
+}
+
+int ccb_reduce(ccb_ctx* ctx, ccb_totals* out) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (!out) return CCB_ERR_INVALID;
+  const int nb = kReduceBlocks;
+  double* d_out = ctx->d_reduce;
+  unsigned long long* d_fr = reinterpret_cast<unsigned long long*>(ctx->d_reduce + 6 * nb);
+  if (ctx->milne) LAUNCH((reduce_totals_kernel<true>), nb, 256, ctx->dv, ctx->t, d_out, d_fr);
+  else LAUNCH((reduce_totals_kernel<false>), nb, 256, ctx->dv, ctx->t, d_out, d_fr);
+  std::vector<double> h(7 * nb);
+  CUDA_OK(cudaMemcpyAsync(h.data(), d_out, sizeof(double) * 7 * nb, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  double acc[6] = {0., 0., 0., 0., 0., 0.};
+  unsigned long long fr = 0;
+  for (int b = 0; b < nb; ++b) {
+    for (int k = 0; k < 6; ++k) acc[k] += h[b * 6 + k];
+    unsigned long long f;
+    std::memcpy(&f, &h[6 * nb + b], sizeof(f));
+    fr += f;
+  }
+  out->S = acc[0]; out->B = acc[1]; out->Sq = acc[2]; out->Q = acc[3]; out->E = acc[4]; out->Ez = acc[5];
+  out->n_frozen = (int64_t)fr;
+  return CCB_OK;
+}
+
+int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
+  if (!ctx || !ic || ic->n <= 0 || !ic->r || !ic->e_or_s) return CCB_ERR_INVALID;
+  int rc = allocate_particles(ctx, ic->n);
+  if (rc) return rc;
+  const int64_t n = ctx->n, cap = ctx->cap;
+  ctx->t = ctx->cfg.t0;
+  DeviceView& dv = ctx->dv;
+  std::vector<double> colbuf(n);
+  // positions, velocities; sph_mass = extensive = 1 (process_initial_conditions, src/sph_workstation.cpp:1229-1340)
+  for (int d = 0; d < ctx->D; ++d) {
+    for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->r[i * 3 + d];
+    CUDA_OK(cudaMemcpyAsync(dv.f[CCB_F_POSITION] + (int64_t)d * cap, colbuf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->u ? ic->u[i * 3 + d] : 0.0;
+    CUDA_OK(cudaMemcpyAsync(dv.f[CCB_F_U] + (int64_t)d * cap, colbuf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  for (int c = 0; c < 4; ++c) {
+    LAUNCH(fill_kernel, cdiv(n, 256), 256, dv.f[CCB_F_SPH_MASS] + (int64_t)c * cap, 1.0, n);
+    LAUNCH(fill_kernel, cdiv(n, 256), 256, dv.f[CCB_F_EXTENSIVE] + (int64_t)c * cap, 1.0, n);
+  }
+  // neighbour grid + initial sigma (calculate_intial_sigma, src/sph_workstation.cpp:583-640)
+  if ((rc = do_build_cells(ctx))) return rc;
+  if ((rc = do_prologue(ctx))) return rc;
+  if ((rc = do_gather_fields(ctx))) return rc;
+  // IC densities into temporary columns, in the current (cell-sorted) order
+  CUDA_OK(cudaMalloc(&ctx->init_tmp, sizeof(double) * 10 * cap));
+  CUDA_OK(cudaMemsetAsync(ctx->init_tmp, 0, sizeof(double) * 10 * cap, ctx->stream));
+  const double* src1[5] = {ic->e_or_s, ic->rhoB, ic->rhoS, ic->rhoQ, ic->bulk};
+  for (int k = 0; k < 5; ++k)
+    if (src1[k] && (rc = upload_id_ordered(ctx, src1[k], ctx->init_tmp + (int64_t)k * cap))) return rc;
+  if (ic->shv6) {
+    const int pick[5] = {0, 1, 2, 3, 4};  // xx, xy, x-eta, yy, y-eta of the six-component row
+    for (int c = 0; c < 5; ++c) {
+      for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->shv6[i * 6 + pick[c]];
+      if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->init_tmp + (int64_t)(5 + c) * cap))) return rc;
+    }
+  }
+  const StageParams sp = make_stage(ctx, 0.0, 0);
+  if (ctx->D == 2) rc = ctx->milne ? launch_init<2, true>(ctx, sp) : launch_init<2, false>(ctx, sp);
+  else rc = ctx->milne ? launch_init<3, true>(ctx, sp) : launch_init<3, false>(ctx, sp);
+  if (rc) return rc;
+  // initial_smoothing (src/sph_workstation.cpp:395-457): smooth with the true extensive densities,
+  // rebuild pi^{mu nu}, update thermodynamics
+  if ((rc = do_prologue(ctx))) return rc;
+  if ((rc = do_gather_fields(ctx))) return rc;
+  if ((rc = do_eos_local(ctx, 1, 1))) return rc;
+  rc = surface_device_error(ctx);
+  cudaFree(ctx->init_tmp);
+  ctx->init_tmp = nullptr;
+  return rc;
+}
+
+}  // extern "C"

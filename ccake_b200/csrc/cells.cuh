@@ -1,0 +1,215 @@
+// Phase 01: neighbour search as a cell-list build.
+// Replaces Cabana::VerletList / LinkedCellList (reference src/system_state.cpp:651-719):
+// instead of a CSR neighbour list (N * N_ngb int32, ~2 GB for config 1) the particles
+// themselves are sorted by cell key, so that every later gather walks contiguous memory.
+//
+//   cell key  : k = (ix * ny + iy) * nz + iz,  i_d = floor((x_d - min_d) * rdx_d) clamped,
+//               same grid as the reference (cell edge >= 2h, grid = 2x (Milne) or 6x
+//               (Cartesian) the IC box);
+//   sort      : stable LSD radix sort of (key, index), 8 bits per pass, hand-written
+//               (block histogram -> exclusive scan -> stable block scatter);
+//   cell_start: histogram of keys + exclusive scan;
+//   permute   : every persistent column is gathered through the permutation.
+// All kernels stream: they are graded against HBM bandwidth.
+#pragma once
+
+#include "state.cuh"
+
+namespace ccb {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;                      // keys per thread per tile
+constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// ---- cell keys + per-cell histogram ---------------------------------------------
+__global__ void cell_key_kernel(DeviceView dv, CellGrid g, uint32_t* __restrict__ key, uint32_t* __restrict__ idx,
+                                uint32_t* __restrict__ cell_count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  int c[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const double x = dv.f[CCB_F_POSITION][(int64_t)d * dv.cap + i];
+    int ci = (int)floor((x - g.min[d]) * g.rdx[d]);
+    ci = ci < 0 ? 0 : (ci > g.nc[d] - 1 ? g.nc[d] - 1 : ci);
+    c[d] = ci;
+  }
+  const uint32_t k = (uint32_t)(((int64_t)c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+  key[i] = k;
+  idx[i] = (uint32_t)i;
+  atomicAdd(&cell_count[k], 1u);
+}
+
+// ---- device-wide exclusive scan (uint32), three small kernels --------------------
+__global__ void scan_block_sums(const uint32_t* __restrict__ in, uint32_t* __restrict__ sums, int64_t n) {
+  __shared__ uint32_t sh[kScanThreads / 32];
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  uint32_t acc = 0;
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + (int64_t)k * kScanThreads + threadIdx.x;
+    if (i < n) acc += in[i];
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) t += sh[w];
+    sums[blockIdx.x] = t;
+  }
+}
+// single block: exclusive scan of the block sums in place
+__global__ void scan_sums_inplace(uint32_t* __restrict__ sums, int64_t nb) {
+  __shared__ uint32_t sh[1024];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nb; base += 1024) {
+    const int64_t i = base + threadIdx.x;
+    const uint32_t v = (i < nb) ? sums[i] : 0u;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const uint32_t t = (threadIdx.x >= o) ? sh[threadIdx.x - o] : 0u;
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) sums[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += sh[1023];
+    __syncthreads();
+  }
+}
+// per tile: exclusive scan with the tile's offset; element order inside a tile is
+// (k, thread) -> base + k * threads + thread, i.e. plain index order.
+__global__ void scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, const uint32_t* __restrict__ sums,
+                           int64_t n, int write_total) {
+  __shared__ uint32_t wsum[kScanThreads / 32];
+  __shared__ uint32_t running;
+  const int64_t base = (int64_t)blockIdx.x * kScanTile;
+  if (threadIdx.x == 0) running = sums[blockIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < kScanItems; ++k) {
+    const int64_t i = base + (int64_t)k * kScanThreads + threadIdx.x;
+    const uint32_t v = (i < n) ? in[i] : 0u;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    const uint32_t r = running;
+    if (i < n) out[i] = r + woff + x - v;
+    __syncthreads();
+    if (threadIdx.x == kScanThreads - 1) running = r + woff + x;
+    __syncthreads();
+  }
+  // out[n] = grand total (cell_start needs ncells + 1 entries)
+  if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;
+}
+
+// ---- LSD radix sort, one 8-bit digit per pass -----------------------------------
+__global__ void radix_hist(const uint32_t* __restrict__ key, uint32_t* __restrict__ hist, int64_t n, int shift, int nblocks) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * kSortTile;
+  for (int k = 0; k < kSortItems; ++k) {
+    const int64_t i = base + (int64_t)k * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(key[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+// Stable scatter. Within a tile elements are visited in index order (round k, thread t);
+// the rank of an element among equal digits is (#equal in earlier rounds) + (#equal in
+// lower warps of this round) + (#equal in lower lanes of this warp).
+__global__ void radix_scatter(const uint32_t* __restrict__ key_in, const uint32_t* __restrict__ idx_in,
+                              uint32_t* __restrict__ key_out, uint32_t* __restrict__ idx_out,
+                              const uint32_t* __restrict__ offs, int64_t n, int shift, int nblocks) {
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t wcount[kSortThreads / 32][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  base[threadIdx.x] = offs[(int64_t)threadIdx.x * nblocks + blockIdx.x];
+  for (int w = 0; w < kSortThreads / 32; ++w) wcount[w][threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t tile = (int64_t)blockIdx.x * kSortTile;
+  for (int k = 0; k < kSortItems; ++k) {
+    const int64_t i = tile + (int64_t)k * kSortThreads + threadIdx.x;
+    const bool valid = i < n;
+    uint32_t kk = 0, vv = 0, d = 256u;  // 256 = "no digit" for the tail
+    if (valid) { kk = key_in[i]; vv = idx_in[i]; d = (kk >> shift) & 255u; }
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank_in_warp == 0) wcount[warp][d] = __popc(peers);
+    __syncthreads();
+    if (valid) {
+      uint32_t o = base[d] + rank_in_warp;
+      for (int w = 0; w < warp; ++w) o += wcount[w][d];
+      key_out[o] = kk;
+      idx_out[o] = vv;
+    }
+    __syncthreads();
+    {
+      uint32_t t = 0;
+      for (int w = 0; w < kSortThreads / 32; ++w) { t += wcount[w][threadIdx.x]; wcount[w][threadIdx.x] = 0; }
+      base[threadIdx.x] += t;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- permutation of the persistent columns --------------------------------------
+struct PermuteList {
+  int ncols;
+  const double* src[96];
+  double* dst[96];
+  int nints;
+  const int32_t* isrc[4];
+  int32_t* idst[4];
+};
+__global__ void permute_columns(PermuteList pl, const uint32_t* __restrict__ perm, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t j = perm[i];
+  for (int c = 0; c < pl.ncols; ++c) pl.dst[c][i] = pl.src[c][j];
+  for (int c = 0; c < pl.nints; ++c) pl.idst[c][i] = pl.isrc[c][j];
+}
+
+// first particle of every chunk of <= 32 targets that share a cell -> work list of the gathers
+__global__ void build_tasks(const uint32_t* __restrict__ key, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ tasks,
+                            int32_t* __restrict__ ntasks, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t rank = (uint32_t)i - cell_start[key[i]];
+  if ((rank & 31u) == 0u) tasks[atomicAdd(ntasks, 1)] = (int32_t)i;
+}
+
+// scatter a column (current order) into id order for download, and the reverse for upload
+__global__ void scatter_by_id(const double* __restrict__ src, double* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[id[i]] = src[i];
+}
+__global__ void gather_by_id(const double* __restrict__ src, double* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[id[i]];
+}
+__global__ void scatter_int_by_id(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[id[i]] = src[i];
+}
+__global__ void gather_int_by_id(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[id[i]];
+}
+
+}  // namespace ccb

@@ -1,0 +1,307 @@
+// Per-particle kernels: the work the reference spreads over ~18 launches per RK
+// stage collapsed into four streaming kernels:
+//   prologue      : 02 gamma/v (src/eom_default.cpp:18-38) + packing of the field-gather records
+//   eos_local     : 04 EoS inversion (src/sph_workstation.cpp:1714-1772; serial host code in the
+//                   reference), 05 pi^{mu nu}/q^mu rebuild (src/eom_default.cpp:57-172),
+//                   08 transport coefficients (src/sph_workstation.cpp:1623-1699) + packing of
+//                   the gradient-gather records
+//   eom_rk        : 10 equations of motion (src/eom_default.cpp:212-869) fused with the
+//                   Runge-Kutta stage update of Evolver::step_rk (src/evolver.cpp:345-485)
+//   reduce_totals : conservation sums (src/system_state.cpp:739-885) in one pass
+// One thread per particle, every column is read or written once: HBM-bound.
+#pragma once
+
+#include "gather.cuh"
+#include "stage_params.h"
+
+namespace ccb {
+
+template <int D, bool MILNE>
+__global__ void prologue_kernel(DeviceView dv, double t) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  Metric<MILNE> m(t);
+  double u[D], x[3];
+#pragma unroll
+  for (int d = 0; d < D; ++d) u[d] = col(dv.f[CCB_F_U], dv.cap, d, i);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x[d] = col(dv.f[CCB_F_POSITION], dv.cap, d, i);
+  const double gamma = gamma_of_u<D, MILNE>(m, u);
+  dv.f[CCB_F_GAMMA][i] = gamma;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) col(dv.f[CCB_F_V], dv.cap, d, i) = d < D ? u[d < D ? d : 0] / gamma : 0.0;
+  double* r = dv.rec_fields + i * REC_F;
+  const double ms = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
+  double2* q = reinterpret_cast<double2*>(r);
+  q[0] = make_double2(x[0], x[1]);
+  q[1] = make_double2(x[2], ms);
+  q[2] = make_double2(ms * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 0, i),
+                      col(dv.f[CCB_F_SPH_MASS], dv.cap, 1, i) * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 1, i));
+  q[3] = make_double2(col(dv.f[CCB_F_SPH_MASS], dv.cap, 2, i) * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 2, i),
+                      col(dv.f[CCB_F_SPH_MASS], dv.cap, 3, i) * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 3, i));
+}
+
+__device__ __forceinline__ void raise_error(DeviceView& dv, int code, int id) {
+  if (atomicCAS(&dv.err[0], 0, code) == 0) dv.err[1] = id;
+}
+
+__device__ __forceinline__ void load_thermo(const DeviceView& dv, int64_t i, Thermo& th) {
+  double* T = dv.f[CCB_F_THERMO];
+  th.T = col(T, dv.cap, 0, i); th.muB = col(T, dv.cap, 1, i); th.muS = col(T, dv.cap, 2, i); th.muQ = col(T, dv.cap, 3, i);
+  th.e = col(T, dv.cap, 4, i); th.s = col(T, dv.cap, 5, i); th.rhoB = col(T, dv.cap, 6, i); th.rhoS = col(T, dv.cap, 7, i);
+  th.rhoQ = col(T, dv.cap, 8, i); th.p = col(T, dv.cap, 9, i); th.cs2 = col(T, dv.cap, 10, i); th.w = col(T, dv.cap, 11, i);
+  th.dwds = col(T, dv.cap, 12, i); th.dwdB = col(T, dv.cap, 13, i); th.dwdS = col(T, dv.cap, 14, i); th.dwdQ = col(T, dv.cap, 15, i);
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) th.dalpha[a][x] = col(dv.f[CCB_F_DALPHA], dv.cap, a * 4 + x, i);
+  th.chiBB = 0.; th.chiBB0 = 0.;
+}
+__device__ __forceinline__ void store_thermo(const DeviceView& dv, int64_t i, const Thermo& th) {
+  double* T = dv.f[CCB_F_THERMO];
+  col(T, dv.cap, 0, i) = th.T; col(T, dv.cap, 1, i) = th.muB; col(T, dv.cap, 2, i) = th.muS; col(T, dv.cap, 3, i) = th.muQ;
+  col(T, dv.cap, 4, i) = th.e; col(T, dv.cap, 5, i) = th.s; col(T, dv.cap, 6, i) = th.rhoB; col(T, dv.cap, 7, i) = th.rhoS;
+  col(T, dv.cap, 8, i) = th.rhoQ; col(T, dv.cap, 9, i) = th.p; col(T, dv.cap, 10, i) = th.cs2; col(T, dv.cap, 11, i) = th.w;
+  col(T, dv.cap, 12, i) = th.dwds; col(T, dv.cap, 13, i) = th.dwdB; col(T, dv.cap, 14, i) = th.dwdS; col(T, dv.cap, 15, i) = th.dwdQ;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) col(dv.f[CCB_F_DALPHA], dv.cap, a * 4 + x, i) = th.dalpha[a][x];
+  col(dv.f[CCB_F_TSEED], dv.cap, 0, i) = th.T; col(dv.f[CCB_F_TSEED], dv.cap, 1, i) = th.muB;
+  col(dv.f[CCB_F_TSEED], dv.cap, 2, i) = th.muS; col(dv.f[CCB_F_TSEED], dv.cap, 3, i) = th.muQ;
+}
+
+// (s, rhoB, rhoS, rhoQ) in the local rest frame -> full thermodynamics.
+// Reference: SPHWorkstation::locate_phase_diagram_point_sBSQ (src/sph_workstation.cpp:659-741)
+// -> EquationOfState::update_s (src/eos.cpp:574-804) -> set_thermo (include/eos.h:121-148).
+__device__ __forceinline__ bool eos_from_sBSQ(const StageParams& sp, double s, double B, double S, double Q, Thermo& th) {
+  double T, muB, muS, muQ;
+  if (!conformal_invert_s(sp.conf, s, B, S, Q, T, muB, muS, muQ)) return false;
+  double r[TH_N];
+  conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
+  thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+  return true;
+}
+
+template <int D, bool MILNE>
+__global__ void eos_local_kernel(DeviceView dv, StageParams sp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  Metric<MILNE> m(sp.t);
+  Thermo th;
+  if (sp.do_eos) {
+    const double s = col(dv.f[CCB_F_THERMO], dv.cap, 5, i), B = col(dv.f[CCB_F_THERMO], dv.cap, 6, i),
+                 S = col(dv.f[CCB_F_THERMO], dv.cap, 7, i), Q = col(dv.f[CCB_F_THERMO], dv.cap, 8, i);
+    if (!eos_from_sBSQ(sp, s, B, S, Q, th)) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
+    store_thermo(dv, i, th);
+  } else {
+    load_thermo(dv, i, th);
+  }
+  if (!sp.do_local) return;
+  double u[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) u[d] = col(dv.f[CCB_F_U], dv.cap, d, i);
+  const double gamma = dv.f[CCB_F_GAMMA][i], sigma = dv.f[CCB_F_SIGMA][i], sig_lab = dv.f[CCB_F_SIGMA_LAB][i];
+  const double bulk = dv.f[CCB_F_EXTENSIVE_BULK][i] * sigma;
+  dv.f[CCB_F_BULK][i] = bulk;
+  double ext_shv[5], shv[4][4], ext_q[9], q[3][4];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) ext_shv[c] = col(dv.f[CCB_F_EXTENSIVE_SHV], dv.cap, c, i);
+  rebuild_shear<D, MILNE>(m, u, gamma, sigma, ext_shv, shv);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) col(dv.f[CCB_F_SHV], dv.cap, a * 4 + b, i) = shv[a][b];
+#pragma unroll
+  for (int c = 0; c < 9; ++c) ext_q[c] = sp.fl.diffusion ? col(dv.f[CCB_F_EXTENSIVE_DIFFUSION], dv.cap, c, i) : 0.0;
+  rebuild_diffusion<D, MILNE>(m, u, gamma, sigma, ext_q, q);
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int mu = 0; mu < 4; ++mu) col(dv.f[CCB_F_DIFFUSION], dv.cap, c * 4 + mu, i) = q[c][mu];
+  Transport tc;
+  transport_coefficients(th, sp.tp, tc);
+  {
+    double* TC = dv.f[CCB_F_TRANSPORT];
+    const double v[13] = {tc.eta_pi, tc.tau_pi, tc.zeta_Pi, tc.tau_Pi, tc.delta_PiPi, tc.delta_pipi, tc.lambda_piPi,
+                          tc.lambda_Pipi, tc.phi1, tc.phi3, tc.phi6, tc.phi7, tc.tau_pipi};
+#pragma unroll
+    for (int c = 0; c < 13; ++c) col(TC, dv.cap, c, i) = v[c];
+  }
+  // gradient-gather record, pre-scaled by 1/sigma_lab^2 where the pair formula needs it
+  const int REC = sp.fl.diffusion ? REC_G1 : REC_G0;
+  double* r = dv.rec_grad + i * REC;
+  const double sigsqr = 1.0 / (sig_lab * sig_lab);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) r[RG_X + d] = col(dv.f[CCB_F_POSITION], dv.cap, d, i);
+  r[RG_M] = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
+  r[RG_PT] = sigsqr * th.p;
+  r[RG_BT] = bulk / sig_lab / sig_lab;
+  r[RG_E] = th.e;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) r[RG_V + d] = col(dv.f[CCB_F_V], dv.cap, d, i);
+#pragma unroll
+  for (int d = 0; d < 3; ++d) r[RG_S0 + d] = sigsqr * shv[0][d + 1];
+  r[RG_SM + 0] = sigsqr * shv[1][1]; r[RG_SM + 1] = sigsqr * shv[1][2]; r[RG_SM + 2] = sigsqr * shv[1][3];
+  r[RG_SM + 3] = sigsqr * shv[2][2]; r[RG_SM + 4] = sigsqr * shv[2][3]; r[RG_SM + 5] = sigsqr * shv[3][3];
+  r[RG_SIGLAB] = sig_lab;
+  if (sp.fl.diffusion) {
+    r[RG_ALPHA + 0] = th.muB / th.T; r[RG_ALPHA + 1] = th.muS / th.T; r[RG_ALPHA + 2] = th.muQ / th.T;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[RG_Q0 + c] = sigsqr * q[c][0];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) r[RG_QI + c * 3 + d] = sigsqr * q[c][d + 1];
+    }
+    r[35] = 0.0;
+  }
+}
+
+template <int D, bool MILNE>
+__global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams sp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  Metric<MILNE> m(sp.t);
+  Thermo th;
+  load_thermo(dv, i, th);
+  Transport tc;
+  transport_coefficients(th, sp.tp, tc);
+  double kappa[3][3], tauq[3][3];
+  diffusion_coefficients(th, sp.tp, kappa, tauq);
+  EomIn<D> in;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    in.u[d] = col(dv.f[CCB_F_U], dv.cap, d, i);
+    in.v[d] = col(dv.f[CCB_F_V], dv.cap, d, i);
+    in.gradP[d] = col(dv.f[CCB_F_GRADP], dv.cap, d, i);
+    in.gradBulk[d] = col(dv.f[CCB_F_GRADBULK], dv.cap, d, i);
+    in.gradshear[d] = col(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i);
+    in.divshear[d] = col(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i);
+#pragma unroll
+    for (int e = 0; e < D; ++e) in.gradV[d][e] = col(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) in.grad_alpha[d][c] = sp.fl.diffusion ? col(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) : 0.0;
+  }
+  in.gamma = dv.f[CCB_F_GAMMA][i];
+  in.sigma = dv.f[CCB_F_SIGMA][i];
+  in.sigma_lab = dv.f[CCB_F_SIGMA_LAB][i];
+  in.mass_s = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
+  in.bulk = dv.f[CCB_F_BULK][i];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) in.shv[a][b] = col(dv.f[CCB_F_SHV], dv.cap, a * 4 + b, i);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int mu = 0; mu < 4; ++mu) in.q[c][mu] = sp.fl.diffusion ? col(dv.f[CCB_F_DIFFUSION], dv.cap, c * 4 + mu, i) : 0.0;
+    in.div_qa[c] = sp.fl.diffusion ? col(dv.f[CCB_F_DIV_QA], dv.cap, c, i) : 0.0;
+    in.grad_qa[c] = sp.fl.diffusion ? col(dv.f[CCB_F_GRAD_QA], dv.cap, c, i) : 0.0;
+  }
+  EomOut<D> out;
+  eom_evaluate<D, MILNE>(m, in, th, tc, kappa, tauq, sp.fl, out);
+
+  // derivatives are kept: Output, RK4 accumulation and the parity tests read them
+#pragma unroll
+  for (int d = 0; d < 3; ++d) col(dv.f[CCB_F_DU_DT], dv.cap, d, i) = d < D ? out.du_dt[d < D ? d : 0] : 0.0;
+  col(dv.f[CCB_F_D_EXTENSIVE_DT], dv.cap, 0, i) = out.ds_dt;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) col(dv.f[CCB_F_D_EXTENSIVE_DT], dv.cap, 1 + c, i) = out.dN_dt[c];
+  dv.f[CCB_F_D_BULK_DT][i] = out.dbulk_dt;
+#pragma unroll
+  for (int c = 0; c < 5; ++c) col(dv.f[CCB_F_D_SHV_DT], dv.cap, c, i) = out.dshv_dt[c];
+  if (sp.fl.diffusion) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int d = 0; d < 3; ++d) col(dv.f[CCB_F_D_DIFFUSION_DT], dv.cap, c * 3 + d, i) = out.dq_dt[c][d];
+  }
+  dv.f[CCB_F_THETA][i] = out.theta;
+  dv.f[CCB_F_SHV_NABLA_U][i] = out.shv_nabla_u;
+  dv.f[CCB_F_DEZ][i] = out.dEz;
+
+  if (!sp.do_update) return;
+  // Evolver::step_rk, src/evolver.cpp:363-475: y = y0 + h * f
+  const double h = sp.h_stage;
+  double ext_s = dv.y0[CCB_F_EXTENSIVE][i] + h * out.ds_dt;
+  if (ext_s < 0.0) {
+    if (dv.freeze[i] > 3) ext_s = 1.e-3;
+    else raise_error(dv, CCB_ERR_NEG_ENTROPY, dv.id[i]);
+  }
+  col(dv.f[CCB_F_EXTENSIVE], dv.cap, 0, i) = ext_s;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+    col(dv.f[CCB_F_EXTENSIVE], dv.cap, 1 + c, i) = col(dv.y0[CCB_F_EXTENSIVE], dv.cap, 1 + c, i) + h * out.dN_dt[c];
+  dv.f[CCB_F_EXTENSIVE_BULK][i] = dv.y0[CCB_F_EXTENSIVE_BULK][i] + h * out.dbulk_dt;
+  dv.f[CCB_F_EZ][i] = dv.y0[CCB_F_EZ][i] + h * out.dEz;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    if (d < D) {
+      col(dv.f[CCB_F_POSITION], dv.cap, d, i) = col(dv.y0[CCB_F_POSITION], dv.cap, d, i) + h * in.v[d < D ? d : 0];
+      col(dv.f[CCB_F_U], dv.cap, d, i) = col(dv.y0[CCB_F_U], dv.cap, d, i) + h * out.du_dt[d < D ? d : 0];
+    } else {
+      col(dv.f[CCB_F_POSITION], dv.cap, d, i) = 0.0;
+      col(dv.f[CCB_F_U], dv.cap, d, i) = 0.0;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 5; ++c)
+    col(dv.f[CCB_F_EXTENSIVE_SHV], dv.cap, c, i) = col(dv.y0[CCB_F_EXTENSIVE_SHV], dv.cap, c, i) + h * out.dshv_dt[c];
+  if (sp.fl.diffusion) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c)
+      col(dv.f[CCB_F_EXTENSIVE_DIFFUSION], dv.cap, c, i) =
+          col(dv.y0[CCB_F_EXTENSIVE_DIFFUSION], dv.cap, c, i) + h * out.dq_dt[c / 3][c % 3];
+  }
+}
+
+// S, B, S, Q, E, Ez, n_frozen in one pass (block reduce, one partial per block).
+// Mirrors the reference sums term by term, including its use of sph_mass.s in the
+// S and Q diffusion terms (src/system_state.cpp:770, 803, 812).
+template <bool MILNE>
+__global__ void reduce_totals_kernel(DeviceView dv, double t, double* __restrict__ out, unsigned long long* __restrict__ nfrozen) {
+  double acc[6] = {0., 0., 0., 0., 0., 0.};
+  unsigned int frozen = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < dv.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ms = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i), mB = col(dv.f[CCB_F_SPH_MASS], dv.cap, 1, i),
+                 mS = col(dv.f[CCB_F_SPH_MASS], dv.cap, 2, i), mQ = col(dv.f[CCB_F_SPH_MASS], dv.cap, 3, i);
+    const double gamma = dv.f[CCB_F_GAMMA][i], sigma = dv.f[CCB_F_SIGMA][i], sig_lab = dv.f[CCB_F_SIGMA_LAB][i];
+    acc[0] += col(dv.f[CCB_F_EXTENSIVE], dv.cap, 0, i) * ms;
+    const double qb0 = col(dv.f[CCB_F_DIFFUSION], dv.cap, 0, i), qs0 = col(dv.f[CCB_F_DIFFUSION], dv.cap, 4, i),
+                 qq0 = col(dv.f[CCB_F_DIFFUSION], dv.cap, 8, i);
+    acc[1] += col(dv.f[CCB_F_EXTENSIVE], dv.cap, 1, i) * mB + (qb0 * mB / sigma / gamma) * mB / gamma;
+    acc[2] += col(dv.f[CCB_F_EXTENSIVE], dv.cap, 2, i) * mS + (qs0 * ms / sigma / gamma);
+    acc[3] += col(dv.f[CCB_F_EXTENSIVE], dv.cap, 3, i) * mQ + (qq0 * ms / sigma / gamma);
+    const double w = col(dv.f[CCB_F_THERMO], dv.cap, 11, i), p = col(dv.f[CCB_F_THERMO], dv.cap, 9, i);
+    const double bulk = dv.f[CCB_F_BULK][i], shv00 = dv.f[CCB_F_SHV][i];
+    const double C = w + bulk, g2 = gamma * gamma;
+    acc[4] += (C * g2 - p - bulk + shv00) * ms * (MILNE ? t : 1.0) / sig_lab;
+    acc[5] += dv.f[CCB_F_EZ][i];
+    frozen += (dv.freeze[i] >= 4) ? 1u : 0u;
+  }
+  __shared__ double sh[6][8];
+  __shared__ unsigned int shf[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double v = acc[k];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[k][warp] = v;
+  }
+  for (int o = 16; o > 0; o >>= 1) frozen += __shfl_down_sync(0xffffffffu, frozen, o);
+  if (lane == 0) shf[warp] = frozen;
+  __syncthreads();
+  // one partial per block, summed by the host in block order: deterministic totals
+  if (threadIdx.x < 6) {
+    double v = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh[threadIdx.x][w];
+    out[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+  if (threadIdx.x == 6) {
+    unsigned int v = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += shf[w];
+    nfrozen[blockIdx.x] = (unsigned long long)v;
+  }
+}
+
+}  // namespace ccb

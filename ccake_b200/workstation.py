@@ -1,0 +1,186 @@
+"""Host-side mirror of the reference's SystemState / SPHWorkstation / Evolver
+surface for the hot path, on top of the C ABI (``include/ccake_b200.h``).
+
+Method names follow the reference (``reset_neighbour_list``,
+``smooth_all_particle_fields``, ``advance_timestep`` ...,
+``include/sph_workstation.h:113-156``, ``include/system_state.h:40-127``) so that the
+parity tests read like the reference's own unit tests.  The C++ twin of this file
+is ``include/ccake_b200_host.hpp``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .settings import DEFAULTS, to_config
+
+
+class CCAKEError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ccake_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class SPHWorkstation:
+    """One context (= one GPU) holding the particle system and running the phases."""
+
+    def __init__(self, settings: dict, device: int = 0, rank: int = 0, nranks: int = 1):
+        self.settings = dict(DEFAULTS)
+        self.settings.update(settings)
+        self._L = _capi.lib()
+        self._cfg = to_config(self.settings, device=device, rank=rank, nranks=nranks)
+        self._ctx = C.c_void_p()
+        rc = self._L.ccb_create(C.byref(self._ctx), C.byref(self._cfg))
+        if rc:
+            msg = self._L.ccb_last_error(self._ctx).decode() if self._ctx else "ccb_create failed"
+            if self._ctx:
+                self._L.ccb_destroy(self._ctx)
+                self._ctx = C.c_void_p()
+            raise CCAKEError(rc, msg)
+
+    # -- plumbing --------------------------------------------------------------
+    def _check(self, rc):
+        if rc:
+            raise CCAKEError(rc, self._L.ccb_last_error(self._ctx).decode())
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._L.ccb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- SystemState -----------------------------------------------------------
+    @property
+    def n_particles(self):
+        return self._L.ccb_n(self._ctx)
+
+    @property
+    def t(self):
+        return self._L.ccb_time(self._ctx)
+
+    @t.setter
+    def t(self, v):
+        self._check(self._L.ccb_set_time(self._ctx, float(v)))
+
+    def allocate(self, n):
+        """SystemState::allocate_cabana_particles for n blank particles."""
+        self._check(self._L.ccb_allocate(self._ctx, int(n)))
+
+    def upload_initial_conditions(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None):
+        """BSQHydro::read_ccake rows + BSQHydro::initialize_hydrodynamics, on the device."""
+        r = np.asarray(r, dtype=np.float64)
+        n = r.shape[0]
+        r3 = np.zeros((n, 3))
+        r3[:, : r.shape[1]] = r
+        keep = [r3, np.ascontiguousarray(e_or_s, dtype=np.float64)]
+        ic = _capi.IC()
+        ic.n = n
+        ic.r = _dp(keep[0])
+        ic.e_or_s = _dp(keep[1])
+        for name, a, w in (("rhoB", rhoB, 1), ("rhoS", rhoS, 1), ("rhoQ", rhoQ, 1), ("u", u, 3), ("bulk", bulk, 1), ("shv6", shv6, 6)):
+            if a is None:
+                continue
+            a = np.asarray(a, dtype=np.float64)
+            if w == 3:
+                a3 = np.zeros((n, 3))
+                a3[:, : a.shape[1]] = a
+                a = a3
+            a = np.ascontiguousarray(a)
+            keep.append(a)
+            setattr(ic, name, _dp(a))
+        self._check(self._L.ccb_upload_ic(self._ctx, C.byref(ic)))
+
+    def get(self, field):
+        """copy_device_to_host for one field, particle-id order; shape (n,) or (n, width)."""
+        fid, w = _capi.FIELDS[field]
+        out = np.empty((self.n_particles, w), dtype=np.float64)
+        self._check(self._L.ccb_get_field(self._ctx, fid, _dp(out)))
+        return out[:, 0] if w == 1 else out
+
+    def set(self, field, values):
+        fid, w = _capi.FIELDS[field]
+        a = np.ascontiguousarray(np.asarray(values, dtype=np.float64).reshape(self.n_particles, w))
+        self._check(self._L.ccb_set_field(self._ctx, fid, _dp(a)))
+
+    def get_int(self, field):
+        out = np.empty(self.n_particles, dtype=np.int32)
+        self._check(self._L.ccb_get_int_field(self._ctx, _capi.INT_FIELDS[field], out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def set_int(self, field, values):
+        a = np.ascontiguousarray(values, dtype=np.int32)
+        self._check(self._L.ccb_set_int_field(self._ctx, _capi.INT_FIELDS[field], a.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def grid_shape(self):
+        nc = (C.c_int32 * 3)()
+        self._check(self._L.ccb_grid_shape(self._ctx, nc))
+        return np.array(list(nc), dtype=np.int32)
+
+    def conservation(self):
+        """conservation_entropy / conservation_BSQ / conservation_energy in one device pass."""
+        t = _capi.Totals()
+        self._check(self._L.ccb_reduce(self._ctx, C.byref(t)))
+        return dict(S=t.S, B=t.B, Sq=t.Sq, Q=t.Q, E=t.E, Ez=t.Ez, n_frozen=t.n_frozen)
+
+    # -- SPHWorkstation phases ---------------------------------------------------
+    def reset_neighbour_list(self):
+        self._check(self._L.ccb_build_cells(self._ctx))
+
+    def smooth_all_particle_fields(self):
+        """calculate_gamma_and_velocities + smooth_all_particle_fields."""
+        self._check(self._L.ccb_smooth_fields(self._ctx))
+
+    def update_all_particle_thermodynamics(self):
+        self._check(self._L.ccb_update_thermodynamics(self._ctx))
+
+    def reset_pi_tensor_and_viscosities(self):
+        """reset_pi_tensor + update_all_particle_viscosities."""
+        self._check(self._L.ccb_local_update(self._ctx))
+
+    def smooth_all_particle_gradients(self):
+        self._check(self._L.ccb_smooth_gradients(self._ctx))
+
+    def evaluate_time_derivatives(self):
+        self._check(self._L.ccb_time_derivatives(self._ctx))
+
+    def get_time_derivatives(self):
+        self._check(self._L.ccb_get_time_derivatives(self._ctx))
+
+    def advance_timestep(self, dt, rk_order=2):
+        if rk_order != self._cfg.rk_order:
+            raise ValueError("rk_order is fixed at context creation")
+        self._check(self._L.ccb_step(self._ctx, float(dt)))
+
+    def synchronize(self):
+        self._check(self._L.ccb_synchronize(self._ctx))
+
+    # -- instrumentation ---------------------------------------------------------
+    @property
+    def kernel_launches(self):
+        return self._L.ccb_kernel_launches(self._ctx)
+
+    def profile(self, on=True):
+        self._check(self._L.ccb_profile_enable(self._ctx, int(on)))
+
+    def profile_table(self):
+        out = {}
+        for k, name in enumerate(_capi.PHASE_NAMES):
+            ms, calls = C.c_double(), C.c_int64()
+            self._L.ccb_profile_get(self._ctx, k, C.byref(ms), C.byref(calls))
+            out[name] = (ms.value, calls.value)
+        return out
+
+    @property
+    def stream(self):
+        return self._L.ccb_stream(self._ctx)

@@ -1,0 +1,195 @@
+/* ccake_b200.h -- C ABI of the B200-native CCAKE SPH hot path.
+ *
+ * CCAKE has no plugin/FFI boundary of its own: the per-timestep path is ordinary
+ * C++ templates (SystemState<D>, SPHWorkstation<D,TEOM>, Evolver<D>) linked into
+ * one binary. This header is the seam a maintainer binds those classes to; every
+ * entry point names the reference member function(s) it replaces (file:line under
+ * the reference tree). INTEGRATION.md shows the C++ glue.
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns a ccb_status;
+ *     ccb_last_error(ctx) gives a library-owned, human-readable string.
+ *   - one ccb_ctx per GPU; a context is NOT thread-safe; the caller is the
+ *     simulation's main-loop thread.
+ *   - all host buffers are caller-owned; the library owns every device allocation.
+ *   - per-particle host arrays are in PARTICLE-ID order (the order of upload);
+ *     on the device particles are physically re-sorted by cell every RK stage.
+ *   - units and index conventions are the reference's: fm, fm^-1 ... ; charges
+ *     0=B 1=S 2=Q; shv[4][4] with 0=tau 1=x 2=y 3=eta.
+ */
+#ifndef CCAKE_B200_H
+#define CCAKE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ccb_ctx ccb_ctx;
+
+typedef enum {
+  CCB_OK = 0,
+  CCB_ERR_INVALID = 1,      /* bad argument / unsupported configuration */
+  CCB_ERR_CUDA = 2,         /* CUDA runtime failure (no device, launch error, OOM) */
+  CCB_ERR_NEG_ENTROPY = 3,  /* reference: exit(EXIT_FAILURE), src/evolver.cpp:437-450 */
+  CCB_ERR_EOS_NO_ROOT = 4,  /* reference: exit(404), src/sph_workstation.cpp:1748-1760 */
+  CCB_ERR_OUT_OF_GRID = 5,  /* particle left the neighbour grid (reference: undefined behaviour, src/system_state.cpp:636-638) */
+  CCB_ERR_STATE = 6         /* call sequence error (e.g. step before upload) */
+} ccb_status;
+
+enum { CCB_COORD_HYPERBOLIC = 0, CCB_COORD_CARTESIAN = 1 };
+enum { CCB_EOS_CONFORMAL = 0, CCB_EOS_TABLE = 1 };
+
+/* Mirror of the Settings fields the hot path consumes (reference include/settings.h,
+ * SURVEY.md appendix B). Mode integers take the values of the reference enums in
+ * include/transport_coefficients.h:18-97. */
+typedef struct {
+  int dim;                 /* 2 or 3 (Settings::dim) */
+  int coordinate_system;   /* CCB_COORD_* (Settings::coordinate_system) */
+  int rk_order;            /* 2 (Settings::rk_order) */
+  int factorized_kernel;   /* Settings::factorized_kernel (D == 3 only) */
+  double t0, hT, hEta;
+  double xmin, ymin, etamin;          /* IC header minima -> neighbour grid (src/system_state.cpp:656-692) */
+  double stepx, stepy, stepEta;       /* IC lattice spacing (init only) */
+  int using_shear, using_diffusion, using_vorticity; /* Settings::check_consistency */
+  int input_as_entropy, input_initial_shear, bulk_from_trace;
+  /* transport (src/transport_coefficients.cpp:9-279) */
+  int shear_mode, shear_relax_mode, zeta_mode, bulk_relax_mode, diffusion_mode, diffusion_relax_mode;
+  int delta_pipi_mode, tau_pipi_mode, lambda_piPi_mode, phi6_mode, phi7_mode;
+  int delta_PiPi_mode, lambda_Pipi_mode, phi1_mode, phi3_mode;
+  int modulate_zeta_with_tanh, critical_scaling_bulk;
+  double constant_eta_over_s, constant_zeta_over_s, cs2_dependent_zeta_A, cs2_dependent_zeta_p, C_B;
+  double constant_kappa_over_T2[9];
+  /* equation of state */
+  int eos_type;            /* CCB_EOS_* */
+  double conformal_c, conformal_T0, conformal_muB0, conformal_muS0, conformal_muQ0;
+  double freeze_out_temperature_MeV;
+  int prohibit_unstable_cs2, prohibit_acausal_cs2;
+  /* runtime */
+  int device;              /* CUDA device ordinal */
+  int rank, nranks;        /* slab decomposition (1 process per GPU) */
+} ccb_config;
+
+/* Initial-condition rows, one entry per particle, units as in the reference's IC
+ * text format (BSQHydro::read_ccake, src/BSQHydro.cpp:207-425): positions in fm,
+ * e in GeV/fm^3 (or s in fm^-3 when input_as_entropy), rho in fm^-3, u^i
+ * dimensionless, bulk and shv6 = (xx, xy, x-eta, yy, y-eta, eta-eta) in GeV/fm^3.
+ * r and u are n x 3, row-major; unused dimensions are ignored. Any pointer except
+ * r and e_or_s may be NULL (= zeros). */
+typedef struct {
+  int64_t n;
+  const double* r;
+  const double* e_or_s;
+  const double* rhoB;
+  const double* rhoS;
+  const double* rhoQ;
+  const double* u;
+  const double* bulk;
+  const double* shv6;
+} ccb_ic;
+
+/* Per-particle fields addressable through ccb_get_field / ccb_set_field.
+ * Width = doubles per particle. Names follow the reference members. */
+typedef enum {
+  CCB_F_POSITION = 0,      /* 3  particle_info::position */
+  CCB_F_U,                 /* 3  hydro_vector_info::u */
+  CCB_F_EXTENSIVE,         /* 4  extensive s, rhoB, rhoS, rhoQ */
+  CCB_F_SPH_MASS,          /* 4  sph_mass  s, rhoB, rhoS, rhoQ */
+  CCB_F_EXTENSIVE_BULK,    /* 1 */
+  CCB_F_EXTENSIVE_SHV,     /* 5  xx, xy, x-eta, yy, y-eta */
+  CCB_F_EXTENSIVE_DIFFUSION,/* 9 [icharge][idir] */
+  CCB_F_EZ,                /* 1  contribution_to_total_Ez */
+  CCB_F_TSEED,             /* 4  thermo T, muB, muS, muQ (EoS warm start / result) */
+  CCB_F_V,                 /* 3 */
+  CCB_F_GAMMA,             /* 1 */
+  CCB_F_SIGMA_LAB,         /* 1 */
+  CCB_F_SIGMA,             /* 1 */
+  CCB_F_SMOOTHED,          /* 4  lab-frame smoothed s, rhoB, rhoS, rhoQ */
+  CCB_F_THERMO,            /* 16 T muB muS muQ e s rhoB rhoS rhoQ p cs2 w dwds dwdB dwdS dwdQ */
+  CCB_F_DALPHA,            /* 12 dalpha_{B,S,Q}/d{s,B,S,Q} */
+  CCB_F_BULK,              /* 1 */
+  CCB_F_SHV,               /* 16 full pi^{mu nu} */
+  CCB_F_DIFFUSION,         /* 12 q^mu_a [icharge][mu] */
+  CCB_F_TRANSPORT,         /* 13 eta_pi tau_pi zeta_Pi tau_Pi delta_PiPi delta_pipi lambda_piPi lambda_Pipi phi1 phi3 phi6 phi7 tau_pipi */
+  CCB_F_GRADP,             /* 3 */
+  CCB_F_GRADE,             /* 3 */
+  CCB_F_GRADBULK,          /* 3 */
+  CCB_F_GRADSHEAR,         /* 3 */
+  CCB_F_DIVSHEAR,          /* 3 */
+  CCB_F_GRADV,             /* 9 [i][j] = d_i v_j */
+  CCB_F_DIV_QA,            /* 3 */
+  CCB_F_GRAD_QA,           /* 3 */
+  CCB_F_GRAD_ALPHA,        /* 9 [idir][icharge] */
+  CCB_F_DU_DT,             /* 3 */
+  CCB_F_D_EXTENSIVE_DT,    /* 4  s, rhoB, rhoS, rhoQ */
+  CCB_F_D_BULK_DT,         /* 1 */
+  CCB_F_D_SHV_DT,          /* 5 */
+  CCB_F_D_DIFFUSION_DT,    /* 9 */
+  CCB_F_THETA,             /* 1 */
+  CCB_F_SHV_NABLA_U,       /* 1 */
+  CCB_F_DEZ,               /* 1  contribution_to_total_dEz */
+  CCB_F_COUNT
+} ccb_field;
+
+typedef enum { CCB_I_ID = 0, CCB_I_BTRACK, CCB_I_FREEZE, CCB_I_CELL, CCB_I_COUNT } ccb_int_field;
+
+typedef struct {
+  double S, B, Sq, Q, E, Ez;  /* SystemState::conservation_{entropy,BSQ,energy}, src/system_state.cpp:739-885 */
+  int64_t n_frozen;           /* SPHWorkstation::continue_evolution, src/sph_workstation.cpp:2011-2016 */
+} ccb_totals;
+
+/* --- lifetime ------------------------------------------------------------- */
+int ccb_create(ccb_ctx** out, const ccb_config* cfg);   /* SystemState<D>/SPHWorkstation<D,TEOM> ctors + SPHWorkstation::initialize (src/sph_workstation.cpp:38-84) */
+int ccb_destroy(ccb_ctx* ctx);
+const char* ccb_last_error(ccb_ctx* ctx);
+int ccb_field_width(int field);
+
+/* --- state in / out ------------------------------------------------------- */
+/* n blank particles (ids 0..n-1); state is then injected with ccb_set_field.
+ * Replaces SystemState::allocate_cabana_particles (src/system_state.cpp:58-63). */
+int ccb_allocate(ccb_ctx* ctx, int64_t n);
+/* IC rows -> device + the whole of BSQHydro::initialize_hydrodynamics
+ * (src/BSQHydro.cpp:569-611): e_cutoff is the caller's job. */
+int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic);
+/* SystemState::copy_host_to_device / copy_device_to_host (src/system_state.cpp:72-555), field by field */
+int ccb_set_field(ccb_ctx* ctx, int field, const double* host);
+int ccb_get_field(ccb_ctx* ctx, int field, double* host);
+int ccb_set_int_field(ccb_ctx* ctx, int field, const int32_t* host);
+int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host);
+int64_t ccb_n(ccb_ctx* ctx);
+double ccb_time(ccb_ctx* ctx);
+int ccb_set_time(ccb_ctx* ctx, double t);
+/* neighbour-grid shape of the last cell build: cells per axis (src/system_state.cpp:651-700) */
+int ccb_grid_shape(ccb_ctx* ctx, int32_t ncell[3]);
+
+/* --- the ten phases of SPHWorkstation::get_time_derivatives (src/sph_workstation.cpp:1543-1583) --- */
+int ccb_build_cells(ccb_ctx* ctx);        /* 01 SystemState::reset_neighbour_list (src/system_state.cpp:651-719) */
+int ccb_smooth_fields(ccb_ctx* ctx);      /* 02+03 TEOM::update_velocity (src/eom_default.cpp:18-38) + smooth_all_particle_fields (src/sph_workstation.cpp:495-578) */
+int ccb_update_thermodynamics(ccb_ctx* ctx); /* 04 update_all_particle_thermodynamics (src/sph_workstation.cpp:1714-1772) */
+int ccb_local_update(ccb_ctx* ctx);       /* 05+08 TEOM::reset_pi_tensor (src/eom_default.cpp:57-172) + update_all_particle_viscosities (src/sph_workstation.cpp:1623-1699) */
+int ccb_smooth_gradients(ccb_ctx* ctx);   /* 09 smooth_all_particle_gradients (src/sph_workstation.cpp:797-986) */
+int ccb_time_derivatives(ccb_ctx* ctx);   /* 10 TEOM::evaluate_time_derivatives (src/eom_default.cpp:212-869) */
+int ccb_get_time_derivatives(ccb_ctx* ctx); /* all of the above in order */
+
+/* --- time stepping -------------------------------------------------------- */
+/* SPHWorkstation::advance_timestep -> Evolver::execute_timestep (src/sph_workstation.cpp:2043-2073,
+ * src/evolver.cpp:98-561): one full RK step of size dt; asynchronous on the context's stream. */
+int ccb_step(ccb_ctx* ctx, double dt);
+int ccb_synchronize(ccb_ctx* ctx);        /* waits for the stream and surfaces device-side error flags */
+int ccb_reduce(ccb_ctx* ctx, ccb_totals* out);
+
+/* --- instrumentation ------------------------------------------------------ */
+/* number of kernels launched by this context since creation, and device time (ms) per
+ * reference phase name ("01_neighbour_list" ...) when profiling is on (CCAKE_PROFILE, include/phase_profiler.h) */
+int64_t ccb_kernel_launches(ccb_ctx* ctx);
+int ccb_profile_enable(ccb_ctx* ctx, int on);
+int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls);
+void* ccb_stream(ccb_ctx* ctx);           /* cudaStream_t of the context */
+/* device pointer of a field in CURRENT (cell-sorted) order, for zero-copy consumers (halo packing) */
+int ccb_device_field(ccb_ctx* ctx, int field, int component, double** dptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

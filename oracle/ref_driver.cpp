@@ -189,6 +189,8 @@ std::shared_ptr<Settings> parse_settings(const char* kv) {
   s->delta_PiPi_mode = "default"; s->lambda_Pipi_mode = "default"; s->phi1_mode = "default"; s->phi3_mode = "default";
   s->source_type = "disabled"; s->jets_type = "disabled"; s->print_conservation_status = false;
   s->buffer_event = false; s->modulate_zeta_with_tanh = false; s->rk_order = 2;
+  s->constant_eta_over_s = 0.08; s->constant_zeta_over_s = 0.005;
+  s->cs2_dependent_zeta_A = 1.67552; s->cs2_dependent_zeta_p = 2.0;
   std::istringstream in(kv);
   std::string line;
   while (std::getline(in, line)) {
@@ -248,7 +250,12 @@ std::shared_ptr<Settings> parse_settings(const char* kv) {
     else if (k.rfind("kappa_", 0) == 0 && k.size() == 8) s->constant_kappa_over_T2[k[6] - '0'][k[7] - '0'] = std::stod(v);
     else { std::fprintf(stderr, "ccake_ref: unknown setting '%s'\n", k.c_str()); return nullptr; }
   }
-  s->check_consistency();
+  // Derived switches exactly as Input::decode_settings sets them (src/input.cpp:390-408,
+  // :419-421, :577-582). NB Settings::check_consistency() is never called by the reference.
+  if (s->etaMode == "disabled") s->using_shear = false;
+  else if (s->etaMode == "constant") s->using_shear = !(s->constant_eta_over_s <= 1.E-3);
+  s->using_diffusion = (s->diffusionMode != "disabled");
+  s->using_vorticity = s->use_vorticity;
   return s;
 }
 

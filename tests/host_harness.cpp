@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE ONLY. Not part of the product path.
+//
+// Compiles the per-particle physics headers of the library
+// (ccake_b200/csrc/physics_*.cuh, stage_params.h) with the HOST compiler and exposes
+// them over arrays, so that the arithmetic the CUDA kernels run can be compared with
+// the oracle here, without a GPU. The shipped library never calls these on the host.
+#include <cstdint>
+
+#include "../ccake_b200/csrc/stage_params.h"
+
+using namespace ccb;
+
+extern "C" {
+
+// thermo[16] + dalpha[12] from LRF densities (conformal EoS), per particle
+int hh_eos(const ccb_config* cfg, int64_t n, const double* sBSQ, double* thermo, double* dalpha) {
+  const StageParams sp = make_stage_params(*cfg, cfg->t0, 0., 0);
+  for (int64_t i = 0; i < n; ++i) {
+    double T, muB, muS, muQ;
+    if (!conformal_invert_s(sp.conf, sBSQ[4 * i], sBSQ[4 * i + 1], sBSQ[4 * i + 2], sBSQ[4 * i + 3], T, muB, muS, muQ)) return 1;
+    double r[TH_N];
+    conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
+    Thermo th;
+    thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+    const double v[16] = {th.T, th.muB, th.muS, th.muQ, th.e, th.s, th.rhoB, th.rhoS, th.rhoQ, th.p, th.cs2, th.w, th.dwds, th.dwdB, th.dwdS, th.dwdQ};
+    for (int k = 0; k < 16; ++k) thermo[16 * i + k] = v[k];
+    for (int a = 0; a < 3; ++a) for (int x = 0; x < 4; ++x) dalpha[12 * i + a * 4 + x] = th.dalpha[a][x];
+  }
+  return 0;
+}
+
+}  // extern "C"
+template <int D, bool MILNE>
+static void local_impl(const StageParams& sp, double t, int64_t n, const double* u, const double* gamma, const double* sigma,
+                       const double* ext_shv, const double* ext_q, const double* thermo, double* shv, double* q, double* transport) {
+  Metric<MILNE> m(t);
+  for (int64_t i = 0; i < n; ++i) {
+    double uu[D];
+    for (int d = 0; d < D; ++d) uu[d] = u[3 * i + d];
+    double s4[4][4] = {}, qq[3][4];
+    rebuild_shear<D, MILNE>(m, uu, gamma[i], sigma[i], ext_shv + 5 * i, s4);
+    rebuild_diffusion<D, MILNE>(m, uu, gamma[i], sigma[i], ext_q + 9 * i, qq);
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) shv[16 * i + 4 * a + b] = s4[a][b];
+    for (int c = 0; c < 3; ++c) for (int mu = 0; mu < 4; ++mu) q[12 * i + 4 * c + mu] = qq[c][mu];
+    Thermo th{};
+    const double* T = thermo + 16 * i;
+    th.T = T[0]; th.muB = T[1]; th.muS = T[2]; th.muQ = T[3]; th.e = T[4]; th.s = T[5]; th.rhoB = T[6]; th.rhoS = T[7];
+    th.rhoQ = T[8]; th.p = T[9]; th.cs2 = T[10]; th.w = T[11];
+    Transport tc;
+    transport_coefficients(th, sp.tp, tc);
+    const double v[13] = {tc.eta_pi, tc.tau_pi, tc.zeta_Pi, tc.tau_Pi, tc.delta_PiPi, tc.delta_pipi, tc.lambda_piPi, tc.lambda_Pipi,
+                          tc.phi1, tc.phi3, tc.phi6, tc.phi7, tc.tau_pipi};
+    for (int k = 0; k < 13; ++k) transport[13 * i + k] = v[k];
+  }
+}
+
+extern "C" {
+int hh_local(const ccb_config* cfg, double t, int64_t n, const double* u, const double* gamma, const double* sigma,
+             const double* ext_shv, const double* ext_q, const double* thermo, double* shv, double* q, double* transport) {
+  const StageParams sp = make_stage_params(*cfg, t, 0., 0);
+  const bool milne = cfg->coordinate_system == CCB_COORD_HYPERBOLIC;
+  if (cfg->dim == 2) { if (milne) local_impl<2, true>(sp, t, n, u, gamma, sigma, ext_shv, ext_q, thermo, shv, q, transport); else local_impl<2, false>(sp, t, n, u, gamma, sigma, ext_shv, ext_q, thermo, shv, q, transport); }
+  else { if (milne) local_impl<3, true>(sp, t, n, u, gamma, sigma, ext_shv, ext_q, thermo, shv, q, transport); else local_impl<3, false>(sp, t, n, u, gamma, sigma, ext_shv, ext_q, thermo, shv, q, transport); }
+  return 0;
+}
+
+struct hh_eom_arrays {
+  const double *u, *v, *gamma, *sigma, *sigma_lab, *mass_s, *bulk, *shv, *q, *thermo, *dalpha;
+  const double *gradP, *gradBulk, *gradshear, *divshear, *gradV, *div_qa, *grad_qa, *grad_alpha;
+  double *du_dt, *d_ext, *d_bulk, *d_shv, *d_q, *theta, *shv_nabla_u, *dEz;
+};
+
+}  // extern "C"
+template <int D, bool MILNE> static void eom_impl(const StageParams& sp, double t, int64_t n, const hh_eom_arrays& A) {
+  Metric<MILNE> m(t);
+  for (int64_t i = 0; i < n; ++i) {
+    Thermo th{};
+    const double* T = A.thermo + 16 * i;
+    th.T = T[0]; th.muB = T[1]; th.muS = T[2]; th.muQ = T[3]; th.e = T[4]; th.s = T[5]; th.rhoB = T[6]; th.rhoS = T[7];
+    th.rhoQ = T[8]; th.p = T[9]; th.cs2 = T[10]; th.w = T[11]; th.dwds = T[12]; th.dwdB = T[13]; th.dwdS = T[14]; th.dwdQ = T[15];
+    for (int a = 0; a < 3; ++a) for (int x = 0; x < 4; ++x) th.dalpha[a][x] = A.dalpha[12 * i + 4 * a + x];
+    Transport tc;
+    transport_coefficients(th, sp.tp, tc);
+    double kappa[3][3], tauq[3][3];
+    diffusion_coefficients(th, sp.tp, kappa, tauq);
+    EomIn<D> in;
+    for (int d = 0; d < D; ++d) {
+      in.u[d] = A.u[3 * i + d]; in.v[d] = A.v[3 * i + d]; in.gradP[d] = A.gradP[3 * i + d]; in.gradBulk[d] = A.gradBulk[3 * i + d];
+      in.gradshear[d] = A.gradshear[3 * i + d]; in.divshear[d] = A.divshear[3 * i + d];
+      for (int e = 0; e < D; ++e) in.gradV[d][e] = A.gradV[9 * i + 3 * d + e];
+      for (int c = 0; c < 3; ++c) in.grad_alpha[d][c] = A.grad_alpha[9 * i + 3 * d + c];
+    }
+    in.gamma = A.gamma[i]; in.sigma = A.sigma[i]; in.sigma_lab = A.sigma_lab[i]; in.mass_s = A.mass_s[i]; in.bulk = A.bulk[i];
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) in.shv[a][b] = A.shv[16 * i + 4 * a + b];
+    for (int c = 0; c < 3; ++c) {
+      for (int mu = 0; mu < 4; ++mu) in.q[c][mu] = A.q[12 * i + 4 * c + mu];
+      in.div_qa[c] = A.div_qa[3 * i + c]; in.grad_qa[c] = A.grad_qa[3 * i + c];
+    }
+    EomOut<D> out;
+    eom_evaluate<D, MILNE>(m, in, th, tc, kappa, tauq, sp.fl, out);
+    for (int d = 0; d < 3; ++d) A.du_dt[3 * i + d] = d < D ? out.du_dt[d < D ? d : 0] : 0.;
+    A.d_ext[4 * i] = out.ds_dt;
+    for (int c = 0; c < 3; ++c) A.d_ext[4 * i + 1 + c] = out.dN_dt[c];
+    A.d_bulk[i] = out.dbulk_dt;
+    for (int c = 0; c < 5; ++c) A.d_shv[5 * i + c] = out.dshv_dt[c];
+    for (int c = 0; c < 3; ++c) for (int d = 0; d < 3; ++d) A.d_q[9 * i + 3 * c + d] = out.dq_dt[c][d];
+    A.theta[i] = out.theta; A.shv_nabla_u[i] = out.shv_nabla_u; A.dEz[i] = out.dEz;
+  }
+}
+
+extern "C" {
+int hh_eom(const ccb_config* cfg, double t, int64_t n, const hh_eom_arrays* A) {
+  const StageParams sp = make_stage_params(*cfg, t, 0., 0);
+  const bool milne = cfg->coordinate_system == CCB_COORD_HYPERBOLIC;
+  if (cfg->dim == 2) { if (milne) eom_impl<2, true>(sp, t, n, *A); else eom_impl<2, false>(sp, t, n, *A); }
+  else { if (milne) eom_impl<3, true>(sp, t, n, *A); else eom_impl<3, false>(sp, t, n, *A); }
+  return 0;
+}
+
+// kernel values for the golden vectors of unit_tests/kernel_test.cpp
+double hh_kernel(int D, double r, double h) { const KernelNorm k = make_kernel_norm(D, h); return sph_w(k, r); }
+double hh_grad_kernel_factor(int D, double r, double h) { const KernelNorm k = make_kernel_norm(D, h); return sph_gradw_factor(k, r); }
+
+}  // extern "C"
