@@ -1,0 +1,289 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the reference
+build (oracle/_ref) on identical initial conditions.
+
+Bars (BASELINE.json north_star): cell assignments and neighbour counts bit-exact;
+fields within 1e-10 (field-scale-relative) per derivative evaluation / per step;
+within 1e-6 after a longer evolution; conserved totals at the reference's level."""
+import math
+
+import numpy as np
+import pytest
+
+from common import (blob_ic_3d, charged_settings, gubser_ic, have_ref, ideal_settings, make_ref, ref_dalpha12,
+                    ref_thermo16, rel_err, viscous_settings)
+
+pytestmark = [pytest.mark.gpu]
+TOL = 1e-10
+
+D3 = dict(dim=3, hT=0.5, hEta=0.5, stepx=0.25, stepy=0.25, stepEta=0.25, xmin=-1.5, ymin=-1.5, etamin=-1.5)
+CASES = {
+    "ideal_2d": (lambda: ideal_settings(), lambda: gubser_ic(dx=0.1)),
+    "viscous_2d": (lambda: viscous_settings(), lambda: gubser_ic(dx=0.1, shear=True)),
+    "viscous_2d_vorticity_cs2zeta": (lambda: viscous_settings(use_vorticity=True, zetaMode="cs2_dependent"), lambda: gubser_ic(dx=0.1, shear=True)),
+    "charged_2d_diffusion": (lambda: charged_settings(), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "ideal_2d_cartesian": (lambda: ideal_settings(coordinate_system="cartesian"), lambda: gubser_ic(dx=0.1)),
+    "viscous_3d_milne": (lambda: viscous_settings(**D3), lambda: blob_ic_3d(n_side=14)),
+    "charged_3d_milne_diffusion": (lambda: charged_settings(**D3), lambda: blob_ic_3d(n_side=14)),
+    "viscous_3d_cartesian": (lambda: viscous_settings(coordinate_system="cartesian", **D3), lambda: blob_ic_3d(n_side=14)),
+    "viscous_3d_milne_factorized": (lambda: viscous_settings(factorized_kernel=True, **dict(D3, hEta=0.4)), lambda: blob_ic_3d(n_side=14)),
+}
+
+
+def _make_ws(settings, ic):
+    from ccake_b200 import SPHWorkstation
+
+    ws = SPHWorkstation(settings)
+    ws.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    return ws
+
+
+@pytest.fixture(scope="module", params=sorted(CASES))
+def pair(request):
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    mk_s, mk_ic = CASES[request.param]
+    settings, ic = mk_s(), mk_ic()
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = _make_ws(settings, ic)
+    return request.param, settings, ic, sim, ws
+
+
+def _cmp(name, what, got, ref, tol=TOL, scale=None):
+    sc = max(np.max(np.abs(ref)), 1e-12) if scale is None else scale
+    e = rel_err(got, ref, sc)
+    assert e < tol, (name, what, e)
+
+
+def _ext_shv5(sim, field="extensive_shv"):
+    es = sim.get("hydro_shear_aux_vector", field)
+    return np.stack([es[:, 0, 0], es[:, 0, 1], es[:, 0, 2], es[:, 1, 1], es[:, 1, 2]], 1)
+
+
+def test_initialisation(pair):
+    """BSQHydro::initialize_hydrodynamics: extensive densities, sigma, thermodynamics, pi^{mu nu}."""
+    name, settings, ic, sim, ws = pair
+    n = sim.n
+    assert ws.n_particles == n
+    _cmp(name, "position", ws.get("position"), sim.member("position"))
+    ext = sim.member("extensive")
+    _cmp(name, "extensive", ws.get("extensive"), ext[:, [0, 2, 3, 4]])
+    _cmp(name, "sigma_lab", ws.get("sigma_lab"), sim.get("hydro_scalar", "sigma_lab"))
+    _cmp(name, "sigma", ws.get("sigma"), sim.get("hydro_scalar", "sigma"))
+    _cmp(name, "extensive_shv", ws.get("extensive_shv"), _ext_shv5(sim))
+    th, th_ref = ws.get("thermo"), ref_thermo16(sim)
+    for k in range(16):
+        _cmp(name, "thermo%d" % k, th[:, k], th_ref[:, k])
+    _cmp(name, "shv", ws.get("shv"), sim.get("hydro_spacetime_matrix", "shv").reshape(n, 16))
+
+
+def test_derivative_evaluation(pair):
+    """One SPHWorkstation::get_time_derivatives: every phase output."""
+    name, settings, ic, sim, ws = pair
+    n = sim.n
+    sim.get_time_derivatives()
+    ws.get_time_derivatives()
+    ws.synchronize()
+    # 01: cells and neighbour counts are integers: bit-exact
+    off, idx, cell_ref, nc_ref = sim.neighbours()
+    assert np.array_equal(ws.grid_shape(), nc_ref), name
+    assert np.array_equal(ws.get_int("cell"), cell_ref), name
+    assert np.array_equal(ws.get_int("btrack"), np.diff(off).astype(np.int32)), name
+    assert np.array_equal(np.sort(ws.get_int("id")), np.arange(n)), name
+    # 02-03
+    _cmp(name, "gamma", ws.get("gamma"), sim.get("hydro_scalar", "gamma"))
+    _cmp(name, "v", ws.get("v"), sim.get("hydro_vector", "v"))
+    _cmp(name, "sigma_lab", ws.get("sigma_lab"), sim.get("hydro_scalar", "sigma_lab"))
+    _cmp(name, "smoothed", ws.get("smoothed"), sim.member("smoothed")[:, [0, 2, 3, 4]])
+    # 04
+    th, th_ref = ws.get("thermo"), ref_thermo16(sim)
+    for k in range(16):
+        _cmp(name, "thermo%d" % k, th[:, k], th_ref[:, k])
+    if np.any(np.abs(th_ref[:, 6:9]) > 0):
+        _cmp(name, "dalpha", ws.get("dalpha"), ref_dalpha12(sim), tol=1e-8)
+    # 05, 08
+    _cmp(name, "bulk", ws.get("bulk"), sim.get("hydro_scalar", "bulk"), scale=max(np.max(np.abs(th_ref[:, 9])), 1e-12))
+    _cmp(name, "shv", ws.get("shv"), sim.get("hydro_spacetime_matrix", "shv").reshape(n, 16))
+    _cmp(name, "diffusion", ws.get("diffusion"), sim.member("hydro_diffusion").reshape(n, 12), scale=max(np.max(np.abs(th_ref[:, 6:9])), 1e-12))
+    # 09: gradients; scale = the natural scale of the quantity, not the (possibly tiny) gradient itself
+    pscale = np.max(np.abs(th_ref[:, 9])) / settings["hT"]
+    for f in ("gradP", "gradBulk", "gradshear", "divshear"):
+        _cmp(name, f, ws.get(f), sim.get("hydro_vector", f), scale=pscale)
+    _cmp(name, "gradE", ws.get("gradE"), sim.get("hydro_vector", "gradE"), scale=3 * pscale)
+    _cmp(name, "gradV", ws.get("gradV"), sim.get("hydro_space_matrix", "gradV").reshape(n, 9), scale=1.0 / settings["hT"])
+    from ccake_b200 import DEFAULTS, derived_switches
+    full = dict(DEFAULTS); full.update(settings)
+    sw = derived_switches(full)
+    if sw["using_diffusion"]:
+        _cmp(name, "div_qa", ws.get("div_qa"), sim.get("hydro_vector", "div_qa"), scale=pscale)
+        _cmp(name, "grad_qa", ws.get("grad_qa"), sim.get("hydro_vector", "grad_qa"), scale=pscale)
+        _cmp(name, "grad_alpha", ws.get("grad_alpha"), sim.get("hydro_space_matrix", "grad_alpha_a").reshape(n, 9), scale=1.0 / settings["hT"])
+    # 10
+    _cmp(name, "du_dt", ws.get("du_dt"), sim.get("hydro_vector", "du_dt"))
+    dd = sim.member("d_dt_extensive")
+    _cmp(name, "d_extensive_dt", ws.get("d_extensive_dt"), dd[:, [0, 2, 3, 4]], scale=max(np.max(np.abs(dd)), 1e-12))
+    _cmp(name, "d_bulk_dt", ws.get("d_bulk_dt"), sim.get("hydro_scalar", "d_extensive_bulk_dt"))
+    _cmp(name, "theta", ws.get("theta"), sim.get("hydro_scalar", "theta"))
+    _cmp(name, "dEz", ws.get("dEz"), sim.member("contribution_to_total_dEz"))
+    if sw["using_shear"]:
+        _cmp(name, "d_shv_dt", ws.get("d_shv_dt"), _ext_shv5(sim, "d_extensive_shv_dt"))
+        _cmp(name, "shv_nabla_u", ws.get("shv_nabla_u"), sim.get("hydro_scalar", "shv_nabla_u"))
+    if sw["using_diffusion"]:
+        _cmp(name, "d_diffusion_dt", ws.get("d_diffusion_dt"), sim.get("hydro_space_matrix", "d_extensive_q_dt").reshape(n, 9))
+
+
+def test_time_steps(pair):
+    """Evolver RK2 steps: per-step 1e-10, and the conserved totals."""
+    name, settings, ic, sim, ws = pair
+    n = sim.n
+    dt = settings["dt"]
+    for step in range(3):
+        sim.advance(dt, 2)
+        ws.advance_timestep(dt)
+        ws.synchronize()
+        assert abs(ws.t - sim.t) < 1e-14
+        tol = TOL * (step + 1)
+        _cmp(name, "position", ws.get("position"), sim.member("position"), tol)
+        _cmp(name, "u", ws.get("u"), sim.get("hydro_vector", "u"), tol)
+        ext = sim.member("extensive")
+        _cmp(name, "extensive", ws.get("extensive"), ext[:, [0, 2, 3, 4]], tol)
+        _cmp(name, "extensive_bulk", ws.get("extensive_bulk"), sim.get("hydro_scalar", "extensive_bulk"), tol,
+             scale=max(np.max(np.abs(sim.get("hydro_scalar", "extensive_bulk"))), 1e-6))
+        _cmp(name, "extensive_shv", ws.get("extensive_shv"), _ext_shv5(sim), tol,
+             scale=max(np.max(np.abs(_ext_shv5(sim))), 1e-6))
+        _cmp(name, "Ez", ws.get("Ez"), sim.member("contribution_to_total_Ez"), tol,
+             scale=max(np.max(np.abs(sim.member("contribution_to_total_Ez"))), 1e-6))
+    tot, ref_tot = ws.conservation(), sim.totals()
+    for k in ("S", "B", "Sq", "Q", "E", "Ez"):
+        assert abs(tot[k] - ref_tot[k]) <= 1e-9 * max(abs(ref_tot[k]), 1.0), (name, k, tot[k], ref_tot[k])
+
+
+def test_long_evolution_ideal_gubser():
+    """40 RK2 steps of ideal Gubser flow: 1e-6 against the reference at the end, entropy conserved."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    settings = ideal_settings(dt=0.005)
+    ic = gubser_ic(dx=0.1)
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = _make_ws(settings, ic)
+    S0 = ws.conservation()["S"] if False else None
+    for _ in range(40):
+        sim.advance(settings["dt"], 2)
+        ws.advance_timestep(settings["dt"])
+    ws.synchronize()
+    _cmp("long", "position", ws.get("position"), sim.member("position"), 1e-6)
+    _cmp("long", "u", ws.get("u"), sim.get("hydro_vector", "u"), 1e-6)
+    _cmp("long", "extensive", ws.get("extensive")[:, 0], sim.member("extensive")[:, 0], 1e-6)
+    tot, ref_tot = ws.conservation(), sim.totals()
+    assert abs(tot["S"] - ref_tot["S"]) <= 1e-9 * abs(ref_tot["S"])
+
+
+# ---- golden vectors of the reference's own unit tests, through the C ABI -----------
+def test_golden_smoothing_sum():
+    """unit_tests/smoothing_test.cpp:33-147: 4 particles, h=1 -> smoothed s(0) = 20/(7 pi), rhoB 4x, rhoQ 9x, rhoS 16x."""
+    from ccake_b200 import SPHWorkstation
+
+    ws = SPHWorkstation(ideal_settings(hT=1.0, hEta=1.0, xmin=-4.0, ymin=-6.0, etamin=-2.0))
+    ws.allocate(4)
+    pos = np.zeros((4, 3)); pos[:, :2] = [[0, 0], [0, .5], [.8, .6], [1.5, 0]]
+    ws.set("position", pos)
+    m = np.tile(np.array([1.0, 2.0, 4.0, 3.0]), (4, 1))  # s, rhoB, rhoS, rhoQ
+    ws.set("sph_mass", m)
+    ws.set("extensive", m)
+    ws.reset_neighbour_list()
+    ws.smooth_all_particle_fields()
+    ws.synchronize()
+    sm = ws.get("smoothed")
+    g = 20.0 / 7.0 / math.pi
+    assert abs(sm[0, 0] - g) < 1e-14
+    assert abs(sm[0, 1] - 4 * g) < 1e-13 and abs(sm[0, 3] - 9 * g) < 1e-13 and abs(sm[0, 2] - 16 * g) < 1e-13
+    assert abs(ws.get("sigma_lab")[0] - g) < 1e-14
+    assert list(ws.get_int("btrack")) == [3, 3, 3, 3]
+
+
+def test_golden_gradP():
+    """unit_tests/grad_smoothing_test.cpp:25-70: 5 particles on the x axis, P=(1,.5,1.5,2.5,1), sigma_lab=1 -> gradP_x(0) = 45/(8 pi)."""
+    from ccake_b200 import SPHWorkstation
+
+    ws = SPHWorkstation(ideal_settings(hT=1.0, hEta=1.0, xmin=-4.0, ymin=-4.0, etamin=-2.0))
+    ws.allocate(5)
+    pos = np.zeros((5, 3)); pos[:, 0] = [0.0, 0.5, 1.0, 1.5, -1.5]; pos[4, 1] = 1.5
+    ws.set("position", pos)
+    ws.set("sph_mass", np.ones((5, 4)))
+    ws.set("extensive", np.ones((5, 4)))
+    ws.reset_neighbour_list()
+    ws.smooth_all_particle_fields()
+    th = np.zeros((5, 16)); th[:, 9] = [1.0, 0.5, 1.5, 2.5, 1.0]; th[:, 0] = 1.0
+    ws.set("thermo", th)
+    ws.set("sigma_lab", np.ones(5))
+    ws.set("sigma", np.ones(5))
+    ws.reset_pi_tensor_and_viscosities()
+    ws.smooth_all_particle_gradients()
+    ws.synchronize()
+    gp = ws.get("gradP")
+    assert abs(gp[0, 0] - 45.0 / (8.0 * math.pi)) < 1e-13, gp[0]
+    assert abs(gp[0, 1]) < 1e-15
+
+
+def test_golden_pi_reconstruction():
+    """unit_tests/eom_default_test.cpp:185-210: u=(3,4), t=2, pi^{xx,xy,yy}=(3,4,5)."""
+    from ccake_b200 import SPHWorkstation
+
+    ws = SPHWorkstation(viscous_settings(t0=2.0, hT=1.0, xmin=-4.0, ymin=-4.0))
+    ws.allocate(1)
+    ws.set("position", np.zeros((1, 3)))
+    ws.set("u", np.array([[3.0, 4.0, 0.0]]))
+    ws.set("sph_mass", np.ones((1, 4)))
+    ws.set("extensive", np.ones((1, 4)))
+    ws.reset_neighbour_list()
+    ws.smooth_all_particle_fields()
+    th = np.zeros((1, 16)); th[:, 0] = 1.0; th[:, 9] = 1.0; th[:, 11] = 4.0; th[:, 10] = 1.0 / 3.0
+    ws.set("thermo", th)
+    ws.set("sigma", np.ones(1))
+    ws.set("extensive_shv", np.array([[3.0, 4.0, 0.0, 5.0, 0.0]]))
+    ws.reset_pi_tensor_and_viscosities()
+    ws.synchronize()
+    shv = ws.get("shv").reshape(4, 4)
+    g = math.sqrt(26.0)
+    assert abs(ws.get("gamma")[0] - g) < 1e-14
+    assert abs(shv[0, 1] - 25.0 / g) < 1e-13 and abs(shv[0, 2] - 32.0 / g) < 1e-13
+    assert abs(shv[0, 0] - 203.0 / 26.0) < 1e-13 and abs(shv[3, 3] + 5.0 / 104.0) < 1e-14
+
+
+# ---- size-independent properties at larger sizes ------------------------------------
+@pytest.mark.parametrize("dx", [0.025])
+def test_cell_build_properties_large(dx):
+    """160k-particle ideal Gubser lattice (BASELINE config 1 size): the sort is a permutation,
+    keys come out sorted, neighbour counts match a KD-tree, smoothing is linear in the extensive density."""
+    from scipy.spatial import cKDTree
+    from ccake_b200 import SPHWorkstation
+
+    settings = ideal_settings(hT=0.4, stepx=dx, stepy=dx, xmin=-5.0, ymin=-5.0)
+    ic = gubser_ic(dx=dx, xmax=5.0)
+    n = ic["r"].shape[0]
+    ws = SPHWorkstation(settings)
+    ws.allocate(n)
+    pos = np.zeros((n, 3)); pos[:, :2] = ic["r"]
+    ws.set("position", pos)
+    ws.set("sph_mass", np.ones((n, 4)))
+    rng = np.random.default_rng(0)
+    e1 = rng.uniform(0.5, 2.0, (n, 4))
+    ws.set("extensive", e1)
+    ws.reset_neighbour_list()
+    ws.smooth_all_particle_fields()
+    ws.synchronize()
+    ids = ws.get_int("id")
+    assert np.array_equal(np.sort(ids), np.arange(n))
+    sm1 = ws.get("smoothed")
+    bt = ws.get_int("btrack")
+    # neighbour counts: away from the knife edge r == 2h (lattice distances hit it exactly) the count is unambiguous
+    tree = cKDTree(pos)
+    lo = tree.query_ball_point(pos[::997], 2 * 0.4 * (1 - 1e-9), return_length=True) - 1
+    hi = tree.query_ball_point(pos[::997], 2 * 0.4 * (1 + 1e-9), return_length=True) - 1
+    assert np.all((bt[::997] >= lo) & (bt[::997] <= hi))
+    # linearity: smoothing(a*e1) = a*smoothing(e1) to rounding
+    ws.set("extensive", 3.0 * e1)
+    ws.smooth_all_particle_fields()
+    ws.synchronize()
+    assert rel_err(ws.get("smoothed"), 3.0 * sm1) < 1e-14

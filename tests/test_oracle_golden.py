@@ -1,0 +1,225 @@
+"""CPU tests (no GPU): the oracle against every still-valid known answer of the
+reference's own unit tests, the C-ABI library's exports, and the
+host-side settings logic."""
+import ctypes as C
+import math
+import os
+
+import numpy as np
+import pytest
+
+from common import ROOT, gubser_ic, harness, have_ref, ideal_settings, make_ref, viscous_settings
+
+needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+PI = math.pi
+
+
+# ---- kernel known answers, unit_tests/kernel_test.cpp:7-322 ---------------------------
+KERNEL_GOLD = [
+    (1, 0.5, 23. / 48.), (1, 1.0, 1. / 6.), (1, 1.5, 1. / 48.), (1, 2.0, 0.0),
+    (2, 0.5, 115. / (112. * PI)), (2, 1.0, 5. / (14. * PI)), (2, 1.5, 5. / (112. * PI)), (2, 2.0, 0.0),
+    (3, 0.5, 23. / (32. * PI)), (3, 1.0, 1. / (4. * PI)), (3, 1.5, 1. / (32. * PI)), (3, 2.0, 0.0),
+]
+
+
+@pytest.mark.parametrize("D,q,val", KERNEL_GOLD)
+def test_kernel_values(D, q, val):
+    H = harness()
+    H.hh_kernel.restype = C.c_double
+    assert abs(H.hh_kernel(C.c_int(D), C.c_double(q), C.c_double(1.0)) - val) < 1e-14
+
+
+@pytest.mark.parametrize("h", [1.0, 0.5])
+@pytest.mark.parametrize("q,val", [(0.5, -75. / (56. * PI)), (1.0, -15. / (14. * PI)), (1.5, -15. / (56. * PI))])
+def test_grad_kernel_2d(h, q, val):
+    """grad W along +x at distance q*h: magnitude val / h^3 (kernel_test.cpp:117-322)."""
+    H = harness()
+    H.hh_grad_kernel_factor.restype = C.c_double
+    r = q * h
+    g = H.hh_grad_kernel_factor(C.c_int(2), C.c_double(r), C.c_double(h)) * r
+    assert abs(g - val / h ** 3) < 1e-13 / h ** 3
+
+
+# ---- the reference build reproduces the reference's own known answers --------------------
+@needs_ref
+def test_ref_smoothing_sum():
+    """unit_tests/smoothing_test.cpp:33-147."""
+    from oracle import ref
+
+    s = ref.RefSim(dict(dim=2, t0=1.0, hT=1.0, hEta=1.0, xmin=-4, ymin=-6, etamin=-2))
+    s.allocate_raw(4)
+    pos = np.zeros((4, 3)); pos[:, :2] = [[0, 0], [0, .5], [.8, .6], [1.5, 0]]
+    s.set_member("position", pos)
+    m = np.zeros((4, 5)); m[:, 0] = 1; m[:, 2] = 2; m[:, 4] = 3; m[:, 3] = 4
+    s.set_member("sph_mass", m); s.set_member("extensive", m)
+    s.put("hydro_scalar", "gamma", np.ones(4))
+    s.phase("neighbour_list"); s.phase("smooth_fields")
+    sm = s.member("smoothed")
+    g = 20. / 7. / PI
+    assert abs(sm[0, 0] - g) < 1e-14 and abs(sm[0, 2] - 4 * g) < 1e-13
+    assert abs(sm[0, 4] - 9 * g) < 1e-13 and abs(sm[0, 3] - 16 * g) < 1e-13
+    assert abs(s.get("hydro_scalar", "sigma_lab")[0] - g) < 1e-14
+
+
+@needs_ref
+def test_ref_gradP():
+    """unit_tests/grad_smoothing_test.cpp:25-70 (with sigma_lab = 1)."""
+    from oracle import ref
+
+    s = ref.RefSim(dict(dim=2, t0=1.0, hT=1.0, hEta=1.0, xmin=-4, ymin=-6, etamin=-2))
+    s.allocate_raw(5)
+    pos = np.zeros((5, 3)); pos[:, 0] = [0, .5, 1.0, 1.5, -1.5]; pos[4, 1] = 1.5
+    s.set_member("position", pos)
+    m = np.ones((5, 5))
+    s.set_member("sph_mass", m); s.set_member("extensive", m)
+    s.put("hydro_scalar", "sigma_lab", np.ones(5))
+    s.put("hydro_scalar", "gamma", np.ones(5))
+    th = s.member("thermo"); th[:, ref.THERMO.index("p")] = [1, .5, 1.5, 2.5, 1]
+    s.set_member("thermo", th)
+    s.phase("neighbour_list"); s.phase("smooth_gradients")
+    gp = s.get("hydro_vector", "gradP")
+    assert abs(gp[0, 0] - 45. / 8. / PI) < 1e-13 and abs(gp[0, 1]) < 1e-15
+
+
+@needs_ref
+def test_ref_pi_reconstruction():
+    """unit_tests/eom_default_test.cpp:185-210."""
+    from oracle import ref
+
+    s = ref.RefSim(dict(dim=2, t0=2.0, hT=1.0, hEta=1.0, xmin=-4, ymin=-6, etamin=-2))
+    s.allocate_raw(1)
+    hv = s.member("hydro_vector"); hv[0, ref.HYDRO_VECTOR.index("u"), :2] = [3, 4]
+    s.set_member("hydro_vector", hv)
+    s.put("hydro_scalar", "sigma", np.ones(1))
+    es = s.member("hydro_shear_aux_vector")
+    k = ref.HYDRO_SHEAR_AUX_VECTOR.index("extensive_shv")
+    es[0, k, 0, 0], es[0, k, 0, 1], es[0, k, 1, 1] = 3, 4, 5
+    s.set_member("hydro_shear_aux_vector", es)
+    s.phase("gamma_velocity"); s.phase("reset_pi_tensor")
+    shv = s.get("hydro_spacetime_matrix", "shv")[0]
+    g = math.sqrt(26.)
+    assert abs(s.get("hydro_scalar", "gamma")[0] - g) < 1e-14
+    assert abs(shv[0, 1] - 25. / g) < 1e-13 and abs(shv[0, 2] - 32. / g) < 1e-13
+    assert abs(shv[0, 0] - 203. / 26.) < 1e-13 and abs(shv[3, 3] + 5. / 104.) < 1e-14
+
+
+@needs_ref
+def test_ref_neighbour_list_against_brute_force():
+    """The shim's linked-cell VerletList (Cabana semantics) against an O(N^2) search."""
+    settings = ideal_settings()
+    ic = gubser_ic(dx=0.2)
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    off, idx, cell, nc = sim.neighbours()
+    pos = sim.member("position")
+    d2 = ((pos[:, None, :] - pos[None, :, :]) ** 2).sum(-1)
+    rs = (2 * settings["hT"]) ** 2
+    for i in range(0, sim.n, 7):
+        want = set(np.nonzero(d2[i] <= rs)[0]) - {i}
+        assert set(idx[off[i]:off[i + 1]]) == want
+
+
+@needs_ref
+def test_ref_ideal_gubser_tracks_analytic_solution():
+    """Physics-level pin (misc/Gubser_checks, utilities/ideal_gubser_ic_generator.py): after a short ideal
+    evolution the energy density at the centre follows the closed-form Gubser solution."""
+    from common import gubser_profile, HBARC
+
+    settings = ideal_settings(dt=0.01, hT=0.3)
+    ic = gubser_ic(dx=0.1, xmax=3.0)
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    pos0 = sim.member("position")
+    e0_num = sim.get("thermo", "e")[np.argmin((pos0[:, :2] ** 2).sum(1))] * HBARC
+    assert abs(e0_num / 80.0 - 1) < 5e-2
+    for _ in range(10):
+        sim.advance(settings["dt"], 2)
+    pos = sim.member("position")
+    c = np.argmin((pos[:, :2] ** 2).sum(1))
+    e_num = sim.get("thermo", "e")[c] * HBARC
+    e_exact = gubser_profile(np.array([0.0]), np.array([0.0]), tau0=sim.t)[0][0]
+    # the decay of the central energy density over the evolved interval (SPH smoothing offsets the
+    # absolute value by O(h^2); it converges with resolution: 3.5% at dx=0.1, 0.9% at dx=0.05)
+    assert abs((e_num / e0_num) / (e_exact / 80.0) - 1) < 3e-2
+
+
+# ---- the C-ABI library ---------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from ccake_b200 import _capi
+
+    assert os.path.exists(_capi.LIB_PATH), "run __graft_entry__.build() first"
+    L = C.CDLL(_capi.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "ccake_b200.h")).read()
+    import re
+
+    declared = sorted(set(re.findall(r"\b(ccb_[a-z_]+)\s*\(", header)))
+    assert set(declared) == set(_capi.EXPORTED), set(declared) ^ set(_capi.EXPORTED)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_field_widths_match_binding():
+    from ccake_b200 import _capi
+
+    L = _capi.lib()
+    for name, (fid, w) in _capi.FIELDS.items():
+        assert L.ccb_field_width(fid) == w, name
+    assert L.ccb_field_width(len(_capi.FIELDS)) == -1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    from ccake_b200 import CCAKEError, SPHWorkstation, _capi
+
+    with pytest.raises(CCAKEError) as ei:
+        SPHWorkstation(ideal_settings())
+    assert ei.value.code == _capi.CCB_ERR_CUDA
+
+
+# ---- host logic -----------------------------------------------------------------------------
+def test_derived_switches_follow_input_cpp():
+    from ccake_b200 import DEFAULTS, derived_switches
+
+    s = dict(DEFAULTS)
+    s.update(etaMode="constant", constant_eta_over_s=0.0)
+    assert derived_switches(s)["using_shear"] is False
+    s.update(constant_eta_over_s=1e-3)
+    assert derived_switches(s)["using_shear"] is False  # `<= 1.E-3` disables (src/input.cpp:404)
+    s.update(constant_eta_over_s=0.08)
+    assert derived_switches(s)["using_shear"] is True
+    s.update(etaMode="disabled")
+    assert derived_switches(s)["using_shear"] is False
+    s.update(diffusionMode="constant_over_T2")
+    assert derived_switches(s)["using_diffusion"] is True
+
+
+def test_yaml_reader_on_reference_inputs(tmp_path):
+    from ccake_b200 import from_yaml, to_config
+
+    y = tmp_path / "visc.yaml"
+    y.write_text("""
+initial_conditions: {type: ccake, file: x.dat, t0: 1.0, dimension: 2, input_as_entropy: false}
+parameters: {dt: 0.001, h_T: 0.1, h_eta: 0.1, rk_order: 2}
+eos: {online_inverter_enabled: true, type: conformal}
+particlization: {enabled: true, T: 153.334025}
+hydro:
+  baryon_charge_enabled: true
+  viscous_parameters:
+    diffusion: {mode: constant_over_T2, constant_kappa_over_T2: [[0.1, 0, 0], [0, 0.2, 0], [0, 0, 0.3]], relaxation_mode: constant_over_T}
+    bulk: {mode: constant, constant_zeta_over_s: 0.0, delta_PiPi_mode: israel-stewart, lambda_Pipi_mode: default, phi1_mode: disabled}
+    shear: {input_initial_shear: true, constant_eta_over_s: 0.2, mode: constant, relaxation_mode: Gubser, delta_pipi_mode: default, tau_pipi_mode: disabled}
+""")
+    s = from_yaml(str(y))
+    assert s["hT"] == 0.1 and s["etaMode"] == "constant" and s["shearRelaxMode"] == "Gubser"
+    c = to_config(s)
+    assert c.using_shear == 1 and c.using_diffusion == 1 and c.shear_relax_mode == 2
+    assert c.delta_PiPi_mode == 1 and c.tau_pipi_mode == 1 and c.phi1_mode == 1
+    assert abs(c.constant_kappa_over_T2[4] - 0.2) < 1e-15
+    assert abs(c.conformal_c - math.pi ** 2 * (16 + 26.25) / 90.0) < 1e-14
