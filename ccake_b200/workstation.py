@@ -88,6 +88,13 @@ class SPHWorkstation:
         ic.n = n
         ic.r = _dp(keep[0])
         ic.e_or_s = _dp(keep[1])
+        # BSQHydro::read_ccake drops a charge density whose `*_charge_enabled` switch is off (src/BSQHydro.cpp:341-343)
+        if not self.settings["baryon_charge_enabled"]:
+            rhoB = None
+        if not self.settings["strange_charge_enabled"]:
+            rhoS = None
+        if not self.settings["electric_charge_enabled"]:
+            rhoQ = None
         for name, a, w in (("rhoB", rhoB, 1), ("rhoS", rhoS, 1), ("rhoQ", rhoQ, 1), ("u", u, 3), ("bulk", bulk, 1), ("shv6", shv6, 6)):
             if a is None:
                 continue
