@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of one full RK2 step of the CCAKE SPH hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W                    (own arm: the CUDA library behind the C ABI)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU implementation, oracle/_ref)
+
+One "step" = SPHWorkstation::advance_timestep (two derivative evaluations + RK2 updates) over the whole
+particle system. Workload at N = 1: BASELINE.json configs[1], the viscous-Gubser 2+1D run with the conformal
+BSQ equation of state (settings of input/config_visc_gubser.yaml) on the 401 x 401 lattice = 160 801 particles.
+Rank 0 prints ONE JSON line. See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "particle_steps_per_s"
+UNIT = "particle-steps/s"
+DEFAULT_WORKLOAD = "config2_viscous_gubser_bsq_2p1d"
+
+
+# ---------------------------------------------------------------------------------------------
+def make_workload(name, scale=1.0):
+    """(settings, ic, description). `scale` < 1 shrinks the lattice EXTENT at fixed spacing and smoothing length
+    (same neighbour count per particle): the bounded sample the CPU arms run."""
+    from ccake_b200 import workloads as W
+
+    if name == "config2_viscous_gubser_bsq_2p1d":
+        xmax = 5.0 * scale
+        xmax = round(xmax / 0.025) * 0.025
+        s, ic = W.config2_viscous_gubser_bsq(dx=0.025, xmax=xmax)
+        desc = "viscous Gubser 2+1D, conformal BSQ EoS, shear + diffusion path, h=0.1, dx=0.025, |x|,|y|<=%.3f" % xmax
+    elif name == "config1_ideal_gubser_2p1d":
+        xmax = round(5.0 * scale / 0.025) * 0.025
+        s, ic = W.config1_ideal_gubser(dx=0.025, xmax=xmax)
+        desc = "ideal Gubser 2+1D, conformal EoS, h=0.4, dx=0.025, |x|,|y|<=%.3f" % xmax
+    elif name.startswith("config5_cartesian_blob_3p1d"):
+        n_target = int(float(name.split(":")[1])) if ":" in name else 1_000_000
+        s, ic = W.config5_cartesian_blob(n_target=int(n_target * scale))
+        desc = "3+1D Cartesian Gaussian blob, conformal EoS, ideal, h=2dx, ~%d particles" % ic["r"].shape[0]
+    else:
+        raise SystemExit("unknown workload %r" % name)
+    return s, ic, desc
+
+
+@contextlib.contextmanager
+def stdout_to_stderr():
+    """The reference build prints progress to stdout; keep stdout for the single JSON line."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        yield
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smmax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smmax = float(f[1]); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smmax, "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def time_reference(workload, scale, steps, warmup):
+    """The reference's own CPU implementation (oracle/_ref: its unmodified translation units compiled against the
+    shims of oracle/shim, OpenMP over all host cores) on a bounded sample of the workload."""
+    from oracle import ref
+
+    if not ref.available():
+        raise SystemExit("oracle/_ref/libccake_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
+    settings, ic, desc = make_workload(workload, scale)
+    with stdout_to_stderr():
+        keys = ref.SETTING_KEYS
+        sim = ref.RefSim({k: v for k, v in settings.items() if k in keys or k.startswith("kappa_")})
+        sim.add_particles(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+        sim.initialize()
+        n = sim.n
+        dt = settings["dt"]
+        for _ in range(warmup):
+            sim.advance(dt, 2)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sim.advance(dt, 2)
+        el = time.perf_counter() - t0
+    cores = ref.omp_threads()
+    return dict(value=n * steps / el, seconds=el, n=n, cores=cores, desc=desc)
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    r = time_reference(args.workload, args.cpu_scale, steps, warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": r["desc"], "particles": r["n"], "rk_order": 2},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                         "sample": "%d of the workload's particles (same spacing, smoothing length and neighbour count; lattice extent x%.2f), "
+                                   "%d RK2 steps after %d warm-up" % (r["n"], args.cpu_scale, steps, warmup)},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# Algorithmic (compulsory) bytes per particle per launch of each kernel: every input column read once, every
+# output column written once, 8 B per f64 (DESIGN.md "Kernels and rooflines").
+def algorithmic_bytes(D, shear, diffusion):
+    rec_g = 36 if diffusion else 20
+    grad_out = 5 * D + D * D + ((3 + 3 + 3 * D) if diffusion else 0)
+    persistent = 3 + 3 + 4 + 4 + 1 + 5 + (9 if diffusion else 0) + 1 + 4
+    evolved = 3 + 3 + 4 + 1 + 5 + (9 if diffusion else 0) + 1
+    return {
+        "01_neighbour_list": 8 * (3 + 2 * (persistent + evolved)) + 4 * (2 + 4 * 2 * 3 + 8),
+        "02_gamma_velocity": 8 * ((D + 3 + 8) + (1 + D + 8)),
+        "03_smooth_fields": 8 * (8 + 1 + 10) + 8,
+        "04_thermodynamics": 8 * (4 + D + 3 + 1 + 5 + (9 if diffusion else 0) + 3 + 4) + 8 * (16 + 12 + 4 + 1 + 16 + 12 + 13 + rec_g),
+        "09_smooth_gradients": 8 * (rec_g + grad_out),
+        "10_time_derivatives": 8 * (28 + 2 * D + 4 + 1 + 16 + (12 + 6 if diffusion else 0) + grad_out + evolved) + 8 * (evolved + D + 4 + 1 + 5 + 3),
+    }
+
+
+PAIR_FLOP = {"03_smooth_fields": 31.0, "09_smooth_gradients": None}  # gradients: computed from D and the switches
+
+
+def gradient_pair_flop(D, shear, diffusion):
+    """fp64 flop per interacting pair in smooth_gradients as the reference writes it (src/sph_workstation.cpp:833-984):
+    distance + gradKernel ~ 20, then the listed sums (mul + add each)."""
+    f = 20 + 2 * D + 4 + 2 * D * 3 + 3 * D * D
+    if shear:
+        f += 2 * D + 3 * D + 4 * D * D
+    if diffusion:
+        f += 3 * (3 + 4 * D + 3 * D)
+    return float(f)
+
+
+def own_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from ccake_b200 import SPHWorkstation, _capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    settings, ic, desc = make_workload(args.workload, 1.0)
+    dt = settings["dt"]
+    ws = SPHWorkstation(settings, device=local_rank, rank=rank, nranks=world)
+    ws.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    n = ws.n_particles
+    stream = torch.cuda.ExternalStream(ws.stream, device=local_rank)
+    D = int(settings["dim"])
+    from ccake_b200 import DEFAULTS, derived_switches
+    full = dict(DEFAULTS); full.update(settings)
+    sw = derived_switches(full)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        ws.advance_timestep(dt)
+    ws.synchronize()
+
+    # ---- device-resident timed region ------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ws.profile(True)
+    launches0 = ws.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); torch.cuda.synchronize(); ws.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        ws.advance_timestep(dt)
+    e1.record(stream)
+    ws.synchronize(); torch.cuda.synchronize(); barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = ws.kernel_launches - launches0
+    phases = ws.profile_table()
+    ws.profile(False)
+    clocks = sampler.stop()
+
+    # ---- end to end through the public API with HOST buffers --------------------------------
+    w = ws.state_width
+    host = torch.empty((w, n), dtype=torch.float64, pin_memory=True).numpy()
+    ws.copy_device_to_host(host)
+    for _ in range(2):
+        ws.copy_host_to_device(host); ws.advance_timestep(dt); ws.copy_device_to_host(host)
+    barrier(); torch.cuda.synchronize()
+    e0.record(stream)
+    t_host0 = time.perf_counter()
+    for _ in range(args.steps):
+        ws.copy_host_to_device(host)   # SystemState::copy_host_to_device
+        ws.advance_timestep(dt)        # SPHWorkstation::advance_timestep
+        ws.copy_device_to_host(host)   # SystemState::copy_device_to_host (synchronises)
+    e1.record(stream)
+    ws.synchronize(); torch.cuda.synchronize()
+    t_host = time.perf_counter() - t_host0
+    barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * t_host))
+    assert np.all(np.isfinite(host))
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak, peak_src = (peaks["hbm_gbs"], "MEASURED_PEAKS.json") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    tf = _capi.C.c_double()
+    _capi.lib().ccb_measure_dfma_peak(local_rank, _capi.C.byref(tf))
+    alg = algorithmic_bytes(D, sw["using_shear"], sw["using_diffusion"])
+    per_kernel = {}
+    for name, (pms, calls) in phases.items():
+        if calls:
+            per_kernel[name] = {"ms_per_launch": pms / calls, "launches": calls, "share": pms / ms}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"])
+    t_dom = per_kernel[dom]["ms_per_launch"] * 1e-3
+    achieved = alg.get(dom, 0) * n / t_dom / 1e9
+    bt = ws.get_int("btrack")
+    pairs = float(np.sum(bt[bt > 0])) + n
+    flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop(D, sw["using_shear"], sw["using_diffusion"])
+    fp64_achieved = pairs * flop_pair / t_dom / 1e12 if dom in ("03_smooth_fields", "09_smooth_gradients") else None
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": alg.get(dom),
+                "ms_per_launch": per_kernel[dom]["ms_per_launch"],
+                "fp64": {"achieved": fp64_achieved, "peak": tf.value, "unit": "TFLOP/s",
+                         "frac": (fp64_achieved / tf.value) if (fp64_achieved and tf.value) else None,
+                         "pairs_per_launch": pairs, "flop_per_pair": flop_pair, "peak_source": "ccb_measure_dfma_peak (this run)"},
+                "per_kernel": {k: {"ms_per_launch": round(v["ms_per_launch"], 5), "launches": v["launches"], "share": round(v["share"], 4),
+                                   "GBps": round(alg.get(k, 0) * n / (v["ms_per_launch"] * 1e-3) / 1e9, 1)} for k, v in per_kernel.items()}}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = time_reference(args.workload, args.cpu_scale, 2, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+               "sample": "%d particles (lattice extent x%.2f at the workload's spacing, smoothing length and neighbour count), 2 RK2 steps "
+                         "after 1 warm-up, %.1f s" % (r["n"], args.cpu_scale, r["seconds"])}
+
+    bytes_state = 8 * w * n
+    out = {
+        "metric": METRIC, "value": world * n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "particles_per_gpu": n, "rk_order": 2,
+                   "mean_neighbours": float(np.mean(bt[bt >= 0])),
+                   "parallelism": "single GPU" if world == 1 else "%d independent replicas (slab decomposition not enabled)" % world,
+                   "l2": "no flush: per-step working set %.0f MB of particle columns > 126 MB L2" % (8e-6 * n * 190)},
+        "e2e": {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
+                "d2h_bytes_per_step": bytes_state, "ms_per_step": ms_e2e / args.steps,
+                "api": "copy_host_to_device(pinned state) + advance_timestep + copy_device_to_host via the C ABI"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
+    ap.add_argument("--cpu-scale", type=float, default=0.25, help="lattice-extent factor of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        own_arm(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,10 @@ def lib():
     L.ccb_kernel_launches.restype = C.c_int64
     L.ccb_profile_enable.argtypes = [ctx, C.c_int]
     L.ccb_profile_get.argtypes = [ctx, C.c_int, dp, C.POINTER(C.c_int64)]
+    L.ccb_state_width.argtypes = [ctx]
+    L.ccb_upload_state.argtypes = [ctx, dp]
+    L.ccb_download_state.argtypes = [ctx, dp]
+    L.ccb_measure_dfma_peak.argtypes = [C.c_int, dp]
     L.ccb_stream.argtypes = [ctx]
     L.ccb_stream.restype = C.c_void_p
     L.ccb_device_field.argtypes = [ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -125,4 +129,5 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_set_time", "ccb_grid_shape", "ccb_build_cells", "ccb_smooth_fields", "ccb_update_thermodynamics",
             "ccb_local_update", "ccb_smooth_gradients", "ccb_time_derivatives", "ccb_get_time_derivatives", "ccb_step",
             "ccb_synchronize", "ccb_reduce", "ccb_kernel_launches", "ccb_profile_enable", "ccb_profile_get",
-            "ccb_stream", "ccb_device_field"]
+            "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
+            "ccb_measure_dfma_peak"]

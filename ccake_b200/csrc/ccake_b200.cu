@@ -10,8 +10,7 @@
 #include <vector>
 
 #include "cells.cuh"
-#include "gather.cuh"
-#include "local.cuh"
+#include "launchers.h"
 
 using namespace ccb;
 
@@ -51,7 +50,9 @@ struct ccb_ctx {
   int64_t launches = 0;
   // phase timing (CCAKE_PROFILE analogue)
   bool profiling = false;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  struct EventPair { cudaEvent_t a, b; int phase; };
+  std::vector<EventPair> ev_pool;
+  size_t ev_used = 0;
   double phase_ms[PH_COUNT];
   int64_t phase_calls[PH_COUNT];
   KernelNorm kD, k2, k1;
@@ -81,6 +82,7 @@ namespace {
   } while (0)
 
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+constexpr int kStageCols = 26;  // widest id-ordered transfer: the whole evolved state
 
 int field_offset(int field) {
   int o = 0;
@@ -89,19 +91,37 @@ int field_offset(int field) {
 }
 int total_width() { return field_offset(CCB_F_COUNT); }
 
+// Phase timing without stalling the stream: every phase records a (start, stop) event pair from a
+// pool; the pairs are resolved into per-phase totals when the host next synchronises.
+using EventPair = ccb_ctx::EventPair;
 struct PhaseTimer {
-  ccb_ctx* ctx; int ph;
-  PhaseTimer(ccb_ctx* c, int p) : ctx(c), ph(p) { if (ctx->profiling) cudaEventRecord(ctx->ev0, ctx->stream); }
-  ~PhaseTimer() {
+  ccb_ctx* ctx; int ph; size_t slot;
+  PhaseTimer(ccb_ctx* c, int p) : ctx(c), ph(p), slot(0) {
     if (!ctx->profiling) return;
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    cudaEventSynchronize(ctx->ev1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    ctx->phase_ms[ph] += ms;
-    ctx->phase_calls[ph]++;
+    if (ctx->ev_used == ctx->ev_pool.size()) {
+      EventPair e; e.phase = p;
+      cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+      ctx->ev_pool.push_back(e);
+    }
+    slot = ctx->ev_used++;
+    ctx->ev_pool[slot].phase = p;
+    cudaEventRecord(ctx->ev_pool[slot].a, ctx->stream);
   }
+  ~PhaseTimer() { if (ctx->profiling) cudaEventRecord(ctx->ev_pool[slot].b, ctx->stream); }
 };
+
+void resolve_phase_events(ccb_ctx* ctx) {
+  if (ctx->ev_used == 0) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (size_t k = 0; k < ctx->ev_used; ++k) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ctx->ev_pool[k].a, ctx->ev_pool[k].b) == cudaSuccess) {
+      ctx->phase_ms[ctx->ev_pool[k].phase] += ms;
+      ctx->phase_calls[ctx->ev_pool[k].phase]++;
+    }
+  }
+  ctx->ev_used = 0;
+}
 
 // The neighbour grid of the reference (src/system_state.cpp:651-700 + Cabana's Cartesian grid).
 void setup_grid(ccb_ctx* ctx) {
@@ -186,7 +206,7 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   CUDA_OK(cudaMalloc(&ctx->hist, sizeof(uint32_t) * ctx->hist_alloc));
   CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G1 * cap));
   CUDA_OK(cudaMalloc(&ctx->tasks, sizeof(int32_t) * cap));
-  CUDA_OK(cudaMalloc(&ctx->d_stage, sizeof(double) * 16 * cap));
+  CUDA_OK(cudaMalloc(&ctx->d_stage, sizeof(double) * kStageCols * cap));
   dv.key = ctx->key_a;
   dv.cell_start = ctx->cell_count;
   dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
@@ -303,14 +323,26 @@ int do_build_cells(ccb_ctx* ctx) {
   return CCB_OK;
 }
 
-template <int D, bool MILNE> int launch_prologue(ccb_ctx* ctx) {
-  LAUNCH((prologue_kernel<D, MILNE>), cdiv(ctx->n, 256), 256, ctx->dv, ctx->t);
-  return CCB_OK;
-}
+// Dispatch over (dimension, metric) to the per-instantiation object files (launchers.h).
+#define LAUNCHER(what, call)                                                          \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    ctx->launches++;                                                                  \
+    if (e__ != cudaSuccess) {                                                         \
+      ctx->err = std::string(what) + ": " + cudaGetErrorString(e__);                  \
+      return CCB_ERR_CUDA;                                                            \
+    }                                                                                 \
+  } while (0)
+#define DISPATCH_DM(what, fn, ...)                                                    \
+  do {                                                                                \
+    if (ctx->D == 2) { if (ctx->milne) LAUNCHER(what, (fn<2, true>(__VA_ARGS__))); else LAUNCHER(what, (fn<2, false>(__VA_ARGS__))); } \
+    else { if (ctx->milne) LAUNCHER(what, (fn<3, true>(__VA_ARGS__))); else LAUNCHER(what, (fn<3, false>(__VA_ARGS__))); }             \
+  } while (0)
+
 int do_prologue(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_GAMMA);
-  if (ctx->D == 2) return ctx->milne ? launch_prologue<2, true>(ctx) : launch_prologue<2, false>(ctx);
-  return ctx->milne ? launch_prologue<3, true>(ctx) : launch_prologue<3, false>(ctx);
+  DISPATCH_DM("prologue_kernel", launch_prologue, ctx->stream, ctx->dv, ctx->t);
+  return CCB_OK;
 }
 
 int do_gather_fields(ccb_ctx* ctx) {
@@ -318,54 +350,35 @@ int do_gather_fields(ccb_ctx* ctx) {
   const GatherParams gp = make_gather(ctx);
   const int grid = gather_grid(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
-  if (ctx->D == 2) LAUNCH((gather_fields_kernel<2, false>), grid, kGatherThreads, ctx->dv, ctx->grid, gp);
-  else if (fact) LAUNCH((gather_fields_kernel<3, true>), grid, kGatherThreads, ctx->dv, ctx->grid, gp);
-  else LAUNCH((gather_fields_kernel<3, false>), grid, kGatherThreads, ctx->dv, ctx->grid, gp);
+  if (ctx->D == 2) LAUNCHER("gather_fields_kernel", launch_gather_fields<2>(false, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
+  else LAUNCHER("gather_fields_kernel", launch_gather_fields<3>(fact, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
 }
 
-template <int D, bool MILNE> int launch_eos_local(ccb_ctx* ctx, const StageParams& sp) {
-  LAUNCH((eos_local_kernel<D, MILNE>), cdiv(ctx->n, 128), 128, ctx->dv, sp);
-  return CCB_OK;
-}
 int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
   PhaseTimer pt(ctx, do_eos ? PH_THERMO : PH_LOCAL);
   StageParams sp = make_stage(ctx, 0.0, 0);
   sp.do_eos = do_eos; sp.do_local = do_local;
-  if (ctx->D == 2) return ctx->milne ? launch_eos_local<2, true>(ctx, sp) : launch_eos_local<2, false>(ctx, sp);
-  return ctx->milne ? launch_eos_local<3, true>(ctx, sp) : launch_eos_local<3, false>(ctx, sp);
-}
-
-template <int D> int launch_gather_grad(ccb_ctx* ctx, const GatherParams& gp, bool shear, bool diff, bool fact) {
-  const int grid = gather_grid(ctx);
-#define CCB_GG(S, F, X) LAUNCH((gather_gradients_kernel<D, S, F, X>), grid, kGatherThreads, ctx->dv, ctx->grid, gp)
-  if (fact) {
-    if (shear) { if (diff) CCB_GG(true, true, (D == 3)); else CCB_GG(true, false, (D == 3)); }
-    else { if (diff) CCB_GG(false, true, (D == 3)); else CCB_GG(false, false, (D == 3)); }
-  } else {
-    if (shear) { if (diff) CCB_GG(true, true, false); else CCB_GG(true, false, false); }
-    else { if (diff) CCB_GG(false, true, false); else CCB_GG(false, false, false); }
-  }
-#undef CCB_GG
+  DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
   return CCB_OK;
 }
+
 int do_gather_gradients(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_GRAD);
   const GatherParams gp = make_gather(ctx);
+  const int grid = gather_grid(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
-  return ctx->D == 2 ? launch_gather_grad<2>(ctx, gp, sh, df, false) : launch_gather_grad<3>(ctx, gp, sh, df, fact);
-}
-
-template <int D, bool MILNE> int launch_eom(ccb_ctx* ctx, const StageParams& sp) {
-  LAUNCH((eom_rk_kernel<D, MILNE>), cdiv(ctx->n, 128), 128, ctx->dv, sp);
+  if (ctx->D == 2) LAUNCHER("gather_gradients_kernel", launch_gather_gradients<2>(sh, df, false, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
+  else LAUNCHER("gather_gradients_kernel", launch_gather_gradients<3>(sh, df, fact, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
 }
+
 int do_eom(ccb_ctx* ctx, double h_stage, int do_update) {
   PhaseTimer pt(ctx, PH_TIME_DERIV);
   const StageParams sp = make_stage(ctx, h_stage, do_update);
-  if (ctx->D == 2) return ctx->milne ? launch_eom<2, true>(ctx, sp) : launch_eom<2, false>(ctx, sp);
-  return ctx->milne ? launch_eom<3, true>(ctx, sp) : launch_eom<3, false>(ctx, sp);
+  DISPATCH_DM("eom_rk_kernel", launch_eom_rk, ctx->stream, ctx->dv, sp);
+  return CCB_OK;
 }
 
 int derivative_evaluation(ccb_ctx* ctx, double h_stage, int do_update) {
@@ -400,45 +413,9 @@ int surface_device_error(ccb_ctx* ctx) {
   return CCB_OK;
 }
 
-// ---- initialisation kernels (BSQHydro::initialize_hydrodynamics on the device) ---
-// tmp columns (current order): 0 e_or_s, 1 rhoB, 2 rhoS, 3 rhoQ, 4 bulk, 5..9 shv (xx,xy,xeta,yy,yeta)
-template <int D, bool MILNE>
-__global__ void init_particles_kernel(DeviceView dv, StageParams sp, const double* __restrict__ tmp, int input_as_entropy,
-                                      int input_initial_shear, int bulk_from_trace, double efcheck) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dv.n) return;
-  const int64_t cap = dv.cap;
-  const double hc = kHbarcGeVfm;
-  const double rhoB = tmp[1 * cap + i], rhoS = tmp[2 * cap + i], rhoQ = tmp[3 * cap + i];
-  double T, muB, muS, muQ;
-  bool ok;
-  double e_in = 0., s_in = 0.;
-  // SPHWorkstation::initialize_entropy_and_charge_densities, src/sph_workstation.cpp:253-375
-  if (input_as_entropy) { s_in = tmp[i]; ok = conformal_invert_s(sp.conf, s_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
-  else { e_in = tmp[i] / hc; ok = conformal_invert_e(sp.conf, e_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
-  if (!ok) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
-  double r[TH_N];
-  conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
-  Thermo th;
-  thermo_from_forward(T, muB, muQ, muS, r, 0, th);
-  if (input_as_entropy) e_in = th.e; else s_in = th.s;
-  store_thermo(dv, i, th);
-  dv.freeze[i] = (e_in > efcheck && dv.freeze[i] != 4) ? 0 : 4;
-  const double sigma = dv.f[CCB_F_SIGMA][i];
-  col(dv.f[CCB_F_EXTENSIVE], cap, 0, i) = s_in / sigma;
-  col(dv.f[CCB_F_EXTENSIVE], cap, 1, i) = rhoB / sigma;
-  col(dv.f[CCB_F_EXTENSIVE], cap, 2, i) = rhoS / sigma;
-  col(dv.f[CCB_F_EXTENSIVE], cap, 3, i) = rhoQ / sigma;
-  if (s_in < 0.0) dv.freeze[i] = 4;
-  // calculate_extensive_shv / set_bulk_Pi / set_diffusion, src/sph_workstation.cpp:1350-1460
-#pragma unroll
-  for (int c = 0; c < 5; ++c) col(dv.f[CCB_F_EXTENSIVE_SHV], cap, c, i) = input_initial_shear ? (tmp[(5 + c) * cap + i] / hc) / sigma : 0.0;
-  dv.f[CCB_F_EXTENSIVE_BULK][i] = bulk_from_trace ? (tmp[4 * cap + i] / hc - th.p) / sigma : 0.0;
-}
-
-template <int D, bool MILNE> int launch_init(ccb_ctx* ctx, const StageParams& sp) {
-  LAUNCH((init_particles_kernel<D, MILNE>), cdiv(ctx->n, 128), 128, ctx->dv, sp, ctx->init_tmp, ctx->cfg.input_as_entropy,
-         ctx->cfg.input_initial_shear, ctx->cfg.bulk_from_trace, ctx->efcheck);
+int do_init_particles(ccb_ctx* ctx, const StageParams& sp) {
+  DISPATCH_DM("init_particles_kernel", launch_init_particles, ctx->stream, ctx->dv, sp, ctx->init_tmp, ctx->cfg.input_as_entropy,
+              ctx->cfg.input_initial_shear, ctx->cfg.bulk_from_trace, ctx->efcheck);
   return CCB_OK;
 }
 
@@ -474,8 +451,6 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
   CUDA_OK(cudaSetDevice(cfg->device));
   CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaEventCreate(&ctx->ev0));
-  CUDA_OK(cudaEventCreate(&ctx->ev1));
   CUDA_OK(cudaMalloc(&ctx->d_small, sizeof(int32_t) * 8));
   CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t) * 8, ctx->stream));
   CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
@@ -501,8 +476,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
-  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
-  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CCB_OK;
@@ -518,12 +492,14 @@ int ccb_grid_shape(ccb_ctx* ctx, int32_t nc[3]) { if (!ctx) return CCB_ERR_INVAL
 
 int ccb_profile_enable(ccb_ctx* ctx, int on) {
   if (!ctx) return CCB_ERR_INVALID;
+  resolve_phase_events(ctx);
   ctx->profiling = on != 0;
   for (int p = 0; p < PH_COUNT; ++p) { ctx->phase_ms[p] = 0.; ctx->phase_calls[p] = 0; }
   return CCB_OK;
 }
 int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls) {
   if (!ctx || phase < 0 || phase >= PH_COUNT) return CCB_ERR_INVALID;
+  resolve_phase_events(ctx);
   if (ms) *ms = ctx->phase_ms[phase];
   if (calls) *calls = ctx->phase_calls[phase];
   return CCB_OK;
@@ -601,6 +577,81 @@ int ccb_device_field(ccb_ctx* ctx, int field, int component, double** dptr) {
   return CCB_OK;
 }
 
+// Evolved state (the reference's EvolverCache member list, include/evolver.h:21-47) as one
+// column-major block [column][particle id]: position 3, u 3, extensive 4, extensive_bulk 1,
+// extensive_shv 5, (extensive_diffusion 9 when diffusion is on), Ez 1.
+static int state_columns(ccb_ctx* ctx, ColumnList& cl) {
+  cl.ncols = 0;
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    for (int c = 0; c < kFieldWidth[f]; ++c) cl.col[cl.ncols++] = ctx->dv.f[f] + (int64_t)c * ctx->cap;
+  }
+  return cl.ncols;
+}
+int ccb_state_width(ccb_ctx* ctx) {
+  if (!ctx) return -1;
+  int w = 0;
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    w += kFieldWidth[f];
+  }
+  return w;
+}
+int ccb_upload_state(ccb_ctx* ctx, const double* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (!host) return CCB_ERR_INVALID;
+  ColumnList cl;
+  const int w = state_columns(ctx, cl);
+  CUDA_OK(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(gather_columns_by_id, dim3((unsigned)cdiv(ctx->n, 256), w), 256, ctx->d_stage, cl, ctx->dv.id, ctx->n);
+  ctx->cells_valid = false;
+  return CCB_OK;
+}
+int ccb_download_state(ccb_ctx* ctx, double* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (!host) return CCB_ERR_INVALID;
+  ColumnList cl;
+  const int w = state_columns(ctx, cl);
+  LAUNCH(scatter_columns_by_id, dim3((unsigned)cdiv(ctx->n, 256), w), 256, cl, ctx->d_stage, ctx->dv.id, ctx->n);
+  CUDA_OK(cudaMemcpyAsync(host, ctx->d_stage, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  return surface_device_error(ctx);
+}
+
+// fp64 FMA peak of the device, for the roofline of the neighbour gathers (the driver measures HBM
+// and bf16 only). 16 independent DFMA chains per thread, 8 resident blocks of 256 per SM.
+int ccb_measure_dfma_peak(int device, double* tflops) {
+  if (!tflops) return CCB_ERR_INVALID;
+  if (cudaSetDevice(device) != cudaSuccess) return CCB_ERR_CUDA;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return CCB_ERR_CUDA;
+  double* d = nullptr;
+  if (cudaMalloc(&d, sizeof(double) * 256) != cudaSuccess) return CCB_ERR_CUDA;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  const int iters = 4096, blocks = sms * 8;
+  dfma_peak_kernel<<<blocks, 256>>>(d, iters, 1.0000001);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    dfma_peak_kernel<<<blocks, 256>>>(d, iters, 1.0000001);
+    cudaEventRecord(b);
+    if (cudaEventSynchronize(b) != cudaSuccess) { cudaFree(d); return CCB_ERR_CUDA; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    const double fl = 2.0 * 16.0 * (double)iters * 256.0 * blocks;
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (tf > best) best = tf;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  cudaFree(d);
+  *tflops = best;
+  return CCB_OK;
+}
+
 int ccb_build_cells(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : do_build_cells(ctx); }
 int ccb_smooth_fields(ccb_ctx* ctx) {
   int rc = check_ready(ctx, true);
@@ -629,7 +680,9 @@ int ccb_step(ccb_ctx* ctx, double dt) {
 
 int ccb_synchronize(ccb_ctx* ctx) {
   if (!ctx) return CCB_ERR_INVALID;
-  return surface_device_error(ctx);
+  const int rc = surface_device_error(ctx);
+  resolve_phase_events(ctx);
+  return rc;
 }
 
 int ccb_reduce(ccb_ctx* ctx, ccb_totals* out) {
@@ -639,8 +692,8 @@ int ccb_reduce(ccb_ctx* ctx, ccb_totals* out) {
   const int nb = kReduceBlocks;
   double* d_out = ctx->d_reduce;
   unsigned long long* d_fr = reinterpret_cast<unsigned long long*>(ctx->d_reduce + 6 * nb);
-  if (ctx->milne) LAUNCH((reduce_totals_kernel<true>), nb, 256, ctx->dv, ctx->t, d_out, d_fr);
-  else LAUNCH((reduce_totals_kernel<false>), nb, 256, ctx->dv, ctx->t, d_out, d_fr);
+  if (ctx->milne) LAUNCHER("reduce_totals_kernel", launch_reduce_totals<true>(nb, ctx->stream, ctx->dv, ctx->t, d_out, d_fr));
+  else LAUNCHER("reduce_totals_kernel", launch_reduce_totals<false>(nb, ctx->stream, ctx->dv, ctx->t, d_out, d_fr));
   std::vector<double> h(7 * nb);
   CUDA_OK(cudaMemcpyAsync(h.data(), d_out, sizeof(double) * 7 * nb, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
@@ -696,9 +749,7 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
     }
   }
   const StageParams sp = make_stage(ctx, 0.0, 0);
-  if (ctx->D == 2) rc = ctx->milne ? launch_init<2, true>(ctx, sp) : launch_init<2, false>(ctx, sp);
-  else rc = ctx->milne ? launch_init<3, true>(ctx, sp) : launch_init<3, false>(ctx, sp);
-  if (rc) return rc;
+  if ((rc = do_init_particles(ctx, sp))) return rc;
   // initial_smoothing (src/sph_workstation.cpp:395-457): smooth with the true extensive densities,
   // rebuild pi^{mu nu}, update thermodynamics
   if ((rc = do_prologue(ctx))) return rc;

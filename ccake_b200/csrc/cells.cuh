@@ -194,6 +194,35 @@ __global__ void build_tasks(const uint32_t* __restrict__ key, const uint32_t* __
   if ((rank & 31u) == 0u) tasks[atomicAdd(ntasks, 1)] = (int32_t)i;
 }
 
+// whole blocks of columns at once (ccb_upload_state / ccb_download_state): blockIdx.y = column
+struct ColumnList {
+  int ncols;
+  double* col[32];
+};
+__global__ void gather_columns_by_id(const double* __restrict__ stage, ColumnList cl, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) cl.col[blockIdx.y][i] = stage[(int64_t)blockIdx.y * n + id[i]];
+}
+__global__ void scatter_columns_by_id(ColumnList cl, double* __restrict__ stage, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stage[(int64_t)blockIdx.y * n + id[i]] = cl.col[blockIdx.y][i];
+}
+
+// 16 independent fp64 FMA chains per thread: the DFMA issue-rate ceiling (ccb_measure_dfma_peak)
+__global__ void dfma_peak_kernel(double* out, int iters, double m) {
+  double a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = 1.0 + 1e-9 * (threadIdx.x + k);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fma(a[k], m, 1e-12);
+  }
+  double s = 0.;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 123.456) out[threadIdx.x] = s;
+}
+
 // scatter a column (current order) into id order for download, and the reverse for upload
 __global__ void scatter_by_id(const double* __restrict__ src, double* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

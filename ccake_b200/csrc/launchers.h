@@ -1,0 +1,25 @@
+// Launch entry points of the templated kernels. Each (D, metric) instantiation lives in
+// its own object file (inst_gather.cu / inst_local.cu compiled once per -DCCB_INST_*
+// combination by __graft_entry__.build()), so the library builds in parallel.
+#pragma once
+
+#include "gather_params.cuh"
+#include "stage_params.h"
+
+namespace ccb {
+
+template <int D> cudaError_t launch_gather_fields(bool fact, int grid, int block, cudaStream_t s, const DeviceView& dv,
+                                                  const CellGrid& g, const GatherParams& gp);
+template <int D> cudaError_t launch_gather_gradients(bool shear, bool diff, bool fact, int grid, int block, cudaStream_t s,
+                                                     const DeviceView& dv, const CellGrid& g, const GatherParams& gp);
+template <int D, bool MILNE> cudaError_t launch_prologue(cudaStream_t s, const DeviceView& dv, double t);
+template <int D, bool MILNE> cudaError_t launch_eos_local(cudaStream_t s, const DeviceView& dv, const StageParams& sp);
+template <int D, bool MILNE> cudaError_t launch_eom_rk(cudaStream_t s, const DeviceView& dv, const StageParams& sp);
+template <int D, bool MILNE>
+cudaError_t launch_init_particles(cudaStream_t s, const DeviceView& dv, const StageParams& sp, const double* tmp,
+                                  int input_as_entropy, int input_initial_shear, int bulk_from_trace, double efcheck);
+template <bool MILNE>
+cudaError_t launch_reduce_totals(int nblocks, cudaStream_t s, const DeviceView& dv, double t, double* out,
+                                 unsigned long long* nfrozen);
+
+}  // namespace ccb

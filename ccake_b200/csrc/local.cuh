@@ -255,6 +255,42 @@ __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams 
   }
 }
 
+// ---- initialisation kernels (BSQHydro::initialize_hydrodynamics on the device) ---
+// tmp columns (current order): 0 e_or_s, 1 rhoB, 2 rhoS, 3 rhoQ, 4 bulk, 5..9 shv (xx,xy,xeta,yy,yeta)
+template <int D, bool MILNE>
+__global__ void init_particles_kernel(DeviceView dv, StageParams sp, const double* __restrict__ tmp, int input_as_entropy,
+                                      int input_initial_shear, int bulk_from_trace, double efcheck) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  const int64_t cap = dv.cap;
+  const double hc = kHbarcGeVfm;
+  const double rhoB = tmp[1 * cap + i], rhoS = tmp[2 * cap + i], rhoQ = tmp[3 * cap + i];
+  double T, muB, muS, muQ;
+  bool ok;
+  double e_in = 0., s_in = 0.;
+  // SPHWorkstation::initialize_entropy_and_charge_densities, src/sph_workstation.cpp:253-375
+  if (input_as_entropy) { s_in = tmp[i]; ok = conformal_invert_s(sp.conf, s_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
+  else { e_in = tmp[i] / hc; ok = conformal_invert_e(sp.conf, e_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
+  if (!ok) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
+  double r[TH_N];
+  conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
+  Thermo th;
+  thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+  if (input_as_entropy) e_in = th.e; else s_in = th.s;
+  store_thermo(dv, i, th);
+  dv.freeze[i] = (e_in > efcheck && dv.freeze[i] != 4) ? 0 : 4;
+  const double sigma = dv.f[CCB_F_SIGMA][i];
+  col(dv.f[CCB_F_EXTENSIVE], cap, 0, i) = s_in / sigma;
+  col(dv.f[CCB_F_EXTENSIVE], cap, 1, i) = rhoB / sigma;
+  col(dv.f[CCB_F_EXTENSIVE], cap, 2, i) = rhoS / sigma;
+  col(dv.f[CCB_F_EXTENSIVE], cap, 3, i) = rhoQ / sigma;
+  if (s_in < 0.0) dv.freeze[i] = 4;
+  // calculate_extensive_shv / set_bulk_Pi / set_diffusion, src/sph_workstation.cpp:1350-1460
+#pragma unroll
+  for (int c = 0; c < 5; ++c) col(dv.f[CCB_F_EXTENSIVE_SHV], cap, c, i) = input_initial_shear ? (tmp[(5 + c) * cap + i] / hc) / sigma : 0.0;
+  dv.f[CCB_F_EXTENSIVE_BULK][i] = bulk_from_trace ? (tmp[4 * cap + i] / hc - th.p) / sigma : 0.0;
+}
+
 // S, B, S, Q, E, Ez, n_frozen in one pass (block reduce, one partial per block).
 // Mirrors the reference sums term by term, including its use of sph_mass.s in the
 // S and Q diffusion terms (src/system_state.cpp:770, 803, 812).

@@ -1,0 +1,120 @@
+"""Synthetic initial conditions and settings of the BASELINE.json configs.
+
+Everything is generated from closed forms with fixed seeds: no file of the reference tree is
+read at run time (``/root/reference`` does not exist on the GPU box).  Settings dicts use the
+reference's ``Settings`` member names, so the same dict drives the CUDA library and the oracle.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+HBARC_GEVFM = 0.1973269804  # reference include/constants.h:15
+CONFORMAL_C = math.pi ** 2 * (2.0 * (3.0 ** 2 - 1.0) + 3.5 * 3.0 * 2.5) / 90.0  # src/eos_initialization.cpp:216-231
+
+
+def gubser_energy_u(x, y, tau0=1.0, eps0=80.0, q=1.0):
+    """Ideal Gubser flow at tau0 (reference utilities/ideal_gubser_ic_generator.py:22-37):
+    energy density [GeV/fm^3] and u^x, u^y."""
+    r = np.hypot(x, y)
+    eps = (eps0 / tau0 ** (4.0 / 3.0)) * (2 * q) ** (8.0 / 3.0) / \
+        (1 + 2 * q ** 2 * (tau0 ** 2 + r ** 2) + (q ** 2 * (tau0 ** 2 - r ** 2)) ** 2) ** (4.0 / 3.0)
+    kap = np.arctanh(2 * q ** 2 * tau0 * r / (1 + (q * tau0) ** 2 + (q * r) ** 2))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ux = np.where(r > 0, np.sinh(kap) * x / r, 0.0)
+        uy = np.where(r > 0, np.sinh(kap) * y / r, 0.0)
+    return eps, ux, uy
+
+
+def gubser_charge(x, y, tau0=1.0, q=1.0):
+    """chargeGubser(tau, r) of reference misc/Gubser_checks/plot_gubser_profiles.py:46-50."""
+    r2 = x * x + y * y
+    return (1.0 / tau0 ** 3) * (4.0 * q ** 2 * tau0 ** 2) / (1.0 + 2.0 * q ** 2 * (tau0 ** 2 + r2) + q ** 4 * (tau0 ** 2 - r2) ** 2)
+
+
+def lattice_2d(dx, xmax):
+    xs = np.arange(-xmax, xmax + dx / 2, dx)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    return X.ravel(), Y.ravel()
+
+
+_COMMON = dict(dim=2, coordinate_system="hyperbolic", t0=1.0, rk_order=2, eos_type="conformal", input_as_entropy=False,
+               e_cutoff=0.0, print_conservation_status=False)
+
+
+def config1_ideal_gubser(dx=0.025, xmax=5.0):
+    """BASELINE config 1: input/input_parameters_ideal_gubser_checks.yaml (h = 0.4, dt = 0.001, ideal fluid, no charges), 401^2 lattice."""
+    x, y = lattice_2d(dx, xmax)
+    eps, ux, uy = gubser_energy_u(x, y)
+    settings = dict(_COMMON, dt=0.001, hT=0.4, hEta=0.4, stepx=dx, stepy=dx, stepEta=0.1, xmin=-xmax, ymin=-xmax, etamin=-0.1,
+                    etaMode="constant", constant_eta_over_s=0.0, shearRelaxMode="default", zetaMode="constant",
+                    constant_zeta_over_s=0.0, bulkRelaxMode="default", diffusionMode="disabled",
+                    baryon_charge_enabled=False, strange_charge_enabled=False, electric_charge_enabled=False,
+                    modulate_zeta_with_tanh=False, input_initial_shear=False)
+    ic = dict(r=np.stack([x, y], 1), e=eps, u=np.stack([ux, uy], 1), rhoB=None, rhoS=None, rhoQ=None, bulk=None, shv6=None)
+    return settings, ic
+
+
+def config2_viscous_gubser_bsq(dx=0.025, xmax=5.0, seed=7):
+    """BASELINE config 2: the settings of input/config_visc_gubser.yaml (h = 0.1, dt = 0.001, eta/s = 0.2 with the
+    Gubser relaxation time, conformal EoS at finite mu_B, mu_S, mu_Q, diffusion code path on with kappa = 0,
+    initial shear read from the IC). The IC file that YAML names is external to the reference tree, so the
+    profile is synthetic: ideal-Gubser e and u^i, Gubser charge profiles with mu_B/T ~ 0.3 at the centre, and a
+    smooth pi^{ij} of 2 % of e. NB the YAML spells `relaxation_mode: gubser`; the reference only recognises
+    "Gubser" (src/transport_coefficients.cpp:42) and otherwise leaves the enum unset: the intended mode is used."""
+    x, y = lattice_2d(dx, xmax)
+    eps, ux, uy = gubser_energy_u(x, y)
+    e_fm = eps / HBARC_GEVFM
+    s = 4.0 * CONFORMAL_C * (e_fm / (3.0 * CONFORMAL_C)) ** 0.75  # conformal s(e) at mu = 0
+    g = gubser_charge(x, y)
+    g = g / g.max()
+    rhoB, rhoS, rhoQ = 0.30 * s.max() * g, -0.10 * s.max() * g, 0.12 * s.max() * g
+    rng = np.random.default_rng(seed)
+    amp = 0.02 * eps
+    pixx = amp * np.cos(1.3 * x) * (1 + 0.05 * rng.standard_normal(x.size))
+    piyy = amp * np.sin(0.7 * y + 0.3)
+    pixy = 0.5 * amp * np.sin(x * y)
+    z = np.zeros_like(x)
+    settings = dict(_COMMON, dt=0.001, hT=0.1, hEta=0.1, stepx=dx, stepy=dx, stepEta=0.1, xmin=-xmax, ymin=-xmax, etamin=-0.1,
+                    Freeze_Out_Temperature=153.334025,
+                    baryon_charge_enabled=True, strange_charge_enabled=True, electric_charge_enabled=True,
+                    etaMode="constant", constant_eta_over_s=0.2, shearRelaxMode="Gubser", use_vorticity=False,
+                    delta_pipi_mode="default", tau_pipi_mode="disabled", lambda_piPi_mode="disabled", phi6_mode="disabled",
+                    phi7_mode="disabled", input_initial_shear=True,
+                    zetaMode="constant", constant_zeta_over_s=0.0, cs2_dependent_zeta_A=1.67552, cs2_dependent_zeta_p=2.0,
+                    bulk_from_trace=False, bulkRelaxMode="default", modulate_zeta_with_tanh=False,
+                    delta_PiPi_mode="israel-stewart", lambda_Pipi_mode="default", phi1_mode="disabled", phi3_mode="disabled",
+                    diffusionMode="constant_over_T2", diffusionRelaxMode="constant_over_T")
+    ic = dict(r=np.stack([x, y], 1), e=eps, u=np.stack([ux, uy], 1), rhoB=rhoB, rhoS=rhoS, rhoQ=rhoQ, bulk=None,
+              shv6=np.stack([pixx, pixy, z, piyy, z, z], 1))
+    return settings, ic
+
+
+def config5_cartesian_blob(n_target=1_000_000, sigma=3.0, seed=11):
+    """BASELINE config 5: 3+1D Cartesian Gaussian blob on a cubic lattice inside radius 3 sigma, h = 2 dx
+    (N_ngb ~ 268), conformal EoS, ideal fluid at rest."""
+    R = 3.0 * sigma
+    dx = (4.0 / 3.0 * math.pi * R ** 3 / n_target) ** (1.0 / 3.0)
+    m = int(math.floor(R / dx))
+    xs = np.arange(-m, m + 1) * dx
+    X, Y, Z = np.meshgrid(xs, xs, xs, indexing="ij")
+    keep = (X * X + Y * Y + Z * Z) <= R * R
+    x, y, z = X[keep], Y[keep], Z[keep]
+    r2 = x * x + y * y + z * z
+    eps = 30.0 * np.exp(-r2 / (2 * sigma ** 2)) + 0.3
+    lo = -(m + 1) * dx
+    settings = dict(_COMMON, dim=3, coordinate_system="cartesian", dt=0.01, hT=2 * dx, hEta=2 * dx, stepx=dx, stepy=dx,
+                    stepEta=dx, xmin=lo, ymin=lo, etamin=lo, etaMode="constant", constant_eta_over_s=0.0,
+                    shearRelaxMode="default", zetaMode="constant", constant_zeta_over_s=0.0, bulkRelaxMode="default",
+                    diffusionMode="disabled", baryon_charge_enabled=False, strange_charge_enabled=False,
+                    electric_charge_enabled=False, modulate_zeta_with_tanh=False, input_initial_shear=False)
+    ic = dict(r=np.stack([x, y, z], 1), e=eps, u=np.zeros((x.size, 3)), rhoB=None, rhoS=None, rhoQ=None, bulk=None, shv6=None)
+    return settings, ic
+
+
+WORKLOADS = {
+    "config1_ideal_gubser_2p1d": config1_ideal_gubser,
+    "config2_viscous_gubser_bsq_2p1d": config2_viscous_gubser_bsq,
+    "config5_cartesian_blob_3p1d": config5_cartesian_blob,
+}

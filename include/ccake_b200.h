@@ -157,6 +157,14 @@ int ccb_set_field(ccb_ctx* ctx, int field, const double* host);
 int ccb_get_field(ccb_ctx* ctx, int field, double* host);
 int ccb_set_int_field(ccb_ctx* ctx, int field, const int32_t* host);
 int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host);
+/* the whole evolved state (reference EvolverCache member list, include/evolver.h:21-47) as ONE column-major
+ * block [column][particle id] of ccb_state_width() columns: position 3, u 3, extensive 4, extensive_bulk 1,
+ * extensive_shv 5, extensive_diffusion 9 (only when using_diffusion), Ez 1. One host<->device copy each way
+ * (pass pinned memory for full PCIe speed). upload is asynchronous on the context's stream; download
+ * synchronises and surfaces device-side errors. */
+int ccb_state_width(ccb_ctx* ctx);
+int ccb_upload_state(ccb_ctx* ctx, const double* host);
+int ccb_download_state(ccb_ctx* ctx, double* host);
 int64_t ccb_n(ccb_ctx* ctx);
 double ccb_time(ccb_ctx* ctx);
 int ccb_set_time(ccb_ctx* ctx, double t);
@@ -185,6 +193,8 @@ int ccb_reduce(ccb_ctx* ctx, ccb_totals* out);
 int64_t ccb_kernel_launches(ccb_ctx* ctx);
 int ccb_profile_enable(ccb_ctx* ctx, int on);
 int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls);
+/* fp64 FMA peak (TFLOP/s) of a device from a DFMA micro-benchmark: roofline denominator of the gathers */
+int ccb_measure_dfma_peak(int device, double* tflops);
 void* ccb_stream(ccb_ctx* ctx);           /* cudaStream_t of the context */
 /* device pointer of a field in CURRENT (cell-sorted) order, for zero-copy consumers (halo packing) */
 int ccb_device_field(ccb_ctx* ctx, int field, int component, double** dptr);

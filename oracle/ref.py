@@ -77,6 +77,18 @@ PHASES = {"neighbour_list": 1, "gamma_velocity": 2, "smooth_fields": 3, "thermod
           "regulate_diffusion": 6, "viscosities": 8, "smooth_gradients": 9, "time_derivatives": 10}
 
 
+# Settings members the driver's key=value parser accepts (oracle/ref_driver.cpp: parse_settings)
+SETTING_KEYS = frozenset([
+    "dim", "coordinate_system", "t0", "dt", "hT", "hEta", "rk_order", "factorized_kernel", "e_cutoff", "input_as_entropy",
+    "stepx", "stepy", "stepEta", "xmin", "ymin", "etamin", "max_tau", "eos_type", "eos_path", "normalize_by_T",
+    "Freeze_Out_Temperature", "baryon_charge_enabled", "strange_charge_enabled", "electric_charge_enabled", "etaMode",
+    "constant_eta_over_s", "shearRelaxMode", "use_vorticity", "delta_pipi_mode", "tau_pipi_mode", "lambda_piPi_mode",
+    "phi6_mode", "phi7_mode", "input_initial_shear", "zetaMode", "constant_zeta_over_s", "cs2_dependent_zeta_A",
+    "cs2_dependent_zeta_p", "bulk_from_trace", "bulkRelaxMode", "modulate_zeta_with_tanh", "delta_PiPi_mode",
+    "lambda_Pipi_mode", "phi1_mode", "phi3_mode", "diffusionMode", "diffusionRelaxMode", "print_conservation_status",
+    "prohibit_unstable_cs2", "prohibit_acausal_cs2"])
+
+
 def available() -> bool:
     return os.path.exists(LIB_PATH)
 
@@ -112,8 +124,14 @@ def lib():
         L.ccake_ref_neighbours.restype = C.c_long
         L.ccake_ref_neighbours.argtypes = [C.c_void_p, lp, ip, ip, ip]
         L.ccake_ref_totals.argtypes = [C.c_void_p, dp]
+        L.ccake_ref_omp_threads.restype = C.c_int
         _lib = L
     return _lib
+
+
+def omp_threads() -> int:
+    """Threads the reference's parallel loops run on (omp_get_max_threads of the build)."""
+    return int(lib().ccake_ref_omp_threads())
 
 
 def _dp(a):

@@ -12,6 +12,8 @@
 // State is read back member-block by member-block (the CabanaParticle member
 // order of include/particle.h:54-100), so tests can compare any intermediate of
 // the pipeline with the CUDA path.
+#include <omp.h>
+
 #include <cstring>
 #include <map>
 #include <memory>
@@ -294,5 +296,6 @@ long ccake_ref_neighbours(void* h, long* offsets, int* idx, int* cell_of, int* n
   return static_cast<RefBase*>(h)->neighbours(offsets, idx, cell_of, ncell);
 }
 int ccake_ref_totals(void* h, double* out) { return static_cast<RefBase*>(h)->totals(out); }
+int ccake_ref_omp_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

@@ -117,14 +117,7 @@ def have_ref():
 
 def make_ref(settings, ic):
     ref = ref_module()
-    keys = set(["dim", "coordinate_system", "t0", "dt", "hT", "hEta", "rk_order", "factorized_kernel", "e_cutoff",
-                "input_as_entropy", "stepx", "stepy", "stepEta", "xmin", "ymin", "etamin", "max_tau", "eos_type",
-                "eos_path", "Freeze_Out_Temperature", "baryon_charge_enabled", "strange_charge_enabled",
-                "electric_charge_enabled", "etaMode", "constant_eta_over_s", "shearRelaxMode", "use_vorticity",
-                "delta_pipi_mode", "tau_pipi_mode", "lambda_piPi_mode", "phi6_mode", "phi7_mode", "input_initial_shear",
-                "zetaMode", "constant_zeta_over_s", "cs2_dependent_zeta_A", "cs2_dependent_zeta_p", "bulk_from_trace",
-                "bulkRelaxMode", "modulate_zeta_with_tanh", "delta_PiPi_mode", "lambda_Pipi_mode", "phi1_mode",
-                "phi3_mode", "diffusionMode", "diffusionRelaxMode", "print_conservation_status"])
+    keys = ref.SETTING_KEYS
     st = {k: v for k, v in settings.items() if k in keys or k.startswith("kappa_")}
     sim = ref.RefSim(st)
     sim.add_particles(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
