@@ -57,6 +57,8 @@ struct ccb_ctx {
   int64_t phase_calls[PH_COUNT];
   KernelNorm kD, k2, k1;
   double efcheck = 0.0;
+  int chunk = 64;   // targets per gather task (= threads per CTA): 64 or 128
+  int sms = 148;
 };
 
 namespace {
@@ -204,7 +206,7 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   CUDA_OK(cudaMalloc(&ctx->idx_a, sizeof(uint32_t) * cap)); CUDA_OK(cudaMalloc(&ctx->idx_b, sizeof(uint32_t) * cap));
   ctx->hist_alloc = 256 * cdiv(cap, kSortTile);
   CUDA_OK(cudaMalloc(&ctx->hist, sizeof(uint32_t) * ctx->hist_alloc));
-  CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G1 * cap));
+  CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G_MAX * cap));
   CUDA_OK(cudaMalloc(&ctx->tasks, sizeof(int32_t) * cap));
   CUDA_OK(cudaMalloc(&ctx->d_stage, sizeof(double) * kStageCols * cap));
   dv.key = ctx->key_a;
@@ -247,19 +249,13 @@ GatherParams make_gather(ccb_ctx* ctx) {
   gp.kD = ctx->kD; gp.k2 = ctx->k2; gp.k1 = ctx->k1;
   const double radius = 2 * ctx->cfg.hT;
   gp.rsqr = radius * radius;
+  gp.rsqr_f = (float)(gp.rsqr * (1.0 + 1e-4));  // fp32 pre-filter: never misses a true neighbour (gather.cuh)
   gp.t = ctx->t;
   gp.milne = ctx->milne ? 1 : 0;
   return gp;
 }
 
-constexpr int kGatherThreads = 128;
 constexpr int kReduceBlocks = 296;
-int gather_grid(ccb_ctx* ctx) {
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device);
-  return sms * 8;
-}
-
 // ---- phase implementations ------------------------------------------------------
 int do_build_cells(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_NEIGHBOUR);
@@ -318,7 +314,7 @@ int do_build_cells(ccb_ctx* ctx) {
   if (kin != ctx->key_a) { std::swap(ctx->key_a, ctx->key_b); std::swap(ctx->idx_a, ctx->idx_b); }
   // work list of the gathers
   CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t), ctx->stream));
-  LAUNCH(build_tasks, cdiv(n, 256), 256, dv.key, dv.cell_start, dv.tasks, dv.ntasks, n);
+  LAUNCH(build_tasks, cdiv(n, 256), 256, dv.key, dv.cell_start, dv.tasks, dv.ntasks, n, (uint32_t)ctx->chunk);
   ctx->cells_valid = true;
   return CCB_OK;
 }
@@ -348,10 +344,11 @@ int do_prologue(ccb_ctx* ctx) {
 int do_gather_fields(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
   const GatherParams gp = make_gather(ctx);
-  const int grid = gather_grid(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
-  if (ctx->D == 2) LAUNCHER("gather_fields_kernel", launch_gather_fields<2>(false, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
-  else LAUNCHER("gather_fields_kernel", launch_gather_fields<3>(fact, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
+  int* counter = ctx->d_small + 3;
+  CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+  if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
+  else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
   return CCB_OK;
 }
 
@@ -366,11 +363,12 @@ int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
 int do_gather_gradients(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_GRAD);
   const GatherParams gp = make_gather(ctx);
-  const int grid = gather_grid(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
-  if (ctx->D == 2) LAUNCHER("gather_gradients_kernel", launch_gather_gradients<2>(sh, df, false, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
-  else LAUNCHER("gather_gradients_kernel", launch_gather_gradients<3>(sh, df, fact, grid, kGatherThreads, ctx->stream, ctx->dv, ctx->grid, gp));
+  int* counter = ctx->d_small + 3;
+  CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
+  if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
+  else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
   return CCB_OK;
 }
 
@@ -456,6 +454,15 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
   for (int p = 0; p < PH_COUNT; ++p) { ctx->phase_ms[p] = 0.; ctx->phase_calls[p] = 0; }
   setup_grid(ctx);
+  cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  {  // expected particles per neighbour cell from the IC lattice spacing: dense cells get 128-target tasks
+    double ppc = 0.0;
+    if (cfg->stepx > 0 && cfg->stepy > 0) {
+      ppc = (2 * cfg->hT / cfg->stepx) * (2 * cfg->hT / cfg->stepy);
+      if (cfg->dim == 3) ppc = cfg->stepEta > 0 ? ppc * (2 * cfg->hT / cfg->stepEta) : 0.0;
+    }
+    ctx->chunk = ppc >= 96.0 ? 128 : 64;
+  }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);
   ctx->k2 = make_kernel_norm(2, cfg->hT);

@@ -185,13 +185,13 @@ __global__ void permute_columns(PermuteList pl, const uint32_t* __restrict__ per
   for (int c = 0; c < pl.nints; ++c) pl.idst[c][i] = pl.isrc[c][j];
 }
 
-// first particle of every chunk of <= 32 targets that share a cell -> work list of the gathers
+// first particle of every chunk of <= `chunk` targets that share a cell -> work list of the gathers
 __global__ void build_tasks(const uint32_t* __restrict__ key, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ tasks,
-                            int32_t* __restrict__ ntasks, int64_t n) {
+                            int32_t* __restrict__ ntasks, int64_t n, uint32_t chunk) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t rank = (uint32_t)i - cell_start[key[i]];
-  if ((rank & 31u) == 0u) tasks[atomicAdd(ntasks, 1)] = (int32_t)i;
+  if ((rank % chunk) == 0u) tasks[atomicAdd(ntasks, 1)] = (int32_t)i;
 }
 
 // whole blocks of columns at once (ccb_upload_state / ccb_download_state): blockIdx.y = column

@@ -1,107 +1,39 @@
-// Phases 03 and 09: the two SPH neighbour sums, as atomic-free warp-per-cell gathers.
+// Phases 03 and 09: the two SPH neighbour sums as atomic-free, shared-memory-tiled gathers.
 //
-// Reference: SPHWorkstation::smooth_all_particle_fields (src/sph_workstation.cpp:495-578)
-// and smooth_all_particle_gradients (:797-986). There, one Kokkos team per particle
-// walks a CSR neighbour list and issues 5 (fields) or 5D+D^2 [+6+3D] (gradients)
-// atomic adds PER PAIR into a 4.5 KB/particle AoSoA. Here:
-//   * particles are already sorted by cell, so the neighbours of a cell are the
-//     contiguous particle ranges of its 3^D surrounding cells;
-//   * a warp owns up to 32 target particles of ONE cell; every lane streams the same
-//     source records (warp-uniform 128-bit loads of a packed record), so the loads are
-//     broadcast and the cost is the fp64 pipe, not memory;
-//   * sums accumulate in registers and are written once: no atomics, and results are
-//     reproducible run to run (the reference's atomic ordering is not).
-// The source records are packed and pre-scaled by the per-particle kernel that runs
-// just before (p/sigma^2, bulk/sigma^2, pi/sigma^2 ...), which removes the divisions
-// the reference re-evaluates for every pair.
+// Reference: SPHWorkstation::smooth_all_particle_fields (src/sph_workstation.cpp:495-578) and
+// smooth_all_particle_gradients (:797-986). There, one Kokkos team per particle walks a CSR
+// neighbour list and issues 5 (fields) or 5D+D^2 [+6+3D] (gradients) atomic adds PER PAIR into
+// a 4.5 KB/particle AoSoA. Here (particles are already sorted by cell, phase 01):
+//
+//   * a CTA takes a task = up to NT target particles of ONE cell (one target per thread, its
+//     record and its sums in registers); tasks are handed out through an atomic counter, so the
+//     148 SMs stay busy whatever the cell occupancies are;
+//   * the neighbours of a cell are the particles of its 3^D surrounding cells; the 3 cells of a
+//     row along the fastest grid axis are one CONTIGUOUS range of the sorted records, so the
+//     sources are 3 (2-D) or 9 (3-D) contiguous segments, streamed through shared memory in
+//     tiles of 128 records with 128-bit loads;
+//   * phase 1 (per tile): every thread tests its target against all 128 staged sources in fp32
+//     (coordinates relative to the task's first particle; cut-off widened by 1e-5 so that no
+//     true neighbour is missed) and keeps the hits as 4 x 32-bit masks. The reads are
+//     warp-uniform (shared-memory broadcast) and run on the fp32 pipe, off the fp64 pipe;
+//   * phase 2: every thread walks ITS OWN hit bits, re-tests exactly in fp64 (the reference's
+//     predicate dx*dx + dy*dy + dz*dz <= (2h)^2, unfused) and evaluates the pair term from the
+//     staged record. A warp iterates max-over-lanes(hits) times instead of once per candidate:
+//     only ~1/3 (2-D) to ~1/6 (3-D) of the candidates in the 3^D cells are neighbours, which is
+//     what a lane-per-target loop over all candidates wastes;
+//   * sums stay in registers and are written once: no atomics, reproducible run to run (the
+//     reference's atomic ordering is not).
 #pragma once
 
 #include "gather_params.cuh"
 
 namespace ccb {
 
-__device__ __forceinline__ void load_rec(const double* __restrict__ p, int n, double* r) {
-  const double2* q = reinterpret_cast<const double2*>(p);
-#pragma unroll
-  for (int k = 0; k < n / 2; ++k) { const double2 v = __ldg(q + k); r[2 * k] = v.x; r[2 * k + 1] = v.y; }
-}
+constexpr int kGatherTile = 128;  // source records per shared-memory tile
 
 // Exactly the predicate of the neighbour list: dist_sqr = dx*dx + dy*dy + dz*dz, no FMA contraction.
 __device__ __forceinline__ double dist_sqr_exact(double dx, double dy, double dz) {
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-}
-
-template <int D, bool FACT>
-__global__ void __launch_bounds__(128) gather_fields_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
-  const int ntasks = *dv.ntasks;
-  for (int64_t task = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < ntasks; task += nwarps) {
-    const int first = dv.tasks[task];
-    const uint32_t key = dv.key[first];
-    const uint32_t cend = dv.cell_start[key + 1];
-    const int64_t i = (int64_t)first + lane;
-    const bool active = i < cend;
-    const int64_t ii = active ? i : first;
-    double ra[REC_F];
-    load_rec(dv.rec_fields + ii * REC_F, REC_F, ra);
-    const int cz = key % g.nc[2], cy = (key / g.nc[2]) % g.nc[1], cx = key / (g.nc[2] * g.nc[1]);
-    double a_sig = 0., a_s = 0., a_B = 0., a_S = 0., a_Q = 0.;
-    int cnt = 0;
-    for (int ox = (cx > 0 ? -1 : 0); ox <= (cx < g.nc[0] - 1 ? 1 : 0); ++ox)
-      for (int oy = (cy > 0 ? -1 : 0); oy <= (cy < g.nc[1] - 1 ? 1 : 0); ++oy)
-        for (int oz = (cz > 0 ? -1 : 0); oz <= (cz < g.nc[2] - 1 ? 1 : 0); ++oz) {
-          const uint32_t nb = (uint32_t)(((int64_t)(cx + ox) * g.nc[1] + (cy + oy)) * g.nc[2] + (cz + oz));
-          const uint32_t js = dv.cell_start[nb], je = dv.cell_start[nb + 1];
-          for (uint32_t j = js; j < je; ++j) {
-            double rb[REC_F];
-            load_rec(dv.rec_fields + (int64_t)j * REC_F, REC_F, rb);
-            const double dx = ra[0] - rb[0], dy = ra[1] - rb[1], dz = ra[2] - rb[2];
-            const double r2 = dist_sqr_exact(dx, dy, dz);
-            if (r2 <= gp.rsqr) {
-              ++cnt;
-              double w;
-              if (FACT) {
-                const double rp = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-                w = sph_w(gp.k2, rp) * sph_w(gp.k1, fabs(dz));
-              } else {
-                w = sph_w(gp.kD, sqrt(r2));
-              }
-              a_sig += rb[3] * w;
-              a_s += rb[4] * w;
-              a_B += rb[5] * w;
-              a_S += rb[6] * w;
-              a_Q += rb[7] * w;
-            }
-          }
-        }
-    if (active) {
-      const double gamma = dv.f[CCB_F_GAMMA][i];
-      double sigma, s, rB, rS, rQ;
-      if (gp.milne) {
-        Metric<true> m(gp.t);
-        sigma = to_lrf(m, a_sig, gamma); s = to_lrf(m, a_s, gamma); rB = to_lrf(m, a_B, gamma);
-        rS = to_lrf(m, a_S, gamma); rQ = to_lrf(m, a_Q, gamma);
-      } else {
-        Metric<false> m(gp.t);
-        sigma = to_lrf(m, a_sig, gamma); s = to_lrf(m, a_s, gamma); rB = to_lrf(m, a_B, gamma);
-        rS = to_lrf(m, a_S, gamma); rQ = to_lrf(m, a_Q, gamma);
-      }
-      dv.f[CCB_F_SIGMA_LAB][i] = a_sig;
-      dv.f[CCB_F_SIGMA][i] = sigma;
-      col(dv.f[CCB_F_SMOOTHED], dv.cap, 0, i) = a_s;
-      col(dv.f[CCB_F_SMOOTHED], dv.cap, 1, i) = a_B;
-      col(dv.f[CCB_F_SMOOTHED], dv.cap, 2, i) = a_S;
-      col(dv.f[CCB_F_SMOOTHED], dv.cap, 3, i) = a_Q;
-      col(dv.f[CCB_F_THERMO], dv.cap, 5, i) = s;
-      col(dv.f[CCB_F_THERMO], dv.cap, 6, i) = rB;
-      col(dv.f[CCB_F_THERMO], dv.cap, 7, i) = rS;
-      col(dv.f[CCB_F_THERMO], dv.cap, 8, i) = rQ;
-      // btrack = number of neighbours (self excluded), sticky at -1 (src/system_state.cpp:712-715)
-      if (dv.btrack[i] != -1) dv.btrack[i] = cnt - 1;
-    }
-  }
 }
 
 // grad_a W(r_a - r_b): plain kernel (src/kernel.cpp:97-118) or factorised D=3 variant (:153-170)
@@ -117,7 +49,6 @@ __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double
     gK[2] = W2 * (f1 * rel[2]);
     return true;
   }
-  if (r2 >= 4.0 * gp.kD.h * gp.kD.h * 1.0000001) return false;  // cheap reject; exact branch below
   const double r = sqrt(r2);
   const double f = sph_gradw_factor(gp.kD, r);
 #pragma unroll
@@ -125,114 +56,281 @@ __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double
   return f != 0.0;
 }
 
-template <int D, bool SHEAR, bool DIFF, bool FACT>
-__global__ void __launch_bounds__(128) gather_gradients_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
-  constexpr int REC = DIFF ? REC_G1 : REC_G0;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int64_t nwarps = (int64_t)gridDim.x * warps_per_block;
+// ------------------------------------------------------------------------------------------
+// smooth_fields: sigma_lab, smoothed s, rho_B, rho_S, rho_Q, neighbour count
+template <int D_, bool FACT>
+struct FieldsPolicy {
+  static constexpr int D = D_, REC = REC_F, STRIDE = REC_F_STRIDE;
+  struct Target { double x[3]; };
+  struct Acc { double sig, s, B, S, Q; int cnt; };
+  __device__ static const double* records(const DeviceView& dv) { return dv.rec_fields; }
+  __device__ static void init(Acc& a) { a.sig = a.s = a.B = a.S = a.Q = 0.; a.cnt = 0; }
+  __device__ static void load_target(const double* r, Target& t) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(r)), b = __ldg(reinterpret_cast<const double2*>(r) + 1);
+    t.x[0] = a.x; t.x[1] = a.y; t.x[2] = b.x;
+  }
+  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, bool /*self*/, Acc& a) {
+    const double2 b0 = sb[0], b1 = sb[1];
+    const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = t.x[2] - b1.x;
+    const double r2 = dist_sqr_exact(dx, dy, dz);
+    if (r2 <= gp.rsqr) {  // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523)
+      ++a.cnt;
+      double w;
+      if (FACT) {
+        const double rp = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+        w = sph_w(gp.k2, rp) * sph_w(gp.k1, fabs(dz));
+      } else {
+        w = sph_w(gp.kD, sqrt(r2));
+      }
+      const double2 b2 = sb[2], b3 = sb[3];
+      a.sig += b1.y * w;
+      a.s += b2.x * w;
+      a.B += b2.y * w;
+      a.S += b3.x * w;
+      a.Q += b3.y * w;
+    }
+  }
+  __device__ static void store(const DeviceView& dv, const GatherParams& gp, int64_t i, const Acc& a) {
+    const double gamma = dv.f[CCB_F_GAMMA][i];
+    double sigma, s, rB, rS, rQ;
+    if (gp.milne) {
+      Metric<true> m(gp.t);
+      sigma = to_lrf(m, a.sig, gamma); s = to_lrf(m, a.s, gamma); rB = to_lrf(m, a.B, gamma);
+      rS = to_lrf(m, a.S, gamma); rQ = to_lrf(m, a.Q, gamma);
+    } else {
+      Metric<false> m(gp.t);
+      sigma = to_lrf(m, a.sig, gamma); s = to_lrf(m, a.s, gamma); rB = to_lrf(m, a.B, gamma);
+      rS = to_lrf(m, a.S, gamma); rQ = to_lrf(m, a.Q, gamma);
+    }
+    dv.f[CCB_F_SIGMA_LAB][i] = a.sig;
+    dv.f[CCB_F_SIGMA][i] = sigma;
+    col(dv.f[CCB_F_SMOOTHED], dv.cap, 0, i) = a.s;
+    col(dv.f[CCB_F_SMOOTHED], dv.cap, 1, i) = a.B;
+    col(dv.f[CCB_F_SMOOTHED], dv.cap, 2, i) = a.S;
+    col(dv.f[CCB_F_SMOOTHED], dv.cap, 3, i) = a.Q;
+    col(dv.f[CCB_F_THERMO], dv.cap, 5, i) = s;
+    col(dv.f[CCB_F_THERMO], dv.cap, 6, i) = rB;
+    col(dv.f[CCB_F_THERMO], dv.cap, 7, i) = rS;
+    col(dv.f[CCB_F_THERMO], dv.cap, 8, i) = rQ;
+    // btrack = number of neighbours (self excluded), sticky at -1 (src/system_state.cpp:712-715)
+    if (dv.btrack[i] != -1) dv.btrack[i] = a.cnt - 1;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// smooth_gradients: gradP, gradE, gradBulk, gradV, (gradshear, divshear), (div_qa, grad_qa, grad_alpha)
+template <int D_, bool SHEAR, bool DIFF, bool FACT>
+struct GradPolicy {
+  using R = GradRec<D_, DIFF>;
+  static constexpr int D = D_, REC = R::REC, STRIDE = R::STRIDE;
+  struct Target { double r[REC]; double x[3]; };
+  struct Acc { double gP[D], gE[D], gB[D], gSh[D], dSh[D], gV[D][D], dq[3], gq[3], gal[D][3]; };
+  __device__ static const double* records(const DeviceView& dv) { return dv.rec_grad; }
+  __device__ static void init(Acc& a) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      a.gP[d] = a.gE[d] = a.gB[d] = a.gSh[d] = a.dSh[d] = 0.;
+#pragma unroll
+      for (int e = 0; e < D; ++e) a.gV[d][e] = 0.;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) a.gal[d][c] = 0.;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) a.dq[c] = a.gq[c] = 0.;
+  }
+  __device__ static void load_target(const double* r, Target& t) {
+    const double2* q = reinterpret_cast<const double2*>(r);
+#pragma unroll
+    for (int k = 0; k < REC / 2; ++k) { const double2 v = __ldg(q + k); t.r[2 * k] = v.x; t.r[2 * k + 1] = v.y; }
+    t.x[0] = t.r[R::X]; t.x[1] = t.r[R::X + 1]; t.x[2] = (D == 3) ? t.r[R::X + (D == 3 ? 2 : 0)] : 0.0;
+  }
+  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, bool self, Acc& a) {
+    const double* ra = t.r;
+    const double2 b0 = sb[0];
+    double rel[3];
+    rel[0] = ra[R::X] - b0.x; rel[1] = ra[R::X + 1] - b0.y;
+    double rb[REC];
+    rb[0] = b0.x; rb[1] = b0.y;
+    {
+      const double2 b1 = sb[1];
+      rb[2] = b1.x; rb[3] = b1.y;
+    }
+    rel[2] = (D == 3) ? ra[R::X + (D == 3 ? 2 : 0)] - rb[2] : 0.0;
+    const double r2 = dist_sqr_exact(rel[0], rel[1], rel[2]);
+    if (!(r2 <= gp.rsqr) || self) return;  // outside the neighbour list, or self (grad W(0) = 0)
+    double gK[D];
+    if (!grad_kernel<D, FACT>(gp, rel, r2, gK)) return;
+#pragma unroll
+    for (int k = 2; k < REC / 2; ++k) { const double2 v = sb[k]; rb[2 * k] = v.x; rb[2 * k + 1] = v.y; }
+    const double sig_a = ra[R::SIGLAB];
+    const double m_b = rb[R::M];
+    double sK[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) sK[d] = (m_b * sig_a) * gK[d];
+    const double cP = rb[R::PT] + ra[R::PT], cB = rb[R::BT] + ra[R::BT];
+    const double mos = m_b / sig_a;
+    const double cE = mos * (rb[R::E] - ra[R::E]);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      a.gP[d] += cP * sK[d];
+      a.gE[d] += cE * gK[d];
+      a.gB[d] += cB * sK[d];
+#pragma unroll
+      for (int e = 0; e < D; ++e) a.gV[d][e] += mos * (rb[R::V + e] - ra[R::V + e]) * gK[d];
+    }
+    double Kv = 0.;
+#pragma unroll
+    for (int d = 0; d < D; ++d) Kv += sK[d] * ra[R::V + d];
+    if (SHEAR) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        a.gSh[d] += Kv * (rb[R::S0 + d] + ra[R::S0 + d]);
+        double x = 0.;
+#pragma unroll
+        for (int e = 0; e < D; ++e) x += sK[e] * rb[R::SM + R::sym(d, e)] + sK[e] * ra[R::SM + R::sym(d, e)];
+        a.dSh[d] += x;
+      }
+    }
+    if (DIFF) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        a.gq[c] += Kv * (rb[R::Q0 + c] + ra[R::Q0 + c]);
+        double x = 0.;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          x += sK[d] * rb[R::QI + c * D + d] + sK[d] * ra[R::QI + c * D + d];
+          a.gal[d][c] += mos * (rb[R::ALPHA + c] - ra[R::ALPHA + c]) * gK[d];
+        }
+        a.dq[c] += x;
+      }
+    }
+  }
+  __device__ static void store(const DeviceView& dv, const GatherParams&, int64_t i, const Acc& a) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      col(dv.f[CCB_F_GRADP], dv.cap, d, i) = d < D ? a.gP[d < D ? d : 0] : 0.;
+      col(dv.f[CCB_F_GRADE], dv.cap, d, i) = d < D ? a.gE[d < D ? d : 0] : 0.;
+      col(dv.f[CCB_F_GRADBULK], dv.cap, d, i) = d < D ? a.gB[d < D ? d : 0] : 0.;
+      col(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i) = d < D ? a.gSh[d < D ? d : 0] : 0.;
+      col(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i) = d < D ? a.dSh[d < D ? d : 0] : 0.;
+#pragma unroll
+      for (int e = 0; e < 3; ++e)
+        col(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i) = (d < D && e < D) ? a.gV[d < D ? d : 0][e < D ? e : 0] : 0.;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) col(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) = d < D ? a.gal[d < D ? d : 0][c] : 0.;
+      col(dv.f[CCB_F_DIV_QA], dv.cap, d, i) = a.dq[d];
+      col(dv.f[CCB_F_GRAD_QA], dv.cap, d, i) = a.gq[d];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// The tiled driver shared by both gathers. NT = threads (= targets) per task.
+template <class P, int NT>
+__global__ void __launch_bounds__(NT) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp, int* __restrict__ task_counter) {
+  constexpr int D = P::D, TILE = kGatherTile, NW = TILE / 32, CH = P::REC / 2, RS2 = P::STRIDE / 2;
+  __shared__ __align__(16) double2 srec[TILE * RS2];
+  __shared__ __align__(16) float spos[3][TILE];
+  __shared__ int s_task;
+  const double* __restrict__ rec = P::records(dv);
   const int ntasks = *dv.ntasks;
-  for (int64_t task = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); task < ntasks; task += nwarps) {
+  const int ny = g.nc[1], nz = g.nc[2];
+  const bool flat = (nz == 1);  // 2-D grids: the contiguous rows run along y
+  for (;;) {
+    __syncthreads();  // the previous task's tiles and s_task are no longer in use
+    if (threadIdx.x == 0) s_task = atomicAdd(task_counter, 1);
+    __syncthreads();
+    const int task = s_task;
+    if (task >= ntasks) break;
     const int first = dv.tasks[task];
     const uint32_t key = dv.key[first];
     const uint32_t cend = dv.cell_start[key + 1];
-    const int64_t i = (int64_t)first + lane;
-    const bool active = i < cend;
-    const int64_t ii = active ? i : first;
-    double ra[REC];
-    load_rec(dv.rec_grad + ii * REC, REC, ra);
-    const double sig_a = ra[RG_SIGLAB];
-    const int cz = key % g.nc[2], cy = (key / g.nc[2]) % g.nc[1], cx = key / (g.nc[2] * g.nc[1]);
-    double gP[D], gE[D], gB[D], gSh[D], dSh[D], gV[D][D], dq[3], gq[3], gal[D][3];
+    const int64_t i = (int64_t)first + threadIdx.x;
+    const bool active = i < (int64_t)cend;
+    typename P::Target tg;
+    P::load_target(rec + (active ? i : (int64_t)first) * P::REC, tg);
+    // frame of the fp32 pre-filter: coordinates relative to the task's first particle (|.| <= 3 cell edges)
+    double org[3];
+    float tx[3];
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      gP[d] = gE[d] = gB[d] = gSh[d] = dSh[d] = 0.;
-#pragma unroll
-      for (int e = 0; e < D; ++e) gV[d][e] = 0.;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) gal[d][c] = 0.;
+    for (int d = 0; d < 3; ++d) {
+      org[d] = (d < D) ? __ldg(rec + (int64_t)first * P::REC + d) : 0.0;
+      tx[d] = (float)(tg.x[d] - org[d]);
     }
+    typename P::Acc acc;
+    P::init(acc);
+    const int cz = key % nz, cy = (key / nz) % ny, cx = key / (nz * ny);
+    const int nrows = flat ? 3 : 9;
+    for (int row = 0; row < nrows; ++row) {
+      const int ox = flat ? row - 1 : row / 3 - 1, oy = flat ? 0 : row % 3 - 1;
+      const int x = cx + ox, y = cy + oy;
+      if (x < 0 || x >= g.nc[0] || y < 0 || y >= ny) continue;
+      uint32_t k0, k1;
+      if (flat) { k0 = (uint32_t)(x * ny + (cy > 0 ? cy - 1 : 0)); k1 = (uint32_t)(x * ny + (cy < ny - 1 ? cy + 1 : cy)); }
+      else { const uint32_t b = (uint32_t)((x * ny + y) * nz); k0 = b + (cz > 0 ? cz - 1 : 0); k1 = b + (cz < nz - 1 ? cz + 1 : cz); }
+      const uint32_t js = dv.cell_start[k0], je = dv.cell_start[k1 + 1];
+      for (uint32_t ts = js; ts < je; ts += TILE) {
+        const int nt = (int)min((uint32_t)TILE, je - ts);
+        __syncthreads();  // the previous tile is fully consumed
+        {  // stage nt records (128-bit loads) + their fp32 relative positions
+          const double2* __restrict__ src = reinterpret_cast<const double2*>(rec + (int64_t)ts * P::REC);
+          for (int q = threadIdx.x; q < nt * CH; q += NT) {
+            const int r = q / CH, c = q - r * CH;
+            const double2 v = __ldg(src + q);
+            srec[r * RS2 + c] = v;
+            if (c == 0) { spos[0][r] = (float)(v.x - org[0]); spos[1][r] = (float)(v.y - org[1]); }
+            if (D == 3 && c == 1) spos[2][r] = (float)(v.x - org[2]);
+          }
+          for (int r = nt + threadIdx.x; r < TILE; r += NT) { spos[0][r] = 3.0e18f; spos[1][r] = 0.f; spos[2][r] = 0.f; }
+        }
+        __syncthreads();
+        // ---- phase 1: fp32 pre-filter, hit masks
+        uint32_t m[NW];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) dq[c] = gq[c] = 0.;
-
-    for (int ox = (cx > 0 ? -1 : 0); ox <= (cx < g.nc[0] - 1 ? 1 : 0); ++ox)
-      for (int oy = (cy > 0 ? -1 : 0); oy <= (cy < g.nc[1] - 1 ? 1 : 0); ++oy)
-        for (int oz = (cz > 0 ? -1 : 0); oz <= (cz < g.nc[2] - 1 ? 1 : 0); ++oz) {
-          const uint32_t nb = (uint32_t)(((int64_t)(cx + ox) * g.nc[1] + (cy + oy)) * g.nc[2] + (cz + oz));
-          const uint32_t js = dv.cell_start[nb], je = dv.cell_start[nb + 1];
-          for (uint32_t j = js; j < je; ++j) {
-            const double* pb = dv.rec_grad + (int64_t)j * REC;
-            const double2 b01 = __ldg(reinterpret_cast<const double2*>(pb));
-            const double2 b23 = __ldg(reinterpret_cast<const double2*>(pb) + 1);
-            double rel[3] = {ra[0] - b01.x, ra[1] - b01.y, ra[2] - b23.x};
-            const double r2 = dist_sqr_exact(rel[0], rel[1], rel[2]);
-            if (!(r2 <= gp.rsqr) || (int64_t)j == i) continue;  // outside the neighbour list, or self (grad W(0) = 0)
-            double gK[D];
-            if (!grad_kernel<D, FACT>(gp, rel, r2, gK)) continue;
-            double rb[REC];
-            load_rec(pb, REC, rb);
-            const double m_b = rb[RG_M];
-            double sK[D];
+        for (int w = 0; w < NW; ++w) {
+          uint32_t mw = 0u;
+          if (w * 32 < nt) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) sK[d] = (m_b * sig_a) * gK[d];
-            const double cP = rb[RG_PT] + ra[RG_PT], cB = rb[RG_BT] + ra[RG_BT];
-            const double mos = m_b / sig_a;
-            const double cE = mos * (rb[RG_E] - ra[RG_E]);
+            for (int b4 = 0; b4 < 8; ++b4) {
+              const float4 X = reinterpret_cast<const float4*>(&spos[0][w * 32])[b4];
+              const float4 Y = reinterpret_cast<const float4*>(&spos[1][w * 32])[b4];
+              float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (D == 3) Z = reinterpret_cast<const float4*>(&spos[2][w * 32])[b4];
+              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-              gP[d] += cP * sK[d];
-              gE[d] += cE * gK[d];
-              gB[d] += cB * sK[d];
-#pragma unroll
-              for (int e = 0; e < D; ++e) gV[d][e] += mos * (rb[RG_V + e] - ra[RG_V + e]) * gK[d];
-            }
-            double Kv = 0.;
-#pragma unroll
-            for (int d = 0; d < D; ++d) Kv += sK[d] * ra[RG_V + d];
-            if (SHEAR) {
-              // symmetric spatial block packed as (11,12,13,22,23,33)
-              const int sm[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
-#pragma unroll
-              for (int d = 0; d < D; ++d) {
-                gSh[d] += Kv * (rb[RG_S0 + d] + ra[RG_S0 + d]);
-                double x = 0.;
-#pragma unroll
-                for (int e = 0; e < D; ++e) x += sK[e] * rb[RG_SM + sm[d][e]] + sK[e] * ra[RG_SM + sm[d][e]];
-                dSh[d] += x;
-              }
-            }
-            if (DIFF) {
-#pragma unroll
-              for (int c = 0; c < 3; ++c) {
-                gq[c] += Kv * (rb[RG_Q0 + c] + ra[RG_Q0 + c]);
-                double x = 0.;
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                  x += sK[d] * rb[RG_QI + c * 3 + d] + sK[d] * ra[RG_QI + c * 3 + d];
-                  gal[d][c] += mos * (rb[RG_ALPHA + c] - ra[RG_ALPHA + c]) * gK[d];
-                }
-                dq[c] += x;
+              for (int k = 0; k < 4; ++k) {
+                const float dx = tx[0] - xs[k], dy = tx[1] - ys[k];
+                float r2 = dx * dx + dy * dy;
+                if (D == 3) { const float dz = tx[2] - zs[k]; r2 += dz * dz; }
+                if (r2 <= gp.rsqr_f) mw |= (1u << (b4 * 4 + k));
               }
             }
           }
+          m[w] = active ? mw : 0u;
         }
-    if (active) {
+        // ---- phase 2: every lane walks its own hits
+        int mine = 0;
 #pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        col(dv.f[CCB_F_GRADP], dv.cap, d, i) = d < D ? gP[d < D ? d : 0] : 0.;
-        col(dv.f[CCB_F_GRADE], dv.cap, d, i) = d < D ? gE[d < D ? d : 0] : 0.;
-        col(dv.f[CCB_F_GRADBULK], dv.cap, d, i) = d < D ? gB[d < D ? d : 0] : 0.;
-        col(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i) = d < D ? gSh[d < D ? d : 0] : 0.;
-        col(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i) = d < D ? dSh[d < D ? d : 0] : 0.;
+        for (int w = 0; w < NW; ++w) mine += __popc(m[w]);
+        const int maxc = __reduce_max_sync(0xffffffffu, mine);
+        for (int it = 0; it < maxc; ++it) {
+          if (it < mine) {
+            uint32_t wsel = m[NW - 1];
+            int base = (NW - 1) * 32;
 #pragma unroll
-        for (int e = 0; e < 3; ++e)
-          col(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i) = (d < D && e < D) ? gV[d < D ? d : 0][e < D ? e : 0] : 0.;
+            for (int w = NW - 2; w >= 0; --w)
+              if (m[w]) { wsel = m[w]; base = w * 32; }
+            const uint32_t low = wsel & (0u - wsel);
+            const int j = base + __ffs(wsel) - 1;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) col(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) = d < D ? gal[d < D ? d : 0][c] : 0.;
-        col(dv.f[CCB_F_DIV_QA], dv.cap, d, i) = dq[d];
-        col(dv.f[CCB_F_GRAD_QA], dv.cap, d, i) = gq[d];
+            for (int w = 0; w < NW; ++w)
+              if (base == w * 32) m[w] ^= low;
+            P::pair(gp, tg, srec + j * RS2, (int64_t)ts + j == i, acc);
+          }
+        }
       }
     }
+    if (active) P::store(dv, gp, i, acc);
   }
 }
 

@@ -1,21 +1,47 @@
 // Record layouts and the parameter block of the two neighbour gathers (gather.cuh).
+//
+// A "record" is everything one SOURCE particle contributes to a pair term, packed
+// contiguously (array of structures, 16-byte aligned) by the per-particle kernel that runs
+// just before the gather, and pre-scaled where the pair formula allows (p / sigma^2 ...), so
+// that the gather reads one contiguous block per source instead of ~20 strided columns.
 #pragma once
 
 #include "state.cuh"
 
 namespace ccb {
 
-constexpr int REC_F = 8;    // x y z m_s | m_s*ext_s m_B*ext_B m_S*ext_S m_Q*ext_Q
-constexpr int REC_G0 = 20;  // without diffusion
-constexpr int REC_G1 = 36;  // with diffusion
-// gradient record slots
-enum { RG_X = 0, RG_M = 3, RG_PT = 4, RG_BT = 5, RG_E = 6, RG_V = 7, RG_S0 = 10, RG_SM = 13, RG_SIGLAB = 19,
-       RG_ALPHA = 20, RG_Q0 = 23, RG_QI = 26 };
+// smooth_fields record: x y z m_s | m_s*ext_s m_B*ext_B m_S*ext_S m_Q*ext_Q
+constexpr int REC_F = 8;
+constexpr int REC_F_STRIDE = 10;  // shared-memory stride in doubles: an odd number of 16-byte units
+
+// smooth_gradients record, compacted per dimension D (and with/without the diffusion block).
+template <int D, bool DIFF> struct GradRec {
+  static constexpr int X = 0;                 // position, D doubles
+  static constexpr int M = D;                 // sph_mass.s
+  static constexpr int PT = D + 1;            // p / sigma_lab^2
+  static constexpr int BT = D + 2;            // Pi / sigma_lab^2
+  static constexpr int E = D + 3;             // e
+  static constexpr int V = D + 4;             // v^i, D doubles
+  static constexpr int S0 = 2 * D + 4;        // pi^{0i} / sigma_lab^2, D doubles
+  static constexpr int SM = 3 * D + 4;        // pi^{ij} / sigma_lab^2, i <= j, D(D+1)/2 doubles
+  static constexpr int NSM = D * (D + 1) / 2;
+  static constexpr int SIGLAB = SM + NSM;     // sigma_lab (used of the TARGET only)
+  static constexpr int BASE = SIGLAB + 1;     // 14 (D = 2), 20 (D = 3)
+  static constexpr int ALPHA = BASE;          // mu_a / T, 3 doubles
+  static constexpr int Q0 = BASE + 3;         // q^0_a / sigma_lab^2, 3 doubles
+  static constexpr int QI = BASE + 6;         // q^i_a / sigma_lab^2, [a][i], 3 D doubles
+  static constexpr int FULL = BASE + 6 + 3 * D;
+  static constexpr int REC = DIFF ? ((FULL + 1) / 2) * 2 : BASE;           // doubles per record in global memory (even)
+  static constexpr int STRIDE = ((REC / 2) % 2 == 1) ? REC : REC + 2;      // shared-memory stride: odd number of 16-byte units
+  __host__ __device__ static constexpr int sym(int d, int e) { return d <= e ? d * D - d * (d - 1) / 2 + (e - d) : e * D - e * (e - 1) / 2 + (d - e); }
+};
+constexpr int REC_G_MAX = 36;  // GradRec<3, true>::REC: the record buffer is sized for it
 
 struct GatherParams {
   KernelNorm kD;     // D-dimensional kernel with hT
   KernelNorm k2, k1; // factorised variant: W_2D(r_perp, hT) * W_1D(|d eta|, hEta)
   double rsqr;       // (2 hT)^2: the neighbour cut-off of the reference (src/system_state.cpp:689)
+  float rsqr_f;      // the same with a safety margin, for the fp32 pre-filter
   double t;
   int milne;
 };

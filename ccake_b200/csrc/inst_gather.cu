@@ -8,20 +8,38 @@
 
 namespace ccb {
 
-template <>
-cudaError_t launch_gather_fields<CCB_INST_D>(bool fact, int grid, int block, cudaStream_t s, const DeviceView& dv,
-                                             const CellGrid& g, const GatherParams& gp) {
-  constexpr int D = CCB_INST_D;
-  if (D == 3 && fact) gather_fields_kernel<D, (D == 3)><<<grid, block, 0, s>>>(dv, g, gp);
-  else gather_fields_kernel<D, false><<<grid, block, 0, s>>>(dv, g, gp);
+namespace {
+// persistent grid: as many CTAs as fit on the device at once; tasks come from the atomic counter
+template <class P, int NT>
+cudaError_t launch(int sms, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp, int* task_counter) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel<P, NT>, NT, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+  }
+  gather_kernel<P, NT><<<sms * per_sm, NT, 0, s>>>(dv, g, gp, task_counter);
   return cudaGetLastError();
+}
+template <class P>
+cudaError_t launch_nt(int nt, int sms, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp, int* tc) {
+  return nt == 128 ? launch<P, 128>(sms, s, dv, g, gp, tc) : launch<P, 64>(sms, s, dv, g, gp, tc);
+}
+}  // namespace
+
+template <>
+cudaError_t launch_gather_fields<CCB_INST_D>(bool fact, int nt, int sms, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
+                                             const GatherParams& gp, int* tc) {
+  constexpr int D = CCB_INST_D;
+  if (D == 3 && fact) return launch_nt<FieldsPolicy<D, (D == 3)>>(nt, sms, s, dv, g, gp, tc);
+  return launch_nt<FieldsPolicy<D, false>>(nt, sms, s, dv, g, gp, tc);
 }
 
 template <>
-cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact, int grid, int block, cudaStream_t s,
-                                                const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
+cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact, int nt, int sms, cudaStream_t s,
+                                                const DeviceView& dv, const CellGrid& g, const GatherParams& gp, int* tc) {
   constexpr int D = CCB_INST_D;
-#define CCB_GG(S, F, X) gather_gradients_kernel<D, S, F, X><<<grid, block, 0, s>>>(dv, g, gp)
+#define CCB_GG(S, F, X) return launch_nt<GradPolicy<D, S, F, X>>(nt, sms, s, dv, g, gp, tc)
   if (D == 3 && fact) {
     if (shear) { if (diff) CCB_GG(true, true, (D == 3)); else CCB_GG(true, false, (D == 3)); }
     else { if (diff) CCB_GG(false, true, (D == 3)); else CCB_GG(false, false, (D == 3)); }
@@ -30,7 +48,6 @@ cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact
     else { if (diff) CCB_GG(false, true, false); else CCB_GG(false, false, false); }
   }
 #undef CCB_GG
-  return cudaGetLastError();
 }
 
 }  // namespace ccb

@@ -83,6 +83,41 @@ __device__ __forceinline__ bool eos_from_sBSQ(const StageParams& sp, double s, d
   return true;
 }
 
+// One record of the gradient gather (layout: GradRec<D, DIFF>, gather_params.cuh), written with 128-bit stores.
+template <int D, bool DIFF>
+__device__ __forceinline__ void pack_grad_record(double* __restrict__ rec, int64_t i, const double* x, const double* v, double m_s,
+                                                 double sig_lab, double bulk, const Thermo& th, const double shv[4][4],
+                                                 const double q[3][4]) {
+  using R = GradRec<D, DIFF>;
+  double r[R::REC];
+#pragma unroll
+  for (int k = 0; k < R::REC; ++k) r[k] = 0.0;
+  const double sigsqr = 1.0 / (sig_lab * sig_lab);
+#pragma unroll
+  for (int d = 0; d < D; ++d) { r[R::X + d] = x[d]; r[R::V + d] = v[d]; r[R::S0 + d] = sigsqr * shv[0][d + 1]; }
+  r[R::M] = m_s;
+  r[R::PT] = sigsqr * th.p;
+  r[R::BT] = bulk / sig_lab / sig_lab;
+  r[R::E] = th.e;
+#pragma unroll
+  for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int e = d; e < D; ++e) r[R::SM + R::sym(d, e)] = sigsqr * shv[d + 1][e + 1];
+  r[R::SIGLAB] = sig_lab;
+  if (DIFF) {
+    r[R::ALPHA + 0] = th.muB / th.T; r[R::ALPHA + 1] = th.muS / th.T; r[R::ALPHA + 2] = th.muQ / th.T;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      r[R::Q0 + c] = sigsqr * q[c][0];
+#pragma unroll
+      for (int d = 0; d < D; ++d) r[R::QI + c * D + d] = sigsqr * q[c][d + 1];
+    }
+  }
+  double2* o = reinterpret_cast<double2*>(rec + i * R::REC);
+#pragma unroll
+  for (int k = 0; k < R::REC / 2; ++k) o[k] = make_double2(r[2 * k], r[2 * k + 1]);
+}
+
 template <int D, bool MILNE>
 __global__ void eos_local_kernel(DeviceView dv, StageParams sp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,46 +164,26 @@ __global__ void eos_local_kernel(DeviceView dv, StageParams sp) {
     for (int c = 0; c < 13; ++c) col(TC, dv.cap, c, i) = v[c];
   }
   // gradient-gather record, pre-scaled by 1/sigma_lab^2 where the pair formula needs it
-  const int REC = sp.fl.diffusion ? REC_G1 : REC_G0;
-  double* r = dv.rec_grad + i * REC;
-  const double sigsqr = 1.0 / (sig_lab * sig_lab);
+  double x[3], v[3];
 #pragma unroll
-  for (int d = 0; d < 3; ++d) r[RG_X + d] = col(dv.f[CCB_F_POSITION], dv.cap, d, i);
-  r[RG_M] = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
-  r[RG_PT] = sigsqr * th.p;
-  r[RG_BT] = bulk / sig_lab / sig_lab;
-  r[RG_E] = th.e;
-#pragma unroll
-  for (int d = 0; d < 3; ++d) r[RG_V + d] = col(dv.f[CCB_F_V], dv.cap, d, i);
-#pragma unroll
-  for (int d = 0; d < 3; ++d) r[RG_S0 + d] = sigsqr * shv[0][d + 1];
-  r[RG_SM + 0] = sigsqr * shv[1][1]; r[RG_SM + 1] = sigsqr * shv[1][2]; r[RG_SM + 2] = sigsqr * shv[1][3];
-  r[RG_SM + 3] = sigsqr * shv[2][2]; r[RG_SM + 4] = sigsqr * shv[2][3]; r[RG_SM + 5] = sigsqr * shv[3][3];
-  r[RG_SIGLAB] = sig_lab;
-  if (sp.fl.diffusion) {
-    r[RG_ALPHA + 0] = th.muB / th.T; r[RG_ALPHA + 1] = th.muS / th.T; r[RG_ALPHA + 2] = th.muQ / th.T;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      r[RG_Q0 + c] = sigsqr * q[c][0];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) r[RG_QI + c * 3 + d] = sigsqr * q[c][d + 1];
-    }
-    r[35] = 0.0;
-  }
+  for (int d = 0; d < 3; ++d) { x[d] = col(dv.f[CCB_F_POSITION], dv.cap, d, i); v[d] = col(dv.f[CCB_F_V], dv.cap, d, i); }
+  const double m_s = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
+  if (sp.fl.diffusion) pack_grad_record<D, true>(dv.rec_grad, i, x, v, m_s, sig_lab, bulk, th, shv, q);
+  else pack_grad_record<D, false>(dv.rec_grad, i, x, v, m_s, sig_lab, bulk, th, shv, q);
 }
 
-template <int D, bool MILNE>
-__global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams sp) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dv.n) return;
-  Metric<MILNE> m(sp.t);
-  Thermo th;
-  load_thermo(dv, i, th);
-  Transport tc;
-  transport_coefficients(th, sp.tp, tc);
-  double kappa[3][3], tauq[3][3];
-  diffusion_coefficients(th, sp.tp, kappa, tauq);
-  EomIn<D> in;
+// the 13 transport scalars phase 08 stored (column order of CCB_F_TRANSPORT, include/ccake_b200.h)
+__device__ __forceinline__ void load_transport(const DeviceView& dv, int64_t i, Transport& tc) {
+  const double* TC = dv.f[CCB_F_TRANSPORT];
+  tc.eta_pi = TC[i]; tc.tau_pi = TC[dv.cap + i]; tc.zeta_Pi = TC[2 * dv.cap + i]; tc.tau_Pi = TC[3 * dv.cap + i];
+  tc.delta_PiPi = TC[4 * dv.cap + i]; tc.delta_pipi = TC[5 * dv.cap + i]; tc.lambda_piPi = TC[6 * dv.cap + i];
+  tc.lambda_Pipi = TC[7 * dv.cap + i]; tc.phi1 = TC[8 * dv.cap + i]; tc.phi3 = TC[9 * dv.cap + i]; tc.phi6 = TC[10 * dv.cap + i];
+  tc.phi7 = TC[11 * dv.cap + i]; tc.tau_pipi = TC[12 * dv.cap + i];
+}
+
+// inputs of the equations of motion for particle i, from the SoA columns
+template <int D>
+__device__ __forceinline__ void load_eom_inputs(const DeviceView& dv, const StageParams& sp, int64_t i, EomIn<D>& in) {
 #pragma unroll
   for (int d = 0; d < D; ++d) {
     in.u[d] = col(dv.f[CCB_F_U], dv.cap, d, i);
@@ -198,8 +213,37 @@ __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams 
     in.div_qa[c] = sp.fl.diffusion ? col(dv.f[CCB_F_DIV_QA], dv.cap, c, i) : 0.0;
     in.grad_qa[c] = sp.fl.diffusion ? col(dv.f[CCB_F_GRAD_QA], dv.cap, c, i) : 0.0;
   }
+}
+
+template <int D, bool MILNE>
+__global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams sp) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  Metric<MILNE> m(sp.t);
   EomOut<D> out;
-  eom_evaluate<D, MILNE>(m, in, th, tc, kappa, tauq, sp.fl, out);
+  // Pass 1: the linear solve for du/dt and dN/dt. Pass 2 re-reads its inputs (L1/L2 hits) behind a compiler
+  // barrier, so that nothing of pass 1 but the two results stays live: see physics_eom.cuh.
+  {
+    Thermo th;
+    load_thermo(dv, i, th);
+    Transport tc;
+    load_transport(dv, i, tc);
+    double kappa[3][3], tauq[3][3];
+    diffusion_coefficients(th, sp.tp, kappa, tauq);
+    EomIn<D> in;
+    load_eom_inputs<D>(dv, sp, i, in);
+    eom_pass<D, MILNE, 1>(m, in, th, tc, kappa, tauq, sp.fl, out);
+  }
+  asm volatile("" ::: "memory");
+  Thermo th;
+  load_thermo(dv, i, th);
+  Transport tc;
+  load_transport(dv, i, tc);
+  double kappa[3][3], tauq[3][3];
+  diffusion_coefficients(th, sp.tp, kappa, tauq);
+  EomIn<D> in;
+  load_eom_inputs<D>(dv, sp, i, in);
+  eom_pass<D, MILNE, 2>(m, in, th, tc, kappa, tauq, sp.fl, out);
 
   // derivatives are kept: Output, RK4 accumulation and the parity tests read them
 #pragma unroll

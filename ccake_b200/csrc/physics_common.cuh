@@ -94,7 +94,7 @@ template <bool MILNE> CCB_HD void lower_vec3(const Metric<MILNE>& m, const doubl
 }
 // v_i -> v^i (reference milne.hpp:103-107, :359-360)
 template <int D, bool MILNE> CCB_HD void raise_vec(const Metric<MILNE>& m, const double* in, double* out) {
-  if (D == 2) { out[0] = in[0] / -1.; out[1] = in[1] / -1.; }
+  if (D == 2) { out[0] = -in[0]; out[1] = -in[1]; }
   else {
     CCB_UNROLL for (int i = 0; i < D - 1; ++i) out[i] = -in[i];
     out[D - 1] = in[D - 1] * (-1. / m.g33);
@@ -125,19 +125,21 @@ template <bool MILNE> CCB_HD double to_lrf(const Metric<MILNE>& m, double lab, d
 CCB_HD void inverse3(const double A[3][3], double Ai[3][3]) {
   const double det = A[0][0] * A[1][1] * A[2][2] + A[0][1] * A[1][2] * A[2][0] + A[0][2] * A[1][0] * A[2][1] -
                      A[0][2] * A[1][1] * A[2][0] - A[0][1] * A[1][0] * A[2][2] - A[0][0] * A[1][2] * A[2][1];
-  Ai[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) / det;
-  Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) / det;
-  Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) / det;
-  Ai[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) / det;
-  Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) / det;
-  Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) / det;
-  Ai[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) / det;
-  Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) / det;
-  Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) / det;
+  const double id = 1.0 / det;  // one division instead of the reference's nine (<= 1 ulp per entry)
+  Ai[0][0] = (A[1][1] * A[2][2] - A[1][2] * A[2][1]) * id;
+  Ai[0][1] = (A[0][2] * A[2][1] - A[0][1] * A[2][2]) * id;
+  Ai[0][2] = (A[0][1] * A[1][2] - A[0][2] * A[1][1]) * id;
+  Ai[1][0] = (A[1][2] * A[2][0] - A[1][0] * A[2][2]) * id;
+  Ai[1][1] = (A[0][0] * A[2][2] - A[0][2] * A[2][0]) * id;
+  Ai[1][2] = (A[0][2] * A[1][0] - A[0][0] * A[1][2]) * id;
+  Ai[2][0] = (A[1][0] * A[2][1] - A[1][1] * A[2][0]) * id;
+  Ai[2][1] = (A[0][1] * A[2][0] - A[0][0] * A[2][1]) * id;
+  Ai[2][2] = (A[0][0] * A[1][1] - A[0][1] * A[1][0]) * id;
 }
 CCB_HD void inverse2(const double A[2][2], double Ai[2][2]) {  // reference milne.hpp:797-808
   const double det = A[0][0] * A[1][1] - A[0][1] * A[1][0];
-  Ai[0][0] = A[1][1] / det; Ai[0][1] = -A[0][1] / det; Ai[1][0] = -A[1][0] / det; Ai[1][1] = A[0][0] / det;
+  const double id = 1.0 / det;
+  Ai[0][0] = A[1][1] * id; Ai[0][1] = -A[0][1] * id; Ai[1][0] = -A[1][0] * id; Ai[1][1] = A[0][0] * id;
 }
 
 // ---------------------------------------------------------------------------
