@@ -312,9 +312,6 @@ int do_build_cells(ccb_ctx* ctx) {
   std::swap(dv.eos_id, ctx->alt_int[3]);
   dv.key = kin;  // sorted keys
   if (kin != ctx->key_a) { std::swap(ctx->key_a, ctx->key_b); std::swap(ctx->idx_a, ctx->idx_b); }
-  // work list of the gathers
-  CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t), ctx->stream));
-  LAUNCH(build_tasks, cdiv(n, 256), 256, dv.key, dv.cell_start, dv.tasks, dv.ntasks, n, (uint32_t)ctx->chunk);
   ctx->cells_valid = true;
   return CCB_OK;
 }
@@ -345,10 +342,8 @@ int do_gather_fields(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
   const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
-  int* counter = ctx->d_small + 3;
-  CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-  if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
-  else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
+  if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
+  else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
 }
 
@@ -365,10 +360,8 @@ int do_gather_gradients(ccb_ctx* ctx) {
   const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
-  int* counter = ctx->d_small + 3;
-  CUDA_OK(cudaMemsetAsync(counter, 0, sizeof(int), ctx->stream));
-  if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
-  else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, ctx->sms, ctx->stream, ctx->dv, ctx->grid, gp, counter));
+  if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
+  else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
 }
 

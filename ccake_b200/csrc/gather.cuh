@@ -5,17 +5,18 @@
 // neighbour list and issues 5 (fields) or 5D+D^2 [+6+3D] (gradients) atomic adds PER PAIR into
 // a 4.5 KB/particle AoSoA. Here (particles are already sorted by cell, phase 01):
 //
-//   * a CTA takes a task = up to NT target particles of ONE cell (one target per thread, its
-//     record and its sums in registers); tasks are handed out through an atomic counter, so the
-//     148 SMs stay busy whatever the cell occupancies are;
-//   * the neighbours of a cell are the particles of its 3^D surrounding cells; the 3 cells of a
-//     row along the fastest grid axis are one CONTIGUOUS range of the sorted records, so the
-//     sources are 3 (2-D) or 9 (3-D) contiguous segments, streamed through shared memory in
-//     tiles of 128 records with 128-bit loads;
+//   * a CTA takes a task = NT consecutive particles of the cell-sorted order (one target per thread,
+//     its record and its sums in registers). Consecutive sorted particles lie in consecutive cells of
+//     one grid row, so their neighbours are the particles of the 3^D stencil around that short run
+//     of cells: 3 (2-D) or 9 (3-D) CONTIGUOUS ranges of the sorted records (a row of cells along the
+//     fastest grid axis is contiguous in memory). Every task is full, whatever the cell occupancies;
+//   * the candidate sources are streamed through shared memory in tiles of 128 records (128-bit
+//     loads). Tile k takes every ntiles-th candidate, so each tile is a uniform sample of the whole
+//     neighbourhood and every target finds about the same number of neighbours in it;
 //   * phase 1 (per tile): every thread tests its target against all 128 staged sources in fp32
-//     (coordinates relative to the task's first particle; cut-off widened by 1e-5 so that no
-//     true neighbour is missed) and keeps the hits as 4 x 32-bit masks. The reads are
-//     warp-uniform (shared-memory broadcast) and run on the fp32 pipe, off the fp64 pipe;
+//     (coordinates relative to a nearby cell corner; cut-off widened by 1e-4 so that no true
+//     neighbour is missed) and keeps the hits as 4 x 32-bit masks. The reads are warp-uniform
+//     (shared-memory broadcast) and run on the fp32 pipe, off the fp64 pipe;
 //   * phase 2: every thread walks ITS OWN hit bits, re-tests exactly in fp64 (the reference's
 //     predicate dx*dx + dy*dy + dz*dz <= (2h)^2, unfused) and evaluates the pair term from the
 //     staged record. A warp iterates max-over-lanes(hits) times instead of once per candidate:
@@ -36,6 +37,29 @@ __device__ __forceinline__ double dist_sqr_exact(double dx, double dy, double dz
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
+// r and 1/r from r^2 with one rsqrt (2 ulp) instead of sqrt + divisions; r2 == 0 (self) is handled by the callers
+__device__ __forceinline__ void r_and_inv(double r2, double& r, double& ir) {
+  ir = rsqrt(r2);
+  r = r2 * ir;
+}
+// W(r, h) of src/kernel.cpp:36-48 with q = r * (1/h)
+__device__ __forceinline__ double sph_w_fast(const KernelNorm& k, double r) {
+  const double q = r * k.inv_h;
+  const double tq = 2.0 - q;
+  const double qq = q * q;
+  const double inner = k.norm * (1 - 1.5 * qq + 0.75 * q * qq);
+  const double outer = k.norm2 * tq * tq * tq;
+  return q >= 2.0 ? 0.0 : (q >= 1.0 ? outer : inner);
+}
+// f with grad_a W = f (r_a - r_b), src/kernel.cpp:97-118, from r and 1/r
+__device__ __forceinline__ double sph_gradw_factor_fast(const KernelNorm& k, double r, double ir) {
+  const double q = r * k.inv_h;
+  const double tq = 2.0 - q;
+  const double outer = (k.norm_grad * ir) * tq * tq;
+  const double inner = k.norm_grad2 * (1.5 * q - 2) * k.inv_h;
+  return q >= 2.0 ? 0.0 : (q >= 1.0 ? outer : inner);
+}
+
 // grad_a W(r_a - r_b): plain kernel (src/kernel.cpp:97-118) or factorised D=3 variant (:153-170)
 template <int D, bool FACT>
 __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double* rel, double r2, double* gK) {
@@ -49,8 +73,9 @@ __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double
     gK[2] = W2 * (f1 * rel[2]);
     return true;
   }
-  const double r = sqrt(r2);
-  const double f = sph_gradw_factor(gp.kD, r);
+  double r, ir;
+  r_and_inv(r2, r, ir);
+  const double f = sph_gradw_factor_fast(gp.kD, r, ir);
 #pragma unroll
   for (int d = 0; d < D; ++d) gK[d] = f * rel[d];
   return f != 0.0;
@@ -69,7 +94,7 @@ struct FieldsPolicy {
     const double2 a = __ldg(reinterpret_cast<const double2*>(r)), b = __ldg(reinterpret_cast<const double2*>(r) + 1);
     t.x[0] = a.x; t.x[1] = a.y; t.x[2] = b.x;
   }
-  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, bool /*self*/, Acc& a) {
+  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, Acc& a) {
     const double2 b0 = sb[0], b1 = sb[1];
     const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = t.x[2] - b1.x;
     const double r2 = dist_sqr_exact(dx, dy, dz);
@@ -80,7 +105,7 @@ struct FieldsPolicy {
         const double rp = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
         w = sph_w(gp.k2, rp) * sph_w(gp.k1, fabs(dz));
       } else {
-        w = sph_w(gp.kD, sqrt(r2));
+        w = sph_w_fast(gp.kD, sqrt(r2));
       }
       const double2 b2 = sb[2], b3 = sb[3];
       a.sig += b1.y * w;
@@ -123,7 +148,7 @@ template <int D_, bool SHEAR, bool DIFF, bool FACT>
 struct GradPolicy {
   using R = GradRec<D_, DIFF>;
   static constexpr int D = D_, REC = R::REC, STRIDE = R::STRIDE;
-  struct Target { double r[REC]; double x[3]; };
+  struct Target { double r[REC]; double x[3]; double inv_sig; };
   struct Acc { double gP[D], gE[D], gB[D], gSh[D], dSh[D], gV[D][D], dq[3], gq[3], gal[D][3]; };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_grad; }
   __device__ static void init(Acc& a) {
@@ -143,8 +168,9 @@ struct GradPolicy {
 #pragma unroll
     for (int k = 0; k < REC / 2; ++k) { const double2 v = __ldg(q + k); t.r[2 * k] = v.x; t.r[2 * k + 1] = v.y; }
     t.x[0] = t.r[R::X]; t.x[1] = t.r[R::X + 1]; t.x[2] = (D == 3) ? t.r[R::X + (D == 3 ? 2 : 0)] : 0.0;
+    t.inv_sig = 1.0 / t.r[R::SIGLAB];
   }
-  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, bool self, Acc& a) {
+  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, Acc& a) {
     const double* ra = t.r;
     const double2 b0 = sb[0];
     double rel[3];
@@ -157,7 +183,8 @@ struct GradPolicy {
     }
     rel[2] = (D == 3) ? ra[R::X + (D == 3 ? 2 : 0)] - rb[2] : 0.0;
     const double r2 = dist_sqr_exact(rel[0], rel[1], rel[2]);
-    if (!(r2 <= gp.rsqr) || self) return;  // outside the neighbour list, or self (grad W(0) = 0)
+    // outside the neighbour list, or coincident (self): grad W(0) = 0 and every pair term carries grad W
+    if (!(r2 <= gp.rsqr) || r2 == 0.0) return;
     double gK[D];
     if (!grad_kernel<D, FACT>(gp, rel, r2, gK)) return;
 #pragma unroll
@@ -168,7 +195,7 @@ struct GradPolicy {
 #pragma unroll
     for (int d = 0; d < D; ++d) sK[d] = (m_b * sig_a) * gK[d];
     const double cP = rb[R::PT] + ra[R::PT], cB = rb[R::BT] + ra[R::BT];
-    const double mos = m_b / sig_a;
+    const double mos = m_b * t.inv_sig;
     const double cE = mos * (rb[R::E] - ra[R::E]);
 #pragma unroll
     for (int d = 0; d < D; ++d) {
@@ -225,113 +252,155 @@ struct GradPolicy {
 };
 
 // ------------------------------------------------------------------------------------------
-// The tiled driver shared by both gathers. NT = threads (= targets) per task.
-template <class P, int NT>
-__global__ void __launch_bounds__(NT) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp, int* __restrict__ task_counter) {
+// The tiled driver shared by both gathers. NT = threads (= targets) per task, MINB = CTAs per SM the
+// register allocation is bounded for.
+constexpr int kMaxSeg = 9;
+
+template <class P, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
   constexpr int D = P::D, TILE = kGatherTile, NW = TILE / 32, CH = P::REC / 2, RS2 = P::STRIDE / 2;
   __shared__ __align__(16) double2 srec[TILE * RS2];
   __shared__ __align__(16) float spos[3][TILE];
-  __shared__ int s_task;
+  __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
+  __shared__ int s_nseg;
+  __shared__ uint32_t s_next[NT / 32];
   const double* __restrict__ rec = P::records(dv);
-  const int ntasks = *dv.ntasks;
-  const int ny = g.nc[1], nz = g.nc[2];
-  const bool flat = (nz == 1);  // 2-D grids: the contiguous rows run along y
+  const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(rec);
+  const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
+
+  const int64_t first = (int64_t)blockIdx.x * NT;
+  const int64_t last = min(first + NT, dv.n) - 1;
+  const int64_t i = first + threadIdx.x;
+  const bool active = i <= last;
+  typename P::Target tg;
+  P::load_target(rec + (active ? i : first) * P::REC, tg);
+  typename P::Acc acc;
+  P::init(acc);
+
+  // The cells of a grid row along the fastest axis are contiguous in the sorted order: F cells per row,
+  // row index rho = key / F. A task's particles lie in the rows rho_f .. rho_l (almost always one row; two when
+  // the task straddles a row end; more only where rows hold a handful of particles). The task is processed
+  // in passes, one per row that holds targets: in a pass the lanes of that row are live and the sources are
+  // the 3^(D-1) neighbouring rows restricted to the cells [fa - 1, fb + 1] around the targets' cells [fa, fb].
+  const int F = (nz > 1) ? nz : ny;
+  const uint32_t my_key = dv.key[active ? i : first];
+  const uint32_t my_rho = active ? my_key / F : 0xffffffffu;
+  const uint32_t key_f = dv.key[first], key_l = dv.key[last];
+  const uint32_t rho_f = key_f / F, rho_l = key_l / F;
+  uint32_t rho = rho_f;
   for (;;) {
-    __syncthreads();  // the previous task's tiles and s_task are no longer in use
-    if (threadIdx.x == 0) s_task = atomicAdd(task_counter, 1);
-    __syncthreads();
-    const int task = s_task;
-    if (task >= ntasks) break;
-    const int first = dv.tasks[task];
-    const uint32_t key = dv.key[first];
-    const uint32_t cend = dv.cell_start[key + 1];
-    const int64_t i = (int64_t)first + threadIdx.x;
-    const bool active = i < (int64_t)cend;
-    typename P::Target tg;
-    P::load_target(rec + (active ? i : (int64_t)first) * P::REC, tg);
-    // frame of the fp32 pre-filter: coordinates relative to the task's first particle (|.| <= 3 cell edges)
+    const bool in_pass = active && my_rho == rho;
+    const int fa = (rho == rho_f) ? (int)(key_f % F) : 0, fb = (rho == rho_l) ? (int)(key_l % F) : F - 1;
+    const int f0 = max(fa - 1, 0), f1 = min(fb + 1, F - 1);
+    // neighbouring rows: (x +- 1, y +- 1) for a 3-D grid (rho = x ny + y), x +- 1 for a 2-D one (rho = x)
+    const int ry = (nz > 1) ? (int)(rho % ny) : 0, rx = (nz > 1) ? (int)(rho / ny) : (int)rho;
+    const int nrow_y = (nz > 1) ? 3 : 1;
+    // frame of the fp32 pre-filter: coordinates relative to the corner of the pass's first target cell, so that
+    // every coordinate in play is a few cell edges at most
     double org[3];
     float tx[3];
+    {
+      const int c3[3] = {rx, (nz > 1) ? ry : fa, (nz > 1) ? fa : 0};
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      org[d] = (d < D) ? __ldg(rec + (int64_t)first * P::REC + d) : 0.0;
-      tx[d] = (float)(tg.x[d] - org[d]);
+      for (int d = 0; d < 3; ++d) {
+        org[d] = (d < D) ? g.min[d] + c3[d] / g.rdx[d] : 0.0;
+        tx[d] = (float)(tg.x[d] - org[d]);
+      }
     }
-    typename P::Acc acc;
-    P::init(acc);
-    const int cz = key % nz, cy = (key / nz) % ny, cx = key / (nz * ny);
-    const int nrows = flat ? 3 : 9;
-    for (int row = 0; row < nrows; ++row) {
-      const int ox = flat ? row - 1 : row / 3 - 1, oy = flat ? 0 : row % 3 - 1;
-      const int x = cx + ox, y = cy + oy;
-      if (x < 0 || x >= g.nc[0] || y < 0 || y >= ny) continue;
-      uint32_t k0, k1;
-      if (flat) { k0 = (uint32_t)(x * ny + (cy > 0 ? cy - 1 : 0)); k1 = (uint32_t)(x * ny + (cy < ny - 1 ? cy + 1 : cy)); }
-      else { const uint32_t b = (uint32_t)((x * ny + y) * nz); k0 = b + (cz > 0 ? cz - 1 : 0); k1 = b + (cz < nz - 1 ? cz + 1 : cz); }
-      const uint32_t js = dv.cell_start[k0], je = dv.cell_start[k1 + 1];
-      for (uint32_t ts = js; ts < je; ts += TILE) {
-        const int nt = (int)min((uint32_t)TILE, je - ts);
-        __syncthreads();  // the previous tile is fully consumed
-        {  // stage nt records (128-bit loads) + their fp32 relative positions
-          const double2* __restrict__ src = reinterpret_cast<const double2*>(rec + (int64_t)ts * P::REC);
-          for (int q = threadIdx.x; q < nt * CH; q += NT) {
-            const int r = q / CH, c = q - r * CH;
-            const double2 v = __ldg(src + q);
-            srec[r * RS2 + c] = v;
-            if (c == 0) { spos[0][r] = (float)(v.x - org[0]); spos[1][r] = (float)(v.y - org[1]); }
-            if (D == 3 && c == 1) spos[2][r] = (float)(v.x - org[2]);
-          }
-          for (int r = nt + threadIdx.x; r < TILE; r += NT) { spos[0][r] = 3.0e18f; spos[1][r] = 0.f; spos[2][r] = 0.f; }
+    __syncthreads();  // the previous pass's tiles and segment table are no longer in use
+    if (threadIdx.x == 0) {
+      int ns = 0;
+      uint32_t C = 0;
+      for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = 0; dy < nrow_y; ++dy) {
+          const int x = rx + dx, y = (nz > 1) ? ry + dy - 1 : 0;
+          if (x < 0 || x >= nx || y < 0 || y >= ((nz > 1) ? ny : 1)) continue;
+          const uint32_t row = (nz > 1) ? (uint32_t)(x * ny + y) : (uint32_t)x;
+          const uint32_t js = dv.cell_start[row * F + f0], je = dv.cell_start[row * F + f1 + 1];
+          if (je > js) { seg_start[ns] = js; seg_pref[ns] = C; C += je - js; ++ns; }
         }
-        __syncthreads();
-        // ---- phase 1: fp32 pre-filter, hit masks
-        uint32_t m[NW];
+      seg_pref[ns] = C;
+      s_nseg = ns;
+    }
+    __syncthreads();
+    const int nseg = s_nseg;
+    const uint32_t C = seg_pref[nseg];
+    const uint32_t ntiles = (C + TILE - 1) / TILE;
+    for (uint32_t k = 0; k < ntiles; ++k) {
+      const int nt = (int)((C - k + ntiles - 1) / ntiles);  // candidates c = k, k + ntiles, ... < C
+      __syncthreads();  // the previous tile is fully consumed
+      {  // stage nt records (128-bit loads) + their fp32 relative positions
+        for (int q = threadIdx.x; q < nt * CH; q += NT) {
+          const int r = q / CH, c = q - r * CH;
+          const uint32_t cand = (uint32_t)r * ntiles + k;
+          int s = 0;
+          while (cand >= seg_pref[s + 1]) ++s;
+          const int64_t gidx = (int64_t)seg_start[s] + (cand - seg_pref[s]);
+          const double2 v = __ldg(rec2 + gidx * CH + c);
+          srec[r * RS2 + c] = v;
+          if (c == 0) { spos[0][r] = (float)(v.x - org[0]); spos[1][r] = (float)(v.y - org[1]); }
+          if (D == 3 && c == 1) spos[2][r] = (float)(v.x - org[2]);
+        }
+        for (int r = nt + threadIdx.x; r < TILE; r += NT) { spos[0][r] = 3.0e18f; spos[1][r] = 0.f; spos[2][r] = 0.f; }
+      }
+      __syncthreads();
+      // ---- phase 1: fp32 pre-filter, hit masks
+      uint32_t m[NW];
 #pragma unroll
-        for (int w = 0; w < NW; ++w) {
-          uint32_t mw = 0u;
-          if (w * 32 < nt) {
+      for (int w = 0; w < NW; ++w) {
+        uint32_t mw = 0u;
+        if (w * 32 < nt) {
 #pragma unroll
-            for (int b4 = 0; b4 < 8; ++b4) {
-              const float4 X = reinterpret_cast<const float4*>(&spos[0][w * 32])[b4];
-              const float4 Y = reinterpret_cast<const float4*>(&spos[1][w * 32])[b4];
-              float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (D == 3) Z = reinterpret_cast<const float4*>(&spos[2][w * 32])[b4];
-              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+          for (int b4 = 0; b4 < 8; ++b4) {
+            const float4 X = reinterpret_cast<const float4*>(&spos[0][w * 32])[b4];
+            const float4 Y = reinterpret_cast<const float4*>(&spos[1][w * 32])[b4];
+            float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (D == 3) Z = reinterpret_cast<const float4*>(&spos[2][w * 32])[b4];
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float dx = tx[0] - xs[k], dy = tx[1] - ys[k];
-                float r2 = dx * dx + dy * dy;
-                if (D == 3) { const float dz = tx[2] - zs[k]; r2 += dz * dz; }
-                if (r2 <= gp.rsqr_f) mw |= (1u << (b4 * 4 + k));
-              }
+            for (int e = 0; e < 4; ++e) {
+              const float dx = tx[0] - xs[e], dy = tx[1] - ys[e];
+              float r2 = dx * dx + dy * dy;
+              if (D == 3) { const float dz = tx[2] - zs[e]; r2 += dz * dz; }
+              if (r2 <= gp.rsqr_f) mw |= (1u << (b4 * 4 + e));
             }
           }
-          m[w] = active ? mw : 0u;
         }
-        // ---- phase 2: every lane walks its own hits
-        int mine = 0;
+        m[w] = in_pass ? mw : 0u;
+      }
+      // ---- phase 2: every lane walks its own hits
+      int mine = 0;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) mine += __popc(m[w]);
-        const int maxc = __reduce_max_sync(0xffffffffu, mine);
-        for (int it = 0; it < maxc; ++it) {
-          if (it < mine) {
-            uint32_t wsel = m[NW - 1];
-            int base = (NW - 1) * 32;
+      for (int w = 0; w < NW; ++w) mine += __popc(m[w]);
+      const int maxc = __reduce_max_sync(0xffffffffu, mine);
+      for (int it = 0; it < maxc; ++it) {
+        if (it < mine) {
+          uint32_t wsel = m[NW - 1];
+          int base = (NW - 1) * 32;
 #pragma unroll
-            for (int w = NW - 2; w >= 0; --w)
-              if (m[w]) { wsel = m[w]; base = w * 32; }
-            const uint32_t low = wsel & (0u - wsel);
-            const int j = base + __ffs(wsel) - 1;
+          for (int w = NW - 2; w >= 0; --w)
+            if (m[w]) { wsel = m[w]; base = w * 32; }
+          const uint32_t low = wsel & (0u - wsel);
+          const int j = base + __ffs(wsel) - 1;
 #pragma unroll
-            for (int w = 0; w < NW; ++w)
-              if (base == w * 32) m[w] ^= low;
-            P::pair(gp, tg, srec + j * RS2, (int64_t)ts + j == i, acc);
-          }
+          for (int w = 0; w < NW; ++w)
+            if (base == w * 32) m[w] ^= low;
+          P::pair(gp, tg, srec + j * RS2, acc);
         }
       }
     }
-    if (active) P::store(dv, gp, i, acc);
+    // next row that holds targets of this task
+    uint32_t nxt = (active && my_rho > rho) ? my_rho : 0xffffffffu;
+    nxt = __reduce_min_sync(0xffffffffu, nxt);
+    if ((threadIdx.x & 31) == 0) s_next[threadIdx.x >> 5] = nxt;
+    __syncthreads();
+    nxt = s_next[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) nxt = min(nxt, s_next[w]);
+    if (nxt == 0xffffffffu) break;
+    rho = nxt;
   }
+  if (active) P::store(dv, gp, i, acc);
 }
 
 }  // namespace ccb

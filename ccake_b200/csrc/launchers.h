@@ -8,11 +8,11 @@
 
 namespace ccb {
 
-// nt = targets (= threads) per task: 64 or 128, the chunk size the task list was built with.
-template <int D> cudaError_t launch_gather_fields(bool fact, int nt, int sms, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
-                                                  const GatherParams& gp, int* task_counter);
-template <int D> cudaError_t launch_gather_gradients(bool shear, bool diff, bool fact, int nt, int sms, cudaStream_t s,
-                                                     const DeviceView& dv, const CellGrid& g, const GatherParams& gp, int* task_counter);
+// nt = targets (= threads) per task: 64 or 128.
+template <int D> cudaError_t launch_gather_fields(bool fact, int nt, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
+                                                  const GatherParams& gp);
+template <int D> cudaError_t launch_gather_gradients(bool shear, bool diff, bool fact, int nt, cudaStream_t s, const DeviceView& dv,
+                                                     const CellGrid& g, const GatherParams& gp);
 template <int D, bool MILNE> cudaError_t launch_prologue(cudaStream_t s, const DeviceView& dv, double t);
 template <int D, bool MILNE> cudaError_t launch_eos_local(cudaStream_t s, const DeviceView& dv, const StageParams& sp);
 template <int D, bool MILNE> cudaError_t launch_eom_rk(cudaStream_t s, const DeviceView& dv, const StageParams& sp);
