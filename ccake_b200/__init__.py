@@ -6,3 +6,4 @@ tests and ``bench.py`` (the C++ mirror is ``include/ccake_b200_host.hpp``).
 """
 from .settings import DEFAULTS, derived_switches, from_yaml, to_config  # noqa: F401
 from .workstation import CCAKEError, SPHWorkstation  # noqa: F401
+from . import slabs  # noqa: F401,E402

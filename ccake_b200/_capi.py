@@ -13,7 +13,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libccake_b200.so")
 
-CCB_OK, CCB_ERR_INVALID, CCB_ERR_CUDA, CCB_ERR_NEG_ENTROPY, CCB_ERR_EOS_NO_ROOT, CCB_ERR_OUT_OF_GRID, CCB_ERR_STATE = range(7)
+CCB_OK, CCB_ERR_INVALID, CCB_ERR_CUDA, CCB_ERR_NEG_ENTROPY, CCB_ERR_EOS_NO_ROOT, CCB_ERR_OUT_OF_GRID, CCB_ERR_STATE, CCB_ERR_COMM = range(8)
 COORD_HYPERBOLIC, COORD_CARTESIAN = 0, 1
 EOS_CONFORMAL, EOS_TABLE = 0, 1
 
@@ -50,7 +50,7 @@ class IC(C.Structure):
     """``ccb_ic``."""
 
     _fields_ = [("n", C.c_int64)] + [(k, C.POINTER(C.c_double)) for k in
-                                       ("r", "e_or_s", "rhoB", "rhoS", "rhoQ", "u", "bulk", "shv6")]
+                                       ("r", "e_or_s", "rhoB", "rhoS", "rhoQ", "u", "bulk", "shv6")] + [("id", C.POINTER(C.c_int32))]
 
 
 class Totals(C.Structure):
@@ -116,6 +116,14 @@ def lib():
     L.ccb_upload_state.argtypes = [ctx, dp]
     L.ccb_download_state.argtypes = [ctx, dp]
     L.ccb_measure_dfma_peak.argtypes = [C.c_int, dp]
+    L.ccb_comm_unique_id.argtypes = [C.c_char_p]
+    L.ccb_comm_init.argtypes = [ctx, C.c_char_p]
+    L.ccb_comm_init_local.argtypes = [ctx, C.c_int]
+    L.ccb_set_slab.argtypes = [ctx, C.c_int32, C.c_int32]
+    L.ccb_grid_geometry.argtypes = [ctx, dp, dp, ip]
+    L.ccb_migration_counts.argtypes = [ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.ccb_get_field_device_order.argtypes = [ctx, C.c_int, dp]
+    L.ccb_get_int_field_device_order.argtypes = [ctx, C.c_int, ip]
     L.ccb_stream.argtypes = [ctx]
     L.ccb_stream.restype = C.c_void_p
     L.ccb_device_field.argtypes = [ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -130,4 +138,5 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_local_update", "ccb_smooth_gradients", "ccb_time_derivatives", "ccb_get_time_derivatives", "ccb_step",
             "ccb_synchronize", "ccb_reduce", "ccb_kernel_launches", "ccb_profile_enable", "ccb_profile_get",
             "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
-            "ccb_measure_dfma_peak"]
+            "ccb_measure_dfma_peak", "ccb_comm_unique_id", "ccb_comm_init", "ccb_comm_init_local", "ccb_set_slab",
+            "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order"]

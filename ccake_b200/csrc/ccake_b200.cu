@@ -5,11 +5,14 @@
 // There is deliberately NO host fallback: every entry point that computes launches
 // CUDA kernels on the context's stream and returns CCB_ERR_CUDA if no device is usable.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "cells.cuh"
+#include "comm.h"
 #include "launchers.h"
 
 using namespace ccb;
@@ -59,6 +62,18 @@ struct ccb_ctx {
   double efcheck = 0.0;
   int chunk = 64;   // targets per gather task (= threads per CTA): 64 or 128
   int sms = 148;
+  // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
+  std::unique_ptr<ccb::Link> comm;
+  int slab_lo = 0, slab_hi = 0;
+  int64_t rec_cap = 0;                       // records the gather buffer holds (own + ghosts)
+  uint32_t* ghost_tab = nullptr;             // 2 x (P + 1) rebased column tables + 2 x (P + 1) receive scratch
+  int32_t* d_info = nullptr;                 // small device scratch for counts
+  int64_t ghost_n[2] = {0, 0};               // ghost records per side
+  int64_t send_start[2] = {0, 0}, send_n[2] = {0, 0};  // own edge columns (sorted order): halo sends
+  double* mig_d[2] = {nullptr, nullptr};     // migration buffers [send, recv]
+  int32_t* mig_i[2] = {nullptr, nullptr};
+  int64_t mig_cap = 0;
+  int64_t migrated_out = 0, migrated_in = 0; // running totals (instrumentation)
 };
 
 namespace {
@@ -154,6 +169,8 @@ int free_particles(ccb_ctx* ctx) {
   cudaFree(ctx->slab); cudaFree(ctx->y0_slab); cudaFree(ctx->alt_slab); cudaFree(ctx->ints);
   cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
   cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
+  for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); ctx->mig_d[k] = nullptr; ctx->mig_i[k] = nullptr; }
+  ctx->mig_cap = 0;
   ctx->slab = ctx->y0_slab = ctx->alt_slab = nullptr; ctx->ints = nullptr;
   ctx->key_a = ctx->key_b = ctx->idx_a = ctx->idx_b = ctx->hist = nullptr;
   ctx->rec = nullptr; ctx->tasks = nullptr; ctx->d_stage = nullptr; ctx->init_tmp = nullptr;
@@ -172,7 +189,9 @@ __global__ void fill_kernel(double* p, double v, int64_t n) {
 int allocate_particles(ccb_ctx* ctx, int64_t n) {
   free_particles(ctx);
   ctx->n = n;
-  ctx->cap = ((n + 63) / 64) * 64;
+  // with a slab decomposition particles arrive from the neighbours: 25 % + 8192 of slack
+  const int64_t want = ctx->cfg.nranks > 1 ? n + n / 4 + 8192 : n;
+  ctx->cap = ((want + 63) / 64) * 64;
   if (ctx->cap == 0) ctx->cap = 64;
   const int64_t cap = ctx->cap;
   const int W = total_width();
@@ -207,6 +226,7 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   ctx->hist_alloc = 256 * cdiv(cap, kSortTile);
   CUDA_OK(cudaMalloc(&ctx->hist, sizeof(uint32_t) * ctx->hist_alloc));
   CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G_MAX * cap));
+  ctx->rec_cap = cap;
   CUDA_OK(cudaMalloc(&ctx->tasks, sizeof(int32_t) * cap));
   CUDA_OK(cudaMalloc(&ctx->d_stage, sizeof(double) * kStageCols * cap));
   dv.key = ctx->key_a;
@@ -226,6 +246,10 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
 }
 
 int exclusive_scan(ccb_ctx* ctx, const uint32_t* in, uint32_t* out, int64_t n, int write_total) {
+  if (n <= 1024 * kScanSmallPer) {
+    LAUNCH(scan_small, 1, 1024, in, out, n, write_total);
+    return CCB_OK;
+  }
   const int64_t nb = cdiv(n, kScanTile);
   LAUNCH(scan_block_sums, nb, kScanThreads, in, ctx->scan_sums, n);
   LAUNCH(scan_sums_inplace, 1, 1024, ctx->scan_sums, nb);
@@ -257,24 +281,27 @@ GatherParams make_gather(ccb_ctx* ctx) {
 
 constexpr int kReduceBlocks = 296;
 // ---- phase implementations ------------------------------------------------------
-int do_build_cells(ccb_ctx* ctx) {
-  PhaseTimer pt(ctx, PH_NEIGHBOUR);
-  const int64_t n = ctx->n;
+// (key, index) radix sort of the first n particles + permutation of every persistent column.
+// drop_outside: keys outside the slab become the sentinel `ncells` (sorted last, not counted as particles).
+int sort_and_permute(ccb_ctx* ctx, int64_t n, int drop_outside) {
   DeviceView& dv = ctx->dv;
   const CellGrid& g = ctx->grid;
-  if (g.ncells + 1 > ctx->ncells_alloc) {
+  if (g.ncells + 3 > ctx->ncells_alloc) {
     cudaFree(ctx->cell_count);
-    CUDA_OK(cudaMalloc(&ctx->cell_count, sizeof(uint32_t) * (g.ncells + 2)));
-    ctx->ncells_alloc = g.ncells + 1;
+    CUDA_OK(cudaMalloc(&ctx->cell_count, sizeof(uint32_t) * (g.ncells + 3)));
+    ctx->ncells_alloc = g.ncells + 3;
   }
   dv.cell_start = ctx->cell_count;
-  CUDA_OK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(uint32_t) * (g.ncells + 1), ctx->stream));
-  LAUNCH(cell_key_kernel, cdiv(n, 256), 256, dv, g, ctx->key_a, ctx->idx_a, ctx->cell_count);
-  int rc = exclusive_scan(ctx, ctx->cell_count, ctx->cell_count, g.ncells, 1);
+  const int64_t P = (int64_t)g.nc[1] * g.nc[2];
+  const uint32_t key_lo = (uint32_t)(ctx->slab_lo * P), key_hi = (uint32_t)(ctx->slab_hi * P), sentinel = (uint32_t)g.ncells;
+  CUDA_OK(cudaMemsetAsync(ctx->cell_count, 0, sizeof(uint32_t) * (g.ncells + 2), ctx->stream));
+  LAUNCH(cell_key_kernel, cdiv(n, 256), 256, dv, g, ctx->key_a, ctx->idx_a, ctx->cell_count, n, drop_outside, key_lo, key_hi, sentinel);
+  // cell_start[c] for c <= ncells; cell_start[ncells] = number of particles that carry a real key
+  int rc = exclusive_scan(ctx, ctx->cell_count, ctx->cell_count, g.ncells + 1, 1);
   if (rc) return rc;
-  // LSD radix sort over the significant bits of the key
+  // LSD radix sort over the significant bits of the key (the sentinel included)
   int bits = 1;
-  while (((int64_t)1 << bits) < g.ncells) ++bits;
+  while (((int64_t)1 << bits) < g.ncells + 1) ++bits;
   const int nblocks = (int)cdiv(n, kSortTile);
   uint32_t *kin = ctx->key_a, *kout = ctx->key_b, *iin = ctx->idx_a, *iout = ctx->idx_b;
   for (int shift = 0; shift < bits; shift += 8) {
@@ -312,6 +339,171 @@ int do_build_cells(ccb_ctx* ctx) {
   std::swap(dv.eos_id, ctx->alt_int[3]);
   dv.key = kin;  // sorted keys
   if (kin != ctx->key_a) { std::swap(ctx->key_a, ctx->key_b); std::swap(ctx->idx_a, ctx->idx_b); }
+  return CCB_OK;
+}
+
+#define COMM_OK(call)                                                                 \
+  do {                                                                                \
+    if ((call)) { ctx->err = std::string(ctx->comm->name()) + " transport: " + ctx->comm->err; return CCB_ERR_COMM; } \
+  } while (0)
+
+// every column that travels with a particle (the permuted set), in its CURRENT buffer
+void migrate_list(ccb_ctx* ctx, MigrateList& ml) {
+  DeviceView& dv = ctx->dv;
+  ml.ncols = 0;
+  for (int f = 0; f < kNumPersistentFields; ++f) {
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    for (int c = 0; c < kFieldWidth[f]; ++c) ml.col[ml.ncols++] = dv.f[f] + (int64_t)c * dv.cap;
+  }
+  for (int k = 0; k < kNumEvolvedFields; ++k) {
+    const int f = kEvolvedFields[k];
+    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
+    for (int c = 0; c < kFieldWidth[f]; ++c) ml.col[ml.ncols++] = dv.y0[f] + (int64_t)c * dv.cap;
+  }
+  ml.icol[0] = dv.id; ml.icol[1] = dv.btrack; ml.icol[2] = dv.freeze; ml.icol[3] = dv.eos_id;
+}
+
+// Particles whose cell column left the slab go to the neighbouring rank (they sit at the two ends of the
+// sorted order); arrivals are appended and a second sort, which drops the leavers, puts everything in place.
+int migrate(ccb_ctx* ctx) {
+  const CellGrid& g = ctx->grid;
+  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+  const int64_t P = (int64_t)g.nc[1] * g.nc[2];
+  const int left = rank - 1, right = rank + 1 < nranks ? rank + 1 : -1;
+  int32_t* info = ctx->d_info;  // [0] out left, [1] out right, [2] in from left, [3] in from right
+  CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 4, ctx->stream));
+  LAUNCH(leaver_counts, 1, 32, ctx->dv.cell_start, (uint32_t)(ctx->slab_lo * P), (uint32_t)(ctx->slab_hi * P), (uint32_t)g.ncells, info);
+  COMM_OK(ctx->comm->group_begin());
+  if (left >= 0) COMM_OK(ctx->comm->send(info + 0, sizeof(int32_t), left, ctx->stream));
+  if (right >= 0) COMM_OK(ctx->comm->send(info + 1, sizeof(int32_t), right, ctx->stream));
+  if (left >= 0) COMM_OK(ctx->comm->recv(info + 2, sizeof(int32_t), left, ctx->stream));
+  if (right >= 0) COMM_OK(ctx->comm->recv(info + 3, sizeof(int32_t), right, ctx->stream));
+  COMM_OK(ctx->comm->group_end());
+  int32_t h[4];
+  CUDA_OK(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  int64_t outL = h[0], outR = h[1];
+  const int64_t inL = h[2], inR = h[3];
+  if ((left < 0 && outL) || (right < 0 && outR)) {
+    // a particle of an outermost rank left the slab outwards: it stays (its key is still on the grid)
+    if (left < 0) outL = 0;
+    if (right < 0) outR = 0;
+  }
+  if (outL + outR + inL + inR == 0) return CCB_OK;
+  const int64_t n = ctx->n;
+  if (n + inL + inR > ctx->cap) { ctx->err = "slab overflow: more arrivals than the particle capacity holds"; return CCB_ERR_STATE; }
+  MigrateList ml;
+  migrate_list(ctx, ml);
+  const int64_t need = std::max<int64_t>(std::max(outL + outR, inL + inR), 1);
+  if (need > ctx->mig_cap) {
+    for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); }
+    ctx->mig_cap = need * 2 + 1024;
+    for (int k = 0; k < 2; ++k) {
+      CUDA_OK(cudaMalloc(&ctx->mig_d[k], sizeof(double) * ml.ncols * ctx->mig_cap));
+      CUDA_OK(cudaMalloc(&ctx->mig_i[k], sizeof(int32_t) * 4 * ctx->mig_cap));
+    }
+  }
+  double *sd = ctx->mig_d[0], *rd = ctx->mig_d[1];
+  int32_t *si = ctx->mig_i[0], *ri = ctx->mig_i[1];
+  // leavers: [0, outL) and [n - outR, n) of the sorted order
+  if (outL) LAUNCH(pack_rows, cdiv(outL, 128), 128, ml, (int64_t)0, outL, sd, si);
+  if (outR) LAUNCH(pack_rows, cdiv(outR, 128), 128, ml, n - outR, outR, sd + ml.ncols * outL, si + 4 * outL);
+  COMM_OK(ctx->comm->group_begin());
+  if (left >= 0 && outL) { COMM_OK(ctx->comm->send(sd, sizeof(double) * ml.ncols * outL, left, ctx->stream)); COMM_OK(ctx->comm->send(si, sizeof(int32_t) * 4 * outL, left, ctx->stream)); }
+  if (right >= 0 && outR) { COMM_OK(ctx->comm->send(sd + ml.ncols * outL, sizeof(double) * ml.ncols * outR, right, ctx->stream)); COMM_OK(ctx->comm->send(si + 4 * outL, sizeof(int32_t) * 4 * outR, right, ctx->stream)); }
+  if (left >= 0 && inL) { COMM_OK(ctx->comm->recv(rd, sizeof(double) * ml.ncols * inL, left, ctx->stream)); COMM_OK(ctx->comm->recv(ri, sizeof(int32_t) * 4 * inL, left, ctx->stream)); }
+  if (right >= 0 && inR) { COMM_OK(ctx->comm->recv(rd + ml.ncols * inL, sizeof(double) * ml.ncols * inR, right, ctx->stream)); COMM_OK(ctx->comm->recv(ri + 4 * inL, sizeof(int32_t) * 4 * inR, right, ctx->stream)); }
+  COMM_OK(ctx->comm->group_end());
+  if (inL) LAUNCH(unpack_rows, cdiv(inL, 128), 128, ml, n, inL, rd, ri);
+  if (inR) LAUNCH(unpack_rows, cdiv(inR, 128), 128, ml, n + inL, inR, rd + ml.ncols * inL, ri + 4 * inL);
+  // second sort over own + arrivals; the leavers' keys are outside the slab -> sentinel -> dropped
+  const int64_t n_tmp = n + inL + inR;
+  ctx->dv.n = n_tmp;
+  int rc = sort_and_permute(ctx, n_tmp, 1);
+  if (rc) return rc;
+  ctx->n = n_tmp - outL - outR;
+  ctx->dv.n = ctx->n;
+  ctx->migrated_out += outL + outR;
+  ctx->migrated_in += inL + inR;
+  return CCB_OK;
+}
+
+// Exchange the cell tables of the edge columns with the two neighbours: afterwards this rank knows which of its
+// own records each neighbour needs (send_start / send_n) and where the ghost records it receives will sit.
+int exchange_column_tables(ccb_ctx* ctx) {
+  const CellGrid& g = ctx->grid;
+  DeviceView& dv = ctx->dv;
+  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+  const int64_t P = (int64_t)g.nc[1] * g.nc[2], T = P + 1;
+  const int left = rank - 1, right = rank + 1 < nranks ? rank + 1 : -1;
+  uint32_t* tab = ctx->ghost_tab;  // [0] ghost table left, [1] ghost table right, [2] recv scratch left, [3] recv scratch right
+  const uint32_t* own_first = dv.cell_start + (int64_t)ctx->slab_lo * P;
+  const uint32_t* own_last = dv.cell_start + (int64_t)(ctx->slab_hi - 1) * P;
+  COMM_OK(ctx->comm->group_begin());
+  if (left >= 0) COMM_OK(ctx->comm->send(own_first, sizeof(uint32_t) * T, left, ctx->stream));
+  if (right >= 0) COMM_OK(ctx->comm->send(own_last, sizeof(uint32_t) * T, right, ctx->stream));
+  if (left >= 0) COMM_OK(ctx->comm->recv(tab + 2 * T, sizeof(uint32_t) * T, left, ctx->stream));
+  if (right >= 0) COMM_OK(ctx->comm->recv(tab + 3 * T, sizeof(uint32_t) * T, right, ctx->stream));
+  COMM_OK(ctx->comm->group_end());
+  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // own first column [start, end], own last column, left table ends, right table ends
+  CUDA_OK(cudaMemcpyAsync(h + 0, own_first, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(h + 1, own_first + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(h + 2, own_last, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(h + 3, own_last + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (left >= 0) { CUDA_OK(cudaMemcpyAsync(h + 4, tab + 2 * T, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); CUDA_OK(cudaMemcpyAsync(h + 5, tab + 2 * T + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
+  if (right >= 0) { CUDA_OK(cudaMemcpyAsync(h + 6, tab + 3 * T, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); CUDA_OK(cudaMemcpyAsync(h + 7, tab + 3 * T + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->send_start[0] = h[0]; ctx->send_n[0] = left >= 0 ? (int64_t)h[1] - h[0] : 0;
+  ctx->send_start[1] = h[2]; ctx->send_n[1] = right >= 0 ? (int64_t)h[3] - h[2] : 0;
+  ctx->ghost_n[0] = left >= 0 ? (int64_t)h[5] - h[4] : 0;
+  ctx->ghost_n[1] = right >= 0 ? (int64_t)h[7] - h[6] : 0;
+  if (left >= 0) LAUNCH(rebase_ghost_table, cdiv(T, 256), 256, tab + 2 * T, tab, T, (uint32_t)ctx->n);
+  if (right >= 0) LAUNCH(rebase_ghost_table, cdiv(T, 256), 256, tab + 3 * T, tab + T, T, (uint32_t)(ctx->n + ctx->ghost_n[0]));
+  dv.ghost_col[0] = left >= 0 ? ctx->slab_lo - 1 : -1;
+  dv.ghost_col[1] = right >= 0 ? ctx->slab_hi : -1;
+  dv.ghost_start[0] = tab; dv.ghost_start[1] = tab + T;
+  // room for the ghost records behind the own ones
+  const int64_t need = ctx->n + ctx->ghost_n[0] + ctx->ghost_n[1];
+  if (need > ctx->rec_cap) {
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->rec);
+    ctx->rec_cap = need + need / 8 + 1024;
+    CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G_MAX * ctx->rec_cap));
+    dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
+  }
+  return CCB_OK;
+}
+
+// Ghost records of one gather (rec_doubles per record): own edge columns -> neighbours, theirs -> behind our own.
+int exchange_halo(ccb_ctx* ctx, int rec_doubles) {
+  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+  const int left = rank - 1, right = rank + 1 < nranks ? rank + 1 : -1;
+  double* rec = ctx->rec;
+  const size_t rb = sizeof(double) * rec_doubles;
+  COMM_OK(ctx->comm->group_begin());
+  if (left >= 0 && ctx->send_n[0]) COMM_OK(ctx->comm->send(rec + ctx->send_start[0] * rec_doubles, rb * ctx->send_n[0], left, ctx->stream));
+  if (right >= 0 && ctx->send_n[1]) COMM_OK(ctx->comm->send(rec + ctx->send_start[1] * rec_doubles, rb * ctx->send_n[1], right, ctx->stream));
+  if (left >= 0 && ctx->ghost_n[0]) COMM_OK(ctx->comm->recv(rec + ctx->n * rec_doubles, rb * ctx->ghost_n[0], left, ctx->stream));
+  if (right >= 0 && ctx->ghost_n[1]) COMM_OK(ctx->comm->recv(rec + (ctx->n + ctx->ghost_n[0]) * rec_doubles, rb * ctx->ghost_n[1], right, ctx->stream));
+  COMM_OK(ctx->comm->group_end());
+  return CCB_OK;
+}
+
+int grad_record_doubles(ccb_ctx* ctx) {
+  const bool df = ctx->cfg.using_diffusion;
+  if (ctx->D == 2) return df ? GradRec<2, true>::REC : GradRec<2, false>::REC;
+  return df ? GradRec<3, true>::REC : GradRec<3, false>::REC;
+}
+
+int do_build_cells(ccb_ctx* ctx) {
+  PhaseTimer pt(ctx, PH_NEIGHBOUR);
+  ctx->dv.n = ctx->n;
+  int rc = sort_and_permute(ctx, ctx->n, 0);
+  if (rc) return rc;
+  if (ctx->comm) {
+    if ((rc = migrate(ctx))) return rc;
+    if ((rc = exchange_column_tables(ctx))) return rc;
+  }
   ctx->cells_valid = true;
   return CCB_OK;
 }
@@ -342,6 +534,7 @@ int do_gather_fields(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
   const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
+  if (ctx->comm) { const int rc = exchange_halo(ctx, REC_F); if (rc) return rc; }
   if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
   else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
@@ -360,6 +553,7 @@ int do_gather_gradients(ccb_ctx* ctx) {
   const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
+  if (ctx->comm) { const int rc = exchange_halo(ctx, grad_record_doubles(ctx)); if (rc) return rc; }
   if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
   else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
@@ -447,6 +641,9 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
   for (int p = 0; p < PH_COUNT; ++p) { ctx->phase_ms[p] = 0.; ctx->phase_calls[p] = 0; }
   setup_grid(ctx);
+  ctx->slab_lo = 0; ctx->slab_hi = ctx->grid.nc[0];
+  ctx->dv.ghost_col[0] = ctx->dv.ghost_col[1] = -1;
+  ctx->dv.ghost_start[0] = ctx->dv.ghost_start[1] = nullptr;
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, cfg->device);
   {  // expected particles per neighbour cell from the IC lattice spacing: dense cells get 128-target tasks
     double ppc = 0.0;
@@ -455,6 +652,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
       if (cfg->dim == 3) ppc = cfg->stepEta > 0 ? ppc * (2 * cfg->hT / cfg->stepEta) : 0.0;
     }
     ctx->chunk = ppc >= 96.0 ? 128 : 64;
+    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = v; }  // tuning override
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);
@@ -476,6 +674,8 @@ int ccb_destroy(ccb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
+  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info);
+  ctx->comm.reset();
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -516,6 +716,7 @@ int ccb_allocate(ccb_ctx* ctx, int64_t n) {
 int ccb_set_field(ccb_ctx* ctx, int field, const double* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
+  if (ctx->comm) { ctx->err = "ccb_set_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
   const int w = kFieldWidth[field];
   std::vector<double> colbuf(ctx->n);
@@ -530,6 +731,7 @@ int ccb_set_field(ccb_ctx* ctx, int field, const double* host) {
 int ccb_get_field(ccb_ctx* ctx, int field, double* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
+  if (ctx->comm) { ctx->err = "ccb_get_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
   const int w = kFieldWidth[field];
   std::vector<double> buf((size_t)ctx->n * w);
@@ -546,6 +748,7 @@ int ccb_get_field(ccb_ctx* ctx, int field, double* host) {
 int ccb_set_int_field(ccb_ctx* ctx, int field, const int32_t* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
+  if (ctx->comm) { ctx->err = "ccb_set_int_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < CCB_I_BTRACK || field > CCB_I_FREEZE || !host) return CCB_ERR_INVALID;
   int32_t* dst = field == CCB_I_BTRACK ? ctx->dv.btrack : ctx->dv.freeze;
   int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
@@ -558,6 +761,7 @@ int ccb_set_int_field(ccb_ctx* ctx, int field, const int32_t* host) {
 int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
+  if (ctx->comm) { ctx->err = "ccb_get_int_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
   const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
                                                                                                                       : reinterpret_cast<const int32_t*>(ctx->dv.key);
@@ -602,6 +806,7 @@ int ccb_state_width(ccb_ctx* ctx) {
 int ccb_upload_state(ccb_ctx* ctx, const double* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
+  if (ctx->comm) { ctx->err = "ccb_upload_state: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (!host) return CCB_ERR_INVALID;
   ColumnList cl;
   const int w = state_columns(ctx, cl);
@@ -613,6 +818,7 @@ int ccb_upload_state(ccb_ctx* ctx, const double* host) {
 int ccb_download_state(ccb_ctx* ctx, double* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
+  if (ctx->comm) { ctx->err = "ccb_download_state: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (!host) return CCB_ERR_INVALID;
   ColumnList cl;
   const int w = state_columns(ctx, cl);
@@ -649,6 +855,87 @@ int ccb_measure_dfma_peak(int device, double* tflops) {
   cudaEventDestroy(a); cudaEventDestroy(b);
   cudaFree(d);
   *tflops = best;
+  return CCB_OK;
+}
+
+// ---- slab decomposition --------------------------------------------------------------------
+static int comm_buffers(ccb_ctx* ctx) {
+  const int64_t T = (int64_t)ctx->grid.nc[1] * ctx->grid.nc[2] + 1;
+  CUDA_OK(cudaMalloc(&ctx->ghost_tab, sizeof(uint32_t) * 4 * T));
+  CUDA_OK(cudaMemset(ctx->ghost_tab, 0, sizeof(uint32_t) * 4 * T));
+  CUDA_OK(cudaMalloc(&ctx->d_info, sizeof(int32_t) * 8 + sizeof(double) * 8));
+  return CCB_OK;
+}
+int ccb_comm_unique_id(char id[128]) {
+  if (!id) return CCB_ERR_INVALID;
+  std::string err;
+  NcclApi& api = NcclApi::get();
+  if (!api.load(err)) return CCB_ERR_COMM;
+  NcclApi::unique_id uid;
+  if (api.GetUniqueId(&uid)) return CCB_ERR_COMM;
+  std::memcpy(id, uid.internal, 128);
+  return CCB_OK;
+}
+int ccb_comm_init(ccb_ctx* ctx, const char id[128]) {
+  if (!ctx || !id) return CCB_ERR_INVALID;
+  if (ctx->cfg.nranks < 2) { ctx->err = "ccb_comm_init: nranks < 2"; return CCB_ERR_INVALID; }
+  if (ctx->have_state) { ctx->err = "ccb_comm_init must precede the particle upload"; return CCB_ERR_STATE; }
+  CUDA_OK(cudaSetDevice(ctx->cfg.device));
+  auto t = std::make_unique<NcclLink>();
+  if (t->init(id, ctx->cfg.rank, ctx->cfg.nranks)) { ctx->err = "ccb_comm_init: " + t->err; return CCB_ERR_COMM; }
+  ctx->comm = std::move(t);
+  return comm_buffers(ctx);
+}
+int ccb_comm_init_local(ccb_ctx* ctx, int group) {
+  if (!ctx) return CCB_ERR_INVALID;
+  if (ctx->cfg.nranks < 2) { ctx->err = "ccb_comm_init_local: nranks < 2"; return CCB_ERR_INVALID; }
+  if (ctx->have_state) { ctx->err = "ccb_comm_init_local must precede the particle upload"; return CCB_ERR_STATE; }
+  ctx->comm = std::make_unique<LocalLink>(group, ctx->cfg.rank, ctx->cfg.nranks);
+  return comm_buffers(ctx);
+}
+int ccb_set_slab(ccb_ctx* ctx, int32_t col_lo, int32_t col_hi) {
+  if (!ctx) return CCB_ERR_INVALID;
+  const int nx = ctx->grid.nc[0];
+  if (ctx->cfg.rank == 0) col_lo = 0;                          // the outermost slabs extend to the grid edge
+  if (ctx->cfg.rank == ctx->cfg.nranks - 1) col_hi = nx;
+  if (col_lo < 0 || col_hi > nx || col_lo >= col_hi) { ctx->err = "ccb_set_slab: empty or out-of-grid column range"; return CCB_ERR_INVALID; }
+  ctx->slab_lo = col_lo; ctx->slab_hi = col_hi;
+  ctx->cells_valid = false;
+  return CCB_OK;
+}
+int ccb_grid_geometry(ccb_ctx* ctx, double min[3], double edge[3], int32_t nc[3]) {
+  if (!ctx || !min || !edge || !nc) return CCB_ERR_INVALID;
+  for (int d = 0; d < 3; ++d) { min[d] = ctx->grid.min[d]; edge[d] = 1.0 / ctx->grid.rdx[d]; nc[d] = ctx->grid.nc[d]; }
+  return CCB_OK;
+}
+int ccb_migration_counts(ccb_ctx* ctx, int64_t* out, int64_t* in) {
+  if (!ctx) return CCB_ERR_INVALID;
+  if (out) *out = ctx->migrated_out;
+  if (in) *in = ctx->migrated_in;
+  return CCB_OK;
+}
+int ccb_get_field_device_order(ccb_ctx* ctx, int field, double* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
+  const int w = kFieldWidth[field];
+  std::vector<double> buf((size_t)ctx->n * w);
+  for (int c = 0; c < w; ++c)
+    CUDA_OK(cudaMemcpyAsync(buf.data() + (size_t)c * ctx->n, ctx->dv.f[field] + (int64_t)c * ctx->cap, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  for (int c = 0; c < w; ++c)
+    for (int64_t i = 0; i < ctx->n; ++i) host[i * w + c] = buf[(size_t)c * ctx->n + i];
+  return CCB_OK;
+}
+int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
+  if (field == CCB_I_CELL && !ctx->cells_valid) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
+  const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
+                                                                                                                      : reinterpret_cast<const int32_t*>(ctx->dv.key);
+  CUDA_OK(cudaMemcpyAsync(host, src, sizeof(int32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return CCB_OK;
 }
 
@@ -705,6 +992,16 @@ int ccb_reduce(ccb_ctx* ctx, ccb_totals* out) {
     std::memcpy(&f, &h[6 * nb + b], sizeof(f));
     fr += f;
   }
+  if (ctx->comm) {  // totals over all slabs
+    double* d = reinterpret_cast<double*>(ctx->d_info + 8);
+    double hbuf[7] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], (double)fr};
+    CUDA_OK(cudaMemcpyAsync(d, hbuf, sizeof(hbuf), cudaMemcpyHostToDevice, ctx->stream));
+    COMM_OK(ctx->comm->allreduce_sum(d, 7, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(hbuf, d, sizeof(hbuf), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 6; ++k) acc[k] = hbuf[k];
+    fr = (unsigned long long)(hbuf[6] + 0.5);
+  }
   out->S = acc[0]; out->B = acc[1]; out->Sq = acc[2]; out->Q = acc[3]; out->E = acc[4]; out->Ez = acc[5];
   out->n_frozen = (int64_t)fr;
   return CCB_OK;
@@ -716,6 +1013,7 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   if (rc) return rc;
   const int64_t n = ctx->n, cap = ctx->cap;
   ctx->t = ctx->cfg.t0;
+  const int64_t mig0 = ctx->migrated_out + ctx->migrated_in;
   DeviceView& dv = ctx->dv;
   std::vector<double> colbuf(n);
   // positions, velocities; sph_mass = extensive = 1 (process_initial_conditions, src/sph_workstation.cpp:1229-1340)
@@ -758,7 +1056,15 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   rc = surface_device_error(ctx);
   cudaFree(ctx->init_tmp);
   ctx->init_tmp = nullptr;
-  return rc;
+  if (rc) return rc;
+  if (ctx->migrated_out + ctx->migrated_in != mig0) { ctx->err = "ccb_upload_ic: rows outside this rank's slab (ccb_set_slab) were uploaded"; return CCB_ERR_INVALID; }
+  if (ic->id) {  // local upload index -> global particle id (slab decomposition)
+    int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
+    CUDA_OK(cudaMemcpyAsync(stage, ic->id, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(gather_int_by_id, cdiv(n, 256), 256, stage, ctx->dv.id, ctx->dv.id, n);
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  return CCB_OK;
 }
 
 }  // extern "C"

@@ -25,10 +25,13 @@ constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // ---- cell keys + per-cell histogram ---------------------------------------------
+// keys outside [key_lo, key_hi) become `sentinel` (= ncells, sorts last) when drop_outside is set: particles that
+// have just been handed to a neighbouring rank.
 __global__ void cell_key_kernel(DeviceView dv, CellGrid g, uint32_t* __restrict__ key, uint32_t* __restrict__ idx,
-                                uint32_t* __restrict__ cell_count) {
+                                uint32_t* __restrict__ cell_count, int64_t n, int drop_outside, uint32_t key_lo, uint32_t key_hi,
+                                uint32_t sentinel) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= dv.n) return;
+  if (i >= n) return;
   int c[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
@@ -37,10 +40,43 @@ __global__ void cell_key_kernel(DeviceView dv, CellGrid g, uint32_t* __restrict_
     ci = ci < 0 ? 0 : (ci > g.nc[d] - 1 ? g.nc[d] - 1 : ci);
     c[d] = ci;
   }
-  const uint32_t k = (uint32_t)(((int64_t)c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+  uint32_t k = (uint32_t)(((int64_t)c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+  if (drop_outside && (k < key_lo || k >= key_hi)) k = sentinel;
   key[i] = k;
   idx[i] = (uint32_t)i;
   atomicAdd(&cell_count[k], 1u);
+}
+
+// ---- slab decomposition helpers -----------------------------------------------------------------
+// migration message = the migrating particles' permuted columns, column-major [column][count], + 4 int columns
+struct MigrateList {
+  int ncols;
+  double* col[96];
+  int32_t* icol[4];
+};
+__global__ void pack_rows(MigrateList ml, int64_t start, int64_t count, double* __restrict__ dbuf, int32_t* __restrict__ ibuf) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  for (int c = 0; c < ml.ncols; ++c) dbuf[(int64_t)c * count + k] = ml.col[c][start + k];
+  for (int c = 0; c < 4; ++c) ibuf[(int64_t)c * count + k] = ml.icol[c][start + k];
+}
+__global__ void unpack_rows(MigrateList ml, int64_t start, int64_t count, const double* __restrict__ dbuf, const int32_t* __restrict__ ibuf) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  for (int c = 0; c < ml.ncols; ++c) ml.col[c][start + k] = dbuf[(int64_t)c * count + k];
+  for (int c = 0; c < 4; ++c) ml.icol[c][start + k] = ibuf[(int64_t)c * count + k];
+}
+// info[0] = particles left of the slab, info[1] = right of it (after the first sort)
+__global__ void leaver_counts(const uint32_t* __restrict__ cell_start, uint32_t key_lo, uint32_t key_hi, uint32_t ncells, int32_t* __restrict__ info) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    info[0] = (int32_t)cell_start[key_lo];
+    info[1] = (int32_t)(cell_start[ncells] - cell_start[key_hi]);
+  }
+}
+// received column table (record offsets in the sender's numbering) -> offsets into this rank's ghost region
+__global__ void rebase_ghost_table(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t nent, uint32_t base) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nent) out[k] = base + (in[k] - in[0]);
 }
 
 // ---- device-wide exclusive scan (uint32), three small kernels --------------------
@@ -114,6 +150,44 @@ __global__ void scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict
   }
   // out[n] = grand total (cell_start needs ncells + 1 entries)
   if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;
+}
+
+// single block: exclusive scan of up to 1024 * kScanSmallPer elements (in place is fine); one launch instead of three
+constexpr int kScanSmallPer = 32;
+__global__ void __launch_bounds__(1024) scan_small(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int write_total) {
+  __shared__ uint32_t wsum[32];
+  const int per = (int)((n + 1023) / 1024);
+  const int64_t lo = (int64_t)threadIdx.x * per, hi = min(lo + per, n);
+  uint32_t v[kScanSmallPer];
+  uint32_t acc = 0;
+#pragma unroll
+  for (int k = 0; k < kScanSmallPer; ++k) {
+    v[k] = (k < per && lo + k < hi) ? in[lo + k] : 0u;
+    acc += v[k];
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t x = acc;
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x += y;
+  }
+  if (lane == 31) wsum[warp] = x;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = wsum[lane], z = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+      if (lane >= o) z += y;
+    }
+    wsum[lane] = z - w;  // exclusive warp offsets
+  }
+  __syncthreads();
+  uint32_t run = wsum[warp] + x - acc;
+#pragma unroll
+  for (int k = 0; k < kScanSmallPer; ++k) {
+    if (k < per && lo + k < hi) { out[lo + k] = run; run += v[k]; }
+  }
+  if (write_total && threadIdx.x == 1023) out[n] = run;
 }
 
 // ---- LSD radix sort, one 8-bit digit per pass -----------------------------------
@@ -236,7 +310,7 @@ __global__ void scatter_int_by_id(const int32_t* __restrict__ src, int32_t* __re
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[id[i]] = src[i];
 }
-__global__ void gather_int_by_id(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
+__global__ void gather_int_by_id(const int32_t* __restrict__ src, int32_t* dst, const int32_t* id, int64_t n) {  // dst may alias id
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[id[i]];
 }

@@ -316,7 +316,11 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
           const int x = rx + dx, y = (nz > 1) ? ry + dy - 1 : 0;
           if (x < 0 || x >= nx || y < 0 || y >= ((nz > 1) ? ny : 1)) continue;
           const uint32_t row = (nz > 1) ? (uint32_t)(x * ny + y) : (uint32_t)x;
-          const uint32_t js = dv.cell_start[row * F + f0], je = dv.cell_start[row * F + f1 + 1];
+          const uint32_t* cs = dv.cell_start;
+          uint32_t koff = 0;  // ghost columns have their own table, indexed from the column's first cell
+          if (x == dv.ghost_col[0]) { cs = dv.ghost_start[0]; koff = (uint32_t)x * ny * nz; }
+          else if (x == dv.ghost_col[1]) { cs = dv.ghost_start[1]; koff = (uint32_t)x * ny * nz; }
+          const uint32_t js = cs[row * F + f0 - koff], je = cs[row * F + f1 + 1 - koff];
           if (je > js) { seg_start[ns] = js; seg_pref[ns] = C; C += je - js; ++ns; }
         }
       seg_pref[ns] = C;

@@ -169,9 +169,10 @@ CCB_HD void rebuild_shear(const Metric<MILNE>& m, const double* u, double gamma,
                 (gamma * gamma - fuc[2] * fuc[2]);
     shv[3][3] = (shv[0][0] - shv[1][1] - shv[2][2]);
   }
+  const double ig = 1.0 / gamma;
   CCB_UNROLL for (int i = 0; i < 3; ++i) {
     double p = 0.;
-    CCB_UNROLL for (int j = 0; j < 3; ++j) p += -shv[i + 1][j + 1] * fuc[j] / gamma;
+    CCB_UNROLL for (int j = 0; j < 3; ++j) p += -shv[i + 1][j + 1] * fuc[j] * ig;
     shv[0][i + 1] = p;
     shv[i + 1][0] = p;
   }
@@ -184,11 +185,12 @@ CCB_HD void rebuild_diffusion(const Metric<MILNE>& m, const double* u, double ga
   double fu[3] = {0., 0., 0.}, fuc[3];
   CCB_UNROLL for (int i = 0; i < D; ++i) fu[i] = u[i];
   lower_vec3<MILNE>(m, fu, fuc);
+  const double ig = 1.0 / gamma;
   CCB_UNROLL for (int c = 0; c < 3; ++c) {
     double q0 = 0.;
     CCB_UNROLL for (int i = 0; i < 3; ++i) {
       q[c][i + 1] = ext_q[c * 3 + i] * sigma;
-      q0 += -q[c][i + 1] * fuc[i] / gamma;
+      q0 += -q[c][i + 1] * fuc[i] * ig;
     }
     q[c][0] = q0;
   }

@@ -86,7 +86,7 @@ CCB_HD double aT_minv_b(const double a[3], double m[3][3], const double b[3]) {
   const double EPS = 1e-3;
   if (fabs(m[1][1]) < EPS) m[1][1] = (m[1][1] >= 0.0 ? EPS : -EPS);
   if (fabs(m[2][2]) < EPS) m[2][2] = (m[2][2] >= 0.0 ? EPS : -EPS);
-  double y[3] = {b[0], b[1], b[2]};
+  double y[3] = {b[0], b[1], b[2]}, ip[3];
   CCB_UNROLL for (int j = 0; j < 3; ++j) {
     int piv = j;
     double amax = fabs(m[j][j]);
@@ -95,15 +95,16 @@ CCB_HD double aT_minv_b(const double a[3], double m[3][3], const double b[3]) {
       CCB_UNROLL for (int k = 0; k < 3; ++k) { const double tmp = m[j][k]; m[j][k] = m[piv][k]; m[piv][k] = tmp; }
       const double tmp = y[j]; y[j] = y[piv]; y[piv] = tmp;
     }
+    ip[j] = 1.0 / m[j][j];  // one reciprocal per pivot, reused by the back substitution
     CCB_UNROLL for (int i = j + 1; i < 3; ++i) {
-      const double f = m[i][j] / m[j][j];
+      const double f = m[i][j] * ip[j];
       CCB_UNROLL for (int k = j; k < 3; ++k) m[i][k] -= f * m[j][k];
       y[i] -= f * y[j];
     }
   }
-  y[2] = y[2] / m[2][2];
-  y[1] = (y[1] - m[1][2] * y[2]) / m[1][1];
-  y[0] = (y[0] - m[0][1] * y[1] - m[0][2] * y[2]) / m[0][0];
+  y[2] = y[2] * ip[2];
+  y[1] = (y[1] - m[1][2] * y[2]) * ip[1];
+  y[0] = (y[0] - m[0][1] * y[1] - m[0][2] * y[2]) * ip[0];
   return a[0] * y[0] + a[1] * y[1] + a[2] * y[2];
 }
 
@@ -205,51 +206,54 @@ CCB_HD void thermo_from_forward(double T, double muB, double muQ, double muS, co
   const double sT = dentr_dt(H, mode);
   const double sB = hasB ? dentr_dmub(H, mode) : 0.0, sS = hasS ? dentr_dmus(H, mode) : 0.0,
                sQ = hasQ ? dentr_dmuq(H, mode) : 0.0;
+  // Reciprocals of T and of each constrained derivative are formed once (the reference divides ~40 times).
+  const double iT = 1.0 / T, iT2 = iT * iT;
+  const double isT = 1.0 / sT, isB = hasB ? 1.0 / sB : 0.0, isS = hasS ? 1.0 / sS : 0.0, isQ = hasQ ? 1.0 / sQ : 0.0;
   {  // dwds, src/eos.cpp:276-292
     double ct = 0.0;
-    if (hasB) ct += B / sB;
-    if (hasQ) ct += Q / sQ;
-    if (hasS) ct += S / sS;
-    th.dwds = T + s / sT + ct;
+    if (hasB) ct += B * isB;
+    if (hasQ) ct += Q * isQ;
+    if (hasS) ct += S * isS;
+    th.dwds = T + s * isT + ct;
   }
   CCB_UNROLL for (int a = 0; a < 3; ++a) CCB_UNROLL for (int x = 0; x < 4; ++x) th.dalpha[a][x] = 0.0;
   // dalpha_X/ds, src/eos.cpp:336-366
-  th.dalpha[0][0] = -muB / T / T / sT + (hasB ? 1 / T / sB : 0.0);
-  th.dalpha[1][0] = -muS / T / T / sT + (hasS ? 1 / T / sS : 0.0);
-  th.dalpha[2][0] = -muQ / T / T / sT + (hasQ ? 1 / T / sQ : 0.0);
+  th.dalpha[0][0] = -muB * iT2 * isT + (hasB ? iT * isB : 0.0);
+  th.dalpha[1][0] = -muS * iT2 * isT + (hasS ? iT * isS : 0.0);
+  th.dalpha[2][0] = -muQ * iT2 * isT + (hasQ ? iT * isQ : 0.0);
   th.dwdB = muB; th.dwdS = muS; th.dwdQ = muQ;
   if (hasB) {  // src/eos.cpp:294-305, :369-404
-    const double bT = db_dt(H, mode), bB = db_dmub(H, mode);
-    double ct = s / bT + B / bB;
-    const double bQ = hasQ ? db_dmuq(H, mode) : 0.0, bS = hasS ? db_dmus(H, mode) : 0.0;
-    if (hasQ) ct += Q / bQ;
-    if (hasS) ct += S / bS;
+    const double ibT = 1.0 / db_dt(H, mode), ibB = 1.0 / db_dmub(H, mode);
+    double ct = s * ibT + B * ibB;
+    const double ibQ = hasQ ? 1.0 / db_dmuq(H, mode) : 0.0, ibS = hasS ? 1.0 / db_dmus(H, mode) : 0.0;
+    if (hasQ) ct += Q * ibQ;
+    if (hasS) ct += S * ibS;
     th.dwdB = muB + ct;
-    th.dalpha[0][1] = 1 / T / bB - muB / T / T / bT;
-    th.dalpha[1][1] = -muS / T / T / bT + (hasS ? 1 / T / bS : 0.0);
-    th.dalpha[2][1] = -muQ / T / T / bT + (hasQ ? 1 / T / bQ : 0.0);
+    th.dalpha[0][1] = iT * ibB - muB * iT2 * ibT;
+    th.dalpha[1][1] = -muS * iT2 * ibT + (hasS ? iT * ibS : 0.0);
+    th.dalpha[2][1] = -muQ * iT2 * ibT + (hasQ ? iT * ibQ : 0.0);
   }
   if (hasS) {  // src/eos.cpp:307-318, :406-446
-    const double xT = ds_dt(H, mode), xS = ds_dmus(H, mode);
-    double ct = s / xT + S / xS;
-    const double xB = hasB ? ds_dmub(H, mode) : 0.0, xQ = hasQ ? ds_dmuq(H, mode) : 0.0;
-    if (hasB) ct += B / xB;
-    if (hasQ) ct += Q / xQ;
+    const double ixT = 1.0 / ds_dt(H, mode), ixS = 1.0 / ds_dmus(H, mode);
+    double ct = s * ixT + S * ixS;
+    const double ixB = hasB ? 1.0 / ds_dmub(H, mode) : 0.0, ixQ = hasQ ? 1.0 / ds_dmuq(H, mode) : 0.0;
+    if (hasB) ct += B * ixB;
+    if (hasQ) ct += Q * ixQ;
     th.dwdS = muS + ct;
-    th.dalpha[0][2] = -muB / T / T / xT + (hasB ? 1 / T / xB : 0.0);
-    th.dalpha[1][2] = -muS / T / T / xT + 1 / T / xS;
-    th.dalpha[2][2] = -muQ / T / T / xT + (hasQ ? 1 / T / xQ : 0.0);
+    th.dalpha[0][2] = -muB * iT2 * ixT + (hasB ? iT * ixB : 0.0);
+    th.dalpha[1][2] = -muS * iT2 * ixT + iT * ixS;
+    th.dalpha[2][2] = -muQ * iT2 * ixT + (hasQ ? iT * ixQ : 0.0);
   }
   if (hasQ) {  // src/eos.cpp:320-331, :448-488
-    const double xT = dq_dt(H, mode), xQ = dq_dmuq(H, mode);
-    double ct = s / xT + Q / xQ;
-    const double xB = hasB ? dq_dmub(H, mode) : 0.0, xS = hasS ? dq_dmus(H, mode) : 0.0;
-    if (hasB) ct += B / xB;
-    if (hasS) ct += S / xS;
+    const double ixT = 1.0 / dq_dt(H, mode), ixQ = 1.0 / dq_dmuq(H, mode);
+    double ct = s * ixT + Q * ixQ;
+    const double ixB = hasB ? 1.0 / dq_dmub(H, mode) : 0.0, ixS = hasS ? 1.0 / dq_dmus(H, mode) : 0.0;
+    if (hasB) ct += B * ixB;
+    if (hasS) ct += S * ixS;
     th.dwdQ = muQ + ct;
-    th.dalpha[0][3] = -muB / T / T / xT + (hasB ? 1 / T / xB : 0.0);
-    th.dalpha[1][3] = -muS / T / T / xT + (hasS ? 1 / T / xS : 0.0);
-    th.dalpha[2][3] = -muQ / T / T / xT + 1 / T / xQ;
+    th.dalpha[0][3] = -muB * iT2 * ixT + (hasB ? iT * ixB : 0.0);
+    th.dalpha[1][3] = -muS * iT2 * ixT + (hasS ? iT * ixS : 0.0);
+    th.dalpha[2][3] = -muQ * iT2 * ixT + iT * ixQ;
   }
 }
 

@@ -47,6 +47,11 @@ struct DeviceView {
   int32_t* tasks;              // first particle of every (cell, 32-target chunk)
   int32_t* ntasks;
   int32_t* err;                // [0] status code, [1] first offending particle id
+  // slab decomposition: the cell columns (index along x) just outside this rank's slab hold GHOST records,
+  // appended to rec_fields / rec_grad behind the n own records; ghost_start[s][c] .. [c + 1] is the record range
+  // of cell c of that column (c = y * nz + z). ghost_col = -1: no neighbour on that side.
+  int32_t ghost_col[2];
+  const uint32_t* ghost_start[2];
 };
 
 CCB_HD double& col(double* base, int64_t cap, int c, int64_t i) { return base[(int64_t)c * cap + i]; }

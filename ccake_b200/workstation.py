@@ -77,7 +77,52 @@ class SPHWorkstation:
         """SystemState::allocate_cabana_particles for n blank particles."""
         self._check(self._L.ccb_allocate(self._ctx, int(n)))
 
-    def upload_initial_conditions(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None):
+    # -- slab decomposition ------------------------------------------------------
+    def grid_geometry(self):
+        """(min[3], edge[3], ncell[3]) of the neighbour grid (src/system_state.cpp:651-700)."""
+        mn, ed, nc = np.zeros(3), np.zeros(3), (C.c_int32 * 3)()
+        self._check(self._L.ccb_grid_geometry(self._ctx, _dp(mn), _dp(ed), nc))
+        return mn, ed, np.array(list(nc), dtype=np.int64)
+
+    def comm_init_local(self, group=0):
+        """In-process transport between the contexts of one process (each driven by its own thread)."""
+        self._check(self._L.ccb_comm_init_local(self._ctx, int(group)))
+
+    def comm_init_nccl(self):
+        """NCCL transport; the unique id travels through torch.distributed (already initialised by the caller)."""
+        import torch
+        import torch.distributed as dist
+
+        buf = C.create_string_buffer(128)
+        if dist.get_rank() == 0:
+            self._check(self._L.ccb_comm_unique_id(buf))
+        t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.broadcast(t, src=0)
+        self._check(self._L.ccb_comm_init(self._ctx, bytes(t.cpu().tolist())))
+
+    def set_slab(self, col_lo, col_hi):
+        self._check(self._L.ccb_set_slab(self._ctx, int(col_lo), int(col_hi)))
+
+    def migration_counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.ccb_migration_counts(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def get_device_order(self, field):
+        """One field of this rank's particles in the CURRENT device order; pair with get_int_device_order('id')."""
+        fid, w = _capi.FIELDS[field]
+        out = np.empty((self.n_particles, w), dtype=np.float64)
+        self._check(self._L.ccb_get_field_device_order(self._ctx, fid, _dp(out)))
+        return out[:, 0] if w == 1 else out
+
+    def get_int_device_order(self, field):
+        out = np.empty(self.n_particles, dtype=np.int32)
+        self._check(self._L.ccb_get_int_field_device_order(self._ctx, _capi.INT_FIELDS[field], out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def upload_initial_conditions(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None, ids=None):
         """BSQHydro::read_ccake rows + BSQHydro::initialize_hydrodynamics, on the device."""
         r = np.asarray(r, dtype=np.float64)
         n = r.shape[0]
@@ -106,6 +151,10 @@ class SPHWorkstation:
             a = np.ascontiguousarray(a)
             keep.append(a)
             setattr(ic, name, _dp(a))
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int32)
+            keep.append(ids)
+            ic.id = ids.ctypes.data_as(C.POINTER(C.c_int32))
         self._check(self._L.ccb_upload_ic(self._ctx, C.byref(ic)))
 
     def get(self, field):

@@ -35,7 +35,8 @@ typedef enum {
   CCB_ERR_NEG_ENTROPY = 3,  /* reference: exit(EXIT_FAILURE), src/evolver.cpp:437-450 */
   CCB_ERR_EOS_NO_ROOT = 4,  /* reference: exit(404), src/sph_workstation.cpp:1748-1760 */
   CCB_ERR_OUT_OF_GRID = 5,  /* particle left the neighbour grid (reference: undefined behaviour, src/system_state.cpp:636-638) */
-  CCB_ERR_STATE = 6         /* call sequence error (e.g. step before upload) */
+  CCB_ERR_STATE = 6,        /* call sequence error (e.g. step before upload) */
+  CCB_ERR_COMM = 7          /* halo / migration transport failure (NCCL) */
 } ccb_status;
 
 enum { CCB_COORD_HYPERBOLIC = 0, CCB_COORD_CARTESIAN = 1 };
@@ -87,6 +88,7 @@ typedef struct {
   const double* u;
   const double* bulk;
   const double* shv6;
+  const int32_t* id;   /* optional: global particle ids of these rows (slab decomposition); NULL = 0 .. n-1 */
 } ccb_ic;
 
 /* Per-particle fields addressable through ccb_get_field / ccb_set_field.
@@ -170,6 +172,24 @@ double ccb_time(ccb_ctx* ctx);
 int ccb_set_time(ccb_ctx* ctx, double t);
 /* neighbour-grid shape of the last cell build: cells per axis (src/system_state.cpp:651-700) */
 int ccb_grid_shape(ccb_ctx* ctx, int32_t ncell[3]);
+
+/* --- slab decomposition over the GPUs of one box (new: the reference is single-process) ----------------------
+ * One context per GPU / process, config.rank of config.nranks. Rank r owns the particles whose neighbour-grid cell
+ * column along x lies in [col_lo, col_hi) (contiguous, ascending with the rank; the outermost slabs extend to the grid
+ * edge). Every cell build then hands particles that left the slab to rank -+ 1 and appends the arrivals; every
+ * gather is preceded by the exchange of the edge columns' packed records (the 2h-wide halo). Transport: NCCL
+ * send/recv (ccb_comm_init; rank 0 creates the id with ccb_comm_unique_id and the caller broadcasts it), or mailboxes
+ * between contexts of ONE process, each driven by its own host thread (ccb_comm_init_local; used by the single-GPU tests).
+ * Call order: ccb_create, ccb_comm_init*, ccb_set_slab, ccb_upload_ic (own rows + global ids). Host arrays in particle-id
+ * order do not exist across slabs: read fields with the *_device_order getters together with CCB_I_ID. */
+int ccb_comm_unique_id(char id[128]);
+int ccb_comm_init(ccb_ctx* ctx, const char id[128]);
+int ccb_comm_init_local(ccb_ctx* ctx, int group);
+int ccb_set_slab(ccb_ctx* ctx, int32_t col_lo, int32_t col_hi);
+int ccb_grid_geometry(ccb_ctx* ctx, double min[3], double edge[3], int32_t ncell[3]);  /* to choose the column ranges */
+int ccb_migration_counts(ccb_ctx* ctx, int64_t* sent, int64_t* received);              /* running totals */
+int ccb_get_field_device_order(ccb_ctx* ctx, int field, double* host);          /* n x width, current (cell-sorted) order */
+int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host);
 
 /* --- the ten phases of SPHWorkstation::get_time_derivatives (src/sph_workstation.cpp:1543-1583) --- */
 int ccb_build_cells(ccb_ctx* ctx);        /* 01 SystemState::reset_neighbour_list (src/system_state.cpp:651-719) */

@@ -1,0 +1,128 @@
+"""Slab decomposition. CPU: the partition logic (also as a 2-process gloo job, the way the ranks agree on it).
+GPU: 2 and 3 slabs on one GPU through the in-process transport against the single-context run and the reference."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from common import ROOT, charged_settings, gubser_ic, have_ref, make_ref, rel_err, viscous_settings, blob_ic_3d
+
+
+def test_partition_columns_balanced_and_tiling():
+    from ccake_b200 import slabs
+
+    rng = np.random.default_rng(0)
+    x = rng.normal(0.0, 2.0, 100000)
+    ncols = 64
+    cols = slabs.column_of(x, -8.0, 0.25, ncols)
+    for nranks in (1, 2, 3, 8):
+        rg = slabs.partition_columns(cols, ncols, nranks)
+        assert rg[0][0] == 0 and rg[-1][1] == ncols
+        assert all(a[1] == b[0] for a, b in zip(rg, rg[1:])) and all(hi > lo for lo, hi in rg)
+        n = [np.count_nonzero((cols >= lo) & (cols < hi)) for lo, hi in rg]
+        assert sum(n) == x.size and max(n) < 1.35 * x.size / nranks
+
+
+def test_partition_degenerate_cases():
+    from ccake_b200 import slabs
+
+    cols = np.zeros(1000, dtype=np.int64)  # everything in column 0: the other ranks still get (empty) columns
+    rg = slabs.partition_columns(cols, 4, 4)
+    assert rg == [(0, 1), (1, 2), (2, 3), (3, 4)]
+    with pytest.raises(ValueError):
+        slabs.partition_columns(cols, 2, 3)
+    ic = dict(r=np.arange(10.0)[:, None] * np.ones((1, 2)), e=np.arange(10.0), u=None)
+    part = slabs.split_initial_conditions(ic, np.arange(10), (3, 6))
+    assert list(part["id"]) == [3, 4, 5] and part["u"] is None and np.array_equal(part["e"], [3.0, 4.0, 5.0])
+
+
+_GLOO_JOB = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from ccake_b200 import slabs
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(5)
+x = rng.normal(0.0, 1.5, 20000)                      # every rank holds the same IC and derives the same cut
+cols = slabs.column_of(x, -6.0, 0.2, 60)
+rg = slabs.partition_columns(cols, 60, world)
+mine = slabs.split_initial_conditions(dict(r=np.stack([x, x], 1), e=x), cols, rg[rank])
+n = torch.tensor([mine["id"].size], dtype=torch.int64)
+dist.all_reduce(n)
+ids = [None] * world
+dist.all_gather_object(ids, mine["id"].tolist())
+allids = sorted(i for part in ids for i in part)
+assert n.item() == x.size and allids == list(range(x.size)), "slabs must tile the particle set"
+lo = torch.tensor([rg[rank][0]]); his = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(his, torch.tensor([rg[rank][1]], dtype=torch.int64))
+if rank > 0: assert his[rank - 1].item() == rg[rank][0]
+dist.destroy_process_group()
+print("OK", rank)
+"""
+
+
+def test_ranks_agree_on_the_partition_gloo_world2(tmp_path):
+    script = tmp_path / "job.py"
+    script.write_text(_GLOO_JOB % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29617")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29617", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("OK") == 2
+
+
+# ---------------------------------------------------------------------------------------------
+D3 = dict(dim=3, hT=0.5, hEta=0.5, stepx=0.25, stepy=0.25, stepEta=0.25, xmin=-1.5, ymin=-1.5, etamin=-1.5)
+SLAB_CASES = {
+    "viscous_2d": (lambda: viscous_settings(dt=0.02), lambda: gubser_ic(dx=0.1, shear=True)),
+    "charged_2d": (lambda: charged_settings(dt=0.02), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "viscous_3d_cartesian": (lambda: viscous_settings(coordinate_system="cartesian", dt=0.02, **D3), lambda: blob_ic_3d(n_side=14)),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", sorted(SLAB_CASES))
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_slabs_match_single_context_and_reference(case, nranks):
+    """Same physics whatever the number of slabs: every field after 4 RK2 steps (large dt, so that particles do migrate)
+    agrees with the single-context run to rounding and with the reference build to 1e-10 per step; ids stay a permutation."""
+    from ccake_b200 import SPHWorkstation
+    from slab_harness import SlabRun
+
+    mk_s, mk_ic = SLAB_CASES[case]
+    settings, ic = mk_s(), mk_ic()
+    one = SPHWorkstation(settings)
+    one.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    run = SlabRun(settings, ic, nranks)
+    assert sum(run.counts()) == one.n_particles
+    assert rel_err(run.gather("sigma_lab"), one.get("sigma_lab")) < 1e-13
+    assert rel_err(run.gather("extensive"), one.get("extensive")) < 1e-13
+    steps, dt = 4, settings["dt"]
+    for _ in range(steps):
+        one.advance_timestep(dt)
+        run.each(lambda r, w: w.advance_timestep(dt))
+    one.synchronize()
+    run.each(lambda r, w: w.synchronize())
+    assert sum(run.counts()) == one.n_particles
+    ids = np.sort(np.concatenate([w.get_int_device_order("id") for w in run.ws]))
+    assert np.array_equal(ids, np.arange(one.n_particles))
+    for f in ("position", "u", "extensive", "extensive_shv", "extensive_bulk", "sigma_lab", "gradP", "du_dt"):
+        ref = one.get(f)
+        assert rel_err(run.gather(f), ref, max(np.max(np.abs(ref)), 1e-12)) < 1e-12, (case, nranks, f)
+    assert np.array_equal(run.gather_int("btrack"), one.get_int("btrack"))
+    tot1 = one.conservation()
+    totn = run.each(lambda r, w: w.conservation())
+    for k in ("S", "B", "Sq", "Q", "E"):
+        assert abs(totn[0][k] - tot1[k]) <= 1e-11 * max(abs(tot1[k]), 1.0), (k, totn[0][k], tot1[k])
+        assert all(t[k] == totn[0][k] for t in totn)      # every rank holds the same totals
+    if have_ref():
+        sim = make_ref(settings, ic)
+        sim.initialize()
+        for _ in range(steps):
+            sim.advance(dt, 2)
+        assert rel_err(run.gather("u"), sim.get("hydro_vector", "u")) < steps * 1e-10
+        assert rel_err(run.gather("extensive")[:, 0], sim.member("extensive")[:, 0]) < steps * 1e-10
+    moved = [w.migration_counts() for w in run.ws]
+    print(case, nranks, "ranges", run.ranges, "counts", run.counts(), "migrated (out, in)", moved)
