@@ -33,10 +33,16 @@ DEFAULT_WORKLOAD = "config2_viscous_gubser_bsq_2p1d"
 
 
 # ---------------------------------------------------------------------------------------------
-def make_workload(name, scale=1.0):
+def make_workload(name, scale=1.0, ntiles=1):
     """(settings, ic, description). `scale` < 1 shrinks the lattice EXTENT at fixed spacing and smoothing length
-    (same neighbour count per particle): the bounded sample the CPU arms run."""
+    (same neighbour count per particle): the bounded sample the CPU arms run. `ntiles` > 1: that many copies side by
+    side along x (weak scaling: one copy per GPU)."""
     from ccake_b200 import workloads as W
+
+    if ntiles > 1:
+        s, ic, desc = make_workload(name, scale, 1)
+        s, ic = W.tile_along_x(s, ic, ntiles, s["stepx"])
+        return s, ic, desc + " x %d copies along x" % ntiles
 
     if name == "config2_viscous_gubser_bsq_2p1d":
         xmax = 5.0 * scale
@@ -202,10 +208,24 @@ def own_arm(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    settings, ic, desc = make_workload(args.workload, 1.0)
+    settings, ic, desc = make_workload(args.workload, 1.0, world)
     dt = settings["dt"]
     ws = SPHWorkstation(settings, device=local_rank, rank=rank, nranks=world)
-    ws.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    n_global = ic["r"].shape[0]
+    if world > 1:
+        # slab decomposition along x: every rank derives the same cut from the (synthetic) IC and uploads its own rows
+        from ccake_b200 import slabs
+
+        mn, ed, nc = ws.grid_geometry()
+        cols = slabs.column_of(ic["r"][:, 0], mn[0], ed[0], int(nc[0]))
+        ranges = slabs.partition_columns(cols, int(nc[0]), world)
+        part = slabs.split_initial_conditions(ic, cols, ranges[rank])
+        ws.comm_init_nccl()
+        ws.set_slab(*ranges[rank])
+        ws.upload_initial_conditions(part["r"], part["e"], part["rhoB"], part["rhoS"], part["rhoQ"], part["u"], part["bulk"], part["shv6"],
+                                     ids=part["id"])
+    else:
+        ws.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
     n = ws.n_particles
     stream = torch.cuda.ExternalStream(ws.stream, device=local_rank)
     D = int(settings["dim"])
@@ -248,7 +268,7 @@ def own_arm(args, rank, world, local_rank):
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     w = ws.state_width
-    host = torch.empty((w, n), dtype=torch.float64, pin_memory=True).numpy()
+    host = torch.empty(w * (n + n // 4 + 8192), dtype=torch.float64, pin_memory=True).numpy()  # room for arrivals (slabs)
     ws.copy_device_to_host(host)
     for _ in range(2):
         ws.copy_host_to_device(host); ws.advance_timestep(dt); ws.copy_device_to_host(host)
@@ -264,7 +284,7 @@ def own_arm(args, rank, world, local_rank):
     t_host = time.perf_counter() - t_host0
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * t_host))
-    assert np.all(np.isfinite(host))
+    assert np.all(np.isfinite(host[: w * ws.n_particles]))
 
     if rank != 0:
         return
@@ -285,7 +305,8 @@ def own_arm(args, rank, world, local_rank):
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"])
     t_dom = per_kernel[dom]["ms_per_launch"] * 1e-3
     achieved = alg.get(dom, 0) * n / t_dom / 1e9
-    bt = ws.get_int("btrack")
+    n = ws.n_particles
+    bt = ws.get_int_device_order("btrack") if world > 1 else ws.get_int("btrack")
     pairs = float(np.sum(bt[bt > 0])) + n
     flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop(D, sw["using_shear"], sw["using_diffusion"])
     fp64_achieved = pairs * flop_pair / t_dom / 1e12 if dom in ("03_smooth_fields", "09_smooth_gradients") else None
@@ -305,16 +326,16 @@ def own_arm(args, rank, world, local_rank):
                "sample": "%d particles (lattice extent x%.2f at the workload's spacing, smoothing length and neighbour count), 2 RK2 steps "
                          "after 1 warm-up, %.1f s" % (r["n"], args.cpu_scale, r["seconds"])}
 
-    bytes_state = 8 * w * n
+    bytes_state = 8 * w * n_global
     out = {
-        "metric": METRIC, "value": world * n * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "particles_per_gpu": n, "rk_order": 2,
+        "config": {"workload": args.workload, "description": desc, "particles": n_global, "particles_rank0": n, "rk_order": 2,
                    "mean_neighbours": float(np.mean(bt[bt >= 0])),
-                   "parallelism": "single GPU" if world == 1 else "%d independent replicas (slab decomposition not enabled)" % world,
-                   "l2": "no flush: per-step working set %.0f MB of particle columns > 126 MB L2" % (8e-6 * n * 190)},
-        "e2e": {"value": world * n * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
+                   "parallelism": "single GPU" if world == 1 else "%d slabs along x (one copy of the workload per GPU), 2h halo + per-stage migration over NCCL" % world,
+                   "l2": "no flush: per-step working set %.0f MB of particle columns per GPU > 126 MB L2" % (8e-6 * n * 190)},
+        "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                 "d2h_bytes_per_step": bytes_state, "ms_per_step": ms_e2e / args.steps,
                 "api": "copy_host_to_device(pinned state) + advance_timestep + copy_device_to_host via the C ABI"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,

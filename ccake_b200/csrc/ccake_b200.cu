@@ -806,10 +806,15 @@ int ccb_state_width(ccb_ctx* ctx) {
 int ccb_upload_state(ccb_ctx* ctx, const double* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
-  if (ctx->comm) { ctx->err = "ccb_upload_state: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (!host) return CCB_ERR_INVALID;
   ColumnList cl;
   const int w = state_columns(ctx, cl);
+  if (ctx->comm) {  // slab decomposition: device order, the layout ccb_download_state produced (column stride = ccb_n)
+    for (int c = 0; c < w; ++c)
+      CUDA_OK(cudaMemcpyAsync(cl.col[c], host + (size_t)c * ctx->n, sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cells_valid = false;
+    return CCB_OK;
+  }
   CUDA_OK(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(gather_columns_by_id, dim3((unsigned)cdiv(ctx->n, 256), w), 256, ctx->d_stage, cl, ctx->dv.id, ctx->n);
   ctx->cells_valid = false;
@@ -818,10 +823,14 @@ int ccb_upload_state(ccb_ctx* ctx, const double* host) {
 int ccb_download_state(ccb_ctx* ctx, double* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
-  if (ctx->comm) { ctx->err = "ccb_download_state: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (!host) return CCB_ERR_INVALID;
   ColumnList cl;
   const int w = state_columns(ctx, cl);
+  if (ctx->comm) {  // slab decomposition: this rank's particles in device order (ids: ccb_get_int_field_device_order)
+    for (int c = 0; c < w; ++c)
+      CUDA_OK(cudaMemcpyAsync(host + (size_t)c * ctx->n, cl.col[c], sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+    return surface_device_error(ctx);
+  }
   LAUNCH(scatter_columns_by_id, dim3((unsigned)cdiv(ctx->n, 256), w), 256, cl, ctx->d_stage, ctx->dv.id, ctx->n);
   CUDA_OK(cudaMemcpyAsync(host, ctx->d_stage, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   return surface_device_error(ctx);

@@ -56,6 +56,28 @@ def config1_ideal_gubser(dx=0.025, xmax=5.0):
     return settings, ic
 
 
+def tile_along_x(settings, ic, ntiles, dx):
+    """Weak-scaling workload: `ntiles` copies of an IC side by side along x (period = extent + dx, so the lattice
+    spacing is uniform across the seams and neighbouring copies interact through their edge particles), centred on
+    x = 0 because the reference's neighbour grid is symmetric about the origin (src/system_state.cpp:656-692)."""
+    if ntiles == 1:
+        return settings, ic
+    x = ic["r"][:, 0]
+    period = (x.max() - x.min()) + dx
+    shifts = (np.arange(ntiles) - (ntiles - 1) / 2.0) * period
+    out = {}
+    for k, v in ic.items():
+        if v is None:
+            out[k] = None
+        elif k == "r":
+            out[k] = np.concatenate([v + np.array([sh] + [0.0] * (v.shape[1] - 1)) for sh in shifts])
+        else:
+            out[k] = np.concatenate([v] * ntiles)
+    s = dict(settings)
+    s["xmin"] = float(out["r"][:, 0].min())
+    return s, out
+
+
 def config2_viscous_gubser_bsq(dx=0.025, xmax=5.0, seed=7):
     """BASELINE config 2: the settings of input/config_visc_gubser.yaml (h = 0.1, dt = 0.001, eta/s = 0.2 with the
     Gubser relaxation time, conformal EoS at finite mu_B, mu_S, mu_Q, diffusion code path on with kappa = 0,

@@ -176,12 +176,12 @@ class SPHWorkstation:
     def copy_host_to_device(self, state):
         """SystemState::copy_host_to_device of the evolved state: ``state`` is a C-contiguous
         (state_width, n) float64 array in particle-id order (pinned memory for full PCIe speed)."""
-        assert state.dtype == np.float64 and state.flags.c_contiguous and state.shape == (self.state_width, self.n_particles)
+        assert state.dtype == np.float64 and state.flags.c_contiguous and state.size >= self.state_width * self.n_particles
         self._check(self._L.ccb_upload_state(self._ctx, _dp(state)))
 
     def copy_device_to_host(self, out):
         """SystemState::copy_device_to_host of the evolved state into ``out`` (same layout); synchronises."""
-        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape == (self.state_width, self.n_particles)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size >= self.state_width * self.n_particles
         self._check(self._L.ccb_download_state(self._ctx, _dp(out)))
 
     def get_int(self, field):

@@ -163,7 +163,9 @@ int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host);
  * block [column][particle id] of ccb_state_width() columns: position 3, u 3, extensive 4, extensive_bulk 1,
  * extensive_shv 5, extensive_diffusion 9 (only when using_diffusion), Ez 1. One host<->device copy each way
  * (pass pinned memory for full PCIe speed). upload is asynchronous on the context's stream; download
- * synchronises and surfaces device-side errors. */
+ * synchronises and surfaces device-side errors. With a slab decomposition the block holds this rank's ccb_n()
+ * particles in DEVICE order (column stride ccb_n(); ids through ccb_get_int_field_device_order), and an upload must
+ * hand back the block of the preceding download. */
 int ccb_state_width(ccb_ctx* ctx);
 int ccb_upload_state(ccb_ctx* ctx, const double* host);
 int ccb_download_state(ccb_ctx* ctx, double* host);
