@@ -41,9 +41,15 @@ class Config(C.Structure):
         ("conformal_c", C.c_double), ("conformal_T0", C.c_double), ("conformal_muB0", C.c_double),
         ("conformal_muS0", C.c_double), ("conformal_muQ0", C.c_double),
         ("freeze_out_temperature_MeV", C.c_double),
-        ("prohibit_unstable_cs2", C.c_int), ("prohibit_acausal_cs2", C.c_int),
+        ("prohibit_unstable_cs2", C.c_int), ("prohibit_acausal_cs2", C.c_int), ("restrict_mu_T_ratios", C.c_int),
         ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
     ]
+
+
+class EosTable(C.Structure):
+    """``ccb_eos_table``."""
+
+    _fields_ = [("n", C.c_int32 * 4), ("grid", C.POINTER(C.c_double)), ("fields", C.POINTER(C.c_double)), ("normalize_by_T", C.c_int)]
 
 
 class IC(C.Structure):
@@ -65,10 +71,10 @@ _FIELD_NAMES = [
     ("smoothed", 4), ("thermo", 16), ("dalpha", 12), ("bulk", 1), ("shv", 16), ("diffusion", 12), ("transport", 13),
     ("gradP", 3), ("gradE", 3), ("gradBulk", 3), ("gradshear", 3), ("divshear", 3), ("gradV", 9), ("div_qa", 3),
     ("grad_qa", 3), ("grad_alpha", 9), ("du_dt", 3), ("d_extensive_dt", 4), ("d_bulk_dt", 1), ("d_shv_dt", 5),
-    ("d_diffusion_dt", 9), ("theta", 1), ("shv_nabla_u", 1), ("dEz", 1),
+    ("d_diffusion_dt", 9), ("theta", 1), ("shv_nabla_u", 1), ("dEz", 1), ("chiBB", 2),
 ]
 FIELDS = {name: (i, w) for i, (name, w) in enumerate(_FIELD_NAMES)}
-INT_FIELDS = {"id": 0, "btrack": 1, "freeze": 2, "cell": 3}
+INT_FIELDS = {"id": 0, "btrack": 1, "freeze": 2, "cell": 3, "eos": 4}
 PHASE_NAMES = ["01_neighbour_list", "02_gamma_velocity", "03_smooth_fields", "04_thermodynamics",
                "05_08_local_update", "09_smooth_gradients", "10_time_derivatives", "other"]
 
@@ -92,6 +98,9 @@ def lib():
     L.ccb_last_error.restype = C.c_char_p
     L.ccb_field_width.argtypes = [C.c_int]
     L.ccb_allocate.argtypes = [ctx, C.c_int64]
+    L.ccb_set_eos_table.argtypes = [ctx, C.POINTER(EosTable)]
+    L.ccb_load_eos_table_dat.argtypes = [ctx, C.c_char_p, C.c_int]
+    L.ccb_eos_chain_parameters.argtypes = [ctx, dp]
     L.ccb_upload_ic.argtypes = [ctx, C.POINTER(IC)]
     L.ccb_set_field.argtypes = [ctx, C.c_int, dp]
     L.ccb_get_field.argtypes = [ctx, C.c_int, dp]
@@ -139,4 +148,5 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_synchronize", "ccb_reduce", "ccb_kernel_launches", "ccb_profile_enable", "ccb_profile_get",
             "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
             "ccb_measure_dfma_peak", "ccb_comm_unique_id", "ccb_comm_init", "ccb_comm_init_local", "ccb_set_slab",
-            "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order"]
+            "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order",
+            "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters"]

@@ -13,6 +13,7 @@
 
 #include "cells.cuh"
 #include "comm.h"
+#include "eos_table_host.h"
 #include "launchers.h"
 
 using namespace ccb;
@@ -60,6 +61,11 @@ struct ccb_ctx {
   int64_t phase_calls[PH_COUNT];
   KernelNorm kD, k2, k1;
   double efcheck = 0.0;
+  // tabulated EoS: host copy (start-up only), device copies, the fall-back chain
+  std::unique_ptr<ccb::HostTable> table;
+  double *d_hot_s = nullptr, *d_hot_e = nullptr, *d_full = nullptr;
+  ccb::EosChain chain;
+  bool have_table = false;
   int chunk = 64;   // targets per gather task (= threads per CTA): 64 or 128
   int sms = 148;
   // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
@@ -541,8 +547,23 @@ int do_gather_fields(ccb_ctx* ctx) {
 }
 
 int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
-  PhaseTimer pt(ctx, do_eos ? PH_THERMO : PH_LOCAL);
   StageParams sp = make_stage(ctx, 0.0, 0);
+  if (ctx->cfg.eos_type == CCB_EOS_TABLE) {
+    // tabulated EoS: the root search has its own kernel (register-heavy, divergent); the streaming
+    // local update then reads the thermodynamics it stored
+    if (!ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
+    if (do_eos) {
+      PhaseTimer pt(ctx, PH_THERMO);
+      LAUNCHER("eos_chain_stage_kernel", launch_eos_chain_stage(ctx->stream, ctx->dv, ctx->chain));
+    }
+    if (do_local) {
+      PhaseTimer pt(ctx, PH_LOCAL);
+      sp.do_eos = 0; sp.do_local = 1;
+      DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
+    }
+    return CCB_OK;
+  }
+  PhaseTimer pt(ctx, do_eos ? PH_THERMO : PH_LOCAL);
   sp.do_eos = do_eos; sp.do_local = do_local;
   DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
   return CCB_OK;
@@ -599,8 +620,56 @@ int surface_device_error(ccb_ctx* ctx) {
 }
 
 int do_init_particles(ccb_ctx* ctx, const StageParams& sp) {
+  int eos_done = 0;
+  if (ctx->cfg.eos_type == CCB_EOS_TABLE) {
+    if (!ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
+    LAUNCHER("eos_chain_init_kernel", launch_eos_chain_init(ctx->stream, ctx->dv, ctx->chain, ctx->init_tmp, ctx->cfg.input_as_entropy));
+    eos_done = 1;
+  }
   DISPATCH_DM("init_particles_kernel", launch_init_particles, ctx->stream, ctx->dv, sp, ctx->init_tmp, ctx->cfg.input_as_entropy,
-              ctx->cfg.input_initial_shear, ctx->cfg.bulk_from_trace, ctx->efcheck);
+              ctx->cfg.input_initial_shear, ctx->cfg.bulk_from_trace, ctx->efcheck, eos_done);
+  return CCB_OK;
+}
+
+// host table -> device copies + fall-back chain + efcheck
+int install_table(ccb_ctx* ctx, bool normalize_by_T) {
+  HostTable& t = *ctx->table;
+  if (!prepare_table(t, normalize_by_T, ctx->err)) return CCB_ERR_INVALID;
+  std::memset(&ctx->chain, 0, sizeof(ctx->chain));
+  if (!match_fallbacks(t, ctx->cfg.freeze_out_temperature_MeV, ctx->chain, ctx->err)) return CCB_ERR_INVALID;
+  ctx->chain.prohibit_unstable_cs2 = ctx->cfg.prohibit_unstable_cs2;
+  ctx->chain.prohibit_acausal_cs2 = ctx->cfg.prohibit_acausal_cs2;
+  ctx->chain.restrict_mu_T_ratios = ctx->cfg.restrict_mu_T_ratios;
+  const long long nodes = t.nodes();
+  std::vector<double> hot((size_t)nodes * 4);
+  cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
+  ctx->d_hot_s = ctx->d_hot_e = ctx->d_full = nullptr;
+  CUDA_OK(cudaMalloc(&ctx->d_hot_s, sizeof(double) * 4 * nodes));
+  CUDA_OK(cudaMalloc(&ctx->d_hot_e, sizeof(double) * 4 * nodes));
+  CUDA_OK(cudaMalloc(&ctx->d_full, sizeof(double) * TH_N * nodes));
+  for (int pass = 0; pass < 2; ++pass) {
+    for (long long i = 0; i < nodes; ++i) {
+      const double* f = &t.fields[(size_t)i * TH_N];
+      hot[(size_t)i * 4 + 0] = pass ? f[TH_E] : f[TH_S];
+      hot[(size_t)i * 4 + 1] = f[TH_B]; hot[(size_t)i * 4 + 2] = f[TH_SS]; hot[(size_t)i * 4 + 3] = f[TH_Q];
+    }
+    CUDA_OK(cudaMemcpy(pass ? ctx->d_hot_e : ctx->d_hot_s, hot.data(), sizeof(double) * 4 * nodes, cudaMemcpyHostToDevice));
+  }
+  CUDA_OK(cudaMemcpy(ctx->d_full, t.fields.data(), sizeof(double) * TH_N * nodes, cudaMemcpyHostToDevice));
+  // efcheck = e(T_FO, 0, 0, 0) of the default EoS: SPHWorkstation::initialize, src/sph_workstation.cpp:66-81
+  {
+    const TableView hv = host_view(t);
+    const double x[4] = {ctx->cfg.freeze_out_temperature_MeV / kHbarcMeVfm, 0.0, 0.0, 0.0};
+    double r[TH_N];
+    if (!table_full_thermo(hv, x, r)) { ctx->err = "EoS table does not cover the freeze-out temperature"; return CCB_ERR_INVALID; }
+    ctx->efcheck = r[TH_E];
+  }
+  TableView& v = ctx->chain.table;
+  for (int d = 0; d < 4; ++d) { v.n[d] = t.n[d]; v.min[d] = t.min[d]; v.max[d] = t.max[d]; v.delta[d] = t.delta[d]; }
+  v.hot_s = ctx->d_hot_s; v.hot_e = ctx->d_hot_e; v.full = ctx->d_full;
+  ctx->have_table = true;
+  // the host copy was only needed for the matching
+  t.grid.clear(); t.grid.shrink_to_fit(); t.fields.clear(); t.fields.shrink_to_fit();
   return CCB_OK;
 }
 
@@ -627,7 +696,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   *out = ctx;  // handed back even on failure so that ccb_last_error works
   if (cfg->dim != 2 && cfg->dim != 3) { ctx->err = "dim must be 2 or 3"; return CCB_ERR_INVALID; }
   if (cfg->rk_order != 2) { ctx->err = "rk_order must be 2"; return CCB_ERR_INVALID; }
-  if (cfg->eos_type != CCB_EOS_CONFORMAL) { ctx->err = "eos_type: only the conformal EoS is available in this build"; return CCB_ERR_INVALID; }
+  if (cfg->eos_type != CCB_EOS_CONFORMAL && cfg->eos_type != CCB_EOS_TABLE) { ctx->err = "eos_type must be CCB_EOS_CONFORMAL or CCB_EOS_TABLE"; return CCB_ERR_INVALID; }
   if (!(cfg->hT > 0.0)) { ctx->err = "hT must be positive"; return CCB_ERR_INVALID; }
   ctx->D = cfg->dim;
   ctx->milne = cfg->coordinate_system == CCB_COORD_HYPERBOLIC;
@@ -675,6 +744,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
   cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info);
+  cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
   ctx->comm.reset();
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -683,6 +753,38 @@ int ccb_destroy(ccb_ctx* ctx) {
 }
 
 const char* ccb_last_error(ccb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int ccb_set_eos_table(ccb_ctx* ctx, const ccb_eos_table* tb) {
+  if (!ctx || !tb || !tb->grid || !tb->fields) return CCB_ERR_INVALID;
+  if (ctx->cfg.eos_type != CCB_EOS_TABLE) { ctx->err = "ccb_set_eos_table: the context was created with another eos_type"; return CCB_ERR_STATE; }
+  if (!ctx->stream) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
+  ctx->table.reset(new HostTable());
+  long long nodes = 1;
+  for (int d = 0; d < 4; ++d) { if (tb->n[d] < 1) { ctx->err = "table grid sizes must be positive"; return CCB_ERR_INVALID; } ctx->table->n[d] = tb->n[d]; nodes *= tb->n[d]; }
+  ctx->table->grid.assign(tb->grid, tb->grid + nodes * 4);
+  ctx->table->fields.assign(tb->fields, tb->fields + nodes * TH_N);
+  return install_table(ctx, tb->normalize_by_T != 0);
+}
+int ccb_load_eos_table_dat(ccb_ctx* ctx, const char* path, int normalize_by_T) {
+  if (!ctx || !path) return CCB_ERR_INVALID;
+  if (ctx->cfg.eos_type != CCB_EOS_TABLE) { ctx->err = "ccb_load_eos_table_dat: the context was created with another eos_type"; return CCB_ERR_STATE; }
+  if (!ctx->stream) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
+  ctx->table.reset(new HostTable());
+  if (!read_thermo_dat(path, *ctx->table, ctx->err)) return CCB_ERR_INVALID;
+  return install_table(ctx, normalize_by_T != 0);
+}
+int ccb_eos_chain_parameters(ccb_ctx* ctx, double out[18]) {
+  if (!ctx || !out) return CCB_ERR_INVALID;
+  if (!ctx->have_table) { ctx->err = "no table loaded"; return CCB_ERR_STATE; }
+  const AnalyticParams* P[3] = {&ctx->chain.tanh_p, &ctx->chain.conf_p, &ctx->chain.diag_p};
+  int o = 0;
+  for (int k = 0; k < 3; ++k) {
+    out[o++] = P[k]->c; out[o++] = P[k]->T0; out[o++] = P[k]->muB0; out[o++] = P[k]->muS0; out[o++] = P[k]->muQ0;
+    if (k == 0) { out[o++] = P[k]->Tc; out[o++] = P[k]->Ts; }
+  }
+  out[17] = ctx->efcheck;
+  return CCB_OK;
+}
 int64_t ccb_n(ccb_ctx* ctx) { return ctx ? ctx->n : -1; }
 double ccb_time(ccb_ctx* ctx) { return ctx ? ctx->t : 0.0; }
 int ccb_set_time(ccb_ctx* ctx, double t) { if (!ctx) return CCB_ERR_INVALID; ctx->t = t; return CCB_OK; }
@@ -749,8 +851,8 @@ int ccb_set_int_field(ccb_ctx* ctx, int field, const int32_t* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
   if (ctx->comm) { ctx->err = "ccb_set_int_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
-  if (field < CCB_I_BTRACK || field > CCB_I_FREEZE || !host) return CCB_ERR_INVALID;
-  int32_t* dst = field == CCB_I_BTRACK ? ctx->dv.btrack : ctx->dv.freeze;
+  if (!(field == CCB_I_BTRACK || field == CCB_I_FREEZE || field == CCB_I_EOS) || !host) return CCB_ERR_INVALID;
+  int32_t* dst = field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze : ctx->dv.eos_id;
   int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
   CUDA_OK(cudaMemcpyAsync(stage, host, sizeof(int32_t) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
   LAUNCH(gather_int_by_id, cdiv(ctx->n, 256), 256, stage, dst, ctx->dv.id, ctx->n);
@@ -764,7 +866,7 @@ int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host) {
   if (ctx->comm) { ctx->err = "ccb_get_int_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
   const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
-                                                                                                                      : reinterpret_cast<const int32_t*>(ctx->dv.key);
+                       : field == CCB_I_EOS ? ctx->dv.eos_id : reinterpret_cast<const int32_t*>(ctx->dv.key);
   if (field == CCB_I_CELL && !ctx->cells_valid) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
   int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
   LAUNCH(scatter_int_by_id, cdiv(ctx->n, 256), 256, src, stage, ctx->dv.id, ctx->n);
@@ -942,7 +1044,7 @@ int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host) {
   if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
   if (field == CCB_I_CELL && !ctx->cells_valid) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
   const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
-                                                                                                                      : reinterpret_cast<const int32_t*>(ctx->dv.key);
+                       : field == CCB_I_EOS ? ctx->dv.eos_id : reinterpret_cast<const int32_t*>(ctx->dv.key);
   CUDA_OK(cudaMemcpyAsync(host, src, sizeof(int32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return CCB_OK;

@@ -27,9 +27,9 @@ template <> cudaError_t launch_eom_rk<D_, M_>(cudaStream_t s, const DeviceView& 
 }
 template <>
 cudaError_t launch_init_particles<D_, M_>(cudaStream_t s, const DeviceView& dv, const StageParams& sp, const double* tmp,
-                                          int input_as_entropy, int input_initial_shear, int bulk_from_trace, double efcheck) {
+                                          int input_as_entropy, int input_initial_shear, int bulk_from_trace, double efcheck, int eos_done) {
   init_particles_kernel<D_, M_><<<(unsigned)cdiv(dv.n, 128), 128, 0, s>>>(dv, sp, tmp, input_as_entropy, input_initial_shear,
-                                                                          bulk_from_trace, efcheck);
+                                                                          bulk_from_trace, efcheck, eos_done);
   return cudaGetLastError();
 }
 #if CCB_INST_D == 2

@@ -18,7 +18,11 @@ template <int D, bool MILNE> cudaError_t launch_eos_local(cudaStream_t s, const 
 template <int D, bool MILNE> cudaError_t launch_eom_rk(cudaStream_t s, const DeviceView& dv, const StageParams& sp);
 template <int D, bool MILNE>
 cudaError_t launch_init_particles(cudaStream_t s, const DeviceView& dv, const StageParams& sp, const double* tmp,
-                                  int input_as_entropy, int input_initial_shear, int bulk_from_trace, double efcheck);
+                                  int input_as_entropy, int input_initial_shear, int bulk_from_trace, double efcheck, int eos_done);
+struct EosChain;
+// tabulated EoS + fall-back chain (eos_kernels.cuh): phase 04 of a derivative evaluation, and the initial e|s -> (T, mu) location
+cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const EosChain& ch);
+cudaError_t launch_eos_chain_init(cudaStream_t s, const DeviceView& dv, const EosChain& ch, const double* tmp, int input_as_entropy);
 template <bool MILNE>
 cudaError_t launch_reduce_totals(int nblocks, cudaStream_t s, const DeviceView& dv, double t, double* out,
                                  unsigned long long* nfrozen);

@@ -55,7 +55,7 @@ __device__ __forceinline__ void load_thermo(const DeviceView& dv, int64_t i, The
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int x = 0; x < 4; ++x) th.dalpha[a][x] = col(dv.f[CCB_F_DALPHA], dv.cap, a * 4 + x, i);
-  th.chiBB = 0.; th.chiBB0 = 0.;
+  th.chiBB = col(dv.f[CCB_F_CHIBB], dv.cap, 0, i); th.chiBB0 = col(dv.f[CCB_F_CHIBB], dv.cap, 1, i);
 }
 __device__ __forceinline__ void store_thermo(const DeviceView& dv, int64_t i, const Thermo& th) {
   double* T = dv.f[CCB_F_THERMO];
@@ -67,6 +67,7 @@ __device__ __forceinline__ void store_thermo(const DeviceView& dv, int64_t i, co
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int x = 0; x < 4; ++x) col(dv.f[CCB_F_DALPHA], dv.cap, a * 4 + x, i) = th.dalpha[a][x];
+  col(dv.f[CCB_F_CHIBB], dv.cap, 0, i) = th.chiBB; col(dv.f[CCB_F_CHIBB], dv.cap, 1, i) = th.chiBB0;
   col(dv.f[CCB_F_TSEED], dv.cap, 0, i) = th.T; col(dv.f[CCB_F_TSEED], dv.cap, 1, i) = th.muB;
   col(dv.f[CCB_F_TSEED], dv.cap, 2, i) = th.muS; col(dv.f[CCB_F_TSEED], dv.cap, 3, i) = th.muQ;
 }
@@ -303,25 +304,29 @@ __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams 
 // tmp columns (current order): 0 e_or_s, 1 rhoB, 2 rhoS, 3 rhoQ, 4 bulk, 5..9 shv (xx,xy,xeta,yy,yeta)
 template <int D, bool MILNE>
 __global__ void init_particles_kernel(DeviceView dv, StageParams sp, const double* __restrict__ tmp, int input_as_entropy,
-                                      int input_initial_shear, int bulk_from_trace, double efcheck) {
+                                      int input_initial_shear, int bulk_from_trace, double efcheck, int eos_done) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dv.n) return;
   const int64_t cap = dv.cap;
   const double hc = kHbarcGeVfm;
   const double rhoB = tmp[1 * cap + i], rhoS = tmp[2 * cap + i], rhoQ = tmp[3 * cap + i];
-  double T, muB, muS, muQ;
-  bool ok;
   double e_in = 0., s_in = 0.;
-  // SPHWorkstation::initialize_entropy_and_charge_densities, src/sph_workstation.cpp:253-375
-  if (input_as_entropy) { s_in = tmp[i]; ok = conformal_invert_s(sp.conf, s_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
-  else { e_in = tmp[i] / hc; ok = conformal_invert_e(sp.conf, e_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ); }
-  if (!ok) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
-  double r[TH_N];
-  conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
   Thermo th;
-  thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+  // SPHWorkstation::initialize_entropy_and_charge_densities, src/sph_workstation.cpp:253-375
+  if (input_as_entropy) s_in = tmp[i]; else e_in = tmp[i] / hc;
+  if (eos_done) {  // tabulated EoS: eos_chain_init_kernel has already located the particle in the phase diagram
+    load_thermo(dv, i, th);
+  } else {
+    double T, muB, muS, muQ;
+    const bool ok = input_as_entropy ? conformal_invert_s(sp.conf, s_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ)
+                                     : conformal_invert_e(sp.conf, e_in, rhoB, rhoS, rhoQ, T, muB, muS, muQ);
+    if (!ok) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
+    double r[TH_N];
+    conformal_full_thermo(sp.conf, T, muB, muQ, muS, r);
+    thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+    store_thermo(dv, i, th);
+  }
   if (input_as_entropy) e_in = th.e; else s_in = th.s;
-  store_thermo(dv, i, th);
   dv.freeze[i] = (e_in > efcheck && dv.freeze[i] != 4) ? 0 : 4;
   const double sigma = dv.f[CCB_F_SIGMA][i];
   col(dv.f[CCB_F_EXTENSIVE], cap, 0, i) = s_in / sigma;

@@ -20,7 +20,8 @@ static const int kFieldWidth[CCB_F_COUNT] = {
     3, 3, 4, 4, 1, 5, 9, 1, 4,        // position .. tseed (persistent, permuted every stage)
     3, 1, 1, 1, 4, 16, 12, 1, 16, 12, 13,  // v .. transport
     3, 3, 3, 3, 3, 9, 3, 3, 9,        // gradients
-    3, 4, 1, 5, 9, 1, 1, 1};          // time derivatives
+    3, 4, 1, 5, 9, 1, 1, 1,           // time derivatives
+    2};                               // chiBB, chiBB0
 static const int kNumPersistentFields = 9;  // CCB_F_POSITION .. CCB_F_TSEED
 // evolved by the Runge-Kutta update; each keeps a y0 snapshot (reference EvolverCache, include/evolver.h:21-47)
 static const int kEvolvedFields[] = {CCB_F_POSITION, CCB_F_U, CCB_F_EXTENSIVE, CCB_F_EXTENSIVE_BULK,

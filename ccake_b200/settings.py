@@ -27,7 +27,7 @@ DEFAULTS = dict(
     # so a missing key leaves the string "1" -> setup_parameters falls to its "unknown -> default" branch.
     delta_PiPi_mode="default", lambda_Pipi_mode="default", phi1_mode="default", phi3_mode="default",
     diffusionMode="disabled", diffusionRelaxMode="default", C_B=0.0, prohibit_unstable_cs2=True,
-    prohibit_acausal_cs2=True,
+    prohibit_acausal_cs2=True, restrict_mu_T_ratios=False, normalize_by_T=True,
 )
 
 _SHEAR = {"default": 0, "constant": 1, "JakiParam": 2, "LinearMus": 3, "interpolate": 4}
@@ -62,8 +62,8 @@ def _mode(table, value, what):
 def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -> _capi.Config:
     s = dict(DEFAULTS)
     s.update(settings)
-    if s["eos_type"] != "conformal":
-        raise NotImplementedError("eos_type %r: only the conformal EoS is available in this build" % s["eos_type"])
+    if s["eos_type"] not in ("conformal", "table"):
+        raise NotImplementedError("eos_type %r: the conformal and the tabulated EoS are available in this build" % s["eos_type"])
     c = _capi.Config()
     c.dim = int(s["dim"])
     c.coordinate_system = _capi.COORD_CARTESIAN if s["coordinate_system"] == "cartesian" else _capi.COORD_HYPERBOLIC
@@ -101,7 +101,7 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     for a in range(3):
         for b in range(3):
             c.constant_kappa_over_T2[a * 3 + b] = float(s.get("kappa_%d%d" % (a, b), 0.0))
-    c.eos_type = _capi.EOS_CONFORMAL
+    c.eos_type = _capi.EOS_TABLE if s["eos_type"] == "table" else _capi.EOS_CONFORMAL
     # EquationOfState::set_up_chosen_EOSs, src/eos_initialization.cpp:216-231
     Nc, Nf = 3.0, 2.5
     c.conformal_c = math.pi * math.pi * (2.0 * (Nc * Nc - 1.0) + (7.0 / 2.0) * Nc * Nf) / 90.0
@@ -109,6 +109,7 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     c.freeze_out_temperature_MeV = float(s["Freeze_Out_Temperature"])
     c.prohibit_unstable_cs2 = int(bool(s["prohibit_unstable_cs2"]))
     c.prohibit_acausal_cs2 = int(bool(s["prohibit_acausal_cs2"]))
+    c.restrict_mu_T_ratios = int(bool(s["restrict_mu_T_ratios"]))
     c.device, c.rank, c.nranks = int(device), int(rank), int(nranks)
     return c
 
@@ -138,6 +139,7 @@ def from_yaml(path: str) -> dict:
         ("e_cutoff", ("parameters", "energy_cutoff")), ("max_tau", ("parameters", "max_tau")),
         ("eos_type", ("eos", "type")), ("eos_path", ("eos", "path")),
         ("prohibit_unstable_cs2", ("eos", "prohibit_unstable_cs2")), ("prohibit_acausal_cs2", ("eos", "prohibit_acausal_cs2")),
+        ("restrict_mu_T_ratios", ("eos", "restrict_mu_T_ratios")), ("normalize_by_T", ("eos", "normalize_by_T")),
         ("Freeze_Out_Temperature", ("particlization", "T")),
         ("baryon_charge_enabled", ("hydro", "baryon_charge_enabled")),
         ("strange_charge_enabled", ("hydro", "strange_charge_enabled")),

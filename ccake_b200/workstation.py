@@ -43,6 +43,18 @@ class SPHWorkstation:
                 self._L.ccb_destroy(self._ctx)
                 self._ctx = C.c_void_p()
             raise CCAKEError(rc, msg)
+        if self.settings["eos_type"] == "table":
+            # EquationOfState::init -> EoS_table(eos_path, normalize_by_T), src/eos_initialization.cpp:273-279
+            import os
+
+            path = os.path.join(str(self.settings["eos_path"]), "thermo.dat")
+            self._check(self._L.ccb_load_eos_table_dat(self._ctx, path.encode(), int(bool(self.settings["normalize_by_T"]))))
+
+    def eos_chain_parameters(self):
+        """Matched parameters of the fall-back EoSs + efcheck (table runs; EquationOfState::set_up_chosen_EOSs)."""
+        out = np.zeros(18)
+        self._check(self._L.ccb_eos_chain_parameters(self._ctx, _dp(out)))
+        return dict(tanh_conformal=out[0:7], conformal=out[7:12], conformal_diagonal=out[12:17], efcheck=out[17])
 
     # -- plumbing --------------------------------------------------------------
     def _check(self, rc):

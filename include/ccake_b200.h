@@ -66,7 +66,7 @@ typedef struct {
   int eos_type;            /* CCB_EOS_* */
   double conformal_c, conformal_T0, conformal_muB0, conformal_muS0, conformal_muQ0;
   double freeze_out_temperature_MeV;
-  int prohibit_unstable_cs2, prohibit_acausal_cs2;
+  int prohibit_unstable_cs2, prohibit_acausal_cs2, restrict_mu_T_ratios;  /* Settings, include/settings.h:143-147 */
   /* runtime */
   int device;              /* CUDA device ordinal */
   int rank, nranks;        /* slab decomposition (1 process per GPU) */
@@ -131,10 +131,13 @@ typedef enum {
   CCB_F_THETA,             /* 1 */
   CCB_F_SHV_NABLA_U,       /* 1 */
   CCB_F_DEZ,               /* 1  contribution_to_total_dEz */
+  CCB_F_CHIBB,             /* 2  thermo chiBB, chiBB0 (include/thermodynamic_info.h:64-65) */
   CCB_F_COUNT
 } ccb_field;
 
-typedef enum { CCB_I_ID = 0, CCB_I_BTRACK, CCB_I_FREEZE, CCB_I_CELL, CCB_I_COUNT } ccb_int_field;
+/* CCB_I_EOS: index of the equation of state the particle last used, in the order of EquationOfState::chosen_EOSs
+ * (thermodynamic_info::eos_name; table run: 0 table, 1 tanh_conformal, 2 conformal, 3 conformal_diagonal) */
+typedef enum { CCB_I_ID = 0, CCB_I_BTRACK, CCB_I_FREEZE, CCB_I_CELL, CCB_I_EOS, CCB_I_COUNT } ccb_int_field;
 
 typedef struct {
   double S, B, Sq, Q, E, Ez;  /* SystemState::conservation_{entropy,BSQ,energy}, src/system_state.cpp:739-885 */
@@ -146,6 +149,28 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg);   /* SystemState<D>/SPHWor
 int ccb_destroy(ccb_ctx* ctx);
 const char* ccb_last_error(ccb_ctx* ctx);
 int ccb_field_width(int field);
+
+/* --- tabulated equation of state (eos_type = CCB_EOS_TABLE) ------------------------------------------------
+ * The 4-D table of EoS_table / InterpolatorND<4> (src/eos_table.cpp:14-122, src/interpolatorND.cpp:125-226) as the
+ * FILE holds it: grid in MeV, T slowest and muS fastest, 17 fields per node in the order
+ * p s B S Q e cs2 chiBB chiQQ chiSS chiBQ chiBS chiQS chiTB chiTQ chiTS chiTT, dimensionless ratios
+ * (normalize_by_T) or MeV^n. The library applies the constructor's unit conversions, copies the table to the
+ * device (a 4-field "hot" copy for the root search + the full table) and matches the fall-back chain
+ * tanh_conformal -> conformal -> conformal_diagonal to it (EquationOfState::set_up_chosen_EOSs,
+ * src/eos_initialization.cpp:273-455). Must be called after ccb_create and before ccb_allocate / ccb_upload_ic.
+ * The caller keeps ownership of the arrays. */
+typedef struct {
+  int32_t n[4];          /* nodes along T, muB, muQ, muS */
+  const double* grid;    /* nodes x 4, row-major */
+  const double* fields;  /* nodes x 17, row-major */
+  int normalize_by_T;    /* Settings::normalize_by_T */
+} ccb_eos_table;
+int ccb_set_eos_table(ccb_ctx* ctx, const ccb_eos_table* table);
+/* same, reading `<path>` in the reference's thermo.dat text format (InterpolatorND::load_data_from_dat) */
+int ccb_load_eos_table_dat(ccb_ctx* ctx, const char* path, int normalize_by_T);
+/* parameters of the matched fall-back EoSs: out[0..6] tanh_conformal (c, T0, muB0, muS0, muQ0, Tc, Ts), out[7..11]
+ * conformal, out[12..16] conformal_diagonal; out[17] = efcheck (src/sph_workstation.cpp:66-81) */
+int ccb_eos_chain_parameters(ccb_ctx* ctx, double out[18]);
 
 /* --- state in / out ------------------------------------------------------- */
 /* n blank particles (ids 0..n-1); state is then injected with ccb_set_field.

@@ -86,7 +86,7 @@ SETTING_KEYS = frozenset([
     "phi6_mode", "phi7_mode", "input_initial_shear", "zetaMode", "constant_zeta_over_s", "cs2_dependent_zeta_A",
     "cs2_dependent_zeta_p", "bulk_from_trace", "bulkRelaxMode", "modulate_zeta_with_tanh", "delta_PiPi_mode",
     "lambda_Pipi_mode", "phi1_mode", "phi3_mode", "diffusionMode", "diffusionRelaxMode", "print_conservation_status",
-    "prohibit_unstable_cs2", "prohibit_acausal_cs2"])
+    "prohibit_unstable_cs2", "prohibit_acausal_cs2", "restrict_mu_T_ratios"])
 
 
 def available() -> bool:
@@ -125,6 +125,8 @@ def lib():
         L.ccake_ref_neighbours.argtypes = [C.c_void_p, lp, ip, ip, ip]
         L.ccake_ref_totals.argtypes = [C.c_void_p, dp]
         L.ccake_ref_omp_threads.restype = C.c_int
+        L.ccake_ref_eos_names.argtypes = [C.c_void_p, ip]
+        L.ccake_ref_eos_thermo.argtypes = [C.c_void_p, C.c_char_p, C.c_long, dp, dp]
         _lib = L
     return _lib
 
@@ -251,6 +253,22 @@ class RefSim:
         lib().ccake_ref_neighbours(self.h, off.ctypes.data_as(C.POINTER(C.c_long)), idx.ctypes.data_as(ip),
                                    cell.ctypes.data_as(ip), nc.ctypes.data_as(ip))
         return off, idx, cell, nc
+
+    def eos_index(self):
+        """Per particle (id order): which member of the EoS chain it last used (0 table, 1 tanh_conformal,
+        2 conformal, 3 conformal_diagonal; -1 = "default"/unset)."""
+        out = np.full(self.n, -1, dtype=np.int32)
+        lib().ccake_ref_eos_names(self.h, out.ctypes.data_as(C.POINTER(C.c_int)))
+        return out
+
+    def eos_thermo(self, name, points):
+        """EoS_base::get_full_thermo of the named chain member at points (T, muB, muQ, muS) [fm^-1]: n x 17."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros((pts.shape[0], 17))
+        rc = lib().ccake_ref_eos_thermo(self.h, name.encode(), pts.shape[0], _dp(pts), _dp(out))
+        if rc:
+            raise KeyError(name)
+        return out
 
     def totals(self):
         out = np.zeros(6)

@@ -47,6 +47,8 @@ struct RefBase {
   virtual int set_ints(int which, const int* in) = 0;
   virtual long neighbours(long* offsets, int* idx, int* cell_of, int* ncell) = 0;
   virtual int totals(double* out) = 0;
+  virtual int eos_names(int* out) = 0;
+  virtual int eos_thermo(const char* name, long n, const double* points, double* out17) = 0;
 };
 
 template <unsigned int D, template <unsigned int> class TEOM>
@@ -174,6 +176,26 @@ struct Ref : RefBase {
     out[0] = sys->S; out[1] = sys->Btotal; out[2] = sys->Stotal; out[3] = sys->Qtotal; out[4] = sys->E; out[5] = sys->Ez;
     return 0;
   }
+  // thermodynamic_info::eos_name of every particle (host side), as the index in the table run's chain
+  int eos_names(int* out) override {
+    for (size_t i = 0; i < sys->particles.size(); ++i) {
+      const std::string& nm = sys->particles[i].thermo.eos_name;
+      out[sys->particles[i].ID] = nm == "table" ? 0 : nm == "tanh_conformal" ? 1 : nm == "conformal" ? 2 : nm == "conformal_diagonal" ? 3 : -1;
+    }
+    return 0;
+  }
+  // EquationOfState::get_thermodynamics at points (T, muB, muQ, muS) with the named member of the chain; the
+  // workstation's own EquationOfState is private, so an identical one is initialised from the same Settings.
+  std::unique_ptr<EquationOfState> eos_probe;
+  int eos_thermo(const char* name, long n, const double* points, double* out17) override {
+    if (!eos_probe) { eos_probe.reset(new EquationOfState()); eos_probe->set_SettingsPtr(st); eos_probe->init(); }
+    if (!eos_probe->chosen_EOS_map.count(name)) return 1;
+    for (long i = 0; i < n; ++i) {
+      double pt[4] = {points[4 * i], points[4 * i + 1], points[4 * i + 2], points[4 * i + 3]};
+      eos_probe->chosen_EOS_map[name]->get_full_thermo(pt, out17 + 17 * i);
+    }
+    return 0;
+  }
 };
 
 bool to_bool(const std::string& v) { return v == "1" || v == "true" || v == "True"; }
@@ -249,6 +271,7 @@ std::shared_ptr<Settings> parse_settings(const char* kv) {
     else if (k == "print_conservation_status") s->print_conservation_status = to_bool(v);
     else if (k == "prohibit_unstable_cs2") s->prohibit_unstable_cs2 = to_bool(v);
     else if (k == "prohibit_acausal_cs2") s->prohibit_acausal_cs2 = to_bool(v);
+    else if (k == "restrict_mu_T_ratios") s->restrict_mu_T_ratios = to_bool(v);
     else if (k.rfind("kappa_", 0) == 0 && k.size() == 8) s->constant_kappa_over_T2[k[6] - '0'][k[7] - '0'] = std::stod(v);
     else { std::fprintf(stderr, "ccake_ref: unknown setting '%s'\n", k.c_str()); return nullptr; }
   }
@@ -296,6 +319,10 @@ long ccake_ref_neighbours(void* h, long* offsets, int* idx, int* cell_of, int* n
   return static_cast<RefBase*>(h)->neighbours(offsets, idx, cell_of, ncell);
 }
 int ccake_ref_totals(void* h, double* out) { return static_cast<RefBase*>(h)->totals(out); }
+int ccake_ref_eos_names(void* h, int* out) { return static_cast<RefBase*>(h)->eos_names(out); }
+int ccake_ref_eos_thermo(void* h, const char* name, long n, const double* points, double* out17) {
+  return static_cast<RefBase*>(h)->eos_thermo(name, n, points, out17);
+}
 int ccake_ref_omp_threads() { return omp_get_max_threads(); }
 
 }  // extern "C"

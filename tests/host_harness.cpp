@@ -5,6 +5,10 @@
 // them over arrays, so that the arithmetic the CUDA kernels run can be compared with
 // the oracle here, without a GPU. The shipped library never calls these on the host.
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
 
 #include "../ccake_b200/csrc/stage_params.h"
 
@@ -120,5 +124,94 @@ int hh_eom(const ccb_config* cfg, double t, int64_t n, const hh_eom_arrays* A) {
 // kernel values for the golden vectors of unit_tests/kernel_test.cpp
 double hh_kernel(int D, double r, double h) { const KernelNorm k = make_kernel_norm(D, h); return sph_w(k, r); }
 double hh_grad_kernel_factor(int D, double r, double h) { const KernelNorm k = make_kernel_norm(D, h); return sph_gradw_factor(k, r); }
+
+}  // extern "C"
+
+// ---- tabulated EoS + fall-back chain (physics_eos_chain.cuh, eos_table_host.h) on the host -------------------
+#include "../ccake_b200/csrc/eos_table_host.h"
+
+namespace {
+struct HostChain {
+  HostTable table;
+  std::vector<double> hot_s, hot_e;
+  EosChain chain;
+};
+}  // namespace
+
+extern "C" {
+
+void* hh_chain_create(const char* thermo_dat, int normalize_by_T, double freeze_out_T_MeV, int prohibit_unstable_cs2,
+                      int prohibit_acausal_cs2, int restrict_mu_T_ratios) {
+  auto* h = new HostChain();
+  std::string err;
+  std::memset(&h->chain, 0, sizeof(h->chain));
+  if (!read_thermo_dat(thermo_dat, h->table, err) || !prepare_table(h->table, normalize_by_T != 0, err) ||
+      !match_fallbacks(h->table, freeze_out_T_MeV, h->chain, err)) {
+    std::fprintf(stderr, "hh_chain_create: %s\n", err.c_str());
+    delete h;
+    return nullptr;
+  }
+  const long long nodes = h->table.nodes();
+  h->hot_s.resize((size_t)nodes * 4); h->hot_e.resize((size_t)nodes * 4);
+  for (long long i = 0; i < nodes; ++i) {
+    const double* f = &h->table.fields[(size_t)i * TH_N];
+    h->hot_s[4 * i] = f[TH_S]; h->hot_e[4 * i] = f[TH_E];
+    for (int c = 1; c < 4; ++c) { const double v = c == 1 ? f[TH_B] : c == 2 ? f[TH_SS] : f[TH_Q]; h->hot_s[4 * i + c] = v; h->hot_e[4 * i + c] = v; }
+  }
+  h->chain.table = host_view(h->table);
+  h->chain.table.hot_s = h->hot_s.data(); h->chain.table.hot_e = h->hot_e.data();
+  h->chain.prohibit_unstable_cs2 = prohibit_unstable_cs2; h->chain.prohibit_acausal_cs2 = prohibit_acausal_cs2;
+  h->chain.restrict_mu_T_ratios = restrict_mu_T_ratios;
+  return h;
+}
+void hh_chain_destroy(void* h) { delete static_cast<HostChain*>(h); }
+
+// interpolated 17 fields at points x = (T, muB, muQ, muS)
+int hh_chain_table_thermo(void* hv, int64_t n, const double* x, double* r17) {
+  auto* h = static_cast<HostChain*>(hv);
+  for (int64_t i = 0; i < n; ++i) table_full_thermo(h->chain.table, x + 4 * i, r17 + TH_N * i);
+  return 0;
+}
+// forward thermodynamics of chain member k at points x
+int hh_chain_member_thermo(void* hv, int k, int64_t n, const double* x, double* r17) {
+  auto* h = static_cast<HostChain*>(hv);
+  for (int64_t i = 0; i < n; ++i) chain_full_thermo(h->chain, k, x + 4 * i, r17 + TH_N * i);
+  return 0;
+}
+void hh_chain_parameters(void* hv, double* out17) {
+  auto* h = static_cast<HostChain*>(hv);
+  const AnalyticParams* P[3] = {&h->chain.tanh_p, &h->chain.conf_p, &h->chain.diag_p};
+  int o = 0;
+  for (int k = 0; k < 3; ++k) {
+    out17[o++] = P[k]->c; out17[o++] = P[k]->T0; out17[o++] = P[k]->muB0; out17[o++] = P[k]->muS0; out17[o++] = P[k]->muQ0;
+    if (k == 0) { out17[o++] = P[k]->Tc; out17[o++] = P[k]->Ts; }
+  }
+}
+
+// phase 04 per particle: sBSQ[4n] targets, seed[4n] = previous (T, muB, muS, muQ), eos[n] in/out.
+// energy != 0: the initial e -> s location (targets[0] = e in fm^-4), seeds unused.
+int hh_chain_solve(void* hv, int energy, int64_t n, const double* targets, const double* seed, int32_t* eos, double* thermo, double* dalpha,
+                   double* chi) {
+  auto* h = static_cast<HostChain*>(hv);
+  int failures = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    ChainResult res;
+    bool ok;
+    if (energy) ok = chain_s_out(h->chain, targets[4 * i], targets[4 * i + 1], targets[4 * i + 2], targets[4 * i + 3], res);
+    else {
+      const double pos[4] = {seed[4 * i], seed[4 * i + 1], seed[4 * i + 3], seed[4 * i + 2]};
+      ok = chain_update_s(h->chain, eos[i], pos, targets[4 * i], targets[4 * i + 1], targets[4 * i + 2], targets[4 * i + 3], res);
+    }
+    if (!ok) { ++failures; eos[i] = -1; continue; }
+    Thermo th;
+    chain_thermo(h->chain, res, th);
+    const double v[16] = {th.T, th.muB, th.muS, th.muQ, th.e, th.s, th.rhoB, th.rhoS, th.rhoQ, th.p, th.cs2, th.w, th.dwds, th.dwdB, th.dwdS, th.dwdQ};
+    for (int k = 0; k < 16; ++k) thermo[16 * i + k] = v[k];
+    for (int a = 0; a < 3; ++a) for (int x = 0; x < 4; ++x) dalpha[12 * i + a * 4 + x] = th.dalpha[a][x];
+    chi[2 * i] = th.chiBB; chi[2 * i + 1] = th.chiBB0;
+    eos[i] = res.eos;
+  }
+  return failures;
+}
 
 }  // extern "C"

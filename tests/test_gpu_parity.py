@@ -29,6 +29,33 @@ CASES = {
 }
 
 
+_TABLE_DIR = []
+
+
+def _table_dir():
+    """Synthetic thermo.dat (coarse grid), written once per test session; read by the library and by the oracle alike."""
+    if not _TABLE_DIR:
+        import tempfile
+
+        from ccake_b200 import eos_table
+
+        _TABLE_DIR.append(eos_table.ensure_table(tempfile.mkdtemp(prefix="ccb_eos_"), coarse=True))
+    return _TABLE_DIR[0]
+
+
+def _table(**kw):
+    return dict(eos_type="table", eos_path=_table_dir(), normalize_by_T=True, Freeze_Out_Temperature=150.0, **kw)
+
+
+# tabulated EoS (configs 3 and 4 flavour): full 4-D inversion on the table, shear + cs2-dependent bulk
+CASES.update({
+    "table_charged_2d_diffusion": (lambda: charged_settings(**_table()), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "table_neutral_2d_shear_bulk": (lambda: viscous_settings(zetaMode="cs2_dependent", modulate_zeta_with_tanh=True, **_table()),
+                                    lambda: gubser_ic(dx=0.1, shear=True)),
+    "table_charged_3d_milne_bulk": (lambda: charged_settings(zetaMode="cs2_dependent", **dict(D3, **_table())), lambda: blob_ic_3d(n_side=14)),
+})
+
+
 def _make_ws(settings, ic):
     from ccake_b200 import SPHWorkstation
 
@@ -170,6 +197,33 @@ def test_time_steps(pair):
     tot, ref_tot = ws.conservation(), sim.totals()
     for k in ("S", "B", "Sq", "Q", "E", "Ez"):
         assert abs(tot[k] - ref_tot[k]) <= 1e-9 * max(abs(ref_tot[k]), 1.0), (name, k, tot[k], ref_tot[k])
+
+
+def test_table_eos_fallback_chain():
+    """Particles the table does not cover (cold corona, T below its first node) are handed to tanh_conformal, exactly
+    the particles the reference hands over, and the run steps on with the mixed population."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    settings = viscous_settings(**_table())
+    ic = gubser_ic(dx=0.1, shear=True)
+    ic["e"] = ic["e"] * np.where(np.hypot(ic["r"][:, 0], ic["r"][:, 1]) > 1.6, 2e-6, 1.0)
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = _make_ws(settings, ic)
+    ref_eos = sim.eos_index()
+    assert (ref_eos == 1).sum() > 50 and (ref_eos == 0).sum() > 50
+    assert np.array_equal(ws.get_int("eos"), ref_eos)
+    sim.advance(settings["dt"], 2)
+    ws.advance_timestep(settings["dt"])
+    ws.synchronize()
+    assert np.array_equal(ws.get_int("eos"), sim.eos_index())
+    th, th_ref = ws.get("thermo"), ref_thermo16(sim)
+    # the reference's root-finder stops at |s - s_target| < 1e-10 fm^-3 absolute: T of a dilute particle is only
+    # defined to 1e-10 / (ds/dT); compare p and e, which are what the equations of motion consume
+    for k in (4, 9, 11):
+        assert np.max(np.abs(th[:, k] - th_ref[:, k])) < 1e-9 * np.max(np.abs(th_ref[:, k])), k
+    _cmp("fallback", "u", ws.get("u"), sim.get("hydro_vector", "u"), 1e-9)
+    _cmp("fallback", "extensive", ws.get("extensive")[:, 0], sim.member("extensive")[:, 0], 1e-9)
 
 
 def test_long_evolution_ideal_gubser():
