@@ -30,9 +30,32 @@ if ROOT not in sys.path:
 METRIC = "particle_steps_per_s"
 UNIT = "particle-steps/s"
 DEFAULT_WORKLOAD = "config2_viscous_gubser_bsq_2p1d"
+# bounded CPU sample: fraction of the lattice extent (configs 1-4) or of the particle count (config 5) the reference's CPU
+# implementation runs, sized for 10-30 s of host work at the workload's own spacing, smoothing length and neighbour count
+CPU_SCALE = {"config1": 0.25, "config2": 0.25, "config3": 0.07, "config4": 0.1, "config5": 0.1}
 
 
 # ---------------------------------------------------------------------------------------------
+_TABLE = {}
+
+
+def eos_table(as_file):
+    """The synthetic fine-grid table of configs 3 and 4 (ccake_b200/eos_table.py): arrays for the CUDA library
+    (ccb_set_eos_table), a thermo.dat under /tmp for the reference build, which reads files."""
+    from ccake_b200 import eos_table as E
+
+    if "data" not in _TABLE:
+        T_axis, mu_axis = E.default_axes(coarse=False)
+        _TABLE["data"] = E.synthetic_table(T_axis, mu_axis, normalize_by_T=True)
+    if not as_file:
+        return _TABLE["data"]
+    d = os.path.join("/tmp", "ccb_eos_fine_%d" % os.getuid())
+    if not os.path.exists(os.path.join(d, "thermo.dat")):
+        E.write_thermo_dat(d + ".partial", _TABLE["data"])
+        os.replace(d + ".partial", d)
+    return d
+
+
 def make_workload(name, scale=1.0, ntiles=1):
     """(settings, ic, description). `scale` < 1 shrinks the lattice EXTENT at fixed spacing and smoothing length
     (same neighbour count per particle): the bounded sample the CPU arms run. `ntiles` > 1: that many copies side by
@@ -53,6 +76,16 @@ def make_workload(name, scale=1.0, ntiles=1):
         xmax = round(5.0 * scale / 0.025) * 0.025
         s, ic = W.config1_ideal_gubser(dx=0.025, xmax=xmax)
         desc = "ideal Gubser 2+1D, conformal EoS, h=0.4, dx=0.025, |x|,|y|<=%.3f" % xmax
+    elif name.startswith("config3_trento_pbpb_table_2p1d"):
+        n_target = int(float(name.split(":")[1])) if ":" in name else 1_000_000
+        s, ic = W.config3_trento_pbpb(n_target=n_target, window=scale)
+        desc = ("TRENTo-like Pb-Pb 2+1D, tabulated EoS (synthetic 155x19^3 thermo.dat grid, T-only inversion), shear + cs2-dependent "
+                "bulk, h=0.3, dx=%.4f, |x|,|y|<=%.2f" % (s["stepx"], 12.0 * scale))
+    elif name.startswith("config4_milne_bsq_table_3p1d"):
+        n_target = int(float(name.split(":")[1])) if ":" in name else 8_000_000
+        s, ic = W.config4_milne_bsq(n_target=n_target, window=scale)
+        desc = ("3+1D Milne with B,S,Q charges, tabulated EoS (synthetic 155x19^3 grid, full 4-D inversion), shear + bulk + diffusion "
+                "path, h=2d, d=%.4f, central %.0f%% window" % (s["stepx"], 100 * scale))
     elif name.startswith("config5_cartesian_blob_3p1d"):
         n_target = int(float(name.split(":")[1])) if ":" in name else 1_000_000
         s, ic = W.config5_cartesian_blob(n_target=int(n_target * scale))
@@ -132,6 +165,8 @@ def time_reference(workload, scale, steps, warmup):
     if not ref.available():
         raise SystemExit("oracle/_ref/libccake_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
     settings, ic, desc = make_workload(workload, scale)
+    if settings["eos_type"] == "table":
+        settings["eos_path"] = eos_table(as_file=True)
     with stdout_to_stderr():
         keys = ref.SETTING_KEYS
         sim = ref.RefSim({k: v for k, v in settings.items() if k in keys or k.startswith("kappa_")})
@@ -209,6 +244,8 @@ def own_arm(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     settings, ic, desc = make_workload(args.workload, 1.0, world)
+    if settings["eos_type"] == "table":
+        settings["eos_table_data"] = eos_table(as_file=False)
     dt = settings["dt"]
     ws = SPHWorkstation(settings, device=local_rank, rank=rank, nranks=world)
     n_global = ic["r"].shape[0]
@@ -350,10 +387,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
-    ap.add_argument("--cpu-scale", type=float, default=0.25, help="lattice-extent factor of the bounded CPU sample")
+    ap.add_argument("--cpu-scale", type=float, default=None, help="lattice-extent factor of the bounded CPU sample (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    if args.cpu_scale is None:
+        args.cpu_scale = next(v for k, v in CPU_SCALE.items() if args.workload.startswith(k))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -280,6 +280,12 @@ GatherParams make_gather(ccb_ctx* ctx) {
   const double radius = 2 * ctx->cfg.hT;
   gp.rsqr = radius * radius;
   gp.rsqr_f = (float)(gp.rsqr * (1.0 + 1e-4));  // fp32 pre-filter: never misses a true neighbour (gather.cuh)
+  gp.rsqr_edge = gp.rsqr * (1.0 - 1e-12);
+  const CellGrid& g = ctx->grid;
+  gp.fast_axis = (g.nc[2] > 1) ? 2 : 1;
+  gp.fast_min = g.min[gp.fast_axis];
+  gp.fast_rdx = g.rdx[gp.fast_axis];
+  gp.fast_nc = g.nc[gp.fast_axis];
   gp.t = ctx->t;
   gp.milne = ctx->milne ? 1 : 0;
   return gp;

@@ -86,7 +86,7 @@ __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double
 template <int D_, bool FACT>
 struct FieldsPolicy {
   static constexpr int D = D_, REC = REC_F, STRIDE = REC_F_STRIDE;
-  struct Target { double x[3]; };
+  struct Target { double x[3]; int cf; };
   struct Acc { double sig, s, B, S, Q; int cnt; };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_fields; }
   __device__ static void init(Acc& a) { a.sig = a.s = a.B = a.S = a.Q = 0.; a.cnt = 0; }
@@ -99,6 +99,16 @@ struct FieldsPolicy {
     const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = t.x[2] - b1.x;
     const double r2 = dist_sqr_exact(dx, dy, dz);
     if (r2 <= gp.rsqr) {  // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523)
+      // A task scans the cells [fa - 1, fb + 1] of its row, wider than the 3-cell stencil of one target. A source further
+      // than one cell away can only pass the cut-off when it sits EXACTLY on it (cell edge = 2h to rounding, lattice
+      // spacing commensurate with h): the reference's list searches +-1 cell and does not hold it. W = 0 there, so only
+      // the neighbour count is at stake; the rare knife-edge pair re-derives the source's cell to decide.
+      if (r2 >= gp.rsqr_edge) {
+        const double xf = (gp.fast_axis == 2) ? b1.x : b0.y;
+        int cj = (int)floor((xf - gp.fast_min) * gp.fast_rdx);
+        cj = cj < 0 ? 0 : (cj > gp.fast_nc - 1 ? gp.fast_nc - 1 : cj);
+        if (abs(cj - t.cf) > 1) return;
+      }
       ++a.cnt;
       double w;
       if (FACT) {
@@ -148,7 +158,7 @@ template <int D_, bool SHEAR, bool DIFF, bool FACT>
 struct GradPolicy {
   using R = GradRec<D_, DIFF>;
   static constexpr int D = D_, REC = R::REC, STRIDE = R::STRIDE;
-  struct Target { double r[REC]; double x[3]; double inv_sig; };
+  struct Target { double r[REC]; double x[3]; double inv_sig; int cf; };
   struct Acc { double gP[D], gE[D], gB[D], gSh[D], dSh[D], gV[D][D], dq[3], gq[3], gal[D][3]; };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_grad; }
   __device__ static void init(Acc& a) {
@@ -274,6 +284,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   const bool active = i <= last;
   typename P::Target tg;
   P::load_target(rec + (active ? i : first) * P::REC, tg);
+  tg.cf = (int)(dv.key[active ? i : first] % (uint32_t)((g.nc[2] > 1) ? g.nc[2] : g.nc[1]));
   typename P::Acc acc;
   P::init(acc);
 

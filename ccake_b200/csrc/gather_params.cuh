@@ -42,6 +42,9 @@ struct GatherParams {
   KernelNorm k2, k1; // factorised variant: W_2D(r_perp, hT) * W_1D(|d eta|, hEta)
   double rsqr;       // (2 hT)^2: the neighbour cut-off of the reference (src/system_state.cpp:689)
   float rsqr_f;      // the same with a safety margin, for the fp32 pre-filter
+  double rsqr_edge;  // rsqr (1 - 1e-12): pairs at or above it sit on the cut-off (knife edge, see FieldsPolicy::pair)
+  double fast_min, fast_rdx;  // the grid's fastest axis (z for a 3-D grid, y for a 2-D one): cell = floor((x - min) rdx)
+  int fast_axis, fast_nc;
   double t;
   int milne;
 };

@@ -11,7 +11,7 @@
 // One thread per particle, every column is read or written once: HBM-bound.
 #pragma once
 
-#include "gather.cuh"
+#include "gather_params.cuh"
 #include "stage_params.h"
 
 namespace ccb {

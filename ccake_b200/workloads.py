@@ -135,8 +135,113 @@ def config5_cartesian_blob(n_target=1_000_000, sigma=3.0, seed=11):
     return settings, ic
 
 
+def _nucleon_positions(n_nucleons, rng, R=6.62, a=0.546):
+    """Nucleon positions of one nucleus sampled from a Woods-Saxon density (rejection sampling), projected on x-y."""
+    out = np.empty((0, 3))
+    while out.shape[0] < n_nucleons:
+        r = rng.uniform(0.0, R + 8 * a, 4 * n_nucleons)
+        keep = rng.uniform(0.0, 1.0, r.size) * (R + 8 * a) ** 2 < r * r / (1.0 + np.exp((r - R) / a))
+        r = r[keep]
+        ct, ph = rng.uniform(-1.0, 1.0, r.size), rng.uniform(0.0, 2 * math.pi, r.size)
+        st = np.sqrt(1.0 - ct * ct)
+        out = np.concatenate([out, np.stack([r * st * np.cos(ph), r * st * np.sin(ph), r * ct], 1)])
+    return out[:n_nucleons, :2]
+
+
+def trento_like_profile(x, y, seed=12345, impact=0.0, sigma=0.5, e_max=90.0):
+    """Synthetic TRENTo-like Pb-Pb transverse energy-density profile [GeV/fm^3]: the geometric mean (TRENTo p = 0) of the two
+    nuclear thickness functions, each a sum of 208 Gaussians of width `sigma` at Woods-Saxon nucleon positions, normalised
+    to `e_max` at its maximum. x, y: 1-D arrays of lattice coordinates; returns the 2-D array [len(x), len(y)]."""
+    rng = np.random.default_rng(seed)
+    T = []
+    for sign in (-1.0, 1.0):
+        pos = _nucleon_positions(208, rng)
+        pos[:, 0] += sign * impact / 2
+        gx = np.exp(-(x[:, None] - pos[None, :, 0]) ** 2 / (2 * sigma ** 2))   # separable Gaussians: [nx, 208] @ [208, ny]
+        gy = np.exp(-(y[:, None] - pos[None, :, 1]) ** 2 / (2 * sigma ** 2))
+        T.append(gx @ gy.T)
+    e = np.sqrt(T[0] * T[1])
+    return e * (e_max / e.max())
+
+
+_TABLE_COMMON = dict(eos_type="table", normalize_by_T=True, Freeze_Out_Temperature=150.0)
+
+
+def config3_trento_pbpb(n_target=1_000_000, xmax=12.0, window=1.0, seed=12345, dx=None):
+    """BASELINE config 3: TRENTo-like Pb-Pb 2+1D with the settings of input/input_trento.yaml (t0 = 0.6, dt = 0.05,
+    h_T = 0.3, e_cutoff = 0.15 GeV/fm^3, no conserved charges, eta/s = 0.08) plus the cs2-dependent bulk viscosity of
+    include/defaults.h:53-56, on the tabulated EoS (T-only inversion of the 4-D table). `window` < 1 keeps
+    the central |x|, |y| <= window * xmax part of the SAME event at the same spacing (the CPU arms' bounded sample).
+    The lattice spacing is chosen so that ~`n_target` particles survive the cut-off: the area above 0.15 GeV/fm^3 is
+    201.5 fm^2, i.e. 503 650 particles at SURVEY's dx = 0.02 and 1.0e6 at dx = 0.0142 (N_ngb = pi (2h)^2 / dx^2 ~ 5600)."""
+    if dx is None:
+        xc = np.arange(-240, 241) * 0.05
+        area = float((trento_like_profile(xc, xc, seed=seed) > 0.15).sum()) * 0.05 ** 2
+        dx = round(math.sqrt(area / n_target), 4)
+    m = int(round(xmax * window / dx))
+    xs = np.arange(-m, m + 1) * dx
+    e2 = trento_like_profile(xs, xs, seed=seed)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    keep = e2 > 0.15                      # BSQHydro::read_ccake drops rows below e_cutoff (src/BSQHydro.cpp:300-306)
+    x, y, eps = X[keep], Y[keep], e2[keep]
+    lo = -(m * dx)
+    settings = dict(_COMMON, **_TABLE_COMMON, t0=0.6, dt=0.05, hT=0.3, hEta=0.1, stepx=dx, stepy=dx, stepEta=0.1, xmin=lo, ymin=lo,
+                    etamin=-0.1, e_cutoff=0.15, baryon_charge_enabled=False, strange_charge_enabled=False,
+                    electric_charge_enabled=False, etaMode="constant", constant_eta_over_s=0.08, shearRelaxMode="default",
+                    use_vorticity=False, delta_pipi_mode="israel-stewart", tau_pipi_mode="disabled", lambda_piPi_mode="disabled",
+                    phi6_mode="disabled", phi7_mode="disabled", input_initial_shear=False,
+                    zetaMode="cs2_dependent", constant_zeta_over_s=0.005, cs2_dependent_zeta_A=1.67552, cs2_dependent_zeta_p=2.0,
+                    bulk_from_trace=False, bulkRelaxMode="default", modulate_zeta_with_tanh=False,
+                    delta_PiPi_mode="default", lambda_Pipi_mode="default", phi1_mode="default", phi3_mode="default",
+                    diffusionMode="disabled")
+    ic = dict(r=np.stack([x, y], 1), e=eps, u=np.zeros((x.size, 2)), rhoB=None, rhoS=None, rhoQ=None, bulk=None, shv6=None)
+    return settings, ic
+
+
+def config4_milne_bsq(n_target=8_000_000, window=1.0, seed=12345):
+    """BASELINE config 4: 3+1D Milne run with B, S, Q charges on the tabulated EoS (full 4-D inversion), settings of
+    input/input_ampt.yaml (t0 = 1, dt = 0.05, eta/s = 0.12, constant zeta/s = 0.08, diffusion path on with kappa = 0,
+    `source` disabled). Profile: the config-3 transverse event x a plateau (|eta| < 2) with Gaussian wings (sigma = 1);
+    rho_B from forward/backward shifted Gaussians in eta, rho_S = 0, rho_Q = 0.4 rho_B. The lattice spacing d
+    (dx = dy = d fm, d_eta = d) is chosen so that ~`n_target` particles survive the energy cut-off, and h_T = h_eta = 2 d
+    keeps the neighbour count of input_ampt.yaml's h / spacing = 2 (N_ngb ~ 268). `window` < 1: central part of the same
+    event at the same spacing."""
+    # volume above the cut-off measured on a coarse lattice, then the spacing that gives n_target
+    def profile(xs, es):
+        e2 = trento_like_profile(xs, xs, seed=seed)
+        ae = np.abs(es)
+        fe = np.where(ae < 2.0, 1.0, np.exp(-(ae - 2.0) ** 2 / 2.0))
+        return e2[:, :, None] * fe[None, None, :]
+    dc = 0.3
+    xc, ec = np.arange(-40, 41) * dc, np.arange(-20, 21) * dc
+    vol = float((profile(xc, ec) > 0.15).sum()) * dc ** 3
+    d = (vol / n_target) ** (1.0 / 3.0)
+    mx, me = int(round(12.0 * window / d)), int(round(6.0 * window / d))
+    xs, es = np.arange(-mx, mx + 1) * d, np.arange(-me, me + 1) * d
+    e3 = profile(xs, es)
+    keep = e3 > 0.15
+    ix, iy, ie = np.nonzero(keep)
+    x, y, eta, eps = xs[ix], xs[iy], es[ie], e3[keep]
+    nB = 0.15 * (eps / 0.1973269804) ** 0.75 * (np.exp(-(eta - 1.5) ** 2 / 2.0) + np.exp(-(eta + 1.5) ** 2 / 2.0))  # fm^-3
+    settings = dict(_COMMON, **_TABLE_COMMON, dim=3, t0=1.0, dt=0.05, hT=2 * d, hEta=2 * d, stepx=d, stepy=d, stepEta=d,
+                    xmin=-(mx * d), ymin=-(mx * d), etamin=-(me * d), e_cutoff=0.15,
+                    baryon_charge_enabled=True, strange_charge_enabled=True, electric_charge_enabled=True,
+                    etaMode="constant", constant_eta_over_s=0.12, shearRelaxMode="default", use_vorticity=False,
+                    delta_pipi_mode="default", tau_pipi_mode="disabled", lambda_piPi_mode="disabled", phi6_mode="disabled",
+                    phi7_mode="disabled", input_initial_shear=False,
+                    zetaMode="constant", constant_zeta_over_s=0.08, cs2_dependent_zeta_A=1.67552, cs2_dependent_zeta_p=2.0,
+                    bulk_from_trace=False, bulkRelaxMode="default", modulate_zeta_with_tanh=False,
+                    delta_PiPi_mode="israel-stewart", lambda_Pipi_mode="default", phi1_mode="disabled", phi3_mode="disabled",
+                    diffusionMode="constant_over_T2", diffusionRelaxMode="constant_over_T")
+    ic = dict(r=np.stack([x, y, eta], 1), e=eps, u=np.zeros((x.size, 3)), rhoB=nB, rhoS=np.zeros_like(nB), rhoQ=0.4 * nB,
+              bulk=None, shv6=None)
+    return settings, ic
+
+
 WORKLOADS = {
     "config1_ideal_gubser_2p1d": config1_ideal_gubser,
     "config2_viscous_gubser_bsq_2p1d": config2_viscous_gubser_bsq,
+    "config3_trento_pbpb_table_2p1d": config3_trento_pbpb,
+    "config4_milne_bsq_table_3p1d": config4_milne_bsq,
     "config5_cartesian_blob_3p1d": config5_cartesian_blob,
 }

@@ -45,10 +45,22 @@ class SPHWorkstation:
             raise CCAKEError(rc, msg)
         if self.settings["eos_type"] == "table":
             # EquationOfState::init -> EoS_table(eos_path, normalize_by_T), src/eos_initialization.cpp:273-279
-            import os
+            data = self.settings.get("eos_table_data")
+            if data is not None:
+                # the same table handed over as arrays (ccb_set_eos_table): what a host that has already read
+                # thermo.dat / thermo.h5 does; `data` is the dict of ccake_b200.eos_table.synthetic_table
+                tab = _capi.EosTable()
+                grid = np.ascontiguousarray(data["grid"], dtype=np.float64)
+                fields = np.ascontiguousarray(data["fields"], dtype=np.float64)
+                for k in range(4):
+                    tab.n[k] = int(data["sizes"][k])
+                tab.grid, tab.fields, tab.normalize_by_T = _dp(grid), _dp(fields), int(bool(data["normalize_by_T"]))
+                self._check(self._L.ccb_set_eos_table(self._ctx, C.byref(tab)))
+            else:
+                import os
 
-            path = os.path.join(str(self.settings["eos_path"]), "thermo.dat")
-            self._check(self._L.ccb_load_eos_table_dat(self._ctx, path.encode(), int(bool(self.settings["normalize_by_T"]))))
+                path = os.path.join(str(self.settings["eos_path"]), "thermo.dat")
+                self._check(self._L.ccb_load_eos_table_dat(self._ctx, path.encode(), int(bool(self.settings["normalize_by_T"]))))
 
     def eos_chain_parameters(self):
         """Matched parameters of the fall-back EoSs + efcheck (table runs; EquationOfState::set_up_chosen_EOSs)."""

@@ -56,6 +56,22 @@ CASES.update({
 })
 
 
+def _event(which, n_target):
+    """Whole synthetic events of BASELINE configs 3 and 4 (ccake_b200/workloads.py) at test size: every particle from the hot
+    core to the e_cutoff edge, on the coarse table."""
+    from ccake_b200 import workloads as W
+
+    s, ic = (W.config3_trento_pbpb if which == 3 else W.config4_milne_bsq)(n_target=n_target)
+    s["eos_path"] = _table_dir()
+    return s, ic
+
+
+CASES.update({
+    "config3_event_20k": (lambda: _event(3, 20000)[0], lambda: _event(3, 20000)[1]),
+    "config4_event_25k": (lambda: _event(4, 25000)[0], lambda: _event(4, 25000)[1]),
+})
+
+
 def _make_ws(settings, ic):
     from ccake_b200 import SPHWorkstation
 
@@ -201,7 +217,12 @@ def test_time_steps(pair):
 
 def test_table_eos_fallback_chain():
     """Particles the table does not cover (cold corona, T below its first node) are handed to tanh_conformal, exactly
-    the particles the reference hands over, and the run steps on with the mixed population."""
+    the particles the reference hands over, and the run steps on with the mixed population.
+
+    The corona is 2e-6 x the Gubser energy density behind a sharp edge: a dilute particle at the edge is accelerated at
+    du/dt ~ 1e5 fm^-1. The reference's root-finder stops at |s - s_target| < 1e-10 fm^-3 ABSOLUTE (include/rootfinder.h:37),
+    so the enthalpy of a particle with s ~ 1e-5 fm^-3 is only defined to 1e-5 relative and its du/dt ~ gradP / w inherits
+    that: the per-particle tolerance below is the reference's own root tolerance propagated through one step."""
     if not have_ref():
         pytest.skip("oracle/_ref not built")
     settings = viscous_settings(**_table())
@@ -213,17 +234,33 @@ def test_table_eos_fallback_chain():
     ref_eos = sim.eos_index()
     assert (ref_eos == 1).sum() > 50 and (ref_eos == 0).sum() > 50
     assert np.array_equal(ws.get_int("eos"), ref_eos)
+    # one derivative evaluation from identical state: every particle located to the root-finder's tolerance
+    sim.get_time_derivatives()
+    ws.get_time_derivatives()
+    ws.synchronize()
+    assert np.array_equal(ws.get_int("eos"), sim.eos_index())
+    th, th_ref = ws.get("thermo"), ref_thermo16(sim)
+    EPS = 1e-10  # Rootfinder::TOLERANCE
+    assert np.max(np.abs(th[:, 5] - th_ref[:, 5])) < 2 * EPS
+    # de = T ds, dp = s dT = s ds / (ds/dT) <= T ds / 3 ..., dw = de + dp
+    for k in (4, 9, 11):
+        assert np.all(np.abs(th[:, k] - th_ref[:, k]) <= 4 * EPS * th_ref[:, 0] + 1e-10 * np.abs(th_ref[:, k])), k
+    rel_w = 4 * EPS * th_ref[:, 0] / th_ref[:, 11] + 1e-10  # relative uncertainty of the enthalpy = of du/dt
+    du, du_ref = ws.get("du_dt"), sim.get("hydro_vector", "du_dt")
+    acc = np.max(np.abs(du_ref), axis=1)
+    assert np.all(np.max(np.abs(du - du_ref), axis=1) <= 10 * rel_w * acc + 1e-10 * np.max(acc))
+    # a full RK2 step with the mixed population: same hand-overs, u and s within the propagated tolerance
     sim.advance(settings["dt"], 2)
     ws.advance_timestep(settings["dt"])
     ws.synchronize()
     assert np.array_equal(ws.get_int("eos"), sim.eos_index())
-    th, th_ref = ws.get("thermo"), ref_thermo16(sim)
-    # the reference's root-finder stops at |s - s_target| < 1e-10 fm^-3 absolute: T of a dilute particle is only
-    # defined to 1e-10 / (ds/dT); compare p and e, which are what the equations of motion consume
-    for k in (4, 9, 11):
-        assert np.max(np.abs(th[:, k] - th_ref[:, k])) < 1e-9 * np.max(np.abs(th_ref[:, k])), k
-    _cmp("fallback", "u", ws.get("u"), sim.get("hydro_vector", "u"), 1e-9)
-    _cmp("fallback", "extensive", ws.get("extensive")[:, 0], sim.member("extensive")[:, 0], 1e-9)
+    # at the edge the second stage starts from a state already perturbed at that level and du/dt varies by 1e5 across one
+    # smoothing length, so there only a loose bound is meaningful (measured: 1e-4 on u ~ 5)
+    _cmp("fallback", "u", ws.get("u"), sim.get("hydro_vector", "u"), 1e-3)
+    dense = ref_eos == 0  # the table-handled interior away from the edge is untouched by all that
+    inner = dense & (np.hypot(ic["r"][:, 0], ic["r"][:, 1]) < 0.9)
+    _cmp("fallback", "u interior", ws.get("u")[inner], sim.get("hydro_vector", "u")[inner], 1e-10)
+    _cmp("fallback", "extensive interior", ws.get("extensive")[inner, 0], sim.member("extensive")[inner, 0], 1e-10)
 
 
 def test_long_evolution_ideal_gubser():
