@@ -154,44 +154,56 @@ struct FieldsPolicy {
 
 // ------------------------------------------------------------------------------------------
 // smooth_gradients: gradP, gradE, gradBulk, gradV, (gradshear, divshear), (div_qa, grad_qa, grad_alpha)
+//
+// Every sum of src/sph_workstation.cpp:833-984 has the form  sum_b (X_b +- X_a) * c_a * m_b grad_a W_ab  with a target-side
+// factor c_a (sigma_a or 1/sigma_a) and, for gradshear / grad_qa, the extra target-side contraction with v_a. With
+// A_b = m_b grad_a W_ab the target-side quantities factor out of the neighbour loop:
+//     sum_b (X_b +- X_a) c_a A_b  =  c_a ( sum_b X_b A_b  +-  X_a sum_b A_b ).
+// The loop therefore accumulates only MOMENTS of the source quantities against A_b (one FMA each) and sum_b A_b; the
+// target's own record is not needed until the epilogue. Against the reference's per-pair expression this halves the
+// fp64 instructions per pair and frees the 20..36 registers that held the target record. The results differ from the
+// per-pair form by rounding only (the sums are re-associated), far inside the 1e-10 parity bar.
 template <int D_, bool SHEAR, bool DIFF, bool FACT>
 struct GradPolicy {
   using R = GradRec<D_, DIFF>;
   static constexpr int D = D_, REC = R::REC, STRIDE = R::STRIDE;
-  struct Target { double r[REC]; double x[3]; double inv_sig; int cf; };
-  struct Acc { double gP[D], gE[D], gB[D], gSh[D], dSh[D], gV[D][D], dq[3], gq[3], gal[D][3]; };
+  struct Target { double x[3]; double v[D]; int cf; };
+  struct Acc {
+    double sA[D], mP[D], mB[D], mE[D], mV[D][D];
+    double sKv, kS0[D], cSh[D];        // shear (sKv also feeds grad_qa)
+    double kQ0[3], cq[3], mAL[D][3];   // diffusion
+  };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_grad; }
   __device__ static void init(Acc& a) {
+    a.sKv = 0.;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      a.gP[d] = a.gE[d] = a.gB[d] = a.gSh[d] = a.dSh[d] = 0.;
+      a.sA[d] = a.mP[d] = a.mB[d] = a.mE[d] = a.kS0[d] = a.cSh[d] = 0.;
 #pragma unroll
-      for (int e = 0; e < D; ++e) a.gV[d][e] = 0.;
+      for (int e = 0; e < D; ++e) a.mV[d][e] = 0.;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) a.gal[d][c] = 0.;
+      for (int c = 0; c < 3; ++c) a.mAL[d][c] = 0.;
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) a.dq[c] = a.gq[c] = 0.;
+    for (int c = 0; c < 3; ++c) a.kQ0[c] = a.cq[c] = 0.;
   }
   __device__ static void load_target(const double* r, Target& t) {
-    const double2* q = reinterpret_cast<const double2*>(r);
 #pragma unroll
-    for (int k = 0; k < REC / 2; ++k) { const double2 v = __ldg(q + k); t.r[2 * k] = v.x; t.r[2 * k + 1] = v.y; }
-    t.x[0] = t.r[R::X]; t.x[1] = t.r[R::X + 1]; t.x[2] = (D == 3) ? t.r[R::X + (D == 3 ? 2 : 0)] : 0.0;
-    t.inv_sig = 1.0 / t.r[R::SIGLAB];
+    for (int d = 0; d < 3; ++d) t.x[d] = (d < D) ? __ldg(r + R::X + (d < D ? d : 0)) : 0.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) t.v[d] = __ldg(r + R::V + d);
   }
   __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, Acc& a) {
-    const double* ra = t.r;
     const double2 b0 = sb[0];
     double rel[3];
-    rel[0] = ra[R::X] - b0.x; rel[1] = ra[R::X + 1] - b0.y;
+    rel[0] = t.x[0] - b0.x; rel[1] = t.x[1] - b0.y;
     double rb[REC];
     rb[0] = b0.x; rb[1] = b0.y;
     {
       const double2 b1 = sb[1];
       rb[2] = b1.x; rb[3] = b1.y;
     }
-    rel[2] = (D == 3) ? ra[R::X + (D == 3 ? 2 : 0)] - rb[2] : 0.0;
+    rel[2] = (D == 3) ? t.x[2] - rb[2] : 0.0;
     const double r2 = dist_sqr_exact(rel[0], rel[1], rel[2]);
     // outside the neighbour list, or coincident (self): grad W(0) = 0 and every pair term carries grad W
     if (!(r2 <= gp.rsqr) || r2 == 0.0) return;
@@ -199,64 +211,98 @@ struct GradPolicy {
     if (!grad_kernel<D, FACT>(gp, rel, r2, gK)) return;
 #pragma unroll
     for (int k = 2; k < REC / 2; ++k) { const double2 v = sb[k]; rb[2 * k] = v.x; rb[2 * k + 1] = v.y; }
-    const double sig_a = ra[R::SIGLAB];
     const double m_b = rb[R::M];
-    double sK[D];
+    double A[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) sK[d] = (m_b * sig_a) * gK[d];
-    const double cP = rb[R::PT] + ra[R::PT], cB = rb[R::BT] + ra[R::BT];
-    const double mos = m_b * t.inv_sig;
-    const double cE = mos * (rb[R::E] - ra[R::E]);
+    for (int d = 0; d < D; ++d) A[d] = m_b * gK[d];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      a.gP[d] += cP * sK[d];
-      a.gE[d] += cE * gK[d];
-      a.gB[d] += cB * sK[d];
+      a.sA[d] += A[d];
+      a.mP[d] = fma(A[d], rb[R::PT], a.mP[d]);
+      a.mB[d] = fma(A[d], rb[R::BT], a.mB[d]);
+      a.mE[d] = fma(A[d], rb[R::E], a.mE[d]);
 #pragma unroll
-      for (int e = 0; e < D; ++e) a.gV[d][e] += mos * (rb[R::V + e] - ra[R::V + e]) * gK[d];
+      for (int e = 0; e < D; ++e) a.mV[d][e] = fma(A[d], rb[R::V + e], a.mV[d][e]);
     }
-    double Kv = 0.;
+    if (SHEAR || DIFF) {
+      double Kv = 0.;
 #pragma unroll
-    for (int d = 0; d < D; ++d) Kv += sK[d] * ra[R::V + d];
-    if (SHEAR) {
+      for (int d = 0; d < D; ++d) Kv = fma(A[d], t.v[d], Kv);
+      a.sKv += Kv;
+      if (SHEAR) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        a.gSh[d] += Kv * (rb[R::S0 + d] + ra[R::S0 + d]);
-        double x = 0.;
+        for (int d = 0; d < D; ++d) {
+          a.kS0[d] = fma(Kv, rb[R::S0 + d], a.kS0[d]);
 #pragma unroll
-        for (int e = 0; e < D; ++e) x += sK[e] * rb[R::SM + R::sym(d, e)] + sK[e] * ra[R::SM + R::sym(d, e)];
-        a.dSh[d] += x;
+          for (int e = 0; e < D; ++e) a.cSh[d] = fma(A[e], rb[R::SM + R::sym(d, e)], a.cSh[d]);
+        }
+      }
+      if (DIFF) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          a.kQ0[c] = fma(Kv, rb[R::Q0 + c], a.kQ0[c]);
+#pragma unroll
+          for (int d = 0; d < D; ++d) {
+            a.cq[c] = fma(A[d], rb[R::QI + c * D + d], a.cq[c]);
+            a.mAL[d][c] = fma(A[d], rb[R::ALPHA + c], a.mAL[d][c]);
+          }
+        }
+      }
+    }
+  }
+  __device__ static void store(const DeviceView& dv, const GatherParams&, int64_t i, const Acc& a) {
+    // epilogue: the target's own record enters here, once
+    double ra[REC];
+    {
+      const double2* q = reinterpret_cast<const double2*>(dv.rec_grad + i * REC);
+#pragma unroll
+      for (int k = 0; k < REC / 2; ++k) { const double2 v = __ldg(q + k); ra[2 * k] = v.x; ra[2 * k + 1] = v.y; }
+    }
+    const double sig = ra[R::SIGLAB], inv_sig = 1.0 / sig;
+    double gP[3] = {0., 0., 0.}, gE[3] = {0., 0., 0.}, gB[3] = {0., 0., 0.}, gSh[3] = {0., 0., 0.}, dSh[3] = {0., 0., 0.};
+    double gV[3][3] = {{0.}}, gal[3][3] = {{0.}}, dq[3] = {0., 0., 0.}, gq[3] = {0., 0., 0.};
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      gP[d] = sig * (a.mP[d] + ra[R::PT] * a.sA[d]);
+      gB[d] = sig * (a.mB[d] + ra[R::BT] * a.sA[d]);
+      gE[d] = inv_sig * (a.mE[d] - ra[R::E] * a.sA[d]);
+#pragma unroll
+      for (int e = 0; e < D; ++e) gV[d][e] = inv_sig * (a.mV[d][e] - ra[R::V + e] * a.sA[d]);
+      if (SHEAR) {
+        gSh[d] = sig * (a.kS0[d] + ra[R::S0 + d] * a.sKv);
+        double x = a.cSh[d];
+#pragma unroll
+        for (int e = 0; e < D; ++e) x = fma(ra[R::SM + R::sym(d, e)], a.sA[e], x);
+        dSh[d] = sig * x;
+      }
+      if (DIFF) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) gal[d][c] = inv_sig * (a.mAL[d][c] - ra[R::ALPHA + (DIFF ? c : 0)] * a.sA[d]);
       }
     }
     if (DIFF) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        a.gq[c] += Kv * (rb[R::Q0 + c] + ra[R::Q0 + c]);
-        double x = 0.;
+        gq[c] = sig * (a.kQ0[c] + ra[R::Q0 + (DIFF ? c : 0)] * a.sKv);
+        double x = a.cq[c];
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          x += sK[d] * rb[R::QI + c * D + d] + sK[d] * ra[R::QI + c * D + d];
-          a.gal[d][c] += mos * (rb[R::ALPHA + c] - ra[R::ALPHA + c]) * gK[d];
-        }
-        a.dq[c] += x;
+        for (int d = 0; d < D; ++d) x = fma(ra[R::QI + (DIFF ? c * D + d : 0)], a.sA[d], x);
+        dq[c] = sig * x;
       }
     }
-  }
-  __device__ static void store(const DeviceView& dv, const GatherParams&, int64_t i, const Acc& a) {
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-      col(dv.f[CCB_F_GRADP], dv.cap, d, i) = d < D ? a.gP[d < D ? d : 0] : 0.;
-      col(dv.f[CCB_F_GRADE], dv.cap, d, i) = d < D ? a.gE[d < D ? d : 0] : 0.;
-      col(dv.f[CCB_F_GRADBULK], dv.cap, d, i) = d < D ? a.gB[d < D ? d : 0] : 0.;
-      col(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i) = d < D ? a.gSh[d < D ? d : 0] : 0.;
-      col(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i) = d < D ? a.dSh[d < D ? d : 0] : 0.;
+      col(dv.f[CCB_F_GRADP], dv.cap, d, i) = gP[d];
+      col(dv.f[CCB_F_GRADE], dv.cap, d, i) = gE[d];
+      col(dv.f[CCB_F_GRADBULK], dv.cap, d, i) = gB[d];
+      col(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i) = gSh[d];
+      col(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i) = dSh[d];
 #pragma unroll
-      for (int e = 0; e < 3; ++e)
-        col(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i) = (d < D && e < D) ? a.gV[d < D ? d : 0][e < D ? e : 0] : 0.;
+      for (int e = 0; e < 3; ++e) col(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i) = gV[d][e];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) col(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) = d < D ? a.gal[d < D ? d : 0][c] : 0.;
-      col(dv.f[CCB_F_DIV_QA], dv.cap, d, i) = a.dq[d];
-      col(dv.f[CCB_F_GRAD_QA], dv.cap, d, i) = a.gq[d];
+      for (int c = 0; c < 3; ++c) col(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) = gal[d][c];
+      col(dv.f[CCB_F_DIV_QA], dv.cap, d, i) = dq[d];
+      col(dv.f[CCB_F_GRAD_QA], dv.cap, d, i) = gq[d];
     }
   }
 };

@@ -39,7 +39,7 @@ template <>
 cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact, int nt, cudaStream_t s,
                                                 const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
   constexpr int D = CCB_INST_D;
-#define CCB_GG(S, F, X) return launch_nt<GradPolicy<D, S, F, X>, 5, 3>(nt, s, dv, g, gp)
+#define CCB_GG(S, F, X) return launch_nt<GradPolicy<D, S, F, X>, 8, 4>(nt, s, dv, g, gp)
   if (D == 3 && fact) {
     if (shear) { if (diff) CCB_GG(true, true, (D == 3)); else CCB_GG(true, false, (D == 3)); }
     else { if (diff) CCB_GG(false, true, (D == 3)); else CCB_GG(false, false, (D == 3)); }

@@ -202,7 +202,9 @@ def config4_milne_bsq(n_target=8_000_000, window=1.0, seed=12345):
     """BASELINE config 4: 3+1D Milne run with B, S, Q charges on the tabulated EoS (full 4-D inversion), settings of
     input/input_ampt.yaml (t0 = 1, dt = 0.05, eta/s = 0.12, constant zeta/s = 0.08, diffusion path on with kappa = 0,
     `source` disabled). Profile: the config-3 transverse event x a plateau (|eta| < 2) with Gaussian wings (sigma = 1);
-    rho_B from forward/backward shifted Gaussians in eta, rho_S = 0, rho_Q = 0.4 rho_B. The lattice spacing d
+    rho_B from forward/backward shifted Gaussians in eta, rho_Q = 0.4 rho_B, and a sign-changing strangeness density
+    rho_S = 0.1 rho_B sin(0.7 x + 0.3) (net ~ 0; SURVEY's rho_S = 0 EXACTLY makes the reference's own output depend on
+    round-off: EquationOfState::dwdS switches on |S| > 1e-25 evaluated at the root-finder's iterate, src/eos.cpp:307-318). The lattice spacing d
     (dx = dy = d fm, d_eta = d) is chosen so that ~`n_target` particles survive the energy cut-off, and h_T = h_eta = 2 d
     keeps the neighbour count of input_ampt.yaml's h / spacing = 2 (N_ngb ~ 268). `window` < 1: central part of the same
     event at the same spacing."""
@@ -233,7 +235,7 @@ def config4_milne_bsq(n_target=8_000_000, window=1.0, seed=12345):
                     bulk_from_trace=False, bulkRelaxMode="default", modulate_zeta_with_tanh=False,
                     delta_PiPi_mode="israel-stewart", lambda_Pipi_mode="default", phi1_mode="disabled", phi3_mode="disabled",
                     diffusionMode="constant_over_T2", diffusionRelaxMode="constant_over_T")
-    ic = dict(r=np.stack([x, y, eta], 1), e=eps, u=np.zeros((x.size, 3)), rhoB=nB, rhoS=np.zeros_like(nB), rhoQ=0.4 * nB,
+    ic = dict(r=np.stack([x, y, eta], 1), e=eps, u=np.zeros((x.size, 3)), rhoB=nB, rhoS=0.1 * nB * np.sin(0.7 * x + 0.3), rhoQ=0.4 * nB,
               bulk=None, shv6=None)
     return settings, ic
 
