@@ -720,14 +720,11 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   ctx->dv.ghost_col[0] = ctx->dv.ghost_col[1] = -1;
   ctx->dv.ghost_start[0] = ctx->dv.ghost_start[1] = nullptr;
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, cfg->device);
-  {  // expected particles per neighbour cell from the IC lattice spacing: dense cells get 128-target tasks
-    double ppc = 0.0;
-    if (cfg->stepx > 0 && cfg->stepy > 0) {
-      ppc = (2 * cfg->hT / cfg->stepx) * (2 * cfg->hT / cfg->stepy);
-      if (cfg->dim == 3) ppc = cfg->stepEta > 0 ? ppc * (2 * cfg->hT / cfg->stepEta) : 0.0;
-    }
-    ctx->chunk = ppc >= 96.0 ? 128 : 64;
-    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = v; }  // tuning override
+  {  // gather launch shape: 128 targets per task, 64 source records per shared-memory tile (measured best on every
+     // BASELINE config, profiles/README.md r01c); environment overrides are for tuning runs only
+    ctx->chunk = 128;
+    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = v; }
+    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64 || v == 128) ctx->chunk += 1000 * v; }
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);

@@ -30,7 +30,7 @@
 
 namespace ccb {
 
-constexpr int kGatherTile = 128;  // source records per shared-memory tile
+constexpr int kGatherTile = 64;  // source records per shared-memory tile (default)
 
 // Exactly the predicate of the neighbour list: dist_sqr = dx*dx + dy*dy + dz*dz, no FMA contraction.
 __device__ __forceinline__ double dist_sqr_exact(double dx, double dy, double dz) {
@@ -94,36 +94,44 @@ struct FieldsPolicy {
     const double2 a = __ldg(reinterpret_cast<const double2*>(r)), b = __ldg(reinterpret_cast<const double2*>(r) + 1);
     t.x[0] = a.x; t.x[1] = a.y; t.x[2] = b.x;
   }
-  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, Acc& a) {
+  // A pair term in two halves:
+  //   prep : exact fp64 predicate + kernel value; returns whether the pair is in the neighbour list
+  //   accum: the sums
+  struct Prep { double w; int hit; };
+  __device__ static bool prep(const GatherParams& gp, const Target& t, const double2* sb, bool valid, Prep& p) {
     const double2 b0 = sb[0], b1 = sb[1];
     const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = t.x[2] - b1.x;
     const double r2 = dist_sqr_exact(dx, dy, dz);
-    if (r2 <= gp.rsqr) {  // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523)
-      // A task scans the cells [fa - 1, fb + 1] of its row, wider than the 3-cell stencil of one target. A source further
-      // than one cell away can only pass the cut-off when it sits EXACTLY on it (cell edge = 2h to rounding, lattice
-      // spacing commensurate with h): the reference's list searches +-1 cell and does not hold it. W = 0 there, so only
-      // the neighbour count is at stake; the rare knife-edge pair re-derives the source's cell to decide.
-      if (r2 >= gp.rsqr_edge) {
-        const double xf = (gp.fast_axis == 2) ? b1.x : b0.y;
-        int cj = (int)floor((xf - gp.fast_min) * gp.fast_rdx);
-        cj = cj < 0 ? 0 : (cj > gp.fast_nc - 1 ? gp.fast_nc - 1 : cj);
-        if (abs(cj - t.cf) > 1) return;
-      }
-      ++a.cnt;
-      double w;
-      if (FACT) {
-        const double rp = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
-        w = sph_w(gp.k2, rp) * sph_w(gp.k1, fabs(dz));
-      } else {
-        w = sph_w_fast(gp.kD, sqrt(r2));
-      }
-      const double2 b2 = sb[2], b3 = sb[3];
-      a.sig += b1.y * w;
-      a.s += b2.x * w;
-      a.B += b2.y * w;
-      a.S += b3.x * w;
-      a.Q += b3.y * w;
+    bool in = valid && r2 <= gp.rsqr;  // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523)
+    // A task scans the cells [fa - 1, fb + 1] of its row, wider than the 3-cell stencil of one target. A source further
+    // than one cell away can only pass the cut-off when it sits EXACTLY on it (cell edge = 2h to rounding, lattice
+    // spacing commensurate with h): the reference's list searches +-1 cell and does not hold it. W = 0 there, so only
+    // the neighbour count is at stake; the rare knife-edge pair re-derives the source's cell to decide.
+    if (in && r2 >= gp.rsqr_edge) {
+      const double xf = (gp.fast_axis == 2) ? b1.x : b0.y;
+      int cj = (int)floor((xf - gp.fast_min) * gp.fast_rdx);
+      cj = cj < 0 ? 0 : (cj > gp.fast_nc - 1 ? gp.fast_nc - 1 : cj);
+      if (abs(cj - t.cf) > 1) in = false;
     }
+    double w;
+    if (FACT) {
+      const double rp = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+      w = sph_w(gp.k2, rp) * sph_w(gp.k1, fabs(dz));
+    } else {
+      w = sph_w_fast(gp.kD, sqrt(r2));
+    }
+    p.w = in ? w : 0.0;
+    p.hit = in ? 1 : 0;
+    return in;
+  }
+  __device__ static void accum(const double2* sb, const Prep& p, Acc& a) {
+    const double2 b1 = sb[1], b2 = sb[2], b3 = sb[3];
+    a.cnt += p.hit;
+    a.sig += b1.y * p.w;
+    a.s += b2.x * p.w;
+    a.B += b2.y * p.w;
+    a.S += b3.x * p.w;
+    a.Q += b3.y * p.w;
   }
   __device__ static void store(const DeviceView& dv, const GatherParams& gp, int64_t i, const Acc& a) {
     const double gamma = dv.f[CCB_F_GAMMA][i];
@@ -168,6 +176,8 @@ struct GradPolicy {
   using R = GradRec<D_, DIFF>;
   static constexpr int D = D_, REC = R::REC, STRIDE = R::STRIDE;
   struct Target { double x[3]; double v[D]; int cf; };
+  // fp64 accumulators live across the neighbour loop: decides the register budget of the launch (inst_gather.cu)
+  static constexpr int NACC = 4 * D + D * D + ((SHEAR || DIFF) ? 1 : 0) + (SHEAR ? 2 * D : 0) + (DIFF ? 6 + 3 * D : 0);
   struct Acc {
     double sA[D], mP[D], mB[D], mE[D], mV[D][D];
     double sKv, kS0[D], cSh[D];        // shear (sKv also feeds grad_qa)
@@ -193,61 +203,89 @@ struct GradPolicy {
 #pragma unroll
     for (int d = 0; d < D; ++d) t.v[d] = __ldg(r + R::V + d);
   }
-  __device__ static void pair(const GatherParams& gp, const Target& t, const double2* sb, Acc& a) {
-    const double2 b0 = sb[0];
+  // one entry `val` of the source record (index idx, a compile-time constant after unrolling) -> the moments it feeds
+  __device__ static __forceinline__ void consume(int idx, double val, const double* A, double Kv, Acc& a) {
+    if (idx == R::PT) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) a.mP[d] = fma(A[d], val, a.mP[d]);
+    } else if (idx == R::BT) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) a.mB[d] = fma(A[d], val, a.mB[d]);
+    } else if (idx == R::E) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) a.mE[d] = fma(A[d], val, a.mE[d]);
+    } else if (idx >= R::V && idx < R::V + D) {
+#pragma unroll
+      for (int e = 0; e < D; ++e)
+        if (e == idx - R::V) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) a.mV[d][e] = fma(A[d], val, a.mV[d][e]);
+        }
+    } else if (SHEAR && idx >= R::S0 && idx < R::S0 + D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        if (d == idx - R::S0) a.kS0[d] = fma(Kv, val, a.kS0[d]);
+    } else if (SHEAR && idx >= R::SM && idx < R::SM + R::NSM) {
+      // pi^{de} / sigma^2 with d <= e feeds divshear_d (with A_e) and, off the diagonal, divshear_e (with A_d)
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int e = d; e < D; ++e)
+          if (R::sym(d, e) == idx - R::SM) {
+            a.cSh[d] = fma(A[e], val, a.cSh[d]);
+            if (e != d) a.cSh[e] = fma(A[d], val, a.cSh[e]);
+          }
+    } else if (DIFF && idx >= R::ALPHA && idx < R::ALPHA + 3) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (c == idx - R::ALPHA) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) a.mAL[d][c] = fma(A[d], val, a.mAL[d][c]);
+        }
+    } else if (DIFF && idx >= R::Q0 && idx < R::Q0 + 3) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        if (c == idx - R::Q0) a.kQ0[c] = fma(Kv, val, a.kQ0[c]);
+    } else if (DIFF && idx >= R::QI && idx < R::QI + 3 * D) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+          if (c * D + d == idx - R::QI) a.cq[c] = fma(A[d], val, a.cq[c]);
+    }
+  }
+  struct Prep { double A[D], Kv; };
+  // exact predicate + A_b = m_b grad_a W_ab (zero for a pair that is not in the neighbour list, or `valid` = false)
+  __device__ static bool prep(const GatherParams& gp, const Target& t, const double2* sb, bool valid, Prep& p) {
+    const double2 b0 = sb[0], b1 = sb[1];
     double rel[3];
     rel[0] = t.x[0] - b0.x; rel[1] = t.x[1] - b0.y;
-    double rb[REC];
-    rb[0] = b0.x; rb[1] = b0.y;
-    {
-      const double2 b1 = sb[1];
-      rb[2] = b1.x; rb[3] = b1.y;
-    }
-    rel[2] = (D == 3) ? t.x[2] - rb[2] : 0.0;
+    rel[2] = (D == 3) ? t.x[2] - b1.x : 0.0;
     const double r2 = dist_sqr_exact(rel[0], rel[1], rel[2]);
     // outside the neighbour list, or coincident (self): grad W(0) = 0 and every pair term carries grad W
-    if (!(r2 <= gp.rsqr) || r2 == 0.0) return;
+    const bool in = valid && (r2 <= gp.rsqr) && r2 != 0.0;
     double gK[D];
-    if (!grad_kernel<D, FACT>(gp, rel, r2, gK)) return;
-#pragma unroll
-    for (int k = 2; k < REC / 2; ++k) { const double2 v = sb[k]; rb[2 * k] = v.x; rb[2 * k + 1] = v.y; }
-    const double m_b = rb[R::M];
-    double A[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) A[d] = m_b * gK[d];
+    grad_kernel<D, FACT>(gp, rel, in ? r2 : gp.rsqr, gK);
+    const double m_b = (R::M == 2) ? b1.x : b1.y;
+    p.Kv = 0.;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-      a.sA[d] += A[d];
-      a.mP[d] = fma(A[d], rb[R::PT], a.mP[d]);
-      a.mB[d] = fma(A[d], rb[R::BT], a.mB[d]);
-      a.mE[d] = fma(A[d], rb[R::E], a.mE[d]);
-#pragma unroll
-      for (int e = 0; e < D; ++e) a.mV[d][e] = fma(A[d], rb[R::V + e], a.mV[d][e]);
+      p.A[d] = in ? m_b * gK[d] : 0.0;
+      p.Kv = fma(p.A[d], t.v[d], p.Kv);
     }
-    if (SHEAR || DIFF) {
-      double Kv = 0.;
+    return in;
+  }
+  // the record is consumed 16 bytes at a time, in layout order: no more than one chunk is live at any point
+  __device__ static void accum(const double2* sb, const Prep& p, Acc& a) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) Kv = fma(A[d], t.v[d], Kv);
-      a.sKv += Kv;
-      if (SHEAR) {
+    for (int d = 0; d < D; ++d) a.sA[d] += p.A[d];
+    if (SHEAR || DIFF) a.sKv += p.Kv;
+    if (R::M == 2) consume(3, sb[1].y, p.A, p.Kv, a);
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          a.kS0[d] = fma(Kv, rb[R::S0 + d], a.kS0[d]);
-#pragma unroll
-          for (int e = 0; e < D; ++e) a.cSh[d] = fma(A[e], rb[R::SM + R::sym(d, e)], a.cSh[d]);
-        }
-      }
-      if (DIFF) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          a.kQ0[c] = fma(Kv, rb[R::Q0 + c], a.kQ0[c]);
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            a.cq[c] = fma(A[d], rb[R::QI + c * D + d], a.cq[c]);
-            a.mAL[d][c] = fma(A[d], rb[R::ALPHA + c], a.mAL[d][c]);
-          }
-        }
-      }
+    for (int k = 2; k < REC / 2; ++k) {
+      const double2 v = sb[k];
+      consume(2 * k, v.x, p.A, p.Kv, a);
+      consume(2 * k + 1, v.y, p.A, p.Kv, a);
     }
   }
   __device__ static void store(const DeviceView& dv, const GatherParams&, int64_t i, const Acc& a) {
@@ -312,9 +350,9 @@ struct GradPolicy {
 // register allocation is bounded for.
 constexpr int kMaxSeg = 9;
 
-template <class P, int NT, int MINB>
+template <class P, int NT, int MINB, int TILE = kGatherTile>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
-  constexpr int D = P::D, TILE = kGatherTile, NW = TILE / 32, CH = P::REC / 2, RS2 = P::STRIDE / 2;
+  constexpr int D = P::D, NW = TILE / 32, CH = P::REC / 2, RS2 = P::STRIDE / 2;
   __shared__ __align__(16) double2 srec[TILE * RS2];
   __shared__ __align__(16) float spos[3][TILE];
   __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
@@ -429,7 +467,8 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
         }
         m[w] = in_pass ? mw : 0u;
       }
-      // ---- phase 2: every lane walks its own hits
+      // ---- phase 2: every lane walks its own hits (a software-pipelined, branch-free variant of this loop measured
+      // 5-10 % slower: the loop is bound by shared-memory gather bandwidth, not by per-warp latency)
       int mine = 0;
 #pragma unroll
       for (int w = 0; w < NW; ++w) mine += __popc(m[w]);
@@ -446,7 +485,8 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
 #pragma unroll
           for (int w = 0; w < NW; ++w)
             if (base == w * 32) m[w] ^= low;
-          P::pair(gp, tg, srec + j * RS2, acc);
+          typename P::Prep pp;
+          if (P::prep(gp, tg, srec + j * RS2, true, pp)) P::accum(srec + j * RS2, pp, acc);
         }
       }
     }

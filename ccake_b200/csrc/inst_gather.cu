@@ -10,20 +10,25 @@ namespace ccb {
 
 namespace {
 // one CTA per task of NT consecutive sorted particles; the hardware block scheduler balances the SMs
-template <class P, int NT, int MINB>
+template <class P, int NT, int MINB, int TILE>
 cudaError_t launch(cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(gather_kernel<P, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gather_kernel<P, NT, MINB, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
   const unsigned ntasks = (unsigned)((dv.n + NT - 1) / NT);
-  gather_kernel<P, NT, MINB><<<ntasks, NT, 0, s>>>(dv, g, gp);
+  gather_kernel<P, NT, MINB, TILE><<<ntasks, NT, 0, s>>>(dv, g, gp);
   return cudaGetLastError();
 }
+// nt = targets per task (64 | 128) + 1000 x (source records per shared-memory tile: 32 | 64 | 128; default 64)
 template <class P, int MINB64, int MINB128>
 cudaError_t launch_nt(int nt, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
-  return nt == 128 ? launch<P, 128, MINB128>(s, dv, g, gp) : launch<P, 64, MINB64>(s, dv, g, gp);
+  const int tile = nt / 1000;
+  nt %= 1000;
+  if (tile == 128) return nt == 128 ? launch<P, 128, MINB128, 128>(s, dv, g, gp) : launch<P, 64, MINB64, 128>(s, dv, g, gp);
+  if (tile == 32) return nt == 128 ? launch<P, 128, MINB128, 32>(s, dv, g, gp) : launch<P, 64, MINB64, 32>(s, dv, g, gp);
+  return nt == 128 ? launch<P, 128, MINB128, 64>(s, dv, g, gp) : launch<P, 64, MINB64, 64>(s, dv, g, gp);
 }
 }  // namespace
 
@@ -39,6 +44,9 @@ template <>
 cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact, int nt, cudaStream_t s,
                                                 const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
   constexpr int D = CCB_INST_D;
+  // register budget: 128 per thread (16 warps per SM) for every variant. The largest one (D = 3, shear + diffusion: 43
+  // accumulators) then spills ~200 bytes inside the neighbour loop, which still measured 6 % faster than 168 registers
+  // without spills at 12 warps per SM (profiles/README.md, r01c).
 #define CCB_GG(S, F, X) return launch_nt<GradPolicy<D, S, F, X>, 8, 4>(nt, s, dv, g, gp)
   if (D == 3 && fact) {
     if (shear) { if (diff) CCB_GG(true, true, (D == 3)); else CCB_GG(true, false, (D == 3)); }
