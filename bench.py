@@ -32,7 +32,7 @@ UNIT = "particle-steps/s"
 DEFAULT_WORKLOAD = "config2_viscous_gubser_bsq_2p1d"
 # bounded CPU sample: fraction of the lattice extent (configs 1-4) or of the particle count (config 5) the reference's CPU
 # implementation runs, sized for 10-30 s of host work at the workload's own spacing, smoothing length and neighbour count
-CPU_SCALE = {"config1": 0.25, "config2": 0.25, "config3": 0.07, "config4": 0.1, "config5": 0.1}
+CPU_SCALE = {"config1": 0.25, "config2": 0.5, "config3": 0.07, "config4": 0.1, "config5": 0.1}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -174,14 +174,18 @@ def time_reference(workload, scale, steps, warmup):
         sim.initialize()
         n = sim.n
         dt = settings["dt"]
+        tw = time.perf_counter()
         for _ in range(warmup):
             sim.advance(dt, 2)
+        tw = (time.perf_counter() - tw) / max(warmup, 1)
+        if steps is None:  # cpu_baseline leg of the own arm: about 15 s of host work, 2..20 steps
+            steps = int(min(20, max(2, round(15.0 / max(tw, 1e-3)))))
         t0 = time.perf_counter()
         for _ in range(steps):
             sim.advance(dt, 2)
         el = time.perf_counter() - t0
     cores = ref.omp_threads()
-    return dict(value=n * steps / el, seconds=el, n=n, cores=cores, desc=desc)
+    return dict(value=n * steps / el, seconds=el, n=n, cores=cores, desc=desc, steps=steps)
 
 
 def reference_arm(args, rank):
@@ -224,7 +228,7 @@ PAIR_FLOP = {"03_smooth_fields": 31.0, "09_smooth_gradients": None}  # gradients
 
 
 def gradient_pair_flop(D, shear, diffusion):
-    """fp64 flop per interacting pair in smooth_gradients as the reference writes it (src/sph_workstation.cpp:833-984):
+    """fp64 flop per interacting pair in smooth_gradients AS THE REFERENCE WRITES IT (src/sph_workstation.cpp:833-984):
     distance + gradKernel ~ 20, then the listed sums (mul + add each)."""
     f = 20 + 2 * D + 4 + 2 * D * 3 + 3 * D * D
     if shear:
@@ -232,6 +236,29 @@ def gradient_pair_flop(D, shear, diffusion):
     if diffusion:
         f += 3 * (3 + 4 * D + 3 * D)
     return float(f)
+
+
+def gradient_pair_flop_executed(D, shear, diffusion):
+    """fp64 flop per pair the CUDA kernel executes (moment form, gather.cuh GradPolicy; FMA = 2): exact distance 8,
+    rsqrt + spline 19, grad W and A_b 2D, sum A_b D, then one FMA per moment."""
+    fma = 3 * D + D * D
+    if shear or diffusion:
+        fma += D  # K.v_a
+    if shear:
+        fma += D + D * D
+    if diffusion:
+        fma += 3 + 6 * D
+    return float(27 + 3 * D + (1 if (shear or diffusion) else 0) + 2 * fma)
+
+
+def committed_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of this
+    workload (profiles/traffic.json, written from the .ncu-rep by scripts/ncu_summary.py --traffic); None if not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(workload, {}).get(kernel)
+    except (OSError, ValueError):
+        return None
 
 
 def own_arm(args, rank, world, local_rank):
@@ -345,23 +372,25 @@ def own_arm(args, rank, world, local_rank):
     n = ws.n_particles
     bt = ws.get_int_device_order("btrack") if world > 1 else ws.get_int("btrack")
     pairs = float(np.sum(bt[bt > 0])) + n
-    flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop(D, sw["using_shear"], sw["using_diffusion"])
+    flop_ref = PAIR_FLOP.get(dom) or gradient_pair_flop(D, sw["using_shear"], sw["using_diffusion"])
+    flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop_executed(D, sw["using_shear"], sw["using_diffusion"])
     fp64_achieved = pairs * flop_pair / t_dom / 1e12 if dom in ("03_smooth_fields", "09_smooth_gradients") else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_particle": alg.get(dom),
+                "traffic": committed_traffic(args.workload, dom), "peak_source": peak_src, "algorithmic_bytes_per_particle": alg.get(dom),
                 "ms_per_launch": per_kernel[dom]["ms_per_launch"],
                 "fp64": {"achieved": fp64_achieved, "peak": tf.value, "unit": "TFLOP/s",
                          "frac": (fp64_achieved / tf.value) if (fp64_achieved and tf.value) else None,
-                         "pairs_per_launch": pairs, "flop_per_pair": flop_pair, "peak_source": "ccb_measure_dfma_peak (this run)"},
+                         "pairs_per_launch": pairs, "flop_per_pair": flop_pair, "flop_per_pair_reference_expression": flop_ref,
+                         "peak_source": "ccb_measure_dfma_peak (this run)"},
                 "per_kernel": {k: {"ms_per_launch": round(v["ms_per_launch"], 5), "launches": v["launches"], "share": round(v["share"], 4),
                                    "GBps": round(alg.get(k, 0) * n / (v["ms_per_launch"] * 1e-3) / 1e9, 1)} for k, v in per_kernel.items()}}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = time_reference(args.workload, args.cpu_scale, 2, 1)
+        r = time_reference(args.workload, args.cpu_scale, None, 1)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
-               "sample": "%d particles (lattice extent x%.2f at the workload's spacing, smoothing length and neighbour count), 2 RK2 steps "
-                         "after 1 warm-up, %.1f s" % (r["n"], args.cpu_scale, r["seconds"])}
+               "sample": "%d particles (lattice extent x%.2f at the workload's spacing, smoothing length and neighbour count), %d RK2 steps "
+                         "after 1 warm-up, %.1f s" % (r["n"], args.cpu_scale, r["steps"], r["seconds"])}
 
     bytes_state = 8 * w * n_global
     out = {
@@ -383,7 +412,7 @@ def own_arm(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)

@@ -281,6 +281,7 @@ GatherParams make_gather(ccb_ctx* ctx) {
   gp.rsqr = radius * radius;
   gp.rsqr_f = (float)(gp.rsqr * (1.0 + 1e-4));  // fp32 pre-filter: never misses a true neighbour (gather.cuh)
   gp.rsqr_edge = gp.rsqr * (1.0 - 1e-12);
+
   const CellGrid& g = ctx->grid;
   gp.fast_axis = (g.nc[2] > 1) ? 2 : 1;
   gp.fast_min = g.min[gp.fast_axis];

@@ -2,6 +2,7 @@
 """Summarise an .ncu-rep (read on the CPU box): one block of key metrics per captured launch."""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
+TRAFFIC = "--traffic" in sys.argv  # print {phase: dram bytes per launch} as JSON instead (feeds profiles/traffic.json)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -25,3 +26,16 @@ for r in rows[2:]:
         if w in hdr:
             i = hdr.index(w)
             print("%-90s %s %s" % (w, r[i], units[i]))
+
+if TRAFFIC:
+    import json
+    PHASE = {"GradPolicy": "09_smooth_gradients", "FieldsPolicy": "03_smooth_fields", "eom_rk_kernel": "10_time_derivatives",
+             "eos_local_kernel": "04_thermodynamics", "eos_table_kernel": "04_thermodynamics"}
+    out = {}
+    ik, ir, iw = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        for pat, ph in PHASE.items():
+            if pat in r[ik]:
+                out[ph] = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+    sys.stderr.write(json.dumps(out) + "\n")
