@@ -43,6 +43,18 @@ class Context {
   ccb_ctx* get() const { return ctx_; }
   void check(int rc) const { if (rc) throw Error(rc, ccb_last_error(ctx_)); }
 
+  // EquationOfState::init for eos_type "table": EoS_table(eos_path, normalize_by_T) (src/eos_initialization.cpp:273-279).
+  // Call right after construction, before any particle is allocated.
+  void load_eos_table(const std::string& eos_path, bool normalize_by_T = true) {
+    check(ccb_load_eos_table_dat(ctx_, (eos_path + "/thermo.dat").c_str(), normalize_by_T ? 1 : 0));
+  }
+  void set_eos_table(const ccb_eos_table& table) { check(ccb_set_eos_table(ctx_, &table)); }
+
+  // Slab decomposition (one Context per GPU / process; new: the reference is single-process). `unique_id` is the 128-byte
+  // id rank 0 obtained from ccb_comm_unique_id and broadcast to the other ranks (MPI_Bcast, a file, a socket ...).
+  void comm_init(const char unique_id[128]) { check(ccb_comm_init(ctx_, unique_id)); }
+  void set_slab(int32_t col_lo, int32_t col_hi) { check(ccb_set_slab(ctx_, col_lo, col_hi)); }
+
  private:
   ccb_ctx* ctx_ = nullptr;
 };
