@@ -725,7 +725,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
      // BASELINE config, profiles/README.md r01c); environment overrides are for tuning runs only
     ctx->chunk = 128;
     if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = v; }
-    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64 || v == 128) ctx->chunk += 1000 * v; }
+    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->chunk += 1000 * v; }
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);

@@ -350,10 +350,20 @@ struct GradPolicy {
 // register allocation is bounded for.
 constexpr int kMaxSeg = 9;
 
+// Ampere-style asynchronous copies (LDGSTS): 16 bytes global -> shared without a register round trip. Used to land tile
+// k + 1 of the source records while tile k is being processed (the tiles are too small and too scattered for TMA boxes:
+// every record of a tile comes from a different 112..288-byte row of the record array).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 template <class P, int NT, int MINB, int TILE = kGatherTile>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
   constexpr int D = P::D, NW = TILE / 32, CH = P::REC / 2, RS2 = P::STRIDE / 2;
-  __shared__ __align__(16) double2 srec[TILE * RS2];
+  __shared__ __align__(16) double2 srec2[2][TILE * RS2];  // double-buffered tiles of source records
   __shared__ __align__(16) float spos[4][TILE];  // fp32 x, y, z relative to the pass origin, and x^2 + y^2 + z^2
   __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
   __shared__ int s_nseg;
@@ -433,31 +443,40 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     const int nseg = s_nseg;
     const uint32_t C = seg_pref[nseg];
     const uint32_t ntiles = (C + TILE - 1) / TILE;
-    for (uint32_t k = 0; k < ntiles; ++k) {
-      // tile k = candidates k, k + ntiles, ... < C: a uniform sample of the neighbourhood, so that every lane finds about
-      // the same number of hits in it (contiguous tiles [k TILE, (k + 1) TILE) measured 1.7x slower: the walk of phase 2
-      // costs max-over-lanes(hits) per tile)
+    // tile k = candidates k, k + ntiles, ... < C: a uniform sample of the neighbourhood, so that every lane finds about
+    // the same number of hits in it (contiguous tiles [k TILE, (k + 1) TILE) measured 1.7x slower: the walk of phase 2
+    // costs max-over-lanes(hits) per tile). Tile k + 1 is in flight (cp.async) while tile k is processed.
+    auto stage = [&](uint32_t k, double2* buf) {
       const int nt = (int)((C - k + ntiles - 1) / ntiles);
-      __syncthreads();  // the previous tile is fully consumed
-      {  // stage nt records (128-bit loads) + their fp32 relative positions
-        for (int q = threadIdx.x; q < nt * CH; q += NT) {
-          const int r = q / CH, c = q - r * CH;
-          const uint32_t cand = (uint32_t)r * ntiles + k;
-          int s = 0;
-          while (cand >= seg_pref[s + 1]) ++s;
-          const int64_t gidx = (int64_t)seg_start[s] + (cand - seg_pref[s]);
-          const double2 v = __ldg(rec2 + gidx * CH + c);
-          srec[r * RS2 + c] = v;
-          if (c == 0) {
-            const float xf = (float)(v.x - org[0]), yf = (float)(v.y - org[1]);
-            float zf = 0.f;
-            if (D == 3) zf = (float)(__ldg(rec2 + gidx * CH + 1).x - org[2]);
-            spos[0][r] = xf; spos[1][r] = yf;
-            if (D == 3) spos[2][r] = zf;
-            spos[3][r] = fmaf(xf, xf, fmaf(yf, yf, zf * zf));
-          }
+      for (int q = threadIdx.x; q < nt * CH; q += NT) {
+        const int r = q / CH, c = q - r * CH;
+        const uint32_t cand = (uint32_t)r * ntiles + k;
+        int s = 0;
+        while (cand >= seg_pref[s + 1]) ++s;
+        const int64_t gidx = (int64_t)seg_start[s] + (cand - seg_pref[s]);
+        cp_async16(buf + r * RS2 + c, rec2 + gidx * CH + c);
+      }
+      cp_async_commit();
+    };
+    if (ntiles) stage(0, srec2[0]);
+    for (uint32_t k = 0; k < ntiles; ++k) {
+      const int nt = (int)((C - k + ntiles - 1) / ntiles);
+      const double2* srec = srec2[k & 1];
+      cp_async_wait_all();
+      __syncthreads();  // tile k has landed for every thread, and tile k - 1 (buffer (k + 1) & 1, spos) is fully consumed
+      if (k + 1 < ntiles) stage(k + 1, srec2[(k + 1) & 1]);
+      for (int r = threadIdx.x; r < TILE; r += NT) {  // fp32 relative positions of tile k
+        if (r < nt) {
+          const double2 v0 = srec[r * RS2];
+          const float xf = (float)(v0.x - org[0]), yf = (float)(v0.y - org[1]);
+          float zf = 0.f;
+          if (D == 3) zf = (float)(srec[r * RS2 + 1].x - org[2]);
+          spos[0][r] = xf; spos[1][r] = yf;
+          if (D == 3) spos[2][r] = zf;
+          spos[3][r] = fmaf(xf, xf, fmaf(yf, yf, zf * zf));
+        } else {
+          spos[0][r] = 0.f; spos[1][r] = 0.f; spos[2][r] = 0.f; spos[3][r] = 3.0e38f;
         }
-        for (int r = nt + threadIdx.x; r < TILE; r += NT) { spos[0][r] = 0.f; spos[1][r] = 0.f; spos[2][r] = 0.f; spos[3][r] = 3.0e38f; }
       }
       __syncthreads();
       // ---- phase 1: fp32 pre-filter, hit masks. |a - b|^2 <= R^2 is tested in the expanded form

@@ -21,12 +21,12 @@ cudaError_t launch(cudaStream_t s, const DeviceView& dv, const CellGrid& g, cons
   gather_kernel<P, NT, MINB, TILE><<<ntasks, NT, 0, s>>>(dv, g, gp);
   return cudaGetLastError();
 }
-// nt = targets per task (64 | 128) + 1000 x (source records per shared-memory tile: 32 | 64 | 128; default 64)
+// nt = targets per task (64 | 128) + 1000 x (source records per shared-memory tile: 32 | 64; default 64). Tiles are
+// double-buffered, so 128-record tiles of the largest record would not fit the 48 KB of static shared memory.
 template <class P, int MINB64, int MINB128>
 cudaError_t launch_nt(int nt, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
   const int tile = nt / 1000;
   nt %= 1000;
-  if (tile == 128) return nt == 128 ? launch<P, 128, MINB128, 128>(s, dv, g, gp) : launch<P, 64, MINB64, 128>(s, dv, g, gp);
   if (tile == 32) return nt == 128 ? launch<P, 128, MINB128, 32>(s, dv, g, gp) : launch<P, 64, MINB64, 32>(s, dv, g, gp);
   return nt == 128 ? launch<P, 128, MINB128, 64>(s, dv, g, gp) : launch<P, 64, MINB64, 64>(s, dv, g, gp);
 }
