@@ -66,7 +66,7 @@ struct ccb_ctx {
   double *d_hot_s = nullptr, *d_hot_e = nullptr, *d_full = nullptr;
   ccb::EosChain chain;
   bool have_table = false;
-  int chunk = 64;   // targets per gather task (= threads per CTA): 64 or 128
+  int chunk = 128, chunk_fields = 64;   // targets per gather task (= threads per CTA) of the gradient / field gather
   int sms = 148;
   // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
   std::unique_ptr<ccb::Link> comm;
@@ -548,8 +548,8 @@ int do_gather_fields(ccb_ctx* ctx) {
   const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   if (ctx->comm) { const int rc = exchange_halo(ctx, REC_F); if (rc) return rc; }
-  if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
-  else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
+  if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk_fields, ctx->stream, ctx->dv, ctx->grid, gp));
+  else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk_fields, ctx->stream, ctx->dv, ctx->grid, gp));
   return CCB_OK;
 }
 
@@ -721,11 +721,11 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   ctx->dv.ghost_col[0] = ctx->dv.ghost_col[1] = -1;
   ctx->dv.ghost_start[0] = ctx->dv.ghost_start[1] = nullptr;
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, cfg->device);
-  {  // gather launch shape: 128 targets per task, 64 source records per shared-memory tile (measured best on every
-     // BASELINE config, profiles/README.md r01c); environment overrides are for tuning runs only
-    ctx->chunk = 128;
-    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = v; }
-    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->chunk += 1000 * v; }
+  {  // gather launch shape: 128 (gradients) / 64 (fields) targets per task, 64 source records per shared-memory tile
+     // (measured best over the BASELINE configs, profiles/README.md r01c); environment overrides are for tuning runs only
+    ctx->chunk = 128; ctx->chunk_fields = 64;
+    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = ctx->chunk_fields = v; }
+    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) { ctx->chunk += 1000 * v; ctx->chunk_fields += 1000 * v; } }
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);
