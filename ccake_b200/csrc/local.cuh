@@ -216,10 +216,35 @@ __device__ __forceinline__ void load_eom_inputs(const DeviceView& dv, const Stag
   }
 }
 
+// The equations of motion read ~130 columns per particle at 8 resident warps per SM (254 registers): too few loads in
+// flight to cover DRAM latency. Every 16th thread therefore asks L2 for the 128-byte line of each input column of its 16
+// neighbours before the arithmetic starts, so that the whole input of the CTA is in flight at once.
+__device__ __forceinline__ void prefetch_l2(const double* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+template <int D>
+__device__ __forceinline__ void prefetch_eom_inputs(const DeviceView& dv, const StageParams& sp, int64_t i) {
+  if ((threadIdx.x & 15) != 0) return;
+#define CCB_PF(F, N) _Pragma("unroll") for (int c = 0; c < (N); ++c) prefetch_l2(dv.f[F] + (int64_t)c * dv.cap + i)
+#define CCB_PF0(F, N) _Pragma("unroll") for (int c = 0; c < (N); ++c) prefetch_l2(dv.y0[F] + (int64_t)c * dv.cap + i)
+  CCB_PF(CCB_F_THERMO, 16); CCB_PF(CCB_F_DALPHA, 12); CCB_PF(CCB_F_CHIBB, 2); CCB_PF(CCB_F_TRANSPORT, 13);
+  CCB_PF(CCB_F_U, D); CCB_PF(CCB_F_V, D); CCB_PF(CCB_F_GRADP, D); CCB_PF(CCB_F_GRADBULK, D); CCB_PF(CCB_F_GRADSHEAR, D);
+  CCB_PF(CCB_F_DIVSHEAR, D); CCB_PF(CCB_F_GRADV, 3 * D);
+  CCB_PF(CCB_F_GAMMA, 1); CCB_PF(CCB_F_SIGMA, 1); CCB_PF(CCB_F_SIGMA_LAB, 1); CCB_PF(CCB_F_SPH_MASS, 1); CCB_PF(CCB_F_BULK, 1);
+  CCB_PF(CCB_F_SHV, 16);
+  if (sp.fl.diffusion) { CCB_PF(CCB_F_GRAD_ALPHA, 3 * D); CCB_PF(CCB_F_DIFFUSION, 12); CCB_PF(CCB_F_DIV_QA, 3); CCB_PF(CCB_F_GRAD_QA, 3); }
+  if (sp.do_update) {
+    CCB_PF0(CCB_F_EXTENSIVE, 4); CCB_PF0(CCB_F_EXTENSIVE_BULK, 1); CCB_PF0(CCB_F_EZ, 1); CCB_PF0(CCB_F_POSITION, D); CCB_PF0(CCB_F_U, D);
+    CCB_PF0(CCB_F_EXTENSIVE_SHV, 5);
+    if (sp.fl.diffusion) { CCB_PF0(CCB_F_EXTENSIVE_DIFFUSION, 9); }
+  }
+#undef CCB_PF
+#undef CCB_PF0
+}
+
 template <int D, bool MILNE>
 __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams sp) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dv.n) return;
+  prefetch_eom_inputs<D>(dv, sp, i);
   Metric<MILNE> m(sp.t);
   EomOut<D> out;
   // Pass 1: the linear solve for du/dt and dN/dt. Pass 2 re-reads its inputs (L1/L2 hits) behind a compiler
