@@ -270,7 +270,8 @@ def own_arm(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
-    settings, ic, desc = make_workload(args.workload, 1.0, world)
+    # weak scaling (default): one copy of the workload per GPU, side by side along x; strong: the ONE workload cut into slabs
+    settings, ic, desc = make_workload(args.workload, 1.0, world if args.scaling == "weak" else 1)
     if settings["eos_type"] == "table":
         settings["eos_table_data"] = eos_table(as_file=False)
     dt = settings["dt"]
@@ -395,11 +396,12 @@ def own_arm(args, rank, world, local_rank):
     bytes_state = 8 * w * n_global
     out = {
         "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "particles": n_global, "particles_rank0": n, "rk_order": 2,
                    "mean_neighbours": float(np.mean(bt[bt >= 0])),
-                   "parallelism": "single GPU" if world == 1 else "%d slabs along x (one copy of the workload per GPU), 2h halo + per-stage migration over NCCL" % world,
+                   "parallelism": "single GPU" if world == 1 else "%d slabs along x (%s), 2h halo + per-stage migration over NCCL" % (
+                       world, "one copy of the workload per GPU" if args.scaling == "weak" else "the one workload cut at particle-count quantiles"),
                    "l2": "no flush: per-step working set %.0f MB of particle columns per GPU > 126 MB L2" % (8e-6 * n * 190)},
         "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                 "d2h_bytes_per_step": bytes_state, "ms_per_step": ms_e2e / args.steps,
@@ -418,6 +420,8 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--cpu-scale", type=float, default=None, help="lattice-extent factor of the bounded CPU sample (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one copy of the workload per GPU (the driver's scaling run), strong = the one workload over N slabs")
     args = ap.parse_args()
 
     if args.cpu_scale is None:

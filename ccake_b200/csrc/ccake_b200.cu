@@ -74,6 +74,8 @@ struct ccb_ctx {
   int64_t rec_cap = 0;                       // records the gather buffer holds (own + ghosts)
   uint32_t* ghost_tab = nullptr;             // 2 x (P + 1) rebased column tables + 2 x (P + 1) receive scratch
   int32_t* d_info = nullptr;                 // small device scratch for counts
+  uint32_t* mig_list = nullptr;              // migrants' device indices, ranked (cap mig_cap)
+  uint32_t* d_ends = nullptr;                // 8 table ends of exchange_column_tables, fetched in one copy
   int64_t ghost_n[2] = {0, 0};               // ghost records per side
   int64_t send_start[2] = {0, 0}, send_n[2] = {0, 0};  // own edge columns (sorted order): halo sends
   double* mig_d[2] = {nullptr, nullptr};     // migration buffers [send, recv]
@@ -176,6 +178,7 @@ int free_particles(ccb_ctx* ctx) {
   cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
   cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
   for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); ctx->mig_d[k] = nullptr; ctx->mig_i[k] = nullptr; }
+  cudaFree(ctx->mig_list); ctx->mig_list = nullptr;
   ctx->mig_cap = 0;
   ctx->slab = ctx->y0_slab = ctx->alt_slab = nullptr; ctx->ints = nullptr;
   ctx->key_a = ctx->key_b = ctx->idx_a = ctx->idx_b = ctx->hist = nullptr;
@@ -376,16 +379,20 @@ void migrate_list(ccb_ctx* ctx, MigrateList& ml) {
   ml.icol[0] = dv.id; ml.icol[1] = dv.btrack; ml.icol[2] = dv.freeze; ml.icol[3] = dv.eos_id;
 }
 
-// Particles whose cell column left the slab go to the neighbouring rank (they sit at the two ends of the
-// sorted order); arrivals are appended and a second sort, which drops the leavers, puts everything in place.
-int migrate(ccb_ctx* ctx) {
+// Particles whose cell column left the slab go to the neighbouring rank. They are found and shipped BEFORE the stage's
+// sort: the arrivals are appended behind the own particles and the one sort that follows (drop_outside) drops the leavers
+// and files the arrivals. Returns the number of rows to sort in *n_sort and the leavers among them in *n_drop.
+int migrate(ccb_ctx* ctx, int64_t* n_sort, int64_t* n_drop) {
   const CellGrid& g = ctx->grid;
   const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
-  const int64_t P = (int64_t)g.nc[1] * g.nc[2];
   const int left = rank - 1, right = rank + 1 < nranks ? rank + 1 : -1;
+  const int64_t n = ctx->n;
+  *n_sort = n; *n_drop = 0;
   int32_t* info = ctx->d_info;  // [0] out left, [1] out right, [2] in from left, [3] in from right
+  uint32_t *list_l = ctx->key_b, *list_r = ctx->idx_b;  // free until the sort
   CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 4, ctx->stream));
-  LAUNCH(leaver_counts, 1, 32, ctx->dv.cell_start, (uint32_t)(ctx->slab_lo * P), (uint32_t)(ctx->slab_hi * P), (uint32_t)g.ncells, info);
+  LAUNCH(find_leavers, cdiv(n, 256), 256, ctx->dv.f[CCB_F_POSITION], g.min[0], g.rdx[0], g.nc[0], ctx->slab_lo, ctx->slab_hi,
+         left >= 0 ? 1 : 0, right >= 0 ? 1 : 0, n, list_l, list_r, info);
   COMM_OK(ctx->comm->group_begin());
   if (left >= 0) COMM_OK(ctx->comm->send(info + 0, sizeof(int32_t), left, ctx->stream));
   if (right >= 0) COMM_OK(ctx->comm->send(info + 1, sizeof(int32_t), right, ctx->stream));
@@ -395,32 +402,33 @@ int migrate(ccb_ctx* ctx) {
   int32_t h[4];
   CUDA_OK(cudaMemcpyAsync(h, info, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  int64_t outL = h[0], outR = h[1];
-  const int64_t inL = h[2], inR = h[3];
-  if ((left < 0 && outL) || (right < 0 && outR)) {
-    // a particle of an outermost rank left the slab outwards: it stays (its key is still on the grid)
-    if (left < 0) outL = 0;
-    if (right < 0) outR = 0;
-  }
+  const int64_t outL = h[0], outR = h[1], inL = h[2], inR = h[3];
   if (outL + outR + inL + inR == 0) return CCB_OK;
-  const int64_t n = ctx->n;
   if (n + inL + inR > ctx->cap) { ctx->err = "slab overflow: more arrivals than the particle capacity holds"; return CCB_ERR_STATE; }
   MigrateList ml;
   migrate_list(ctx, ml);
   const int64_t need = std::max<int64_t>(std::max(outL + outR, inL + inR), 1);
   if (need > ctx->mig_cap) {
     for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); }
+    cudaFree(ctx->mig_list);
     ctx->mig_cap = need * 2 + 1024;
     for (int k = 0; k < 2; ++k) {
       CUDA_OK(cudaMalloc(&ctx->mig_d[k], sizeof(double) * ml.ncols * ctx->mig_cap));
       CUDA_OK(cudaMalloc(&ctx->mig_i[k], sizeof(int32_t) * 4 * ctx->mig_cap));
     }
+    CUDA_OK(cudaMalloc(&ctx->mig_list, sizeof(uint32_t) * ctx->mig_cap));
   }
   double *sd = ctx->mig_d[0], *rd = ctx->mig_d[1];
   int32_t *si = ctx->mig_i[0], *ri = ctx->mig_i[1];
-  // leavers: [0, outL) and [n - outR, n) of the sorted order
-  if (outL) LAUNCH(pack_rows, cdiv(outL, 128), 128, ml, (int64_t)0, outL, sd, si);
-  if (outR) LAUNCH(pack_rows, cdiv(outR, 128), 128, ml, n - outR, outR, sd + ml.ncols * outL, si + 4 * outL);
+  uint32_t* sorted = ctx->mig_list;
+  if (outL) {
+    LAUNCH(rank_sort_u32, cdiv(outL, 256), 256, list_l, sorted, (int)outL);
+    LAUNCH(pack_rows_indexed, cdiv(outL, 128), 128, ml, sorted, outL, sd, si);
+  }
+  if (outR) {
+    LAUNCH(rank_sort_u32, cdiv(outR, 256), 256, list_r, sorted + outL, (int)outR);
+    LAUNCH(pack_rows_indexed, cdiv(outR, 128), 128, ml, sorted + outL, outR, sd + ml.ncols * outL, si + 4 * outL);
+  }
   COMM_OK(ctx->comm->group_begin());
   if (left >= 0 && outL) { COMM_OK(ctx->comm->send(sd, sizeof(double) * ml.ncols * outL, left, ctx->stream)); COMM_OK(ctx->comm->send(si, sizeof(int32_t) * 4 * outL, left, ctx->stream)); }
   if (right >= 0 && outR) { COMM_OK(ctx->comm->send(sd + ml.ncols * outL, sizeof(double) * ml.ncols * outR, right, ctx->stream)); COMM_OK(ctx->comm->send(si + 4 * outL, sizeof(int32_t) * 4 * outR, right, ctx->stream)); }
@@ -429,13 +437,8 @@ int migrate(ccb_ctx* ctx) {
   COMM_OK(ctx->comm->group_end());
   if (inL) LAUNCH(unpack_rows, cdiv(inL, 128), 128, ml, n, inL, rd, ri);
   if (inR) LAUNCH(unpack_rows, cdiv(inR, 128), 128, ml, n + inL, inR, rd + ml.ncols * inL, ri + 4 * inL);
-  // second sort over own + arrivals; the leavers' keys are outside the slab -> sentinel -> dropped
-  const int64_t n_tmp = n + inL + inR;
-  ctx->dv.n = n_tmp;
-  int rc = sort_and_permute(ctx, n_tmp, 1);
-  if (rc) return rc;
-  ctx->n = n_tmp - outL - outR;
-  ctx->dv.n = ctx->n;
+  *n_sort = n + inL + inR;
+  *n_drop = outL + outR;
   ctx->migrated_out += outL + outR;
   ctx->migrated_in += inL + inR;
   return CCB_OK;
@@ -459,12 +462,8 @@ int exchange_column_tables(ccb_ctx* ctx) {
   if (right >= 0) COMM_OK(ctx->comm->recv(tab + 3 * T, sizeof(uint32_t) * T, right, ctx->stream));
   COMM_OK(ctx->comm->group_end());
   uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // own first column [start, end], own last column, left table ends, right table ends
-  CUDA_OK(cudaMemcpyAsync(h + 0, own_first, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_OK(cudaMemcpyAsync(h + 1, own_first + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_OK(cudaMemcpyAsync(h + 2, own_last, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_OK(cudaMemcpyAsync(h + 3, own_last + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  if (left >= 0) { CUDA_OK(cudaMemcpyAsync(h + 4, tab + 2 * T, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); CUDA_OK(cudaMemcpyAsync(h + 5, tab + 2 * T + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
-  if (right >= 0) { CUDA_OK(cudaMemcpyAsync(h + 6, tab + 3 * T, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); CUDA_OK(cudaMemcpyAsync(h + 7, tab + 3 * T + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream)); }
+  LAUNCH(table_ends, 1, 32, own_first, own_last, tab + 2 * T, tab + 3 * T, P, left >= 0 ? 1 : 0, right >= 0 ? 1 : 0, ctx->d_ends);
+  CUDA_OK(cudaMemcpyAsync(h, ctx->d_ends, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   ctx->send_start[0] = h[0]; ctx->send_n[0] = left >= 0 ? (int64_t)h[1] - h[0] : 0;
   ctx->send_start[1] = h[2]; ctx->send_n[1] = right >= 0 ? (int64_t)h[3] - h[2] : 0;
@@ -510,12 +509,18 @@ int grad_record_doubles(ccb_ctx* ctx) {
 
 int do_build_cells(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_NEIGHBOUR);
-  ctx->dv.n = ctx->n;
-  int rc = sort_and_permute(ctx, ctx->n, 0);
-  if (rc) return rc;
+  int rc;
   if (ctx->comm) {
-    if ((rc = migrate(ctx))) return rc;
+    int64_t n_sort = ctx->n, n_drop = 0;
+    if ((rc = migrate(ctx, &n_sort, &n_drop))) return rc;
+    ctx->dv.n = n_sort;
+    if ((rc = sort_and_permute(ctx, n_sort, 1))) return rc;   // leavers -> sentinel key -> sorted last -> dropped
+    ctx->n = n_sort - n_drop;
+    ctx->dv.n = ctx->n;
     if ((rc = exchange_column_tables(ctx))) return rc;
+  } else {
+    ctx->dv.n = ctx->n;
+    if ((rc = sort_and_permute(ctx, ctx->n, 0))) return rc;
   }
   ctx->cells_valid = true;
   return CCB_OK;
@@ -747,7 +752,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
-  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info);
+  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends);
   cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
   ctx->comm.reset();
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -979,6 +984,7 @@ static int comm_buffers(ccb_ctx* ctx) {
   CUDA_OK(cudaMalloc(&ctx->ghost_tab, sizeof(uint32_t) * 4 * T));
   CUDA_OK(cudaMemset(ctx->ghost_tab, 0, sizeof(uint32_t) * 4 * T));
   CUDA_OK(cudaMalloc(&ctx->d_info, sizeof(int32_t) * 8 + sizeof(double) * 8));
+  CUDA_OK(cudaMalloc(&ctx->d_ends, sizeof(uint32_t) * 8));
   return CCB_OK;
 }
 int ccb_comm_unique_id(char id[128]) {

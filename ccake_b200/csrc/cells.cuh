@@ -66,12 +66,50 @@ __global__ void unpack_rows(MigrateList ml, int64_t start, int64_t count, const 
   for (int c = 0; c < ml.ncols; ++c) ml.col[c][start + k] = dbuf[(int64_t)c * count + k];
   for (int c = 0; c < 4; ++c) ml.icol[c][start + k] = ibuf[(int64_t)c * count + k];
 }
-// info[0] = particles left of the slab, info[1] = right of it (after the first sort)
-__global__ void leaver_counts(const uint32_t* __restrict__ cell_start, uint32_t key_lo, uint32_t key_hi, uint32_t ncells, int32_t* __restrict__ info) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    info[0] = (int32_t)cell_start[key_lo];
-    info[1] = (int32_t)(cell_start[ncells] - cell_start[key_hi]);
+// Particles whose cell column has left the slab [col_lo, col_hi), found BEFORE the stage's sort so that one sort places
+// leavers (dropped) and arrivals (appended) together: list[0] = device indices of those bound for rank - 1, list[1] for
+// rank + 1; info[0..1] count them. A side without a neighbour keeps its particles (their keys stay on the grid).
+__global__ void find_leavers(const double* __restrict__ x, double xmin, double rdx, int ncol, int col_lo, int col_hi, int has_left,
+                             int has_right, int64_t n, uint32_t* __restrict__ list_left, uint32_t* __restrict__ list_right,
+                             int32_t* __restrict__ info) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = (int)floor((x[i] - xmin) * rdx);   // cell_key_kernel's formula
+  c = c < 0 ? 0 : (c > ncol - 1 ? ncol - 1 : c);
+  if (has_left && c < col_lo) list_left[atomicAdd(&info[0], 1)] = (uint32_t)i;
+  else if (has_right && c >= col_hi) list_right[atomicAdd(&info[1], 1)] = (uint32_t)i;
+}
+// The atomics above fill the lists in arbitrary order; ranking the (distinct) indices makes the order of the migration
+// message, hence the order of the arrivals behind the neighbour's particles, hence every later sum, reproducible.
+__global__ void rank_sort_u32(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int count) {
+  __shared__ uint32_t tile[256];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t mine = t < count ? in[t] : 0xffffffffu;
+  int rank = 0;
+  for (int base = 0; base < count; base += 256) {
+    __syncthreads();
+    tile[threadIdx.x] = base + threadIdx.x < count ? in[base + threadIdx.x] : 0xffffffffu;
+    __syncthreads();
+    const int m = min(256, count - base);
+    for (int k = 0; k < m; ++k) rank += tile[k] < mine;
   }
+  if (t < count) out[rank] = mine;
+}
+__global__ void pack_rows_indexed(MigrateList ml, const uint32_t* __restrict__ list, int64_t count, double* __restrict__ dbuf,
+                                  int32_t* __restrict__ ibuf) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  const int64_t i = list[k];
+  for (int c = 0; c < ml.ncols; ++c) dbuf[(int64_t)c * count + k] = ml.col[c][i];
+  for (int c = 0; c < 4; ++c) ibuf[(int64_t)c * count + k] = ml.icol[c][i];
+}
+// the eight record offsets exchange_column_tables needs on the host, gathered for ONE device-to-host copy
+__global__ void table_ends(const uint32_t* __restrict__ own_first, const uint32_t* __restrict__ own_last, const uint32_t* __restrict__ tab_left,
+                           const uint32_t* __restrict__ tab_right, int64_t P, int has_left, int has_right, uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  out[0] = own_first[0]; out[1] = own_first[P]; out[2] = own_last[0]; out[3] = own_last[P];
+  out[4] = has_left ? tab_left[0] : 0u; out[5] = has_left ? tab_left[P] : 0u;
+  out[6] = has_right ? tab_right[0] : 0u; out[7] = has_right ? tab_right[P] : 0u;
 }
 // received column table (record offsets in the sender's numbering) -> offsets into this rank's ghost region
 __global__ void rebase_ghost_table(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t nent, uint32_t base) {
