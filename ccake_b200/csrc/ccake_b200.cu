@@ -76,6 +76,8 @@ struct ccb_ctx {
   int32_t* d_info = nullptr;                 // small device scratch for counts
   uint32_t* mig_list = nullptr;              // migrants' device indices, ranked (cap mig_cap)
   uint32_t* d_ends = nullptr;                // 8 table ends of exchange_column_tables, fetched in one copy
+  cudaStream_t comm_stream = nullptr;        // halo exchanges run here, next to the interior tasks of the gather
+  cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
   int64_t ghost_n[2] = {0, 0};               // ghost records per side
   int64_t send_start[2] = {0, 0}, send_n[2] = {0, 0};  // own edge columns (sorted order): halo sends
   double* mig_d[2] = {nullptr, nullptr};     // migration buffers [send, recv]
@@ -284,6 +286,7 @@ GatherParams make_gather(ccb_ctx* ctx) {
   gp.rsqr = radius * radius;
   gp.rsqr_f = (float)(gp.rsqr * (1.0 + 1e-4));  // fp32 pre-filter: never misses a true neighbour (gather.cuh)
   gp.rsqr_edge = gp.rsqr * (1.0 - 1e-12);
+  gp.task_count = gp.task_n0 = gp.task_off0 = gp.task_off1 = 0;
 
   const CellGrid& g = ctx->grid;
   gp.fast_axis = (g.nc[2] > 1) ? 2 : 1;
@@ -487,18 +490,44 @@ int exchange_column_tables(ccb_ctx* ctx) {
 }
 
 // Ghost records of one gather (rec_doubles per record): own edge columns -> neighbours, theirs -> behind our own.
+// The exchange runs on the context's communication stream: it starts when the records are packed (ev_pack) and the
+// boundary tasks of the gather follow it on that stream, while the interior tasks run next to both on the compute stream.
 int exchange_halo(ccb_ctx* ctx, int rec_doubles) {
   const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
   const int left = rank - 1, right = rank + 1 < nranks ? rank + 1 : -1;
+  if (!ctx->comm_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CUDA_OK(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+  }
+  cudaStream_t cs = ctx->comm_stream;
+  CUDA_OK(cudaEventRecord(ctx->ev_pack, ctx->stream));
+  CUDA_OK(cudaStreamWaitEvent(cs, ctx->ev_pack, 0));
   double* rec = ctx->rec;
   const size_t rb = sizeof(double) * rec_doubles;
   COMM_OK(ctx->comm->group_begin());
-  if (left >= 0 && ctx->send_n[0]) COMM_OK(ctx->comm->send(rec + ctx->send_start[0] * rec_doubles, rb * ctx->send_n[0], left, ctx->stream));
-  if (right >= 0 && ctx->send_n[1]) COMM_OK(ctx->comm->send(rec + ctx->send_start[1] * rec_doubles, rb * ctx->send_n[1], right, ctx->stream));
-  if (left >= 0 && ctx->ghost_n[0]) COMM_OK(ctx->comm->recv(rec + ctx->n * rec_doubles, rb * ctx->ghost_n[0], left, ctx->stream));
-  if (right >= 0 && ctx->ghost_n[1]) COMM_OK(ctx->comm->recv(rec + (ctx->n + ctx->ghost_n[0]) * rec_doubles, rb * ctx->ghost_n[1], right, ctx->stream));
+  if (left >= 0 && ctx->send_n[0]) COMM_OK(ctx->comm->send(rec + ctx->send_start[0] * rec_doubles, rb * ctx->send_n[0], left, cs));
+  if (right >= 0 && ctx->send_n[1]) COMM_OK(ctx->comm->send(rec + ctx->send_start[1] * rec_doubles, rb * ctx->send_n[1], right, cs));
+  if (left >= 0 && ctx->ghost_n[0]) COMM_OK(ctx->comm->recv(rec + ctx->n * rec_doubles, rb * ctx->ghost_n[0], left, cs));
+  if (right >= 0 && ctx->ghost_n[1]) COMM_OK(ctx->comm->recv(rec + (ctx->n + ctx->ghost_n[0]) * rec_doubles, rb * ctx->ghost_n[1], right, cs));
   COMM_OK(ctx->comm->group_end());
   return CCB_OK;
+}
+
+// Task ranges of a slab gather with `nt` targets per task: interior = tasks that lie wholly outside the first / last cell
+// column (no ghost records needed), boundary = the rest, at the two ends of the sorted order.
+struct TaskSplit { int64_t ntasks, i0, i1; };
+TaskSplit split_tasks(ccb_ctx* ctx, int nt) {
+  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+  TaskSplit ts;
+  ts.ntasks = cdiv(ctx->n, nt);
+  const int64_t b0 = rank > 0 ? ctx->send_start[0] + ctx->send_n[0] : 0;
+  const int64_t b1 = rank + 1 < nranks ? ctx->send_start[1] : ctx->n;
+  ts.i0 = std::min<int64_t>(cdiv(b0, nt), ts.ntasks);
+  ts.i1 = std::max<int64_t>(std::min<int64_t>(b1 / nt, ts.ntasks), ts.i0);
+  return ts;
 }
 
 int grad_record_doubles(ccb_ctx* ctx) {
@@ -548,14 +577,37 @@ int do_prologue(ccb_ctx* ctx) {
   return CCB_OK;
 }
 
+// One gather over all tasks, or (slab run): the halo exchange followed by the boundary tasks on the communication stream,
+// the interior tasks next to them on the compute stream, which then waits for the boundary tasks.
+template <class F>
+int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& launch) {
+  if (!ctx->comm) return launch(gp, ctx->stream);
+  int rc = exchange_halo(ctx, rec_doubles);
+  if (rc) return rc;
+  const TaskSplit ts = split_tasks(ctx, nt);
+  const int64_t nb = ts.i0 + (ts.ntasks - ts.i1);
+  if (nb > 0) {
+    GatherParams gb = gp;
+    gb.task_count = (int)nb; gb.task_n0 = (int)ts.i0; gb.task_off0 = 0; gb.task_off1 = (int)ts.i1;
+    if ((rc = launch(gb, ctx->comm_stream))) return rc;
+  }
+  CUDA_OK(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
+  if (ts.i1 > ts.i0) {
+    gp.task_count = gp.task_n0 = (int)(ts.i1 - ts.i0); gp.task_off0 = (int)ts.i0; gp.task_off1 = 0;
+    if ((rc = launch(gp, ctx->stream))) return rc;
+  }
+  CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
+  return CCB_OK;
+}
+
 int do_gather_fields(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
-  const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
-  if (ctx->comm) { const int rc = exchange_halo(ctx, REC_F); if (rc) return rc; }
-  if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk_fields, ctx->stream, ctx->dv, ctx->grid, gp));
-  else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk_fields, ctx->stream, ctx->dv, ctx->grid, gp));
-  return CCB_OK;
+  return slab_gather(ctx, REC_F, ctx->chunk_fields % 1000, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
+    if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk_fields, st, ctx->dv, ctx->grid, gp));
+    else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk_fields, st, ctx->dv, ctx->grid, gp));
+    return CCB_OK;
+  });
 }
 
 int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
@@ -583,13 +635,13 @@ int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
 
 int do_gather_gradients(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_GRAD);
-  const GatherParams gp = make_gather(ctx);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
-  if (ctx->comm) { const int rc = exchange_halo(ctx, grad_record_doubles(ctx)); if (rc) return rc; }
-  if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
-  else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, ctx->stream, ctx->dv, ctx->grid, gp));
-  return CCB_OK;
+  return slab_gather(ctx, grad_record_doubles(ctx), ctx->chunk % 1000, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
+    if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, st, ctx->dv, ctx->grid, gp));
+    else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, st, ctx->dv, ctx->grid, gp));
+    return CCB_OK;
+  });
 }
 
 int do_eom(ccb_ctx* ctx, double h_stage, int do_update) {
@@ -753,6 +805,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
   cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends);
+  if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_halo); }
   cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
   ctx->comm.reset();
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }

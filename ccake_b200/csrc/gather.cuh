@@ -372,7 +372,8 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(rec);
   const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
 
-  const int64_t first = (int64_t)blockIdx.x * NT;
+  const int64_t task = (int)blockIdx.x < gp.task_n0 ? (int64_t)gp.task_off0 + blockIdx.x : (int64_t)gp.task_off1 + (blockIdx.x - gp.task_n0);
+  const int64_t first = task * NT;
   const int64_t last = min(first + NT, dv.n) - 1;
   const int64_t i = first + threadIdx.x;
   const bool active = i <= last;

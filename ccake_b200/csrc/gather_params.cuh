@@ -45,6 +45,10 @@ struct GatherParams {
   double rsqr_edge;  // rsqr (1 - 1e-12): pairs at or above it sit on the cut-off (knife edge, see FieldsPolicy::pair)
   double fast_min, fast_rdx;  // the grid's fastest axis (z for a 3-D grid, y for a 2-D one): cell = floor((x - min) rdx)
   int fast_axis, fast_nc;
+  // which tasks a launch covers: block b -> task (b < task_n0 ? task_off0 + b : task_off1 + b - task_n0); task_count = 0
+  // means all of them. A slab run launches the interior tasks first and the two boundary ranges (the first and last cell
+  // column, which need the ghost records) once the halo exchange has completed on the communication stream.
+  int task_count, task_n0, task_off0, task_off1;
   double t;
   int milne;
 };

@@ -17,8 +17,10 @@ cudaError_t launch(cudaStream_t s, const DeviceView& dv, const CellGrid& g, cons
     cudaFuncSetAttribute(gather_kernel<P, NT, MINB, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     configured = true;
   }
-  const unsigned ntasks = (unsigned)((dv.n + NT - 1) / NT);
-  gather_kernel<P, NT, MINB, TILE><<<ntasks, NT, 0, s>>>(dv, g, gp);
+  GatherParams q = gp;
+  unsigned ntasks = (unsigned)q.task_count;
+  if (q.task_count <= 0) { ntasks = (unsigned)((dv.n + NT - 1) / NT); q.task_n0 = (int)ntasks; q.task_off0 = q.task_off1 = 0; }
+  gather_kernel<P, NT, MINB, TILE><<<ntasks, NT, 0, s>>>(dv, g, q);
   return cudaGetLastError();
 }
 // nt = targets per task (64 | 128) + 1000 x (source records per shared-memory tile: 32 | 64; default 64). Tiles are
