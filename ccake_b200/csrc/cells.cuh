@@ -190,42 +190,56 @@ __global__ void scan_apply(const uint32_t* __restrict__ in, uint32_t* __restrict
   if (write_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = running;
 }
 
-// single block: exclusive scan of up to 1024 * kScanSmallPer elements (in place is fine); one launch instead of three
+// single block: exclusive scan of up to 1024 * kScanSmallPer elements (in place is fine); one launch instead of three.
+// Warp w owns the contiguous chunk [w * per * 32, (w + 1) * per * 32) and walks it in rows of 32 (coalesced loads and
+// stores), scanning each row with shuffles and carrying the running total from row to row.
 constexpr int kScanSmallPer = 32;
 __global__ void __launch_bounds__(1024) scan_small(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int64_t n, int write_total) {
   __shared__ uint32_t wsum[32];
   const int per = (int)((n + 1023) / 1024);
-  const int64_t lo = (int64_t)threadIdx.x * per, hi = min(lo + per, n);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (int64_t)warp * per * 32;
   uint32_t v[kScanSmallPer];
-  uint32_t acc = 0;
 #pragma unroll
   for (int k = 0; k < kScanSmallPer; ++k) {
-    v[k] = (k < per && lo + k < hi) ? in[lo + k] : 0u;
-    acc += v[k];
+    const int64_t e = base + (int64_t)k * 32 + lane;
+    v[k] = (k < per && e < n) ? in[e] : 0u;
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t x = acc;
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-    if (lane >= o) x += y;
+  uint32_t carry = 0;
+#pragma unroll
+  for (int k = 0; k < kScanSmallPer; ++k) {
+    if (k < per) {
+      uint32_t x = v[k];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      const uint32_t row_total = __shfl_sync(0xffffffffu, x, 31);
+      v[k] = x - v[k] + carry;  // exclusive within the warp's chunk
+      carry += row_total;
+    }
   }
-  if (lane == 31) wsum[warp] = x;
+  if (lane == 0) wsum[warp] = carry;
   __syncthreads();
   if (warp == 0) {
-    uint32_t w = wsum[lane], z = w;
+    const uint32_t w = wsum[lane];
+    uint32_t z = w;
+#pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
       if (lane >= o) z += y;
     }
     wsum[lane] = z - w;  // exclusive warp offsets
+    if (write_total && lane == 31) out[n] = z;
   }
   __syncthreads();
-  uint32_t run = wsum[warp] + x - acc;
+  const uint32_t off = wsum[warp];
 #pragma unroll
   for (int k = 0; k < kScanSmallPer; ++k) {
-    if (k < per && lo + k < hi) { out[lo + k] = run; run += v[k]; }
+    const int64_t e = base + (int64_t)k * 32 + lane;
+    if (k < per && e < n) out[e] = v[k] + off;
   }
-  if (write_total && threadIdx.x == 1023) out[n] = run;
 }
 
 // ---- LSD radix sort, one 8-bit digit per pass -----------------------------------
