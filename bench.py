@@ -238,17 +238,18 @@ def gradient_pair_flop(D, shear, diffusion):
     return float(f)
 
 
-def gradient_pair_flop_executed(D, shear, diffusion):
-    """fp64 flop per pair the CUDA kernel executes (moment form, gather.cuh GradPolicy; FMA = 2): exact distance 8,
-    rsqrt + spline 19, grad W and A_b 2D, sum A_b D, then one FMA per moment."""
+def gradient_pair_flop_executed(D, shear, diffusion, currents_zero=False):
+    """fp64 flop per pair the CUDA kernel executes (moment form, gather.cuh GradPolicy; FMA = 2): exact distance 3D - 1,
+    rsqrt + spline 19, grad W and A_b 2D, sum A_b D, then one FMA per moment. `currents_zero`: the run keeps q^mu_a = 0
+    (kappa = 0, no initial diffusion), so the kernel skips the q^0_a and q^i_a moments (DeviceView::qflag)."""
     fma = 3 * D + D * D
     if shear or diffusion:
         fma += D  # K.v_a
     if shear:
         fma += D + D * D
     if diffusion:
-        fma += 3 + 6 * D
-    return float(27 + 3 * D + (1 if (shear or diffusion) else 0) + 2 * fma)
+        fma += 3 * D + (0 if currents_zero else 3 + 3 * D)
+    return float(3 * D - 1 + 19 + 3 * D + (1 if (shear or diffusion) else 0) + 2 * fma)
 
 
 def committed_traffic(workload, kernel):
@@ -374,7 +375,8 @@ def own_arm(args, rank, world, local_rank):
     bt = ws.get_int_device_order("btrack") if world > 1 else ws.get_int("btrack")
     pairs = float(np.sum(bt[bt > 0])) + n
     flop_ref = PAIR_FLOP.get(dom) or gradient_pair_flop(D, sw["using_shear"], sw["using_diffusion"])
-    flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop_executed(D, sw["using_shear"], sw["using_diffusion"])
+    currents_zero = all(float(settings.get("kappa_%d%d" % (a, b), 0.0)) == 0.0 for a in range(3) for b in range(3))
+    flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop_executed(D, sw["using_shear"], sw["using_diffusion"], currents_zero)
     fp64_achieved = pairs * flop_pair / t_dom / 1e12 if dom in ("03_smooth_fields", "09_smooth_gradients") else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": committed_traffic(args.workload, dom), "peak_source": peak_src, "algorithmic_bytes_per_particle": alg.get(dom),

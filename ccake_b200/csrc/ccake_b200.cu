@@ -76,6 +76,7 @@ struct ccb_ctx {
   int32_t* d_info = nullptr;                 // small device scratch for counts
   uint32_t* mig_list = nullptr;              // migrants' device indices, ranked (cap mig_cap)
   uint32_t* d_ends = nullptr;                // 8 table ends of exchange_column_tables, fetched in one copy
+  int* d_qflag = nullptr;                    // DeviceView::qflag
   cudaStream_t comm_stream = nullptr;        // halo exchanges run here, next to the interior tasks of the gather
   cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
   int64_t ghost_n[2] = {0, 0};               // ghost records per side
@@ -582,8 +583,18 @@ int do_prologue(ccb_ctx* ctx) {
 template <class F>
 int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& launch) {
   if (!ctx->comm) return launch(gp, ctx->stream);
+  const bool scan_q = rec_doubles != REC_F && ctx->cfg.using_diffusion;  // gradient records: do the ghosts carry q^mu_a != 0?
+  if (scan_q) CUDA_OK(cudaMemsetAsync(ctx->d_qflag + 1, 0, sizeof(int), ctx->stream));
   int rc = exchange_halo(ctx, rec_doubles);
   if (rc) return rc;
+  if (scan_q) {
+    const int64_t ng = ctx->ghost_n[0] + ctx->ghost_n[1];
+    const int q_lo = ctx->D == 2 ? GradRec<2, true>::Q0 : GradRec<3, true>::Q0, q_hi = ctx->D == 2 ? GradRec<2, true>::FULL : GradRec<3, true>::FULL;
+    if (ng > 0) {
+      ghost_q_flag<<<(unsigned)cdiv(ng, 256), 256, 0, ctx->comm_stream>>>(ctx->rec + ctx->n * rec_doubles, ng, rec_doubles, q_lo, q_hi, ctx->d_qflag + 1);
+      ctx->launches++;
+    }
+  }
   const TaskSplit ts = split_tasks(ctx, nt);
   const int64_t nb = ts.i0 + (ts.ntasks - ts.i1);
   if (nb > 0) {
@@ -623,12 +634,14 @@ int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
     if (do_local) {
       PhaseTimer pt(ctx, PH_LOCAL);
       sp.do_eos = 0; sp.do_local = 1;
+      CUDA_OK(cudaMemsetAsync(ctx->d_qflag, 0, sizeof(int), ctx->stream));
       DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
     }
     return CCB_OK;
   }
   PhaseTimer pt(ctx, do_eos ? PH_THERMO : PH_LOCAL);
   sp.do_eos = do_eos; sp.do_local = do_local;
+  if (do_local) CUDA_OK(cudaMemsetAsync(ctx->d_qflag, 0, sizeof(int), ctx->stream));
   DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
   return CCB_OK;
 }
@@ -772,6 +785,13 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   CUDA_OK(cudaMalloc(&ctx->d_small, sizeof(int32_t) * 8));
   CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t) * 8, ctx->stream));
   CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
+  {
+    CUDA_OK(cudaMalloc(&ctx->d_qflag, sizeof(int) * 2));
+    const int one_zero[2] = {1, 0};  // until the first local update has looked: assume non-zero currents
+    CUDA_OK(cudaMemcpy(ctx->d_qflag, one_zero, sizeof(one_zero), cudaMemcpyHostToDevice));
+    ctx->dv.qflag = ctx->d_qflag;
+  }
+
   for (int p = 0; p < PH_COUNT; ++p) { ctx->phase_ms[p] = 0.; ctx->phase_calls[p] = 0; }
   setup_grid(ctx);
   ctx->slab_lo = 0; ctx->slab_hi = ctx->grid.nc[0];
@@ -804,7 +824,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
-  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends);
+  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends); cudaFree(ctx->d_qflag);
   if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_halo); }
   cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
   ctx->comm.reset();

@@ -103,6 +103,14 @@ __global__ void pack_rows_indexed(MigrateList ml, const uint32_t* __restrict__ l
   for (int c = 0; c < ml.ncols; ++c) dbuf[(int64_t)c * count + k] = ml.col[c][i];
   for (int c = 0; c < 4; ++c) ibuf[(int64_t)c * count + k] = ml.icol[c][i];
 }
+// any non-zero entry in [lo, hi) of the `count` received gradient records of `rec_doubles` doubles each -> *flag = 1
+__global__ void ghost_q_flag(const double* __restrict__ rec, int64_t count, int rec_doubles, int lo, int hi, int* __restrict__ flag) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= count) return;
+  bool nz = false;
+  for (int c = lo; c < hi; ++c) nz |= (rec[k * rec_doubles + c] != 0.0);
+  if (nz) *flag = 1;
+}
 // the eight record offsets exchange_column_tables needs on the host, gathered for ONE device-to-host copy
 __global__ void table_ends(const uint32_t* __restrict__ own_first, const uint32_t* __restrict__ own_last, const uint32_t* __restrict__ tab_left,
                            const uint32_t* __restrict__ tab_right, int64_t P, int has_left, int has_right, uint32_t* __restrict__ out) {

@@ -100,8 +100,9 @@ struct FieldsPolicy {
   struct Prep { double w; int hit; };
   __device__ static bool prep(const GatherParams& gp, const Target& t, const double2* sb, bool valid, Prep& p) {
     const double2 b0 = sb[0], b1 = sb[1];
-    const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = t.x[2] - b1.x;
-    const double r2 = dist_sqr_exact(dx, dy, dz);
+    const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = (D == 3) ? t.x[2] - b1.x : 0.0;
+    // D = 2: z = 0 for every particle, and adding the exact zero dz*dz does not change the sum: skipped
+    const double r2 = (D == 3) ? dist_sqr_exact(dx, dy, dz) : __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
     bool in = valid && r2 <= gp.rsqr;  // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523)
     // A task scans the cells [fa - 1, fb + 1] of its row, wider than the 3-cell stencil of one target. A source further
     // than one cell away can only pass the cut-off when it sits EXACTLY on it (cell edge = 2h to rounding, lattice
@@ -124,7 +125,7 @@ struct FieldsPolicy {
     p.hit = in ? 1 : 0;
     return in;
   }
-  __device__ static void accum(const double2* sb, const Prep& p, Acc& a) {
+  __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool /*qnz*/) {
     const double2 b1 = sb[1], b2 = sb[2], b3 = sb[3];
     a.cnt += p.hit;
     a.sig += b1.y * p.w;
@@ -261,7 +262,7 @@ struct GradPolicy {
     double rel[3];
     rel[0] = t.x[0] - b0.x; rel[1] = t.x[1] - b0.y;
     rel[2] = (D == 3) ? t.x[2] - b1.x : 0.0;
-    const double r2 = dist_sqr_exact(rel[0], rel[1], rel[2]);
+    const double r2 = (D == 3) ? dist_sqr_exact(rel[0], rel[1], rel[2]) : __dadd_rn(__dmul_rn(rel[0], rel[0]), __dmul_rn(rel[1], rel[1]));
     // outside the neighbour list, or coincident (self): grad W(0) = 0 and every pair term carries grad W
     const bool in = valid && (r2 <= gp.rsqr) && r2 != 0.0;
     double gK[D];
@@ -276,16 +277,27 @@ struct GradPolicy {
     return in;
   }
   // the record is consumed 16 bytes at a time, in layout order: no more than one chunk is live at any point
-  __device__ static void accum(const double2* sb, const Prep& p, Acc& a) {
+  // qnz = false: every record of this launch carries q^mu_a = 0 (DeviceView::qflag), so the chunks from Q0 on (Q0, QI,
+  // padding) contribute exact zeros and are neither loaded nor accumulated.
+  static constexpr int KQ = DIFF ? (R::Q0 + 1) / 2 : REC / 2;  // first chunk that holds nothing but q^mu_a entries
+  __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool qnz) {
 #pragma unroll
     for (int d = 0; d < D; ++d) a.sA[d] += p.A[d];
     if (SHEAR || DIFF) a.sKv += p.Kv;
     if (R::M == 2) consume(3, sb[1].y, p.A, p.Kv, a);
 #pragma unroll
-    for (int k = 2; k < REC / 2; ++k) {
+    for (int k = 2; k < KQ; ++k) {
       const double2 v = sb[k];
       consume(2 * k, v.x, p.A, p.Kv, a);
       consume(2 * k + 1, v.y, p.A, p.Kv, a);
+    }
+    if (DIFF && qnz) {
+#pragma unroll
+      for (int k = KQ; k < REC / 2; ++k) {
+        const double2 v = sb[k];
+        consume(2 * k, v.x, p.A, p.Kv, a);
+        consume(2 * k + 1, v.y, p.A, p.Kv, a);
+      }
     }
   }
   __device__ static void store(const DeviceView& dv, const GatherParams&, int64_t i, const Acc& a) {
@@ -382,6 +394,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   tg.cf = (int)(dv.key[active ? i : first] % (uint32_t)((g.nc[2] > 1) ? g.nc[2] : g.nc[1]));
   typename P::Acc acc;
   P::init(acc);
+  const bool qnz = (dv.qflag[0] | dv.qflag[1]) != 0;  // gradient gather with diffusion: see GradPolicy::accum
 
   // The cells of a grid row along the fastest axis are contiguous in the sorted order: F cells per row,
   // row index rho = key / F. A task's particles lie in the rows rho_f .. rho_l (almost always one row; two when
@@ -531,7 +544,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
           for (int w = 0; w < NW; ++w)
             if (base == w * 32) m[w] ^= low;
           typename P::Prep pp;
-          if (P::prep(gp, tg, srec + j * RS2, true, pp)) P::accum(srec + j * RS2, pp, acc);
+          if (P::prep(gp, tg, srec + j * RS2, true, pp)) P::accum(srec + j * RS2, pp, acc, qnz);
         }
       }
     }

@@ -88,7 +88,7 @@ __device__ __forceinline__ bool eos_from_sBSQ(const StageParams& sp, double s, d
 template <int D, bool DIFF>
 __device__ __forceinline__ void pack_grad_record(double* __restrict__ rec, int64_t i, const double* x, const double* v, double m_s,
                                                  double sig_lab, double bulk, const Thermo& th, const double shv[4][4],
-                                                 const double q[3][4]) {
+                                                 const double q[3][4], int* __restrict__ qflag) {
   using R = GradRec<D, DIFF>;
   double r[R::REC];
 #pragma unroll
@@ -113,6 +113,12 @@ __device__ __forceinline__ void pack_grad_record(double* __restrict__ rec, int64
 #pragma unroll
       for (int d = 0; d < D; ++d) r[R::QI + c * D + d] = sigsqr * q[c][d + 1];
     }
+    // zero diffusion currents everywhere (kappa = 0 and no initial diffusion, as in the reference's own inputs) let the
+    // gradient gather skip the q^mu_a part of every record: tell it when that is not the case
+    bool nz = false;
+#pragma unroll
+    for (int k = R::Q0; k < R::FULL; ++k) nz |= (r[k] != 0.0);
+    if (nz) *qflag = 1;
   }
   double2* o = reinterpret_cast<double2*>(rec + i * R::REC);
 #pragma unroll
@@ -169,8 +175,8 @@ __global__ void eos_local_kernel(DeviceView dv, StageParams sp) {
 #pragma unroll
   for (int d = 0; d < 3; ++d) { x[d] = col(dv.f[CCB_F_POSITION], dv.cap, d, i); v[d] = col(dv.f[CCB_F_V], dv.cap, d, i); }
   const double m_s = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
-  if (sp.fl.diffusion) pack_grad_record<D, true>(dv.rec_grad, i, x, v, m_s, sig_lab, bulk, th, shv, q);
-  else pack_grad_record<D, false>(dv.rec_grad, i, x, v, m_s, sig_lab, bulk, th, shv, q);
+  if (sp.fl.diffusion) pack_grad_record<D, true>(dv.rec_grad, i, x, v, m_s, sig_lab, bulk, th, shv, q, dv.qflag);
+  else pack_grad_record<D, false>(dv.rec_grad, i, x, v, m_s, sig_lab, bulk, th, shv, q, dv.qflag);
 }
 
 // the 13 transport scalars phase 08 stored (column order of CCB_F_TRANSPORT, include/ccake_b200.h)

@@ -21,6 +21,12 @@ CASES = {
     "viscous_2d": (lambda: viscous_settings(), lambda: gubser_ic(dx=0.1, shear=True)),
     "viscous_2d_vorticity_cs2zeta": (lambda: viscous_settings(use_vorticity=True, zetaMode="cs2_dependent"), lambda: gubser_ic(dx=0.1, shear=True)),
     "charged_2d_diffusion": (lambda: charged_settings(), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    # diffusion code path on with kappa = 0 (the reference's own config_visc_gubser.yaml / input_ampt.yaml): q^mu_a stays zero
+    # and the gradient gather skips that part of the records (DeviceView::qflag)
+    "charged_2d_zero_kappa": (lambda: charged_settings(kappa_00=0.0, kappa_11=0.0, kappa_22=0.0, kappa_01=0.0, kappa_10=0.0),
+                              lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "charged_3d_milne_zero_kappa": (lambda: charged_settings(kappa_00=0.0, kappa_11=0.0, kappa_22=0.0, kappa_01=0.0, kappa_10=0.0, **D3),
+                                    lambda: blob_ic_3d(n_side=14)),
     "ideal_2d_cartesian": (lambda: ideal_settings(coordinate_system="cartesian"), lambda: gubser_ic(dx=0.1)),
     "viscous_3d_milne": (lambda: viscous_settings(**D3), lambda: blob_ic_3d(n_side=14)),
     "charged_3d_milne_diffusion": (lambda: charged_settings(**D3), lambda: blob_ic_3d(n_side=14)),
