@@ -574,6 +574,7 @@ int do_build_cells(ccb_ctx* ctx) {
 
 int do_prologue(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_GAMMA);
+  CUDA_OK(cudaMemsetAsync(ctx->d_qflag + 2, 0, sizeof(int), ctx->stream));
   DISPATCH_DM("prologue_kernel", launch_prologue, ctx->stream, ctx->dv, ctx->t);
   return CCB_OK;
 }
@@ -583,15 +584,19 @@ int do_prologue(ccb_ctx* ctx) {
 template <class F>
 int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& launch) {
   if (!ctx->comm) return launch(gp, ctx->stream);
-  const bool scan_q = rec_doubles != REC_F && ctx->cfg.using_diffusion;  // gradient records: do the ghosts carry q^mu_a != 0?
-  if (scan_q) CUDA_OK(cudaMemsetAsync(ctx->d_qflag + 1, 0, sizeof(int), ctx->stream));
+  // do the ghost records carry what the own records may lack (q^mu_a != 0 for the gradient gather, charges for the fields)?
+  const bool fields = rec_doubles == REC_F;
+  const bool scan = fields || ctx->cfg.using_diffusion;
+  int* gflag = ctx->d_qflag + (fields ? 3 : 1);
+  if (scan) CUDA_OK(cudaMemsetAsync(gflag, 0, sizeof(int), ctx->stream));
   int rc = exchange_halo(ctx, rec_doubles);
   if (rc) return rc;
-  if (scan_q) {
+  if (scan) {
     const int64_t ng = ctx->ghost_n[0] + ctx->ghost_n[1];
-    const int q_lo = ctx->D == 2 ? GradRec<2, true>::Q0 : GradRec<3, true>::Q0, q_hi = ctx->D == 2 ? GradRec<2, true>::FULL : GradRec<3, true>::FULL;
+    const int lo = fields ? 5 : (ctx->D == 2 ? GradRec<2, true>::Q0 : GradRec<3, true>::Q0);
+    const int hi = fields ? 8 : (ctx->D == 2 ? GradRec<2, true>::FULL : GradRec<3, true>::FULL);
     if (ng > 0) {
-      ghost_q_flag<<<(unsigned)cdiv(ng, 256), 256, 0, ctx->comm_stream>>>(ctx->rec + ctx->n * rec_doubles, ng, rec_doubles, q_lo, q_hi, ctx->d_qflag + 1);
+      ghost_q_flag<<<(unsigned)cdiv(ng, 256), 256, 0, ctx->comm_stream>>>(ctx->rec + ctx->n * rec_doubles, ng, rec_doubles, lo, hi, gflag);
       ctx->launches++;
     }
   }
@@ -786,8 +791,8 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t) * 8, ctx->stream));
   CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
   {
-    CUDA_OK(cudaMalloc(&ctx->d_qflag, sizeof(int) * 2));
-    const int one_zero[2] = {1, 0};  // until the first local update has looked: assume non-zero currents
+    CUDA_OK(cudaMalloc(&ctx->d_qflag, sizeof(int) * 4));
+    const int one_zero[4] = {1, 0, 1, 0};  // until the first local update has looked: assume non-zero currents
     CUDA_OK(cudaMemcpy(ctx->d_qflag, one_zero, sizeof(one_zero), cudaMemcpyHostToDevice));
     ctx->dv.qflag = ctx->d_qflag;
   }

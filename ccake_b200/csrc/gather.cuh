@@ -125,14 +125,19 @@ struct FieldsPolicy {
     p.hit = in ? 1 : 0;
     return in;
   }
-  __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool /*qnz*/) {
-    const double2 b1 = sb[1], b2 = sb[2], b3 = sb[3];
+  static constexpr int FLAG = 2;  // DeviceView::qflag[2..3]: some record carries a non-zero B, S or Q entry
+  // charged = false: every B, S, Q entry of this launch's records is zero; their sums stay exact zeros unread
+  __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool charged) {
+    const double2 b1 = sb[1], b2 = sb[2];
     a.cnt += p.hit;
     a.sig += b1.y * p.w;
     a.s += b2.x * p.w;
-    a.B += b2.y * p.w;
-    a.S += b3.x * p.w;
-    a.Q += b3.y * p.w;
+    if (charged) {
+      const double2 b3 = sb[3];
+      a.B += b2.y * p.w;
+      a.S += b3.x * p.w;
+      a.Q += b3.y * p.w;
+    }
   }
   __device__ static void store(const DeviceView& dv, const GatherParams& gp, int64_t i, const Acc& a) {
     const double gamma = dv.f[CCB_F_GAMMA][i];
@@ -279,6 +284,7 @@ struct GradPolicy {
   // the record is consumed 16 bytes at a time, in layout order: no more than one chunk is live at any point
   // qnz = false: every record of this launch carries q^mu_a = 0 (DeviceView::qflag), so the chunks from Q0 on (Q0, QI,
   // padding) contribute exact zeros and are neither loaded nor accumulated.
+  static constexpr int FLAG = 0;  // DeviceView::qflag[0..1]
   static constexpr int KQ = DIFF ? (R::Q0 + 1) / 2 : REC / 2;  // first chunk that holds nothing but q^mu_a entries
   __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool qnz) {
 #pragma unroll
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   tg.cf = (int)(dv.key[active ? i : first] % (uint32_t)((g.nc[2] > 1) ? g.nc[2] : g.nc[1]));
   typename P::Acc acc;
   P::init(acc);
-  const bool qnz = (dv.qflag[0] | dv.qflag[1]) != 0;  // gradient gather with diffusion: see GradPolicy::accum
+  const bool qnz = (dv.qflag[P::FLAG] | dv.qflag[P::FLAG + 1]) != 0;  // sparsity flag of this gather's records: see P::accum
 
   // The cells of a grid row along the fastest axis are contiguous in the sorted order: F cells per row,
   // row index rho = key / F. A task's particles lie in the rows rho_f .. rho_l (almost always one row; two when

@@ -39,6 +39,9 @@ __global__ void prologue_kernel(DeviceView dv, double t) {
                       col(dv.f[CCB_F_SPH_MASS], dv.cap, 1, i) * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 1, i));
   q[3] = make_double2(col(dv.f[CCB_F_SPH_MASS], dv.cap, 2, i) * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 2, i),
                       col(dv.f[CCB_F_SPH_MASS], dv.cap, 3, i) * col(dv.f[CCB_F_EXTENSIVE], dv.cap, 3, i));
+  // a run without conserved charges (all three *_charge_enabled switches off) smooths exact zeros: tell the field
+  // gather when that is NOT the case
+  if (q[2].y != 0.0 || q[3].x != 0.0 || q[3].y != 0.0) dv.qflag[2] = 1;
 }
 
 __device__ __forceinline__ void raise_error(DeviceView& dv, int code, int id) {

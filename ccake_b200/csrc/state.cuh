@@ -45,7 +45,8 @@ struct DeviceView {
   uint32_t* cell_start;        // ncells + 1
   double* rec_fields;          // 8 doubles / particle:  x y z m_s  m_s*ext_s m_B*ext_B m_S*ext_S m_Q*ext_Q
   double* rec_grad;            // REC_GRAD doubles / particle, see gather kernels
-  int* qflag;                  // [0] some own gradient record carries a non-zero diffusion current q^mu_a, [1] some ghost record does
+  int* qflag;                  // [0] some own gradient record carries a non-zero diffusion current q^mu_a, [1] some ghost record does;
+                               // [2], [3] likewise for a non-zero B, S or Q entry of the field records
   int32_t* tasks;              // first particle of every (cell, 32-target chunk)
   int32_t* ntasks;
   int32_t* err;                // [0] status code, [1] first offending particle id
