@@ -693,7 +693,8 @@ int surface_device_error(ccb_ctx* ctx) {
   CUDA_OK(cudaMemcpyAsync(e, ctx->d_small + 1, sizeof(e), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   if (e[0] != 0) {
-    const char* what = e[0] == CCB_ERR_NEG_ENTROPY ? "negative entropy density" : e[0] == CCB_ERR_EOS_NO_ROOT ? "EoS: no solution found" : "device error";
+    const char* what = e[0] == CCB_ERR_NEG_ENTROPY ? "negative entropy density" : e[0] == CCB_ERR_EOS_NO_ROOT ? "EoS: no solution found"
+                       : e[0] == CCB_ERR_OUT_OF_GRID ? "particle left the neighbour grid" : "device error";
     ctx->err = std::string(what) + " (first offending particle id " + std::to_string(e[1]) + ")";
     CUDA_OK(cudaMemsetAsync(ctx->d_small + 1, 0, 2 * sizeof(int32_t), ctx->stream));
     return e[0];

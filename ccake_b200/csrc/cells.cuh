@@ -37,6 +37,11 @@ __global__ void cell_key_kernel(DeviceView dv, CellGrid g, uint32_t* __restrict_
   for (int d = 0; d < 3; ++d) {
     const double x = dv.f[CCB_F_POSITION][(int64_t)d * dv.cap + i];
     int ci = (int)floor((x - g.min[d]) * g.rdx[d]);
+    // More than one cell outside the neighbour grid (NaN included): the clamped cell no longer bounds the particle's
+    // neighbours. The reference indexes out of bounds there (src/system_state.cpp:636-638); here it is an error.
+    if (!(ci >= -1 && ci <= g.nc[d])) {
+      if (atomicCAS(&dv.err[0], 0, (int)CCB_ERR_OUT_OF_GRID) == 0) dv.err[1] = dv.id[i];
+    }
     ci = ci < 0 ? 0 : (ci > g.nc[d] - 1 ? g.nc[d] - 1 : ci);
     c[d] = ci;
   }

@@ -398,3 +398,33 @@ def test_cell_build_properties_large(dx):
     ws.smooth_all_particle_fields()
     ws.synchronize()
     assert rel_err(ws.get("smoothed"), 3.0 * sm1) < 1e-13
+
+
+# ---- device-side failures become status codes (the reference exit()s or indexes out of bounds) ------------------
+def test_error_codes_surface_with_the_offending_particle():
+    from ccake_b200 import SPHWorkstation
+    from ccake_b200.workstation import CCAKEError
+
+    settings, ic = ideal_settings(), gubser_ic(dx=0.2)
+    ws = _make_ws(settings, ic)
+    pos = ws.get("position")
+    pos[7, 0] = 100.0                       # far outside the neighbour grid [-4, 4]
+    ws.set("position", pos)
+    ws.reset_neighbour_list()
+    with pytest.raises(CCAKEError) as e:
+        ws.synchronize()
+    assert e.value.code == 5 and "id 7" in str(e.value)          # CCB_ERR_OUT_OF_GRID
+    # negative entropy after an RK update (src/evolver.cpp:437-450)
+    ws = _make_ws(settings, ic)
+    ext = ws.get("extensive")
+    ext[3, 0] = -1.0
+    ws.set("extensive", ext)
+    with pytest.raises(CCAKEError) as e:
+        ws.advance_timestep(settings["dt"])
+        ws.synchronize()
+    assert e.value.code in (3, 4)                                  # CCB_ERR_NEG_ENTROPY, or the EoS refusing s < 0 first
+    # call-sequence errors
+    ws = SPHWorkstation(settings)
+    with pytest.raises(CCAKEError) as e:
+        ws.advance_timestep(0.01)
+    assert e.value.code == 6                                       # CCB_ERR_STATE
