@@ -160,6 +160,13 @@ __global__ void eos_local_kernel(DeviceView dv, StageParams sp) {
 #pragma unroll
   for (int c = 0; c < 9; ++c) ext_q[c] = sp.fl.diffusion ? col(dv.f[CCB_F_EXTENSIVE_DIFFUSION], dv.cap, c, i) : 0.0;
   rebuild_diffusion<D, MILNE>(m, u, gamma, sigma, ext_q, q);
+  if (sp.reg_enabled) {  // phase 06
+    const double rho[3] = {th.rhoB, th.rhoS, th.rhoQ};
+    if (regulate_diffusion_current(MILNE, sp.t, sp.reg_chi0, sp.reg_e0, sp.reg_xi0, sp.reg_rq_max, th.e, sigma, rho, q, ext_q)) {
+#pragma unroll
+      for (int c = 0; c < 9; ++c) col(dv.f[CCB_F_EXTENSIVE_DIFFUSION], dv.cap, c, i) = ext_q[c];
+    }
+  }
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll

@@ -196,4 +196,32 @@ CCB_HD void rebuild_diffusion(const Metric<MILNE>& m, const double* u, double ga
   }
 }
 
+// SPHWorkstation::regulate_diffusion (src/sph_workstation.cpp:133-218; PhysRevC.98.034916 Eqs. C6-C8): where the spacelike
+// norm |q_a| exceeds rq_max |rho_a| chi0 (F(e) - F(0)), F the Fermi function of (e - e0) / xi0, the current q^mu_a is
+// scaled back onto that bound and extensive_diffusion is made consistent with it. Returns true if anything changed.
+CCB_HD bool regulate_diffusion_current(bool milne, double t, double chi0, double e0, double xi0, double rq_max, double e, double sigma,
+                                       const double rho[3], double q[3][4], double ext_q[9]) {
+  const double fermi_offset = 1.0 / (exp(e0 / xi0) + 1.0);
+  const double t2 = t * t;
+  const double ferm = 1.0 / (exp(-(e - e0) / xi0) + 1.0);
+  const double f_str = chi0 * (ferm - fermi_offset);
+  bool changed = false;
+  CCB_UNROLL for (int c = 0; c < 3; ++c) {
+    const double n_abs = fabs(rho[c]);
+    if (n_abs < 1.0e-15) continue;
+    const double q0 = q[c][0], q1 = q[c][1], q2 = q[c][2], q3 = q[c][3];
+    const double q3_sq = milne ? t2 * q3 * q3 : q3 * q3;
+    const double q_sq = q1 * q1 + q2 * q2 + q3_sq - q0 * q0;
+    if (q_sq <= 0.0) continue;
+    const double q_mag = sqrt(q_sq);
+    const double threshold = rq_max * n_abs * f_str;
+    if (q_mag <= threshold) continue;
+    const double scale = threshold / q_mag;
+    q[c][0] = q0 * scale; q[c][1] = q1 * scale; q[c][2] = q2 * scale; q[c][3] = q3 * scale;
+    CCB_UNROLL for (int d = 0; d < 3; ++d) ext_q[c * 3 + d] = q[c][d + 1] / sigma;
+    changed = true;
+  }
+  return changed;
+}
+
 }  // namespace ccb

@@ -20,6 +20,9 @@ struct StageParams {
   ConformalParams conf;
   int eos_type;
   int prohibit_unstable_cs2, prohibit_acausal_cs2;
+  // SPHWorkstation::regulate_diffusion (src/sph_workstation.cpp:133-218): e0, xi0 already in fm^-4
+  int reg_enabled;
+  double reg_chi0, reg_e0, reg_xi0, reg_rq_max;
 };
 
 inline StageParams make_stage_params(const ccb_config& c, double t, double h_stage, int do_update) {
@@ -39,6 +42,9 @@ inline StageParams make_stage_params(const ccb_config& c, double t, double h_sta
   for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) tp.kappa_over_T2[a][b] = c.constant_kappa_over_T2[a * 3 + b];
   sp.conf.c = c.conformal_c; sp.conf.T0 = c.conformal_T0; sp.conf.muB0 = c.conformal_muB0; sp.conf.muS0 = c.conformal_muS0;
   sp.conf.muQ0 = c.conformal_muQ0;
+  sp.reg_enabled = (c.using_diffusion != 0 && c.diffusion_regulator_enabled != 0) ? 1 : 0;
+  sp.reg_chi0 = c.diffusion_regulator_chi0; sp.reg_rq_max = c.diffusion_regulator_rq_max;
+  sp.reg_e0 = c.diffusion_regulator_e0 / 0.1973269804; sp.reg_xi0 = c.diffusion_regulator_xi0 / 0.1973269804;  // hbarc_GeVfm, include/constants.h:15
   sp.eos_type = c.eos_type; sp.prohibit_unstable_cs2 = c.prohibit_unstable_cs2; sp.prohibit_acausal_cs2 = c.prohibit_acausal_cs2;
   return sp;
 }

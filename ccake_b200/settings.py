@@ -28,6 +28,9 @@ DEFAULTS = dict(
     delta_PiPi_mode="default", lambda_Pipi_mode="default", phi1_mode="default", phi3_mode="default",
     diffusionMode="disabled", diffusionRelaxMode="default", C_B=0.0, prohibit_unstable_cs2=True,
     prohibit_acausal_cs2=True, restrict_mu_T_ratios=False, normalize_by_T=True,
+    # include/defaults.h:119-123
+    diffusion_regulator_enabled=False, diffusion_regulator_chi0=10.0, diffusion_regulator_e0=0.1, diffusion_regulator_xi0=0.01,
+    diffusion_regulator_rq_max=1.0,
 )
 
 _SHEAR = {"default": 0, "constant": 1, "JakiParam": 2, "LinearMus": 3, "interpolate": 4}
@@ -101,6 +104,9 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     for a in range(3):
         for b in range(3):
             c.constant_kappa_over_T2[a * 3 + b] = float(s.get("kappa_%d%d" % (a, b), 0.0))
+    c.diffusion_regulator_enabled = int(bool(s["diffusion_regulator_enabled"]))
+    for k in ("chi0", "e0", "xi0", "rq_max"):
+        setattr(c, "diffusion_regulator_" + k, float(s["diffusion_regulator_" + k]))
     c.eos_type = _capi.EOS_TABLE if s["eos_type"] == "table" else _capi.EOS_CONFORMAL
     # EquationOfState::set_up_chosen_EOSs, src/eos_initialization.cpp:216-231
     Nc, Nf = 3.0, 2.5
@@ -159,6 +165,11 @@ def from_yaml(path: str) -> dict:
         ("phi1_mode", vp + ("bulk", "phi1_mode")), ("phi3_mode", vp + ("bulk", "phi3_mode")),
         ("diffusionMode", vp + ("diffusion", "mode")), ("diffusionRelaxMode", vp + ("diffusion", "relaxation_mode")),
         ("C_B", vp + ("diffusion", "C_B")),
+        ("diffusion_regulator_enabled", vp + ("diffusion", "regulator", "enabled")),
+        ("diffusion_regulator_chi0", vp + ("diffusion", "regulator", "chi0")),
+        ("diffusion_regulator_e0", vp + ("diffusion", "regulator", "e0")),
+        ("diffusion_regulator_xi0", vp + ("diffusion", "regulator", "xi0")),
+        ("diffusion_regulator_rq_max", vp + ("diffusion", "regulator", "rq_max")),
     ]
     for key, p in table:
         s[key] = _get(y, p, s[key])

@@ -62,6 +62,10 @@ typedef struct {
   int modulate_zeta_with_tanh, critical_scaling_bulk;
   double constant_eta_over_s, constant_zeta_over_s, cs2_dependent_zeta_A, cs2_dependent_zeta_p, C_B;
   double constant_kappa_over_T2[9];
+  /* diffusion-current regulator, SPHWorkstation::regulate_diffusion (src/sph_workstation.cpp:133-218; Settings,
+   * include/settings.h:211-215; off by default, include/defaults.h:119-123). e0 and xi0 in GeV/fm^3 as in the YAML. */
+  int diffusion_regulator_enabled;
+  double diffusion_regulator_chi0, diffusion_regulator_e0, diffusion_regulator_xi0, diffusion_regulator_rq_max;
   /* equation of state */
   int eos_type;            /* CCB_EOS_* */
   double conformal_c, conformal_T0, conformal_muB0, conformal_muS0, conformal_muQ0;
@@ -222,7 +226,7 @@ int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host);
 int ccb_build_cells(ccb_ctx* ctx);        /* 01 SystemState::reset_neighbour_list (src/system_state.cpp:651-719) */
 int ccb_smooth_fields(ccb_ctx* ctx);      /* 02+03 TEOM::update_velocity (src/eom_default.cpp:18-38) + smooth_all_particle_fields (src/sph_workstation.cpp:495-578) */
 int ccb_update_thermodynamics(ccb_ctx* ctx); /* 04 update_all_particle_thermodynamics (src/sph_workstation.cpp:1714-1772) */
-int ccb_local_update(ccb_ctx* ctx);       /* 05+08 TEOM::reset_pi_tensor (src/eom_default.cpp:57-172) + update_all_particle_viscosities (src/sph_workstation.cpp:1623-1699) */
+int ccb_local_update(ccb_ctx* ctx);       /* 05+06+08 TEOM::reset_pi_tensor (src/eom_default.cpp:57-172) + regulate_diffusion (src/sph_workstation.cpp:133-218) + update_all_particle_viscosities (src/sph_workstation.cpp:1623-1699) */
 int ccb_smooth_gradients(ccb_ctx* ctx);   /* 09 smooth_all_particle_gradients (src/sph_workstation.cpp:797-986) */
 int ccb_time_derivatives(ccb_ctx* ctx);   /* 10 TEOM::evaluate_time_derivatives (src/eom_default.cpp:212-869) */
 int ccb_get_time_derivatives(ccb_ctx* ctx); /* all of the above in order */

@@ -262,6 +262,11 @@ std::shared_ptr<Settings> parse_settings(const char* kv) {
     else if (k == "bulk_from_trace") s->bulk_from_trace = to_bool(v);
     else if (k == "bulkRelaxMode") s->bulkRelaxMode = v;
     else if (k == "modulate_zeta_with_tanh") s->modulate_zeta_with_tanh = to_bool(v);
+    else if (k == "diffusion_regulator_enabled") s->diffusion_regulator_enabled = to_bool(v);
+    else if (k == "diffusion_regulator_chi0") s->diffusion_regulator_chi0 = std::stod(v);
+    else if (k == "diffusion_regulator_e0") s->diffusion_regulator_e0 = std::stod(v);
+    else if (k == "diffusion_regulator_xi0") s->diffusion_regulator_xi0 = std::stod(v);
+    else if (k == "diffusion_regulator_rq_max") s->diffusion_regulator_rq_max = std::stod(v);
     else if (k == "delta_PiPi_mode") s->delta_PiPi_mode = v;
     else if (k == "lambda_Pipi_mode") s->lambda_Pipi_mode = v;
     else if (k == "phi1_mode") s->phi1_mode = v;

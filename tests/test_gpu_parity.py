@@ -27,6 +27,15 @@ CASES = {
                               lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
     "charged_3d_milne_zero_kappa": (lambda: charged_settings(kappa_00=0.0, kappa_11=0.0, kappa_22=0.0, kappa_01=0.0, kappa_10=0.0, **D3),
                                     lambda: blob_ic_3d(n_side=14)),
+    # SPHWorkstation::regulate_diffusion (phase 06) with a bound tight enough to clip a good part of the currents
+    "charged_2d_diffusion_regulated": (lambda: charged_settings(diffusion_regulator_enabled=True, diffusion_regulator_chi0=2e-5,
+                                                                 diffusion_regulator_e0=2.0, diffusion_regulator_xi0=1.0,
+                                                                 diffusion_regulator_rq_max=1.0, kappa_00=0.4, kappa_11=0.3, kappa_22=0.2),
+                                       lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "charged_3d_milne_diffusion_regulated": (lambda: charged_settings(diffusion_regulator_enabled=True, diffusion_regulator_chi0=2e-5,
+                                                                       diffusion_regulator_e0=2.0, diffusion_regulator_xi0=1.0,
+                                                                       kappa_00=0.4, kappa_11=0.3, kappa_22=0.2, **D3),
+                                             lambda: blob_ic_3d(n_side=14)),
     "ideal_2d_cartesian": (lambda: ideal_settings(coordinate_system="cartesian"), lambda: gubser_ic(dx=0.1)),
     "viscous_3d_milne": (lambda: viscous_settings(**D3), lambda: blob_ic_3d(n_side=14)),
     "charged_3d_milne_diffusion": (lambda: charged_settings(**D3), lambda: blob_ic_3d(n_side=14)),
