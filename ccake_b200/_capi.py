@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libccake_b200.so")
 
 CCB_OK, CCB_ERR_INVALID, CCB_ERR_CUDA, CCB_ERR_NEG_ENTROPY, CCB_ERR_EOS_NO_ROOT, CCB_ERR_OUT_OF_GRID, CCB_ERR_STATE, CCB_ERR_COMM = range(8)
 COORD_HYPERBOLIC, COORD_CARTESIAN = 0, 1
-EOS_CONFORMAL, EOS_TABLE = 0, 1
+EOS_CONFORMAL, EOS_TABLE, EOS_TANH_CONFORMAL, EOS_CONFORMAL_DIAGONAL = 0, 1, 2, 3
 
 
 class Config(C.Structure):

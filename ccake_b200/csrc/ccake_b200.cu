@@ -65,7 +65,8 @@ struct ccb_ctx {
   std::unique_ptr<ccb::HostTable> table;
   double *d_hot_s = nullptr, *d_hot_e = nullptr, *d_full = nullptr;
   ccb::EosChain chain;
-  bool have_table = false;
+  bool have_table = false;   // the EoS chain is ready: table loaded, or an analytic single-member chain (tanh_conformal, conformal_diagonal)
+  bool use_chain = false;    // phase 04 runs through the chain kernels (every eos_type but the closed-form conformal one)
   int chunk = 128, chunk_fields = 64;   // targets per gather task (= threads per CTA) of the gradient / field gather
   int sms = 148;
   // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
@@ -628,8 +629,8 @@ int do_gather_fields(ccb_ctx* ctx) {
 
 int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
   StageParams sp = make_stage(ctx, 0.0, 0);
-  if (ctx->cfg.eos_type == CCB_EOS_TABLE) {
-    // tabulated EoS: the root search has its own kernel (register-heavy, divergent); the streaming
+  if (ctx->use_chain) {
+    // tabulated / chain EoS: the root search has its own kernel (register-heavy, divergent); the streaming
     // local update then reads the thermodynamics it stored
     if (!ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
     if (do_eos) {
@@ -704,7 +705,7 @@ int surface_device_error(ccb_ctx* ctx) {
 
 int do_init_particles(ccb_ctx* ctx, const StageParams& sp) {
   int eos_done = 0;
-  if (ctx->cfg.eos_type == CCB_EOS_TABLE) {
+  if (ctx->use_chain) {
     if (!ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
     LAUNCHER("eos_chain_init_kernel", launch_eos_chain_init(ctx->stream, ctx->dv, ctx->chain, ctx->init_tmp, ctx->cfg.input_as_entropy));
     eos_done = 1;
@@ -779,7 +780,24 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   *out = ctx;  // handed back even on failure so that ccb_last_error works
   if (cfg->dim != 2 && cfg->dim != 3) { ctx->err = "dim must be 2 or 3"; return CCB_ERR_INVALID; }
   if (cfg->rk_order != 2) { ctx->err = "rk_order must be 2"; return CCB_ERR_INVALID; }
-  if (cfg->eos_type != CCB_EOS_CONFORMAL && cfg->eos_type != CCB_EOS_TABLE) { ctx->err = "eos_type must be CCB_EOS_CONFORMAL or CCB_EOS_TABLE"; return CCB_ERR_INVALID; }
+  if (cfg->eos_type < CCB_EOS_CONFORMAL || cfg->eos_type > CCB_EOS_CONFORMAL_DIAGONAL) { ctx->err = "eos_type must be one of CCB_EOS_*"; return CCB_ERR_INVALID; }
+  ctx->use_chain = cfg->eos_type != CCB_EOS_CONFORMAL;
+  if (cfg->eos_type == CCB_EOS_TANH_CONFORMAL || cfg->eos_type == CCB_EOS_CONFORMAL_DIAGONAL) {
+    // EquationOfState::set_up_chosen_EOSs, src/eos_initialization.cpp:249-266: a chain of ONE analytic member
+    std::memset(&ctx->chain, 0, sizeof(ctx->chain));
+    EosChain& ch = ctx->chain;
+    ch.n = 1;
+    const AnalyticParams P{cfg->conformal_c, cfg->conformal_T0, cfg->conformal_muB0, cfg->conformal_muS0, cfg->conformal_muQ0,
+                           220.0 / kHbarcMeVfm, 120.0 / kHbarcMeVfm};
+    double r[TH_N];
+    const double T_FO = cfg->freeze_out_temperature_MeV / kHbarcMeVfm;
+    if (cfg->eos_type == CCB_EOS_TANH_CONFORMAL) { ch.kind[0] = EOS_KIND_TANH; ch.tanh_p = P; tanh_full_thermo(P, T_FO, 0.0, 0.0, 0.0, r); }
+    else { ch.kind[0] = EOS_KIND_DIAGONAL; ch.diag_p = P; ch.diag_p.Tc = ch.diag_p.Ts = 0.0; diagonal_full_thermo(ch.diag_p, T_FO, 0.0, 0.0, 0.0, r); }
+    ch.prohibit_unstable_cs2 = cfg->prohibit_unstable_cs2; ch.prohibit_acausal_cs2 = cfg->prohibit_acausal_cs2;
+    ch.restrict_mu_T_ratios = cfg->restrict_mu_T_ratios;
+    ctx->efcheck = r[TH_E];  // SPHWorkstation::initialize, src/sph_workstation.cpp:66-81
+    ctx->have_table = true;
+  }
   if (!(cfg->hT > 0.0)) { ctx->err = "hT must be positive"; return CCB_ERR_INVALID; }
   ctx->D = cfg->dim;
   ctx->milne = cfg->coordinate_system == CCB_COORD_HYPERBOLIC;
@@ -815,7 +833,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   ctx->k2 = make_kernel_norm(2, cfg->hT);
   ctx->k1 = make_kernel_norm(1, cfg->hEta > 0 ? cfg->hEta : cfg->hT);
   // efcheck = e(T_FO, mu = 0): SPHWorkstation::initialize, src/sph_workstation.cpp:66-81
-  {
+  if (cfg->eos_type == CCB_EOS_CONFORMAL || cfg->eos_type == CCB_EOS_TABLE) {  // (the table's own value replaces it on load)
     const double T = cfg->freeze_out_temperature_MeV / kHbarcMeVfm;
     ConformalParams cp{cfg->conformal_c, cfg->conformal_T0, cfg->conformal_muB0, cfg->conformal_muS0, cfg->conformal_muQ0};
     double r[TH_N];

@@ -41,6 +41,8 @@ _KAPPA = {"constant_over_T2": 0, "DNMR": 1, "kappaB_coth": 2}
 _TAU_Q = {"constant_over_T": 0, "cb_over_T": 1}
 _DELTA = {"default": 0, "israel-stewart": 1, "disabled": 2}
 _ONOFF = {"default": 0, "disabled": 1}
+_EOS = {"conformal": _capi.EOS_CONFORMAL, "table": _capi.EOS_TABLE, "tanh_conformal": _capi.EOS_TANH_CONFORMAL,
+        "conformal_diagonal": _capi.EOS_CONFORMAL_DIAGONAL}
 
 
 def derived_switches(s: dict) -> dict:
@@ -65,8 +67,8 @@ def _mode(table, value, what):
 def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -> _capi.Config:
     s = dict(DEFAULTS)
     s.update(settings)
-    if s["eos_type"] not in ("conformal", "table"):
-        raise NotImplementedError("eos_type %r: the conformal and the tabulated EoS are available in this build" % s["eos_type"])
+    if s["eos_type"] not in _EOS:
+        raise NotImplementedError("eos_type %r: conformal, table, tanh_conformal and conformal_diagonal are available in this build" % s["eos_type"])
     c = _capi.Config()
     c.dim = int(s["dim"])
     c.coordinate_system = _capi.COORD_CARTESIAN if s["coordinate_system"] == "cartesian" else _capi.COORD_HYPERBOLIC
@@ -107,7 +109,7 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     c.diffusion_regulator_enabled = int(bool(s["diffusion_regulator_enabled"]))
     for k in ("chi0", "e0", "xi0", "rq_max"):
         setattr(c, "diffusion_regulator_" + k, float(s["diffusion_regulator_" + k]))
-    c.eos_type = _capi.EOS_TABLE if s["eos_type"] == "table" else _capi.EOS_CONFORMAL
+    c.eos_type = _EOS[s["eos_type"]]
     # EquationOfState::set_up_chosen_EOSs, src/eos_initialization.cpp:216-231
     Nc, Nf = 3.0, 2.5
     c.conformal_c = math.pi * math.pi * (2.0 * (Nc * Nc - 1.0) + (7.0 / 2.0) * Nc * Nf) / 90.0

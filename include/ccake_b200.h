@@ -40,7 +40,9 @@ typedef enum {
 } ccb_status;
 
 enum { CCB_COORD_HYPERBOLIC = 0, CCB_COORD_CARTESIAN = 1 };
-enum { CCB_EOS_CONFORMAL = 0, CCB_EOS_TABLE = 1 };
+/* Settings::eos_type (EquationOfState::set_up_chosen_EOSs, src/eos_initialization.cpp:216-279): "conformal", "table",
+ * "tanh_conformal" (Tc = 220 MeV, Ts = 120 MeV), "conformal_diagonal" */
+enum { CCB_EOS_CONFORMAL = 0, CCB_EOS_TABLE = 1, CCB_EOS_TANH_CONFORMAL = 2, CCB_EOS_CONFORMAL_DIAGONAL = 3 };
 
 /* Mirror of the Settings fields the hot path consumes (reference include/settings.h,
  * SURVEY.md appendix B). Mode integers take the values of the reference enums in

@@ -36,6 +36,10 @@ CASES = {
                                                                        diffusion_regulator_e0=2.0, diffusion_regulator_xi0=1.0,
                                                                        kappa_00=0.4, kappa_11=0.3, kappa_22=0.2, **D3),
                                              lambda: blob_ic_3d(n_side=14)),
+    # the two other analytic equations of state of EquationOfState::set_up_chosen_EOSs as the run's EoS
+    "tanh_conformal_2d_charged": (lambda: charged_settings(eos_type="tanh_conformal"), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "conformal_diagonal_2d_charged": (lambda: charged_settings(eos_type="conformal_diagonal"), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "tanh_conformal_3d_milne": (lambda: viscous_settings(eos_type="tanh_conformal", **D3), lambda: blob_ic_3d(n_side=14)),
     "ideal_2d_cartesian": (lambda: ideal_settings(coordinate_system="cartesian"), lambda: gubser_ic(dx=0.1)),
     "viscous_3d_milne": (lambda: viscous_settings(**D3), lambda: blob_ic_3d(n_side=14)),
     "charged_3d_milne_diffusion": (lambda: charged_settings(**D3), lambda: blob_ic_3d(n_side=14)),
