@@ -37,6 +37,9 @@ class Config(C.Structure):
         ("constant_eta_over_s", C.c_double), ("constant_zeta_over_s", C.c_double), ("cs2_dependent_zeta_A", C.c_double),
         ("cs2_dependent_zeta_p", C.c_double), ("C_B", C.c_double),
         ("constant_kappa_over_T2", C.c_double * 9),
+        ("critical_scaling_diffusion", C.c_int),
+        ("critical_point_T", C.c_double), ("critical_point_muB", C.c_double),
+        ("critical_gaussian_width_T", C.c_double), ("critical_gaussian_width_muB", C.c_double),
         ("diffusion_regulator_enabled", C.c_int),
         ("diffusion_regulator_chi0", C.c_double), ("diffusion_regulator_e0", C.c_double),
         ("diffusion_regulator_xi0", C.c_double), ("diffusion_regulator_rq_max", C.c_double),

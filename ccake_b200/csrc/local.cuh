@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams 
     Transport tc;
     load_transport(dv, i, tc);
     double kappa[3][3], tauq[3][3];
-    diffusion_coefficients(th, sp.tp, kappa, tauq);
+    diffusion_coefficients(th, sp.tp, sp.eos_type == CCB_EOS_TABLE && dv.eos_id[i] == 0, kappa, tauq);
     EomIn<D> in;
     load_eom_inputs<D>(dv, sp, i, in);
     eom_pass<D, MILNE, 1>(m, in, th, tc, kappa, tauq, sp.fl, out);
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams 
   Transport tc;
   load_transport(dv, i, tc);
   double kappa[3][3], tauq[3][3];
-  diffusion_coefficients(th, sp.tp, kappa, tauq);
+  diffusion_coefficients(th, sp.tp, sp.eos_type == CCB_EOS_TABLE && dv.eos_id[i] == 0, kappa, tauq);
   EomIn<D> in;
   load_eom_inputs<D>(dv, sp, i, in);
   eom_pass<D, MILNE, 2>(m, in, th, tc, kappa, tauq, sp.fl, out);

@@ -27,6 +27,9 @@ struct TransportParams {
   int modulate_zeta_with_tanh, critical_scaling_bulk;
   double eta_over_s, zeta_over_s, zeta_A, zeta_p, C_B;
   double kappa_over_T2[3][3];
+  // Gaussian suppression of kappa near the critical point (src/transport_coefficients.cpp:1047-1056), in fm^-1
+  int critical_scaling_diffusion;
+  double crit_T, crit_muB, crit_wT, crit_wmuB;
 };
 
 struct Transport {
@@ -109,7 +112,8 @@ CCB_HD void transport_coefficients(const Thermo& th, const TransportParams& P, T
 }
 
 // kappa_q and tau_q (3x3 over B,S,Q), src/transport_coefficients.cpp:580-623, :934-1022.
-CCB_HD void diffusion_coefficients(const Thermo& th, const TransportParams& P, double kappa[3][3], double tauq[3][3]) {
+// is_table: the particle's thermodynamics came from the tabulated EoS (thermo_info::eos_type_is_table)
+CCB_HD void diffusion_coefficients(const Thermo& th, const TransportParams& P, bool is_table, double kappa[3][3], double tauq[3][3]) {
   CCB_UNROLL for (int i = 0; i < 3; ++i) CCB_UNROLL for (int j = 0; j < 3; ++j) { kappa[i][j] = 0.0; tauq[i][j] = 0.0; }
   if (P.diffusion_mode == KAPPA_DNMR) return;
   if (P.diffusion_mode == KAPPA_B_COTH) {
@@ -126,7 +130,13 @@ CCB_HD void diffusion_coefficients(const Thermo& th, const TransportParams& P, d
     }
     return;
   }
-  CCB_UNROLL for (int i = 0; i < 3; ++i) CCB_UNROLL for (int j = 0; j < 3; ++j) kappa[i][j] = 1.0 * P.kappa_over_T2[i][j] * (th.T * th.T);
+  double suppression = 1.0;
+  if (P.critical_scaling_diffusion && is_table) {
+    const double dT = th.T - P.crit_T, dmuB = th.muB - P.crit_muB;
+    const double exponent = 0.5 * (dT * dT / (P.crit_wT * P.crit_wT) + dmuB * dmuB / (P.crit_wmuB * P.crit_wmuB));
+    suppression = 1.0 - exp(-exponent);
+  }
+  CCB_UNROLL for (int i = 0; i < 3; ++i) CCB_UNROLL for (int j = 0; j < 3; ++j) kappa[i][j] = suppression * P.kappa_over_T2[i][j] * (th.T * th.T);
   CCB_UNROLL for (int i = 0; i < 3; ++i) tauq[i][i] += 0.2 / th.T;
 }
 

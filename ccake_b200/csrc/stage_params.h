@@ -40,6 +40,9 @@ inline StageParams make_stage_params(const ccb_config& c, double t, double h_sta
   tp.eta_over_s = c.constant_eta_over_s; tp.zeta_over_s = c.constant_zeta_over_s; tp.zeta_A = c.cs2_dependent_zeta_A;
   tp.zeta_p = c.cs2_dependent_zeta_p; tp.C_B = c.C_B;
   for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) tp.kappa_over_T2[a][b] = c.constant_kappa_over_T2[a * 3 + b];
+  tp.critical_scaling_diffusion = c.critical_scaling_diffusion;   // MeV -> fm^-1 (hbarc_MeVfm, include/constants.h:16)
+  tp.crit_T = c.critical_point_T / 197.3269804; tp.crit_muB = c.critical_point_muB / 197.3269804;
+  tp.crit_wT = c.critical_gaussian_width_T / 197.3269804; tp.crit_wmuB = c.critical_gaussian_width_muB / 197.3269804;
   sp.conf.c = c.conformal_c; sp.conf.T0 = c.conformal_T0; sp.conf.muB0 = c.conformal_muB0; sp.conf.muS0 = c.conformal_muS0;
   sp.conf.muQ0 = c.conformal_muQ0;
   sp.reg_enabled = (c.using_diffusion != 0 && c.diffusion_regulator_enabled != 0) ? 1 : 0;

@@ -28,6 +28,9 @@ DEFAULTS = dict(
     delta_PiPi_mode="default", lambda_Pipi_mode="default", phi1_mode="default", phi3_mode="default",
     diffusionMode="disabled", diffusionRelaxMode="default", C_B=0.0, prohibit_unstable_cs2=True,
     prohibit_acausal_cs2=True, restrict_mu_T_ratios=False, normalize_by_T=True,
+    # include/defaults.h:67-71
+    critical_scaling_diffusion=False, critical_point_T=150.0, critical_point_muB=350.0, critical_gaussian_width_T=30.0,
+    critical_gaussian_width_muB=50.0,
     # include/defaults.h:119-123
     diffusion_regulator_enabled=False, diffusion_regulator_chi0=10.0, diffusion_regulator_e0=0.1, diffusion_regulator_xi0=0.01,
     diffusion_regulator_rq_max=1.0,
@@ -106,6 +109,9 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     for a in range(3):
         for b in range(3):
             c.constant_kappa_over_T2[a * 3 + b] = float(s.get("kappa_%d%d" % (a, b), 0.0))
+    c.critical_scaling_diffusion = int(bool(s["critical_scaling_diffusion"]))
+    for k in ("critical_point_T", "critical_point_muB", "critical_gaussian_width_T", "critical_gaussian_width_muB"):
+        setattr(c, k, float(s[k]))
     c.diffusion_regulator_enabled = int(bool(s["diffusion_regulator_enabled"]))
     for k in ("chi0", "e0", "xi0", "rq_max"):
         setattr(c, "diffusion_regulator_" + k, float(s["diffusion_regulator_" + k]))
@@ -167,6 +173,11 @@ def from_yaml(path: str) -> dict:
         ("phi1_mode", vp + ("bulk", "phi1_mode")), ("phi3_mode", vp + ("bulk", "phi3_mode")),
         ("diffusionMode", vp + ("diffusion", "mode")), ("diffusionRelaxMode", vp + ("diffusion", "relaxation_mode")),
         ("C_B", vp + ("diffusion", "C_B")),
+        ("critical_scaling_diffusion", vp + ("diffusion", "critical_scaling")),
+        ("critical_point_T", vp + ("diffusion", "critical_point", "T")),
+        ("critical_point_muB", vp + ("diffusion", "critical_point", "muB")),
+        ("critical_gaussian_width_T", vp + ("diffusion", "critical_gaussian_width", "T")),
+        ("critical_gaussian_width_muB", vp + ("diffusion", "critical_gaussian_width", "muB")),
         ("diffusion_regulator_enabled", vp + ("diffusion", "regulator", "enabled")),
         ("diffusion_regulator_chi0", vp + ("diffusion", "regulator", "chi0")),
         ("diffusion_regulator_e0", vp + ("diffusion", "regulator", "e0")),

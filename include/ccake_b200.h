@@ -66,6 +66,10 @@ typedef struct {
   double constant_kappa_over_T2[9];
   /* diffusion-current regulator, SPHWorkstation::regulate_diffusion (src/sph_workstation.cpp:133-218; Settings,
    * include/settings.h:211-215; off by default, include/defaults.h:119-123). e0 and xi0 in GeV/fm^3 as in the YAML. */
+  /* Gaussian suppression of kappa near the critical point (Settings::critical_scaling_diffusion ...,
+   * src/transport_coefficients.cpp:940-943, 1047-1056): table-EoS particles only; T, muB and widths in MeV */
+  int critical_scaling_diffusion;
+  double critical_point_T, critical_point_muB, critical_gaussian_width_T, critical_gaussian_width_muB;
   int diffusion_regulator_enabled;
   double diffusion_regulator_chi0, diffusion_regulator_e0, diffusion_regulator_xi0, diffusion_regulator_rq_max;
   /* equation of state */

@@ -86,7 +86,8 @@ SETTING_KEYS = frozenset([
     "phi6_mode", "phi7_mode", "input_initial_shear", "zetaMode", "constant_zeta_over_s", "cs2_dependent_zeta_A",
     "cs2_dependent_zeta_p", "bulk_from_trace", "bulkRelaxMode", "modulate_zeta_with_tanh", "delta_PiPi_mode",
     "lambda_Pipi_mode", "phi1_mode", "phi3_mode", "diffusionMode", "diffusionRelaxMode", "print_conservation_status",
-    "prohibit_unstable_cs2", "prohibit_acausal_cs2", "restrict_mu_T_ratios", "diffusion_regulator_enabled",
+    "prohibit_unstable_cs2", "prohibit_acausal_cs2", "restrict_mu_T_ratios", "C_B", "critical_scaling_bulk", "critical_scaling_diffusion",
+    "critical_point_T", "critical_point_muB", "critical_gaussian_width_T", "critical_gaussian_width_muB", "diffusion_regulator_enabled",
     "diffusion_regulator_chi0", "diffusion_regulator_e0", "diffusion_regulator_xi0", "diffusion_regulator_rq_max"])
 
 

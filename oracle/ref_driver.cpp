@@ -262,6 +262,13 @@ std::shared_ptr<Settings> parse_settings(const char* kv) {
     else if (k == "bulk_from_trace") s->bulk_from_trace = to_bool(v);
     else if (k == "bulkRelaxMode") s->bulkRelaxMode = v;
     else if (k == "modulate_zeta_with_tanh") s->modulate_zeta_with_tanh = to_bool(v);
+    else if (k == "C_B") s->C_B = std::stod(v);
+    else if (k == "critical_scaling_bulk") s->critical_scaling_bulk = to_bool(v);
+    else if (k == "critical_scaling_diffusion") s->critical_scaling_diffusion = to_bool(v);
+    else if (k == "critical_point_T") s->critical_point_T = std::stod(v);
+    else if (k == "critical_point_muB") s->critical_point_muB = std::stod(v);
+    else if (k == "critical_gaussian_width_T") s->critical_gaussian_width_T = std::stod(v);
+    else if (k == "critical_gaussian_width_muB") s->critical_gaussian_width_muB = std::stod(v);
     else if (k == "diffusion_regulator_enabled") s->diffusion_regulator_enabled = to_bool(v);
     else if (k == "diffusion_regulator_chi0") s->diffusion_regulator_chi0 = std::stod(v);
     else if (k == "diffusion_regulator_e0") s->diffusion_regulator_e0 = std::stod(v);

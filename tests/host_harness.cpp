@@ -86,7 +86,7 @@ template <int D, bool MILNE> static void eom_impl(const StageParams& sp, double 
     Transport tc;
     transport_coefficients(th, sp.tp, tc);
     double kappa[3][3], tauq[3][3];
-    diffusion_coefficients(th, sp.tp, kappa, tauq);
+    diffusion_coefficients(th, sp.tp, false, kappa, tauq);
     EomIn<D> in;
     for (int d = 0; d < D; ++d) {
       in.u[d] = A.u[3 * i + d]; in.v[d] = A.v[3 * i + d]; in.gradP[d] = A.gradP[3 * i + d]; in.gradBulk[d] = A.gradBulk[3 * i + d];

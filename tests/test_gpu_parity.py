@@ -40,12 +40,25 @@ CASES = {
     "tanh_conformal_2d_charged": (lambda: charged_settings(eos_type="tanh_conformal"), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
     "conformal_diagonal_2d_charged": (lambda: charged_settings(eos_type="conformal_diagonal"), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
     "tanh_conformal_3d_milne": (lambda: viscous_settings(eos_type="tanh_conformal", **D3), lambda: blob_ic_3d(n_side=14)),
+    # the transport-coefficient modes the other cases leave out (src/transport_coefficients.cpp)
+    "baryon_2d_kappaB_coth": (lambda: charged_settings(strange_charge_enabled=False, electric_charge_enabled=False, diffusionMode="kappaB_coth",
+                                                        diffusionRelaxMode="cb_over_T", C_B=0.4),
+                              lambda: _dense_baryons(gubser_ic(dx=0.1, shear=True, charges=True))),
+    "viscous_2d_minval": (lambda: viscous_settings(shearRelaxMode="minVal", delta_PiPi_mode="israel-stewart", lambda_Pipi_mode="disabled",
+                                                    phi7_mode="disabled"),
+                          lambda: gubser_ic(dx=0.1, shear=True)),
     "ideal_2d_cartesian": (lambda: ideal_settings(coordinate_system="cartesian"), lambda: gubser_ic(dx=0.1)),
     "viscous_3d_milne": (lambda: viscous_settings(**D3), lambda: blob_ic_3d(n_side=14)),
     "charged_3d_milne_diffusion": (lambda: charged_settings(**D3), lambda: blob_ic_3d(n_side=14)),
     "viscous_3d_cartesian": (lambda: viscous_settings(coordinate_system="cartesian", **D3), lambda: blob_ic_3d(n_side=14)),
     "viscous_3d_milne_factorized": (lambda: viscous_settings(factorized_kernel=True, **dict(D3, hEta=0.4)), lambda: blob_ic_3d(n_side=14)),
 }
+
+
+def _dense_baryons(ic):
+    """mu_B / T ~ 0.2: above the floor below which kappaB_coth switches the coefficient off (src/transport_coefficients.cpp:985-990)"""
+    ic["rhoB"] = 60.0 * ic["rhoB"]
+    return ic
 
 
 _TABLE_DIR = []
@@ -71,6 +84,12 @@ CASES.update({
     "table_charged_2d_diffusion": (lambda: charged_settings(**_table()), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
     "table_neutral_2d_shear_bulk": (lambda: viscous_settings(zetaMode="cs2_dependent", modulate_zeta_with_tanh=True, **_table()),
                                     lambda: gubser_ic(dx=0.1, shear=True)),
+    "table_charged_2d_critical_diffusion": (lambda: charged_settings(critical_scaling_diffusion=True, critical_point_T=400.0, critical_point_muB=20.0,
+                                                                    critical_gaussian_width_T=120.0, critical_gaussian_width_muB=60.0, **_table()),
+                                            lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
+    "table_charged_2d_critical_bulk": (lambda: charged_settings(zetaMode="cs2_dependent", critical_scaling_bulk=True, shearRelaxMode="minVal",
+                                                               **_table()),
+                                       lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
     "table_charged_3d_milne_bulk": (lambda: charged_settings(zetaMode="cs2_dependent", **dict(D3, **_table())), lambda: blob_ic_3d(n_side=14)),
 })
 
