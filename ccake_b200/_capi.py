@@ -107,6 +107,8 @@ def lib():
     L.ccb_set_eos_table.argtypes = [ctx, C.POINTER(EosTable)]
     L.ccb_load_eos_table_dat.argtypes = [ctx, C.c_char_p, C.c_int]
     L.ccb_eos_chain_parameters.argtypes = [ctx, dp]
+    L.ccb_eos_full_thermo.argtypes = [ctx, C.c_int, C.c_int64, dp, dp]
+    L.ccb_eos_locate.argtypes = [ctx, C.c_int, C.c_int64, dp, dp, ip, dp, ip]
     L.ccb_upload_ic.argtypes = [ctx, C.POINTER(IC)]
     L.ccb_set_field.argtypes = [ctx, C.c_int, dp]
     L.ccb_get_field.argtypes = [ctx, C.c_int, dp]
@@ -155,4 +157,4 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
             "ccb_measure_dfma_peak", "ccb_comm_unique_id", "ccb_comm_init", "ccb_comm_init_local", "ccb_set_slab",
             "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order",
-            "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters"]
+            "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]

@@ -58,4 +58,53 @@ __global__ void __launch_bounds__(128) eos_chain_init_kernel(DeviceView dv, EosC
   dv.eos_id[i] = res.eos;
 }
 
+// ---- host-callable queries (C ABI: ccb_eos_full_thermo, ccb_eos_locate) -----------------------------------------------
+// EoS_base::get_full_thermo (include/eos_base.h:12-50) of chain member `member` at n points (T, muB, muQ, muS); a point
+// outside the member's domain gives a row of NaN. conf != nullptr: the closed-form conformal EoS of a conformal run.
+__global__ void eos_query_kernel(EosChain ch, const ConformalParams* conf_or_null, ConformalParams conf, int member, int64_t n,
+                                 const double* __restrict__ pts, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x[4] = {pts[i * 4 + 0], pts[i * 4 + 1], pts[i * 4 + 2], pts[i * 4 + 3]};
+  double r[TH_N];
+  bool ok = true;
+  if (conf_or_null) conformal_full_thermo(conf, x[0], x[1], x[2], x[3], r);
+  else ok = chain_full_thermo(ch, member, x, r);
+  for (int k = 0; k < TH_N; ++k) out[i * TH_N + k] = ok ? r[k] : nan("");
+}
+// EquationOfState::update_s / s_out (src/eos.cpp:574-804, 834-977) + set_thermo for n density vectors (s | e, rhoB, rhoS, rhoQ):
+// located from `seed` (T, muB, muS, muQ; ignored when energy != 0) through the chain, starting at member start[i].
+// thermo: 16 columns per row in CCB_F_THERMO order; eos_out: the member that answered, -1 = no solution.
+__global__ void eos_locate_kernel(EosChain ch, ConformalParams conf, int use_chain, int energy, int64_t n, const double* __restrict__ dens,
+                                  const double* __restrict__ seed, const int32_t* __restrict__ start, double* __restrict__ thermo,
+                                  int32_t* __restrict__ eos_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = dens[i * 4 + 0], B = dens[i * 4 + 1], S = dens[i * 4 + 2], Q = dens[i * 4 + 3];
+  Thermo th;
+  int eos = -1;
+  bool ok;
+  if (use_chain) {
+    ChainResult res;
+    if (energy) ok = chain_s_out(ch, a, B, S, Q, res);
+    else {
+      const double pos[4] = {seed[i * 4 + 0], seed[i * 4 + 1], seed[i * 4 + 3], seed[i * 4 + 2]};  // solver order (T, muB, muQ, muS)
+      ok = chain_update_s(ch, start ? start[i] : 0, pos, a, B, S, Q, res);
+    }
+    if (ok) { chain_thermo(ch, res, th); eos = res.eos; }
+  } else {
+    double T, muB, muS, muQ;
+    ok = energy ? false : conformal_invert_s(conf, a, B, S, Q, T, muB, muS, muQ);
+    if (ok) {
+      double r[TH_N];
+      conformal_full_thermo(conf, T, muB, muQ, muS, r);
+      thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+      eos = 0;
+    }
+  }
+  const double v[16] = {th.T, th.muB, th.muS, th.muQ, th.e, th.s, th.rhoB, th.rhoS, th.rhoQ, th.p, th.cs2, th.w, th.dwds, th.dwdB, th.dwdS, th.dwdQ};
+  for (int k = 0; k < 16; ++k) thermo[i * 16 + k] = ok ? v[k] : nan("");
+  eos_out[i] = eos;
+}
+
 }  // namespace ccb

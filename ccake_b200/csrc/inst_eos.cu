@@ -13,4 +13,16 @@ cudaError_t launch_eos_chain_init(cudaStream_t s, const DeviceView& dv, const Eo
   return cudaGetLastError();
 }
 
+cudaError_t launch_eos_query(cudaStream_t s, const EosChain& ch, const ConformalParams* conf, int member, int64_t n, const double* pts, double* out) {
+  ConformalParams c{};
+  if (conf) c = *conf;
+  eos_query_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ch, conf, c, member, n, pts, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_eos_locate(cudaStream_t s, const EosChain& ch, const ConformalParams& conf, int use_chain, int energy, int64_t n,
+                              const double* dens, const double* seed, const int32_t* start, double* thermo, int32_t* eos_out) {
+  eos_locate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(ch, conf, use_chain, energy, n, dens, seed, start, thermo, eos_out);
+  return cudaGetLastError();
+}
+
 }  // namespace ccb

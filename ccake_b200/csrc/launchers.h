@@ -23,6 +23,10 @@ struct EosChain;
 // tabulated EoS + fall-back chain (eos_kernels.cuh): phase 04 of a derivative evaluation, and the initial e|s -> (T, mu) location
 cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const EosChain& ch);
 cudaError_t launch_eos_chain_init(cudaStream_t s, const DeviceView& dv, const EosChain& ch, const double* tmp, int input_as_entropy);
+// host-callable EoS queries (ccb_eos_full_thermo, ccb_eos_locate)
+cudaError_t launch_eos_query(cudaStream_t s, const EosChain& ch, const ConformalParams* conf, int member, int64_t n, const double* pts, double* out);
+cudaError_t launch_eos_locate(cudaStream_t s, const EosChain& ch, const ConformalParams& conf, int use_chain, int energy, int64_t n,
+                              const double* dens, const double* seed, const int32_t* start, double* thermo, int32_t* eos_out);
 template <bool MILNE>
 cudaError_t launch_reduce_totals(int nblocks, cudaStream_t s, const DeviceView& dv, double t, double* out,
                                  unsigned long long* nfrozen);

@@ -68,6 +68,26 @@ class SPHWorkstation:
         self._check(self._L.ccb_eos_chain_parameters(self._ctx, _dp(out)))
         return dict(tanh_conformal=out[0:7], conformal=out[7:12], conformal_diagonal=out[12:17], efcheck=out[17])
 
+    def eos_full_thermo(self, points, member=0):
+        """EoS_base::get_full_thermo at (T, muB, muQ, muS) points [fm^-1] -> (n, 17) in the table's field order."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 4)
+        out = np.empty((pts.shape[0], 17))
+        self._check(self._L.ccb_eos_full_thermo(self._ctx, int(member), pts.shape[0], _dp(pts), _dp(out)))
+        return out
+
+    def eos_locate(self, densities, seed=None, start=None, energy=False):
+        """EquationOfState::update_s (s, rhoB, rhoS, rhoQ from `seed` = T, muB, muS, muQ) or ::s_out (energy=True: e, rhoB, rhoS, rhoQ)
+        + set_thermo -> ((n, 16) thermo in CCB_F_THERMO order, (n,) answering member of chosen_EOSs; -1 = no solution)."""
+        d = np.ascontiguousarray(densities, dtype=np.float64).reshape(-1, 4)
+        n = d.shape[0]
+        sd = None if seed is None else np.ascontiguousarray(seed, dtype=np.float64).reshape(n, 4)
+        st = None if start is None else np.ascontiguousarray(start, dtype=np.int32)
+        th, eos = np.empty((n, 16)), np.empty(n, dtype=np.int32)
+        ip = C.POINTER(C.c_int32)
+        self._check(self._L.ccb_eos_locate(self._ctx, int(bool(energy)), n, _dp(d), None if sd is None else _dp(sd),
+                                           None if st is None else st.ctypes.data_as(ip), _dp(th), eos.ctypes.data_as(ip)))
+        return th, eos
+
     # -- plumbing --------------------------------------------------------------
     def _check(self, rc):
         if rc:

@@ -182,6 +182,18 @@ int ccb_load_eos_table_dat(ccb_ctx* ctx, const char* path, int normalize_by_T);
  * conformal, out[12..16] conformal_diagonal; out[17] = efcheck (src/sph_workstation.cpp:66-81) */
 int ccb_eos_chain_parameters(ccb_ctx* ctx, double out[18]);
 
+/* --- host queries of the equation of state (EquationOfState / EoS_base surface, include/eos.h:62-210, include/eos_base.h:12-50) ---
+ * Batched and evaluated on the device; all arrays are caller-owned HOST arrays, row-major; both calls synchronise.
+ * ccb_eos_full_thermo: EoS_base::get_full_thermo of member `member` of chosen_EOSs (0 = the run's default EoS) at n points
+ *   (T, muB, muQ, muS) [fm^-1] -> out[n][17] = p s B S Q e cs2 chiBB chiQQ chiSS chiBQ chiBS chiQS chiTB chiTQ chiTS chiTT;
+ *   a point outside the member's domain gives a row of NaN.
+ * ccb_eos_locate: EquationOfState::update_s (energy = 0: dens = s, rhoB, rhoS, rhoQ, located from seed = T, muB, muS, muQ through
+ *   the fall-back chain, starting at member start[i]; start may be NULL) or ::s_out (energy = 1: dens = e, rhoB, rhoS, rhoQ; seed
+ *   ignored, may be NULL) followed by set_thermo -> thermo[n][16] in CCB_F_THERMO order and the answering member eos[n]
+ *   (-1 and a NaN row where the reference would report "no solution"). */
+int ccb_eos_full_thermo(ccb_ctx* ctx, int member, int64_t n, const double* points, double* out);
+int ccb_eos_locate(ccb_ctx* ctx, int energy, int64_t n, const double* dens, const double* seed, const int32_t* start, double* thermo, int32_t* eos);
+
 /* --- state in / out ------------------------------------------------------- */
 /* n blank particles (ids 0..n-1); state is then injected with ccb_set_field.
  * Replaces SystemState::allocate_cabana_particles (src/system_state.cpp:58-63). */

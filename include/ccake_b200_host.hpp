@@ -50,6 +50,20 @@ class Context {
   }
   void set_eos_table(const ccb_eos_table& table) { check(ccb_set_eos_table(ctx_, &table)); }
 
+  // EoS_base::get_full_thermo / EquationOfState::update_s + set_thermo as batched device queries (include/ccake_b200.h).
+  std::vector<double> eos_full_thermo(const std::vector<double>& points_TBQS, int member = 0) {
+    const int64_t n = (int64_t)points_TBQS.size() / 4;
+    std::vector<double> out((size_t)n * 17);
+    check(ccb_eos_full_thermo(ctx_, member, n, points_TBQS.data(), out.data()));
+    return out;
+  }
+  void eos_locate(const std::vector<double>& densities, const std::vector<double>& seed, std::vector<double>& thermo16, std::vector<int32_t>& eos,
+                  bool energy = false) {
+    const int64_t n = (int64_t)densities.size() / 4;
+    thermo16.resize((size_t)n * 16); eos.resize((size_t)n);
+    check(ccb_eos_locate(ctx_, energy ? 1 : 0, n, densities.data(), seed.empty() ? nullptr : seed.data(), nullptr, thermo16.data(), eos.data()));
+  }
+
   // Slab decomposition (one Context per GPU / process; new: the reference is single-process). `unique_id` is the 128-byte
   // id rank 0 obtained from ccb_comm_unique_id and broadcast to the other ranks (MPI_Bcast, a file, a socket ...).
   void comm_init(const char unique_id[128]) { check(ccb_comm_init(ctx_, unique_id)); }

@@ -460,3 +460,54 @@ def test_error_codes_surface_with_the_offending_particle():
     with pytest.raises(CCAKEError) as e:
         ws.advance_timestep(0.01)
     assert e.value.code == 6                                       # CCB_ERR_STATE
+
+
+# ---- host-callable EoS queries (EquationOfState / EoS_base surface) through the C ABI ---------------------------------
+def test_eos_queries_match_reference():
+    """ccb_eos_full_thermo against EoS_base::get_full_thermo of every member of the chain, and ccb_eos_locate against what the
+    reference's phase 04 stored for the same densities and seeds (table run), plus the conformal run's closed-form inversion."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    from ccake_b200 import SPHWorkstation
+
+    HC = 197.3269804
+    settings = charged_settings(**_table())
+    ic = gubser_ic(dx=0.1, shear=True, charges=True)
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = SPHWorkstation(settings)
+    rng = np.random.default_rng(3)
+    pts = np.stack([rng.uniform(60, 620, 300), rng.uniform(-300, 300, 300), rng.uniform(-300, 300, 300), rng.uniform(-300, 300, 300)], 1) / HC
+    for member, name in enumerate(("table", "tanh_conformal", "conformal", "conformal_diagonal")):
+        got, want = ws.eos_full_thermo(pts, member), sim.eos_thermo(name, pts)
+        for k in range(17):
+            tol = 1e-9 if (name == "tanh_conformal" and k == 6) else 1e-12   # tanh cs2: ~2000-flop cofactor expansion in the reference
+            assert rel_err(got[:, k], want[:, k]) < tol or np.max(np.abs(got[:, k] - want[:, k])) < tol, (name, k)
+    outside = ws.eos_full_thermo(np.array([[10.0 / HC, 0.0, 0.0, 0.0]]), 0)      # below the table's first node
+    assert np.all(np.isnan(outside))
+    # update_s: the densities and seeds of the reference's phase 04
+    sim.advance(settings["dt"], 2)
+    for ph in ("neighbour_list", "gamma_velocity", "smooth_fields"):
+        sim.phase(ph)
+    before = sim.member("thermo").copy()
+    start = sim.eos_index()
+    sim.phase("thermodynamics")
+    after = ref_thermo16(sim)
+    th, eos = ws.eos_locate(before[:, 5:9], seed=before[:, 0:4], start=start)
+    assert np.array_equal(eos, sim.eos_index())
+    _cmp_thermo("eos_locate", th, after)
+    # s_out: e -> (T, mu) -> s at initialisation
+    e_fm = ic["e"] / 0.1973269804
+    dens = np.stack([e_fm, ic["rhoB"], ic["rhoS"], ic["rhoQ"]], 1)
+    th0, eos0 = ws.eos_locate(dens, energy=True)
+    assert np.all(eos0 == 0) and np.max(np.abs(th0[:, 4] - e_fm)) < 1e-10
+    # conformal run: closed form
+    wc = SPHWorkstation(charged_settings())
+    simc = make_ref(charged_settings(), ic)
+    simc.initialize()
+    thc = ref_thermo16(simc)
+    got, eosc = wc.eos_locate(thc[:, 5:9], seed=thc[:, 0:4])
+    assert np.all(eosc == 0)
+    _cmp_thermo("eos_locate conformal", got, thc)
+    gotf = wc.eos_full_thermo(np.stack([thc[:, 0], thc[:, 1], thc[:, 3], thc[:, 2]], 1))
+    assert rel_err(gotf[:, 0], thc[:, 9]) < 1e-12 and rel_err(gotf[:, 5], thc[:, 4]) < 1e-12   # p and e
