@@ -62,7 +62,8 @@ class IC(C.Structure):
     """``ccb_ic``."""
 
     _fields_ = [("n", C.c_int64)] + [(k, C.POINTER(C.c_double)) for k in
-                                       ("r", "e_or_s", "rhoB", "rhoS", "rhoQ", "u", "bulk", "shv6")] + [("id", C.POINTER(C.c_int32))]
+                                       ("r", "e_or_s", "rhoB", "rhoS", "rhoQ", "u", "bulk", "shv6")] + [("id", C.POINTER(C.c_int32)),
+                                                                                           ("diffusion", C.POINTER(C.c_double))]
 
 
 class Totals(C.Structure):

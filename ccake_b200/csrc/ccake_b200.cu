@@ -77,6 +77,7 @@ struct ccb_ctx {
   int32_t* d_info = nullptr;                 // small device scratch for counts
   uint32_t* mig_list = nullptr;              // migrants' device indices, ranked (cap mig_cap)
   uint32_t* d_ends = nullptr;                // 8 table ends of exchange_column_tables, fetched in one copy
+  bool init_diffusion = false;               // the IC rows carried q^mu_a (ccb_ic::diffusion)
   int* d_qflag = nullptr;                    // DeviceView::qflag
   cudaStream_t comm_stream = nullptr;        // halo exchanges run here, next to the interior tasks of the gather
   cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
@@ -711,7 +712,7 @@ int do_init_particles(ccb_ctx* ctx, const StageParams& sp) {
     eos_done = 1;
   }
   DISPATCH_DM("init_particles_kernel", launch_init_particles, ctx->stream, ctx->dv, sp, ctx->init_tmp, ctx->cfg.input_as_entropy,
-              ctx->cfg.input_initial_shear, ctx->cfg.bulk_from_trace, ctx->efcheck, eos_done);
+              (ctx->cfg.input_initial_shear ? 1 : 0) | (ctx->init_diffusion ? 2 : 0), ctx->cfg.bulk_from_trace, ctx->efcheck, eos_done);
   return CCB_OK;
 }
 
@@ -1292,8 +1293,8 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   if ((rc = do_prologue(ctx))) return rc;
   if ((rc = do_gather_fields(ctx))) return rc;
   // IC densities into temporary columns, in the current (cell-sorted) order
-  CUDA_OK(cudaMalloc(&ctx->init_tmp, sizeof(double) * 10 * cap));
-  CUDA_OK(cudaMemsetAsync(ctx->init_tmp, 0, sizeof(double) * 10 * cap, ctx->stream));
+  CUDA_OK(cudaMalloc(&ctx->init_tmp, sizeof(double) * 19 * cap));
+  CUDA_OK(cudaMemsetAsync(ctx->init_tmp, 0, sizeof(double) * 19 * cap, ctx->stream));
   const double* src1[5] = {ic->e_or_s, ic->rhoB, ic->rhoS, ic->rhoQ, ic->bulk};
   for (int k = 0; k < 5; ++k)
     if (src1[k] && (rc = upload_id_ordered(ctx, src1[k], ctx->init_tmp + (int64_t)k * cap))) return rc;
@@ -1303,6 +1304,14 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
       for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->shv6[i * 6 + pick[c]];
       if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->init_tmp + (int64_t)(5 + c) * cap))) return rc;
     }
+  }
+  ctx->init_diffusion = ic->diffusion != nullptr && ctx->cfg.using_diffusion;
+  if (ctx->init_diffusion) {
+    for (int c = 0; c < 3; ++c)
+      for (int d = 0; d < 3; ++d) {
+        for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->diffusion[i * 12 + c * 4 + d + 1];
+        if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->init_tmp + (int64_t)(10 + c * 3 + d) * cap))) return rc;
+      }
   }
   const StageParams sp = make_stage(ctx, 0.0, 0);
   if ((rc = do_init_particles(ctx, sp))) return rc;

@@ -342,7 +342,8 @@ __global__ void __launch_bounds__(128) eom_rk_kernel(DeviceView dv, StageParams 
 }
 
 // ---- initialisation kernels (BSQHydro::initialize_hydrodynamics on the device) ---
-// tmp columns (current order): 0 e_or_s, 1 rhoB, 2 rhoS, 3 rhoQ, 4 bulk, 5..9 shv (xx,xy,xeta,yy,yeta)
+// tmp columns (current order): 0 e_or_s, 1 rhoB, 2 rhoS, 3 rhoQ, 4 bulk, 5..9 shv (xx,xy,xeta,yy,yeta), 10..18 q^i_a [charge][i]
+// input_initial_shear: bit 0 = Settings::input_initial_shear, bit 1 = Settings::input_initial_diffusion
 template <int D, bool MILNE>
 __global__ void init_particles_kernel(DeviceView dv, StageParams sp, const double* __restrict__ tmp, int input_as_entropy,
                                       int input_initial_shear, int bulk_from_trace, double efcheck, int eos_done) {
@@ -377,7 +378,11 @@ __global__ void init_particles_kernel(DeviceView dv, StageParams sp, const doubl
   if (s_in < 0.0) dv.freeze[i] = 4;
   // calculate_extensive_shv / set_bulk_Pi / set_diffusion, src/sph_workstation.cpp:1350-1460
 #pragma unroll
-  for (int c = 0; c < 5; ++c) col(dv.f[CCB_F_EXTENSIVE_SHV], cap, c, i) = input_initial_shear ? (tmp[(5 + c) * cap + i] / hc) / sigma : 0.0;
+  for (int c = 0; c < 5; ++c) col(dv.f[CCB_F_EXTENSIVE_SHV], cap, c, i) = (input_initial_shear & 1) ? (tmp[(5 + c) * cap + i] / hc) / sigma : 0.0;
+  if (sp.fl.diffusion) {  // SPHWorkstation::set_diffusion, src/sph_workstation.cpp:1441-1461
+#pragma unroll
+    for (int c = 0; c < 9; ++c) col(dv.f[CCB_F_EXTENSIVE_DIFFUSION], cap, c, i) = (input_initial_shear & 2) ? tmp[(10 + c) * cap + i] / sigma : 0.0;
+  }
   dv.f[CCB_F_EXTENSIVE_BULK][i] = bulk_from_trace ? (tmp[4 * cap + i] / hc - th.p) / sigma : 0.0;
 }
 

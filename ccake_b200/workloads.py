@@ -247,3 +247,63 @@ WORKLOADS = {
     "config4_milne_bsq_table_3p1d": config4_milne_bsq,
     "config5_cartesian_blob_3p1d": config5_cartesian_blob,
 }
+
+
+def read_ccake(path, settings):
+    """The reference's `ccake` initial-condition text format (BSQHydro::read_ccake, src/BSQHydro.cpp:207-425): one header line
+    `# <ignored> stepx stepy stepEta <ignored> xmin ymin etamin`, then rows
+    `x y eta e|s rhoB rhoS rhoQ ux uy ueta bulk pixx pixy pixeta piyy piyeta pietaeta [qB0..3 qS0..3 qQ0..3]`
+    (the twelve currents when settings["input_initial_diffusion"]). Rows below the energy cut-off are dropped exactly as the
+    reference drops them (for entropy input through its ideal pion-gas estimate). Returns (settings updated with the header,
+    ic dict for SPHWorkstation.upload_initial_conditions)."""
+    s = dict(settings)
+    with_q = bool(s.get("input_initial_diffusion", False))
+    rows = []
+    header_done = False
+    with open(path) as f:
+        for line in f:
+            if not header_done:
+                tok = line.split("#", 1)[1].split() if "#" in line else line.split()
+                s["stepx"], s["stepy"], s["stepEta"] = float(tok[1]), float(tok[2]), float(tok[3])
+                s["xmin"], s["ymin"], s["etamin"] = float(tok[5]), float(tok[6]), float(tok[7])
+                header_done = True
+                continue
+            t = line.strip()
+            if not t or t.startswith("#"):
+                continue
+            rows.append([float(v) for v in t.split()[: 29 if with_q else 17]])
+    a = np.array(rows, dtype=np.float64).reshape(len(rows), 29 if with_q else 17)
+    e_or_s = a[:, 3]
+    cut = float(s.get("e_cutoff", 0.0)) / HBARC_GEVFM
+    if s.get("input_as_entropy", False):
+        C = 3.0 * math.pi ** 2 / 90.0
+        keep = (3.0 * C) * (1.0 / (4.0 * C)) ** (4.0 / 3.0) * e_or_s ** (4.0 / 3.0) > cut
+    else:
+        keep = e_or_s / HBARC_GEVFM > cut
+    a = a[keep]
+    D = int(s.get("dim", 2))
+    ic = dict(r=np.ascontiguousarray(a[:, :3] if D == 3 else a[:, :2]), e=a[:, 3].copy(), rhoB=a[:, 4].copy(), rhoS=a[:, 5].copy(),
+              rhoQ=a[:, 6].copy(), u=np.ascontiguousarray(a[:, 7:10] if D == 3 else a[:, 7:9]), bulk=a[:, 10].copy(),
+              shv6=np.ascontiguousarray(a[:, 11:17]))
+    if with_q:
+        ic["diffusion"] = np.ascontiguousarray(a[:, 17:29]).reshape(-1, 3, 4)
+    return s, ic
+
+
+def write_ccake(path, settings, ic):
+    """Write an IC dict in the same format (used by the tests and to hand a synthetic workload to the reference binary)."""
+    n = ic["r"].shape[0]
+    z = np.zeros(n)
+    r3 = np.zeros((n, 3)); r3[:, : ic["r"].shape[1]] = ic["r"]
+    u3 = np.zeros((n, 3))
+    if ic.get("u") is not None:
+        u3[:, : ic["u"].shape[1]] = ic["u"]
+    cols = [r3, ic["e"][:, None]] + [(z if ic.get(k) is None else ic[k])[:, None] for k in ("rhoB", "rhoS", "rhoQ")] + [u3]
+    cols.append((z if ic.get("bulk") is None else ic["bulk"])[:, None])
+    cols.append(np.zeros((n, 6)) if ic.get("shv6") is None else ic["shv6"])
+    if ic.get("diffusion") is not None:
+        cols.append(np.asarray(ic["diffusion"]).reshape(n, 12))
+    with open(path, "w") as f:
+        f.write("#0 %.17g %.17g %.17g 0 %.17g %.17g %.17g\n" % (settings["stepx"], settings["stepy"], settings["stepEta"], settings["xmin"],
+                                                              settings["ymin"], settings["etamin"]))
+        np.savetxt(f, np.concatenate(cols, 1), fmt="%.17g")

@@ -166,7 +166,8 @@ class SPHWorkstation:
         self._check(self._L.ccb_get_int_field_device_order(self._ctx, _capi.INT_FIELDS[field], out.ctypes.data_as(C.POINTER(C.c_int32))))
         return out
 
-    def upload_initial_conditions(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None, ids=None):
+    def upload_initial_conditions(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None, ids=None,
+                                  diffusion=None):
         """BSQHydro::read_ccake rows + BSQHydro::initialize_hydrodynamics, on the device."""
         r = np.asarray(r, dtype=np.float64)
         n = r.shape[0]
@@ -195,6 +196,15 @@ class SPHWorkstation:
             a = np.ascontiguousarray(a)
             keep.append(a)
             setattr(ic, name, _dp(a))
+        if diffusion is not None:
+            # (n, 3, 4) initial q^mu_a; a disabled charge's row is dropped (src/BSQHydro.cpp:345-372)
+            q = np.array(diffusion, dtype=np.float64).reshape(n, 3, 4)
+            for c, key in enumerate(("baryon_charge_enabled", "strange_charge_enabled", "electric_charge_enabled")):
+                if not self.settings[key]:
+                    q[:, c, :] = 0.0
+            q = np.ascontiguousarray(q)
+            keep.append(q)
+            ic.diffusion = _dp(q)
         if ids is not None:
             ids = np.ascontiguousarray(ids, dtype=np.int32)
             keep.append(ids)

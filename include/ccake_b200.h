@@ -99,6 +99,8 @@ typedef struct {
   const double* bulk;
   const double* shv6;
   const int32_t* id;   /* optional: global particle ids of these rows (slab decomposition); NULL = 0 .. n-1 */
+  const double* diffusion; /* optional (Settings::input_initial_diffusion): n x 12 initial q^mu_a, [charge B,S,Q][mu 0..3], as the IC file
+                              holds them (BSQHydro::read_ccake, src/BSQHydro.cpp:261-372); NULL = zeros */
 } ccb_ic;
 
 /* Per-particle fields addressable through ccb_get_field / ccb_set_field.

@@ -106,7 +106,7 @@ def lib():
         L.ccake_ref_create.restype = C.c_void_p
         L.ccake_ref_create.argtypes = [C.c_char_p]
         L.ccake_ref_destroy.argtypes = [C.c_void_p]
-        L.ccake_ref_add_particles.argtypes = [C.c_void_p, C.c_long] + [dp] * 8
+        L.ccake_ref_add_particles.argtypes = [C.c_void_p, C.c_long] + [dp] * 9
         for f in ("initialize", "get_time_derivatives"):
             getattr(L, "ccake_ref_" + f).argtypes = [C.c_void_p]
         L.ccake_ref_phase.argtypes = [C.c_void_p, C.c_int]
@@ -163,7 +163,7 @@ class RefSim:
         except Exception:
             pass
 
-    def add_particles(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None):
+    def add_particles(self, r, e_or_s, rhoB=None, rhoS=None, rhoQ=None, u=None, bulk=None, shv6=None, diffusion=None):
         r = np.ascontiguousarray(r, dtype=np.float64)
         n = r.shape[0]
         r3 = np.zeros((n, 3))
@@ -179,7 +179,8 @@ class RefSim:
         arrs.append(u3)
         arrs.append(z if bulk is None else np.ascontiguousarray(bulk, dtype=np.float64))
         arrs.append(np.zeros((n, 6)) if shv6 is None else np.ascontiguousarray(shv6, dtype=np.float64))
-        lib().ccake_ref_add_particles(self.h, n, *[_dp(a) for a in arrs])
+        q = None if diffusion is None else np.ascontiguousarray(np.asarray(diffusion, dtype=np.float64).reshape(n, 12))
+        lib().ccake_ref_add_particles(self.h, n, *[_dp(a) for a in arrs], None if q is None else _dp(q))
 
     def initialize(self):
         lib().ccake_ref_initialize(self.h)

@@ -31,7 +31,7 @@ namespace {
 struct RefBase {
   virtual ~RefBase() {}
   virtual int add_particles(long n, const double* r, const double* e_or_s, const double* rhoB, const double* rhoS,
-                            const double* rhoQ, const double* u, const double* bulk, const double* shv6) = 0;
+                            const double* rhoQ, const double* u, const double* bulk, const double* shv6, const double* q12) = 0;
   virtual int initialize() = 0;
   virtual int allocate_raw(long n) = 0;
   virtual int phase(int which) = 0;
@@ -64,7 +64,7 @@ struct Ref : RefBase {
 
   // Mirrors the per-row work of BSQHydro::read_ccake (src/BSQHydro.cpp:262-403).
   int add_particles(long n, const double* r, const double* e_or_s, const double* rhoB, const double* rhoS,
-                    const double* rhoQ, const double* u, const double* bulk, const double* shv6) override {
+                    const double* rhoQ, const double* u, const double* bulk, const double* shv6, const double* q12) override {
     const double hc = constants::hbarc_GeVfm;
     for (long i = 0; i < n; ++i) {
       Particle<D> p;
@@ -81,7 +81,9 @@ struct Ref : RefBase {
       p.input.rhoS = st->strange_charge_enabled ? rhoS[i] : 0.0;
       p.input.rhoQ = st->electric_charge_enabled ? rhoQ[i] : 0.0;
       p.hydro.bulk = bulk[i] / hc;
-      for (int c = 0; c < 3; ++c) for (int m = 0; m < 4; ++m) p.hydro.diffusion(c, m) = 0.0;
+      // input_initial_diffusion: a disabled charge's current is dropped (src/BSQHydro.cpp:345-372)
+      const bool on[3] = {st->baryon_charge_enabled, st->strange_charge_enabled, st->electric_charge_enabled};
+      for (int c = 0; c < 3; ++c) for (int m = 0; m < 4; ++m) p.hydro.diffusion(c, m) = (q12 && on[c]) ? q12[12 * i + 4 * c + m] : 0.0;
       if (st->input_as_entropy) {
         const double C = 3.0 * pow(M_PI, 2.) / 90.0;
         const double e_check = (3. * C) * pow(1. / (4. * C), 4. / 3.) * pow(e_or_s[i], 4. / 3.);
@@ -311,8 +313,8 @@ void* ccake_ref_create(const char* kv) {
 void ccake_ref_destroy(void* h) { delete static_cast<RefBase*>(h); }
 int ccake_ref_add_particles(void* h, long n, const double* r, const double* e_or_s, const double* rhoB,
                             const double* rhoS, const double* rhoQ, const double* u, const double* bulk,
-                            const double* shv6) {
-  return static_cast<RefBase*>(h)->add_particles(n, r, e_or_s, rhoB, rhoS, rhoQ, u, bulk, shv6);
+                            const double* shv6, const double* q12) {
+  return static_cast<RefBase*>(h)->add_particles(n, r, e_or_s, rhoB, rhoS, rhoQ, u, bulk, shv6, q12);
 }
 int ccake_ref_initialize(void* h) { return static_cast<RefBase*>(h)->initialize(); }
 int ccake_ref_allocate_raw(void* h, long n) { return static_cast<RefBase*>(h)->allocate_raw(n); }

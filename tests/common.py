@@ -120,7 +120,7 @@ def make_ref(settings, ic):
     keys = ref.SETTING_KEYS
     st = {k: v for k, v in settings.items() if k in keys or k.startswith("kappa_")}
     sim = ref.RefSim(st)
-    sim.add_particles(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    sim.add_particles(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"], ic.get("diffusion"))
     return sim
 
 

@@ -41,6 +41,9 @@ CASES = {
     "conformal_diagonal_2d_charged": (lambda: charged_settings(eos_type="conformal_diagonal"), lambda: gubser_ic(dx=0.1, shear=True, charges=True)),
     "tanh_conformal_3d_milne": (lambda: viscous_settings(eos_type="tanh_conformal", **D3), lambda: blob_ic_3d(n_side=14)),
     # the transport-coefficient modes the other cases leave out (src/transport_coefficients.cpp)
+    "charged_2d_initial_diffusion": (lambda: charged_settings(), lambda: _with_initial_diffusion(gubser_ic(dx=0.1, shear=True, charges=True))),
+    "charged_3d_milne_initial_diffusion_sq_off": (lambda: charged_settings(strange_charge_enabled=False, **D3),
+                                                  lambda: _with_initial_diffusion(blob_ic_3d(n_side=14))),
     "baryon_2d_kappaB_coth": (lambda: charged_settings(strange_charge_enabled=False, electric_charge_enabled=False, diffusionMode="kappaB_coth",
                                                         diffusionRelaxMode="cb_over_T", C_B=0.4),
                               lambda: _dense_baryons(gubser_ic(dx=0.1, shear=True, charges=True))),
@@ -53,6 +56,15 @@ CASES = {
     "viscous_3d_cartesian": (lambda: viscous_settings(coordinate_system="cartesian", **D3), lambda: blob_ic_3d(n_side=14)),
     "viscous_3d_milne_factorized": (lambda: viscous_settings(factorized_kernel=True, **dict(D3, hEta=0.4)), lambda: blob_ic_3d(n_side=14)),
 }
+
+
+def _with_initial_diffusion(ic, seed=9):
+    """Settings::input_initial_diffusion: the IC rows carry q^mu_a (BSQHydro::read_ccake, src/BSQHydro.cpp:261-372)."""
+    rng = np.random.default_rng(seed)
+    n = ic["r"].shape[0]
+    q = 1e-3 * rng.standard_normal((n, 3, 4)) * ic["rhoB"][:, None, None]
+    ic["diffusion"] = q
+    return ic
 
 
 def _dense_baryons(ic):
@@ -114,7 +126,8 @@ def _make_ws(settings, ic):
     from ccake_b200 import SPHWorkstation
 
     ws = SPHWorkstation(settings)
-    ws.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    ws.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"],
+                                 diffusion=ic.get("diffusion"))
     return ws
 
 

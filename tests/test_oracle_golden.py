@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from common import ROOT, gubser_ic, harness, have_ref, ideal_settings, make_ref, viscous_settings
+from common import ROOT, charged_settings, gubser_ic, harness, have_ref, ideal_settings, make_ref, viscous_settings
 
 needs_ref = pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
 PI = math.pi
@@ -223,3 +223,28 @@ hydro:
     assert c.delta_PiPi_mode == 1 and c.tau_pipi_mode == 1 and c.phi1_mode == 1
     assert abs(c.constant_kappa_over_T2[4] - 0.2) < 1e-15
     assert abs(c.conformal_c - math.pi ** 2 * (16 + 26.25) / 90.0) < 1e-14
+
+
+def test_ic_text_format_round_trip(tmp_path):
+    """ccake_b200.workloads.read_ccake parses the reference's IC text format (BSQHydro::read_ccake, src/BSQHydro.cpp:207-425):
+    header -> settings, unit handling left to the library, the energy cut-off applied row by row, optional q^mu_a columns."""
+    from ccake_b200 import workloads as W
+
+    ic = gubser_ic(dx=0.25, shear=True, charges=True)
+    n = ic["r"].shape[0]
+    ic["diffusion"] = np.random.default_rng(1).standard_normal((n, 3, 4))
+    s = charged_settings(stepx=0.25, stepy=0.25, e_cutoff=0.0, input_initial_diffusion=True)
+    path = str(tmp_path / "ic.dat")
+    W.write_ccake(path, s, ic)
+    s2, ic2 = W.read_ccake(path, dict(s, stepx=0.0, xmin=0.0))
+    assert (s2["stepx"], s2["stepy"], s2["xmin"], s2["ymin"]) == (0.25, 0.25, -2.0, -2.0)
+    for k in ("r", "e", "rhoB", "rhoS", "rhoQ", "u", "shv6", "diffusion"):
+        assert np.array_equal(np.asarray(ic2[k]).reshape(n, -1), np.asarray(ic[k]).reshape(n, -1)), k
+    cut = float(np.median(ic["e"]))
+    _, ic3 = W.read_ccake(path, dict(s, e_cutoff=cut))
+    assert ic3["e"].size == int((ic["e"] / 0.1973269804 > cut / 0.1973269804).sum()) and np.all(ic3["e"] > cut)
+    # the sample header of the reference's own documentation parses too
+    with open(path, "w") as f:
+        f.write("#0 .025 .025 .1 0 -5 -5 -.1\n0 0 0 10 0 0 0 0 0 0 0 0 0 0 0 0 0\n")
+    s4, ic4 = W.read_ccake(path, ideal_settings(e_cutoff=0.0))
+    assert s4["stepEta"] == 0.1 and s4["etamin"] == -0.1 and ic4["e"][0] == 10.0
