@@ -37,6 +37,11 @@ struct ccb_ctx {
   double* alt_slab = nullptr;   // ping-pong target of the permutation (persistent + y0 columns)
   double* alt[CCB_F_COUNT];
   double* alt_y0[CCB_F_COUNT];
+  // rk_order 4: the weighted sum of stage derivatives (the reference's `k` cache, src/evolver.cpp:38-60, 172-211): one column per
+  // evolved column; it follows the particles through every sort like y0 does
+  double *k_slab = nullptr, *alt_k_slab = nullptr;
+  double* kacc[CCB_F_COUNT];
+  double* alt_k[CCB_F_COUNT];
   int32_t* ints = nullptr;      // id, btrack, freeze, eos_id + alternates (8 columns)
   int32_t* alt_int[4];
   uint32_t *key_a = nullptr, *key_b = nullptr, *idx_a = nullptr, *idx_b = nullptr, *hist = nullptr, *cell_count = nullptr,
@@ -180,6 +185,7 @@ void setup_grid(ccb_ctx* ctx) {
 
 int free_particles(ccb_ctx* ctx) {
   cudaFree(ctx->slab); cudaFree(ctx->y0_slab); cudaFree(ctx->alt_slab); cudaFree(ctx->ints);
+  cudaFree(ctx->k_slab); cudaFree(ctx->alt_k_slab); ctx->k_slab = ctx->alt_k_slab = nullptr;
   cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
   cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
   for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); ctx->mig_d[k] = nullptr; ctx->mig_i[k] = nullptr; }
@@ -232,6 +238,18 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
     const int f = kEvolvedFields[k];
     dv.y0[f] = ctx->y0_slab + (int64_t)oy * cap; oy += kFieldWidth[f];
     ctx->alt_y0[f] = ctx->alt_slab + (int64_t)oa * cap; oa += kFieldWidth[f];
+  }
+  for (int f = 0; f < CCB_F_COUNT; ++f) { ctx->kacc[f] = nullptr; ctx->alt_k[f] = nullptr; }
+  if (ctx->cfg.rk_order == 4) {
+    CUDA_OK(cudaMalloc(&ctx->k_slab, sizeof(double) * wy0 * cap));
+    CUDA_OK(cudaMalloc(&ctx->alt_k_slab, sizeof(double) * wy0 * cap));
+    CUDA_OK(cudaMemsetAsync(ctx->k_slab, 0, sizeof(double) * wy0 * cap, ctx->stream));
+    CUDA_OK(cudaMemsetAsync(ctx->alt_k_slab, 0, sizeof(double) * wy0 * cap, ctx->stream));
+    int ok = 0;
+    for (int k = 0; k < kNumEvolvedFields; ++k) {
+      const int f = kEvolvedFields[k];
+      ctx->kacc[f] = ctx->k_slab + (int64_t)ok * cap; ctx->alt_k[f] = ctx->alt_k_slab + (int64_t)ok * cap; ok += kFieldWidth[f];
+    }
   }
   dv.id = ctx->ints; dv.btrack = ctx->ints + cap; dv.freeze = ctx->ints + 2 * cap; dv.eos_id = ctx->ints + 3 * cap;
   for (int k = 0; k < 4; ++k) ctx->alt_int[k] = ctx->ints + (4 + k) * cap;
@@ -344,6 +362,8 @@ int sort_and_permute(ccb_ctx* ctx, int64_t n, int drop_outside) {
     const int f = kEvolvedFields[k];
     if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
     for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = dv.y0[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_y0[f] + (int64_t)c * dv.cap; pl.ncols++; }
+    if (ctx->k_slab)
+      for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = ctx->kacc[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_k[f] + (int64_t)c * dv.cap; pl.ncols++; }
   }
   int32_t* icur[4] = {dv.id, dv.btrack, dv.freeze, dv.eos_id};
   for (int k = 0; k < 4; ++k) { pl.isrc[k] = icur[k]; pl.idst[k] = ctx->alt_int[k]; pl.nints++; }
@@ -356,6 +376,7 @@ int sort_and_permute(ccb_ctx* ctx, int64_t n, int drop_outside) {
     const int f = kEvolvedFields[k];
     if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
     std::swap(dv.y0[f], ctx->alt_y0[f]);
+    if (ctx->k_slab) std::swap(ctx->kacc[f], ctx->alt_k[f]);
   }
   std::swap(dv.id, ctx->alt_int[0]); std::swap(dv.btrack, ctx->alt_int[1]); std::swap(dv.freeze, ctx->alt_int[2]);
   std::swap(dv.eos_id, ctx->alt_int[3]);
@@ -381,6 +402,8 @@ void migrate_list(ccb_ctx* ctx, MigrateList& ml) {
     const int f = kEvolvedFields[k];
     if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
     for (int c = 0; c < kFieldWidth[f]; ++c) ml.col[ml.ncols++] = dv.y0[f] + (int64_t)c * dv.cap;
+    if (ctx->k_slab)
+      for (int c = 0; c < kFieldWidth[f]; ++c) ml.col[ml.ncols++] = ctx->kacc[f] + (int64_t)c * dv.cap;
   }
   ml.icol[0] = dv.id; ml.icol[1] = dv.btrack; ml.icol[2] = dv.freeze; ml.icol[3] = dv.eos_id;
 }
@@ -681,6 +704,56 @@ int derivative_evaluation(ccb_ctx* ctx, double h_stage, int do_update) {
   return do_eom(ctx, h_stage, do_update);
 }
 
+// ---- rk_order 4 (Evolver::advance_timestep_rk4, src/evolver.cpp:508-561) ----------------------------------------------
+struct RkCols {
+  int n, s_col, nzero;
+  double* y[40];          // evolved column
+  const double* y0[40];   // its snapshot
+  double* k[40];          // its accumulated weighted derivative
+  const double* f[40];    // the stage derivative that feeds it
+  double* zero[4];        // components >= D of position and u: kept at zero
+};
+// update_k (src/evolver.cpp:172-211): k += w * f
+__global__ void rk4_accumulate_kernel(RkCols c, double w, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int q = 0; q < c.n; ++q) c.k[q][i] += w * c.f[q][i];
+}
+// update_rk4 (src/evolver.cpp:216-339): y = y0 + dt * k, with the negative-entropy guard of every RK update
+__global__ void rk4_final_kernel(RkCols c, double dt, int64_t n, const int32_t* __restrict__ freeze, const int32_t* __restrict__ id,
+                                 int32_t* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int q = 0; q < c.n; ++q) {
+    double v = c.y0[q][i] + dt * c.k[q][i];
+    if (q == c.s_col && v < 0.0) {
+      if (freeze[i] > 3) v = 1.e-3;
+      else if (atomicCAS(&err[0], 0, (int)CCB_ERR_NEG_ENTROPY) == 0) err[1] = id[i];
+    }
+    c.y[q][i] = v;
+  }
+  for (int q = 0; q < c.nzero; ++q) c.zero[q][i] = 0.0;
+}
+RkCols rk_columns(ccb_ctx* ctx) {
+  RkCols c;
+  c.n = 0; c.nzero = 0; c.s_col = -1;
+  const DeviceView& dv = ctx->dv;
+  const int64_t cap = dv.cap;
+  auto add = [&](int fy, int cy, int ff, int cf) {
+    c.y[c.n] = dv.f[fy] + (int64_t)cy * cap; c.y0[c.n] = dv.y0[fy] + (int64_t)cy * cap; c.k[c.n] = ctx->kacc[fy] + (int64_t)cy * cap;
+    c.f[c.n] = dv.f[ff] + (int64_t)cf * cap; c.n++;
+  };
+  for (int d = 0; d < ctx->D; ++d) { add(CCB_F_POSITION, d, CCB_F_V, d); add(CCB_F_U, d, CCB_F_DU_DT, d); }
+  for (int d = ctx->D; d < 3; ++d) { c.zero[c.nzero++] = dv.f[CCB_F_POSITION] + (int64_t)d * cap; c.zero[c.nzero++] = dv.f[CCB_F_U] + (int64_t)d * cap; }
+  c.s_col = c.n;
+  for (int q = 0; q < 4; ++q) add(CCB_F_EXTENSIVE, q, CCB_F_D_EXTENSIVE_DT, q);
+  add(CCB_F_EXTENSIVE_BULK, 0, CCB_F_D_BULK_DT, 0);
+  for (int q = 0; q < 5; ++q) add(CCB_F_EXTENSIVE_SHV, q, CCB_F_D_SHV_DT, q);
+  if (ctx->cfg.using_diffusion) for (int q = 0; q < 9; ++q) add(CCB_F_EXTENSIVE_DIFFUSION, q, CCB_F_D_DIFFUSION_DT, q);
+  add(CCB_F_EZ, 0, CCB_F_DEZ, 0);
+  return c;
+}
+
 int snapshot_y0(ccb_ctx* ctx) {
   for (int k = 0; k < kNumEvolvedFields; ++k) {
     const int f = kEvolvedFields[k];
@@ -780,7 +853,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   ctx->cfg = *cfg;
   *out = ctx;  // handed back even on failure so that ccb_last_error works
   if (cfg->dim != 2 && cfg->dim != 3) { ctx->err = "dim must be 2 or 3"; return CCB_ERR_INVALID; }
-  if (cfg->rk_order != 2) { ctx->err = "rk_order must be 2"; return CCB_ERR_INVALID; }
+  if (cfg->rk_order != 2 && cfg->rk_order != 4) { ctx->err = "rk_order must be 2 or 4 (Evolver::execute_timestep, src/evolver.cpp:98-116)"; return CCB_ERR_INVALID; }
   if (cfg->eos_type < CCB_EOS_CONFORMAL || cfg->eos_type > CCB_EOS_CONFORMAL_DIAGONAL) { ctx->err = "eos_type must be one of CCB_EOS_*"; return CCB_ERR_INVALID; }
   ctx->use_chain = cfg->eos_type != CCB_EOS_CONFORMAL;
   if (cfg->eos_type == CCB_EOS_TANH_CONFORMAL || cfg->eos_type == CCB_EOS_CONFORMAL_DIAGONAL) {
@@ -1214,9 +1287,31 @@ int ccb_get_time_derivatives(ccb_ctx* ctx) { int rc = check_ready(ctx, false); r
 int ccb_step(ccb_ctx* ctx, double dt) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
-  // Evolver::advance_timestep_rk2 (src/evolver.cpp:494-507): midpoint rule
   if ((rc = snapshot_y0(ctx))) return rc;
   const double t0 = ctx->t;
+  if (ctx->cfg.rk_order == 4) {
+    // Evolver::advance_timestep_rk4 (src/evolver.cpp:508-561), stage for stage AS THE REFERENCE RUNS IT: five derivative
+    // evaluations, the first of which only moves the state to the mid-point; the other four enter k with the weights
+    // 1/6, 2/6, 2/6, 2/6 (update_k is called with n = 3 twice, :548-554). Kept for drop-in parity; note the weights sum to 7/6.
+    int wy0 = 0;
+    for (int k = 0; k < kNumEvolvedFields; ++k) wy0 += kFieldWidth[kEvolvedFields[k]];
+    CUDA_OK(cudaMemsetAsync(ctx->k_slab, 0, sizeof(double) * wy0 * ctx->cap, ctx->stream));
+    CUDA_OK(cudaMemsetAsync(ctx->alt_k_slab, 0, sizeof(double) * wy0 * ctx->cap, ctx->stream));
+    const double h[5] = {0.5 * dt, 0.5 * dt, 0.5 * dt, dt, 0.0};
+    const double w[5] = {0.0, 1.0 / 6.0, 2.0 / 6.0, 2.0 / 6.0, 2.0 / 6.0};
+    for (int stage = 0; stage < 5; ++stage) {
+      if ((rc = derivative_evaluation(ctx, h[stage], stage < 4 ? 1 : 0))) return rc;
+      if (stage < 4) ctx->t = t0 + h[stage];
+      if (w[stage] != 0.0) {
+        const RkCols c = rk_columns(ctx);
+        LAUNCH(rk4_accumulate_kernel, cdiv(ctx->n, 256), 256, c, w[stage], ctx->n);
+      }
+    }
+    const RkCols c = rk_columns(ctx);
+    LAUNCH(rk4_final_kernel, cdiv(ctx->n, 256), 256, c, dt, ctx->n, ctx->dv.freeze, ctx->dv.id, ctx->dv.err);
+    return CCB_OK;
+  }
+  // Evolver::advance_timestep_rk2 (src/evolver.cpp:494-507): midpoint rule
   if ((rc = derivative_evaluation(ctx, 0.5 * dt, 1))) return rc;
   ctx->t = t0 + 0.5 * dt;
   if ((rc = derivative_evaluation(ctx, dt, 1))) return rc;

@@ -282,8 +282,8 @@ class SPHWorkstation:
     def get_time_derivatives(self):
         self._check(self._L.ccb_get_time_derivatives(self._ctx))
 
-    def advance_timestep(self, dt, rk_order=2):
-        if rk_order != self._cfg.rk_order:
+    def advance_timestep(self, dt, rk_order=None):
+        if rk_order is not None and rk_order != self._cfg.rk_order:
             raise ValueError("rk_order is fixed at context creation")
         self._check(self._L.ccb_step(self._ctx, float(dt)))
 

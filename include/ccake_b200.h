@@ -50,7 +50,7 @@ enum { CCB_EOS_CONFORMAL = 0, CCB_EOS_TABLE = 1, CCB_EOS_TANH_CONFORMAL = 2, CCB
 typedef struct {
   int dim;                 /* 2 or 3 (Settings::dim) */
   int coordinate_system;   /* CCB_COORD_* (Settings::coordinate_system) */
-  int rk_order;            /* 2 (Settings::rk_order) */
+  int rk_order;            /* 2 or 4 (Settings::rk_order; Evolver::execute_timestep, src/evolver.cpp:98-116) */
   int factorized_kernel;   /* Settings::factorized_kernel (D == 3 only) */
   double t0, hT, hEta;
   double xmin, ymin, etamin;          /* IC header minima -> neighbour grid (src/system_state.cpp:656-692) */
@@ -253,7 +253,8 @@ int ccb_get_time_derivatives(ccb_ctx* ctx); /* all of the above in order */
 
 /* --- time stepping -------------------------------------------------------- */
 /* SPHWorkstation::advance_timestep -> Evolver::execute_timestep (src/sph_workstation.cpp:2043-2073,
- * src/evolver.cpp:98-561): one full RK step of size dt; asynchronous on the context's stream. */
+ * src/evolver.cpp:98-561): one full RK step of size dt (RK2 midpoint, or the reference's five-evaluation RK4 sequence when
+ * rk_order = 4); asynchronous on the context's stream. */
 int ccb_step(ccb_ctx* ctx, double dt);
 int ccb_synchronize(ccb_ctx* ctx);        /* waits for the stream and surfaces device-side error flags */
 int ccb_reduce(ccb_ctx* ctx, ccb_totals* out);

@@ -524,3 +524,29 @@ def test_eos_queries_match_reference():
     _cmp_thermo("eos_locate conformal", got, thc)
     gotf = wc.eos_full_thermo(np.stack([thc[:, 0], thc[:, 1], thc[:, 3], thc[:, 2]], 1))
     assert rel_err(gotf[:, 0], thc[:, 9]) < 1e-12 and rel_err(gotf[:, 5], thc[:, 4]) < 1e-12   # p and e
+
+
+@pytest.mark.parametrize("case", ["charged_2d_diffusion", "viscous_3d_milne"])
+def test_rk4_follows_the_reference_sequence(case):
+    """rk_order: 4 -- Evolver::advance_timestep_rk4 (src/evolver.cpp:508-561) stage for stage, including its weights
+    1/6, 2/6, 2/6, 2/6 over the evaluations 2..5: the same state as the reference after every step."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    mk_s, mk_ic = CASES[case]
+    settings, ic = dict(mk_s(), rk_order=4), mk_ic()
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = _make_ws(settings, ic)
+    for step in range(2):
+        sim.advance(settings["dt"], 4)
+        ws.advance_timestep(settings["dt"])
+        ws.synchronize()
+        assert abs(ws.t - sim.t) < 1e-14
+        tol = 3 * TOL * (step + 1)   # five derivative evaluations per step
+        _cmp(case, "position", ws.get("position"), sim.member("position"), tol)
+        _cmp(case, "u", ws.get("u"), sim.get("hydro_vector", "u"), tol)
+        _cmp(case, "extensive", ws.get("extensive"), sim.member("extensive")[:, [0, 2, 3, 4]], tol)
+        _cmp(case, "extensive_shv", ws.get("extensive_shv"), _ext_shv5(sim), tol, scale=max(np.max(np.abs(_ext_shv5(sim))), 1e-6))
+        _cmp(case, "extensive_bulk", ws.get("extensive_bulk"), sim.get("hydro_scalar", "extensive_bulk"), tol,
+             scale=max(np.max(np.abs(sim.get("hydro_scalar", "extensive_bulk"))), 1e-6))
+        _cmp(case, "Ez", ws.get("Ez"), sim.member("contribution_to_total_Ez"), tol, scale=max(np.max(np.abs(sim.member("contribution_to_total_Ez"))), 1e-6))

@@ -126,3 +126,25 @@ def test_slabs_match_single_context_and_reference(case, nranks):
         assert rel_err(run.gather("extensive")[:, 0], sim.member("extensive")[:, 0]) < steps * 1e-10
     moved = [w.migration_counts() for w in run.ws]
     print(case, nranks, "ranges", run.ranges, "counts", run.counts(), "migrated (out, in)", moved)
+
+
+@pytest.mark.gpu
+def test_slabs_rk4_accumulators_follow_the_particles():
+    """rk_order 4 with two slabs: the k accumulator columns migrate with their particles, so the slab run equals the
+    single-context run to rounding after steps in which particles change slab."""
+    from ccake_b200 import SPHWorkstation
+    from slab_harness import SlabRun
+
+    settings, ic = viscous_settings(dt=0.02, rk_order=4), gubser_ic(dx=0.1, shear=True)
+    one = SPHWorkstation(settings)
+    one.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    run = SlabRun(settings, ic, 2)
+    for _ in range(3):
+        one.advance_timestep(settings["dt"])
+        run.each(lambda r, w: w.advance_timestep(settings["dt"]))
+    one.synchronize()
+    run.each(lambda r, w: w.synchronize())
+    assert sum(m[0] for m in (w.migration_counts() for w in run.ws)) > 0
+    for f in ("position", "u", "extensive", "extensive_shv"):
+        ref = one.get(f)
+        assert rel_err(run.gather(f), ref, max(np.max(np.abs(ref)), 1e-12)) < 1e-12, f
