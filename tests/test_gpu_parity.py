@@ -335,6 +335,30 @@ def test_long_evolution_ideal_gubser():
     assert abs(tot["S"] - ref_tot["S"]) <= 1e-9 * abs(ref_tot["S"])
 
 
+@pytest.mark.parametrize("case,steps", [("charged_2d_diffusion", 100), ("table_charged_3d_milne_bulk", 40)])
+def test_long_evolution_viscous_charged(case, steps):
+    """End-of-evolution bar of the north star (1e-6) on dissipative runs with all three charges: 100 RK2 steps of the charged
+    viscous Gubser case with diffusion, 40 of the 3+1D Milne run on the tabulated EoS; B, S, Q and S totals at the reference's level."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    mk_s, mk_ic = CASES[case]
+    settings, ic = dict(mk_s(), dt=0.004), mk_ic()
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = _make_ws(settings, ic)
+    for _ in range(steps):
+        sim.advance(settings["dt"], 2)
+        ws.advance_timestep(settings["dt"])
+    ws.synchronize()
+    _cmp(case, "position", ws.get("position"), sim.member("position"), 1e-6)
+    _cmp(case, "u", ws.get("u"), sim.get("hydro_vector", "u"), 1e-6)
+    _cmp(case, "extensive", ws.get("extensive"), sim.member("extensive")[:, [0, 2, 3, 4]], 1e-6)
+    _cmp(case, "extensive_shv", ws.get("extensive_shv"), _ext_shv5(sim), 1e-6, scale=max(np.max(np.abs(_ext_shv5(sim))), 1e-6))
+    tot, ref_tot = ws.conservation(), sim.totals()
+    for k in ("S", "B", "Sq", "Q", "E"):
+        assert abs(tot[k] - ref_tot[k]) <= 1e-8 * max(abs(ref_tot[k]), 1.0), (case, k, tot[k], ref_tot[k])
+
+
 # ---- golden vectors of the reference's own unit tests, through the C ABI -----------
 def test_golden_smoothing_sum():
     """unit_tests/smoothing_test.cpp:33-147: 4 particles, h=1 -> smoothed s(0) = 20/(7 pi), rhoB 4x, rhoQ 9x, rhoS 16x."""
