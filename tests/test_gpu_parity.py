@@ -574,3 +574,33 @@ def test_rk4_follows_the_reference_sequence(case):
         _cmp(case, "extensive_bulk", ws.get("extensive_bulk"), sim.get("hydro_scalar", "extensive_bulk"), tol,
              scale=max(np.max(np.abs(sim.get("hydro_scalar", "extensive_bulk"))), 1e-6))
         _cmp(case, "Ez", ws.get("Ez"), sim.member("contribution_to_total_Ez"), tol, scale=max(np.max(np.abs(sim.member("contribution_to_total_Ez"))), 1e-6))
+
+
+def test_config2_full_size_against_the_reference():
+    """BASELINE config 2 at its FULL size (160 801 particles, the bench default) against the reference build: two RK2 steps at the
+    per-step bar, neighbour counts bit-exact, totals at the reference's level. (The reference needs ~4 s per step on 16 cores.)"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    from ccake_b200 import workloads as W
+
+    settings, ic = W.config2_viscous_gubser_bsq()
+    sim = make_ref(settings, ic)
+    sim.initialize()
+    ws = _make_ws(settings, ic)
+    assert ws.n_particles == sim.n == 160801
+    for step in range(2):
+        sim.advance(settings["dt"], 2)
+        ws.advance_timestep(settings["dt"])
+        ws.synchronize()
+        tol = TOL * (step + 1)
+        _cmp("config2", "position", ws.get("position"), sim.member("position"), tol)
+        _cmp("config2", "u", ws.get("u"), sim.get("hydro_vector", "u"), tol)
+        _cmp("config2", "extensive", ws.get("extensive"), sim.member("extensive")[:, [0, 2, 3, 4]], tol)
+        _cmp("config2", "extensive_shv", ws.get("extensive_shv"), _ext_shv5(sim), tol, scale=max(np.max(np.abs(_ext_shv5(sim))), 1e-6))
+    off, idx, cell_ref, nc_ref = sim.neighbours()
+    assert np.array_equal(ws.get_int("cell"), cell_ref)
+    assert np.array_equal(ws.get_int("btrack"), np.diff(off).astype(np.int32))
+    _cmp_thermo("config2", ws.get("thermo"), ref_thermo16(sim))
+    tot, ref_tot = ws.conservation(), sim.totals()
+    for k in ("S", "B", "Sq", "Q", "E"):
+        assert abs(tot[k] - ref_tot[k]) <= 1e-9 * max(abs(ref_tot[k]), 1.0), (k, tot[k], ref_tot[k])
