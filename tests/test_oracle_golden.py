@@ -248,3 +248,38 @@ def test_ic_text_format_round_trip(tmp_path):
         f.write("#0 .025 .025 .1 0 -5 -5 -.1\n0 0 0 10 0 0 0 0 0 0 0 0 0 0 0 0 0\n")
     s4, ic4 = W.read_ccake(path, ideal_settings(e_cutoff=0.0))
     assert s4["stepEta"] == 0.1 and s4["etamin"] == -0.1 and ic4["e"][0] == 10.0
+
+
+def test_yaml_reader_diffusion_block(tmp_path):
+    """Key paths of the diffusion block of src/input.cpp:596-700 (regulator, critical-point suppression, C_B, kappa matrix) and the
+    defaults of include/defaults.h:66-72, 119-123 when a key is missing."""
+    from ccake_b200 import settings as S
+
+    y = tmp_path / "in.yaml"
+    y.write_text("""
+initial_conditions: {dimension: 3, t0: 0.6, coordinate_system: hyperbolic}
+parameters: {dt: 0.02, h_T: 0.25, h_eta: 0.2, rk_order: 4}
+eos: {type: tanh_conformal}
+hydro:
+  viscous_parameters:
+    diffusion:
+      mode: kappaB_coth
+      relaxation_mode: cb_over_T
+      C_B: 0.4
+      critical_scaling: true
+      critical_point: {T: 140.0, muB: 420.0}
+      critical_gaussian_width: {T: 25.0}
+      constant_kappa_over_T2: [[0.1, 0.0, 0.0], [0.0, 0.2, 0.0], [0.0, 0.0, 0.3]]
+      regulator: {enabled: true, chi0: 5.0, e0: 0.2}
+""")
+    s = S.from_yaml(str(y))
+    assert (s["dim"], s["rk_order"], s["eos_type"], s["hT"], s["hEta"]) == (3, 4, "tanh_conformal", 0.25, 0.2)
+    assert s["diffusionMode"] == "kappaB_coth" and s["diffusionRelaxMode"] == "cb_over_T" and s["C_B"] == 0.4
+    assert s["critical_scaling_diffusion"] is True and s["critical_point_T"] == 140.0 and s["critical_point_muB"] == 420.0
+    assert s["critical_gaussian_width_T"] == 25.0 and s["critical_gaussian_width_muB"] == 50.0      # default kept
+    assert s["diffusion_regulator_enabled"] is True and s["diffusion_regulator_chi0"] == 5.0 and s["diffusion_regulator_e0"] == 0.2
+    assert s["diffusion_regulator_xi0"] == 0.01 and s["diffusion_regulator_rq_max"] == 1.0          # defaults kept
+    assert (s["kappa_00"], s["kappa_11"], s["kappa_22"], s["kappa_01"]) == (0.1, 0.2, 0.3, 0.0)
+    c = S.to_config(s)
+    assert c.rk_order == 4 and c.eos_type == 2 and c.diffusion_mode == 2 and c.diffusion_relax_mode == 1
+    assert c.diffusion_regulator_enabled == 1 and c.critical_scaling_diffusion == 1 and c.using_diffusion == 1
