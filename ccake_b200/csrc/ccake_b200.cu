@@ -84,6 +84,12 @@ struct ccb_ctx {
   uint32_t* d_ends = nullptr;                // 8 table ends of exchange_column_tables, fetched in one copy
   bool init_diffusion = false;               // the IC rows carried q^mu_a (ccb_ic::diffusion)
   int* d_qflag = nullptr;                    // DeviceView::qflag
+  // peer-memory halo (CCB_HALO_P2P=1): the boundary tasks read the neighbours' record arrays over NVLink; flag words order the accesses
+  bool p2p = false;
+  int* d_flags = nullptr;                    // own flag words: [0] ready from left, [1] ready from right, [2] done from left, [3] done from right
+  void* peer_rec[2] = {nullptr, nullptr};
+  void* peer_flags[2] = {nullptr, nullptr};
+  int halo_epoch = 0;                        // one epoch per gather
   cudaStream_t comm_stream = nullptr;        // halo exchanges run here, next to the interior tasks of the gather
   cudaEvent_t ev_pack = nullptr, ev_halo = nullptr;
   int64_t ghost_n[2] = {0, 0};               // ghost records per side
@@ -264,6 +270,7 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   dv.key = ctx->key_a;
   dv.cell_start = ctx->cell_count;
   dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
+  dv.ghost_rec[0] = dv.ghost_rec[1] = ctx->rec;
   dv.tasks = ctx->tasks; dv.ntasks = ctx->d_small; dv.err = ctx->d_small + 1;
   const int64_t need_sums = cdiv(std::max<int64_t>(ctx->hist_alloc, ctx->grid.ncells + 1), kScanTile) + 1;
   if (need_sums > ctx->sums_alloc) {
@@ -498,10 +505,16 @@ int exchange_column_tables(ccb_ctx* ctx) {
   ctx->send_start[1] = h[2]; ctx->send_n[1] = right >= 0 ? (int64_t)h[3] - h[2] : 0;
   ctx->ghost_n[0] = left >= 0 ? (int64_t)h[5] - h[4] : 0;
   ctx->ghost_n[1] = right >= 0 ? (int64_t)h[7] - h[6] : 0;
-  if (left >= 0) LAUNCH(rebase_ghost_table, cdiv(T, 256), 256, tab + 2 * T, tab, T, (uint32_t)ctx->n);
-  if (right >= 0) LAUNCH(rebase_ghost_table, cdiv(T, 256), 256, tab + 3 * T, tab + T, T, (uint32_t)(ctx->n + ctx->ghost_n[0]));
   dv.ghost_col[0] = left >= 0 ? ctx->slab_lo - 1 : -1;
   dv.ghost_col[1] = right >= 0 ? ctx->slab_hi : -1;
+  if (ctx->p2p) {
+    // the ghost records stay where they are: the received tables already hold offsets into the neighbour's own record array
+    dv.ghost_start[0] = tab + 2 * T; dv.ghost_start[1] = tab + 3 * T;
+    dv.ghost_rec[0] = static_cast<const double*>(ctx->peer_rec[0]); dv.ghost_rec[1] = static_cast<const double*>(ctx->peer_rec[1]);
+    return CCB_OK;
+  }
+  if (left >= 0) LAUNCH(rebase_ghost_table, cdiv(T, 256), 256, tab + 2 * T, tab, T, (uint32_t)ctx->n);
+  if (right >= 0) LAUNCH(rebase_ghost_table, cdiv(T, 256), 256, tab + 3 * T, tab + T, T, (uint32_t)(ctx->n + ctx->ghost_n[0]));
   dv.ghost_start[0] = tab; dv.ghost_start[1] = tab + T;
   // room for the ghost records behind the own ones
   const int64_t need = ctx->n + ctx->ghost_n[0] + ctx->ghost_n[1];
@@ -512,8 +525,12 @@ int exchange_column_tables(ccb_ctx* ctx) {
     CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G_MAX * ctx->rec_cap));
     dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
   }
+  dv.ghost_rec[0] = dv.ghost_rec[1] = ctx->rec;
   return CCB_OK;
 }
+
+int ensure_comm_stream(ccb_ctx* ctx);
+int p2p_wait_readers(ccb_ctx* ctx);
 
 // Ghost records of one gather (rec_doubles per record): own edge columns -> neighbours, theirs -> behind our own.
 // The exchange runs on the context's communication stream: it starts when the records are packed (ev_pack) and the
@@ -521,13 +538,7 @@ int exchange_column_tables(ccb_ctx* ctx) {
 int exchange_halo(ccb_ctx* ctx, int rec_doubles) {
   const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
   const int left = rank - 1, right = rank + 1 < nranks ? rank + 1 : -1;
-  if (!ctx->comm_stream) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    CUDA_OK(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
-    CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
-  }
+  { const int rc0 = ensure_comm_stream(ctx); if (rc0) return rc0; }
   cudaStream_t cs = ctx->comm_stream;
   CUDA_OK(cudaEventRecord(ctx->ev_pack, ctx->stream));
   CUDA_OK(cudaStreamWaitEvent(cs, ctx->ev_pack, 0));
@@ -599,8 +610,68 @@ int do_build_cells(ccb_ctx* ctx) {
 
 int do_prologue(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_GAMMA);
+  { const int rc = p2p_wait_readers(ctx); if (rc) return rc; }
   CUDA_OK(cudaMemsetAsync(ctx->d_qflag + 2, 0, sizeof(int), ctx->stream));
   DISPATCH_DM("prologue_kernel", launch_prologue, ctx->stream, ctx->dv, ctx->t);
+  return CCB_OK;
+}
+
+int ensure_comm_stream(ccb_ctx* ctx) {
+  if (ctx->comm_stream) return CCB_OK;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  CUDA_OK(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
+  CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_pack, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+  return CCB_OK;
+}
+
+// Before this rank overwrites its record array (the next pack), both neighbours must have finished reading it.
+int p2p_wait_readers(ccb_ctx* ctx) {
+  if (!ctx->comm || !ctx->p2p || ctx->halo_epoch == 0) return CCB_OK;
+  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+  LAUNCH(p2p_wait, 1, 1, rank > 0 ? ctx->d_flags + 2 : nullptr, rank + 1 < nranks ? ctx->d_flags + 3 : nullptr, ctx->halo_epoch, (int*)nullptr, ctx->dv.err);
+  return CCB_OK;
+}
+
+// Slab gather WITHOUT a halo message: the boundary tasks stage the ghost column straight out of the neighbour's record array
+// (NVLink peer memory). Per gather (one epoch): this rank tells its neighbours that its records are packed (ready flag, with its
+// sparsity bit), waits on the communication stream for theirs, runs the boundary tasks there, and tells them it has finished
+// reading (done flag); the interior tasks run meanwhile on the compute stream.
+template <class F>
+int slab_gather_p2p(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& launch) {
+  int rc = ensure_comm_stream(ctx);
+  if (rc) return rc;
+  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+  const bool has_l = rank > 0, has_r = rank + 1 < nranks;
+  const bool fields = rec_doubles == REC_F;
+  int* own_flag = ctx->d_qflag + (fields ? 2 : 0);
+  int* gflag = own_flag + 1;
+  const int e = ++ctx->halo_epoch;
+  int* pl = static_cast<int*>(ctx->peer_flags[0]);
+  int* pr = static_cast<int*>(ctx->peer_flags[1]);
+  cudaStream_t cs = ctx->comm_stream;
+  CUDA_OK(cudaMemsetAsync(gflag, 0, sizeof(int), ctx->stream));
+  LAUNCH(p2p_signal, 1, 1, has_l ? pl + 1 : nullptr, has_r ? pr + 0 : nullptr, e, (const int*)own_flag);   // I am left's right neighbour, right's left one
+  CUDA_OK(cudaEventRecord(ctx->ev_pack, ctx->stream));
+  CUDA_OK(cudaStreamWaitEvent(cs, ctx->ev_pack, 0));
+  p2p_wait<<<1, 1, 0, cs>>>(has_l ? ctx->d_flags + 0 : nullptr, has_r ? ctx->d_flags + 1 : nullptr, e, gflag, ctx->dv.err);
+  ctx->launches++;
+  const TaskSplit ts = split_tasks(ctx, nt);
+  const int64_t nb = ts.i0 + (ts.ntasks - ts.i1);
+  if (nb > 0) {
+    GatherParams gb = gp;
+    gb.task_count = (int)nb; gb.task_n0 = (int)ts.i0; gb.task_off0 = 0; gb.task_off1 = (int)ts.i1;
+    if ((rc = launch(gb, cs))) return rc;
+  }
+  p2p_signal<<<1, 1, 0, cs>>>(has_l ? pl + 3 : nullptr, has_r ? pr + 2 : nullptr, e, (const int*)nullptr);
+  ctx->launches++;
+  CUDA_OK(cudaEventRecord(ctx->ev_halo, cs));
+  if (ts.i1 > ts.i0) {
+    gp.task_count = gp.task_n0 = (int)(ts.i1 - ts.i0); gp.task_off0 = (int)ts.i0; gp.task_off1 = 0;
+    if ((rc = launch(gp, ctx->stream))) return rc;
+  }
+  CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
   return CCB_OK;
 }
 
@@ -609,6 +680,7 @@ int do_prologue(ccb_ctx* ctx) {
 template <class F>
 int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& launch) {
   if (!ctx->comm) return launch(gp, ctx->stream);
+  if (ctx->p2p) return slab_gather_p2p(ctx, rec_doubles, nt, gp, launch);
   // do the ghost records carry what the own records may lack (q^mu_a != 0 for the gradient gather, charges for the fields)?
   const bool fields = rec_doubles == REC_F;
   const bool scan = fields || ctx->cfg.using_diffusion;
@@ -663,6 +735,7 @@ int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
     }
     if (do_local) {
       PhaseTimer pt(ctx, PH_LOCAL);
+      { const int rc = p2p_wait_readers(ctx); if (rc) return rc; }
       sp.do_eos = 0; sp.do_local = 1;
       CUDA_OK(cudaMemsetAsync(ctx->d_qflag, 0, sizeof(int), ctx->stream));
       DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
@@ -671,6 +744,7 @@ int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
   }
   PhaseTimer pt(ctx, do_eos ? PH_THERMO : PH_LOCAL);
   sp.do_eos = do_eos; sp.do_local = do_local;
+  if (do_local) { const int rc = p2p_wait_readers(ctx); if (rc) return rc; }
   if (do_local) CUDA_OK(cudaMemsetAsync(ctx->d_qflag, 0, sizeof(int), ctx->stream));
   DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
   return CCB_OK;
@@ -922,7 +996,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_particles(ctx);
   cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
-  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends); cudaFree(ctx->d_qflag);
+  cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends); cudaFree(ctx->d_qflag); cudaFree(ctx->d_flags);
   if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_halo); }
   cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
   ctx->comm.reset();
@@ -1196,6 +1270,8 @@ static int comm_buffers(ccb_ctx* ctx) {
   CUDA_OK(cudaMemset(ctx->ghost_tab, 0, sizeof(uint32_t) * 4 * T));
   CUDA_OK(cudaMalloc(&ctx->d_info, sizeof(int32_t) * 8 + sizeof(double) * 8));
   CUDA_OK(cudaMalloc(&ctx->d_ends, sizeof(uint32_t) * 8));
+  CUDA_OK(cudaMalloc(&ctx->d_flags, sizeof(int) * 8));
+  CUDA_OK(cudaMemset(ctx->d_flags, 0, sizeof(int) * 8));
   return CCB_OK;
 }
 int ccb_comm_unique_id(char id[128]) {
@@ -1216,6 +1292,9 @@ int ccb_comm_init(ccb_ctx* ctx, const char id[128]) {
   auto t = std::make_unique<NcclLink>();
   if (t->init(id, ctx->cfg.rank, ctx->cfg.nranks)) { ctx->err = "ccb_comm_init: " + t->err; return CCB_ERR_COMM; }
   ctx->comm = std::move(t);
+  // one process per GPU: the boundary tasks read the neighbours' records over NVLink peer memory (CCB_HALO_P2P=0: halo messages)
+  ctx->p2p = true;
+  if (const char* e = std::getenv("CCB_HALO_P2P")) ctx->p2p = std::atoi(e) != 0;
   return comm_buffers(ctx);
 }
 int ccb_comm_init_local(ccb_ctx* ctx, int group) {
@@ -1223,6 +1302,10 @@ int ccb_comm_init_local(ccb_ctx* ctx, int group) {
   if (ctx->cfg.nranks < 2) { ctx->err = "ccb_comm_init_local: nranks < 2"; return CCB_ERR_INVALID; }
   if (ctx->have_state) { ctx->err = "ccb_comm_init_local must precede the particle upload"; return CCB_ERR_STATE; }
   ctx->comm = std::make_unique<LocalLink>(group, ctx->cfg.rank, ctx->cfg.nranks);
+  // several contexts of ONE process on one GPU: halo messages by default. The flag-ordered peer path works here too
+  // (CCB_HALO_P2P=1) but its spinning wait kernels need every stream on its own hardware queue (CUDA_DEVICE_MAX_CONNECTIONS).
+  ctx->p2p = false;
+  if (const char* e = std::getenv("CCB_HALO_P2P")) ctx->p2p = std::atoi(e) != 0;
   return comm_buffers(ctx);
 }
 int ccb_set_slab(ccb_ctx* ctx, int32_t col_lo, int32_t col_hi) {
@@ -1367,6 +1450,16 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   if (rc) return rc;
   const int64_t n = ctx->n, cap = ctx->cap;
   ctx->t = ctx->cfg.t0;
+  if (ctx->comm && ctx->p2p) {  // peer-memory halo: every rank shows its (new) record array and flag words to its neighbours
+    CUDA_OK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 8, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->halo_epoch = 0;
+    const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
+    if (ctx->comm->exchange_pointers(ctx->rec, ctx->d_flags, rank - 1, rank + 1 < nranks ? rank + 1 : -1, ctx->peer_rec, ctx->peer_flags, ctx->stream)) {
+      ctx->err = std::string(ctx->comm->name()) + " transport: peer-memory halo unavailable (" + ctx->comm->err + "); set CCB_HALO_P2P=0 for halo messages";
+      return CCB_ERR_COMM;
+    }
+  }
   const int64_t mig0 = ctx->migrated_out + ctx->migrated_in;
   DeviceView& dv = ctx->dv;
   std::vector<double> colbuf(n);

@@ -116,6 +116,34 @@ __global__ void ghost_q_flag(const double* __restrict__ rec, int64_t count, int 
   for (int c = lo; c < hi; ++c) nz |= (rec[k * rec_doubles + c] != 0.0);
   if (nz) *flag = 1;
 }
+// ---- peer-memory halo: ready / done flags between neighbouring ranks ------------------------------------------------
+// One thread publishes `value` (epoch * 2 + this rank's sparsity flag) into a flag word of each neighbour (peer stores over
+// NVLink; nullptr = no neighbour), after making this rank's records visible system-wide.
+__global__ void p2p_signal(int* peer_a, int* peer_b, int epoch, const int* sparsity_or_null) {
+  const int v = epoch * 2 + ((sparsity_or_null && *sparsity_or_null) ? 1 : 0);
+  __threadfence_system();
+  if (peer_a) *reinterpret_cast<volatile int*>(peer_a) = v;
+  if (peer_b) *reinterpret_cast<volatile int*>(peer_b) = v;
+  __threadfence_system();
+}
+// One thread waits until both own flag words (nullptr = no neighbour) carry at least `epoch`; the neighbours' sparsity bits are
+// OR-ed into *ghost_flag (nullptr = not wanted). Gives up with CCB_ERR_COMM after ~10 s of polling rather than hanging the GPU.
+__global__ void p2p_wait(const int* flag_a, const int* flag_b, int epoch, int* ghost_flag, int32_t* err) {
+  int bits = 0;
+  const int* f[2] = {flag_a, flag_b};
+  for (int k = 0; k < 2; ++k) {
+    if (!f[k]) continue;
+    long long spins = 0;
+    int v;
+    while (((v = *reinterpret_cast<const volatile int*>(f[k])) >> 1) < epoch) {
+      __nanosleep(200);
+      if (++spins > 50000000LL) { atomicCAS(&err[0], 0, (int)CCB_ERR_COMM); return; }
+    }
+    if ((v >> 1) == epoch) bits |= v & 1; else bits |= 1;  // a later epoch already: assume the general case
+  }
+  if (ghost_flag && bits) *ghost_flag = 1;
+  __threadfence_system();
+}
 // the eight record offsets exchange_column_tables needs on the host, gathered for ONE device-to-host copy
 __global__ void table_ends(const uint32_t* __restrict__ own_first, const uint32_t* __restrict__ own_last, const uint32_t* __restrict__ tab_left,
                            const uint32_t* __restrict__ tab_right, int64_t P, int has_left, int has_right, uint32_t* __restrict__ out) {

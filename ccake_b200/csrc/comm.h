@@ -32,6 +32,9 @@ struct Link {
   virtual int send(const void* dbuf, size_t bytes, int peer, cudaStream_t s) = 0;
   virtual int recv(void* dbuf, size_t bytes, int peer, cudaStream_t s) = 0;
   virtual int allreduce_sum(double* dbuf, int n, cudaStream_t s) = 0;  // in place, device buffer
+  // Peer-memory halo: hand the neighbours (rank -+ 1; -1 = none) a view of this rank's record array and flag words and
+  // obtain theirs, as device pointers valid on THIS device (CUDA IPC between processes, plain pointers inside one).
+  virtual int exchange_pointers(void* rec, void* flags, int left, int right, void* peer_rec[2], void* peer_flags[2], cudaStream_t s) = 0;
   std::string err;
 };
 
@@ -81,6 +84,36 @@ struct NcclLink : Link {
   int send(const void* d, size_t bytes, int peer, cudaStream_t s) override { return chk(api.Send(d, bytes, /*ncclChar*/ 0, peer, comm, s)); }
   int recv(void* d, size_t bytes, int peer, cudaStream_t s) override { return chk(api.Recv(d, bytes, 0, peer, comm, s)); }
   int allreduce_sum(double* d, int n, cudaStream_t s) override { return chk(api.AllReduce(d, d, (size_t)n, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm, s)); }
+  std::vector<void*> opened;
+  int exchange_pointers(void* rec, void* flags, int left, int right, void* peer_rec[2], void* peer_flags[2], cudaStream_t s) override {
+    for (void* p : opened) cudaIpcCloseMemHandle(p);
+    opened.clear();
+    cudaIpcMemHandle_t mine[2], theirs[2][2];
+    if (cudaIpcGetMemHandle(&mine[0], rec) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], flags) != cudaSuccess) { err = "cudaIpcGetMemHandle failed"; return 1; }
+    char* d = nullptr;
+    const size_t hb = sizeof(mine);
+    if (cudaMalloc(&d, 3 * hb) != cudaSuccess) { err = "cudaMalloc failed"; return 1; }
+    cudaMemcpyAsync(d, mine, hb, cudaMemcpyHostToDevice, s);
+    const int peer[2] = {left, right};
+    if (group_begin()) return 1;
+    for (int k = 0; k < 2; ++k) if (peer[k] >= 0 && send(d, hb, peer[k], s)) return 1;
+    for (int k = 0; k < 2; ++k) if (peer[k] >= 0 && recv(d + (1 + k) * hb, hb, peer[k], s)) return 1;
+    if (group_end()) return 1;
+    cudaMemcpyAsync(theirs, d + hb, 2 * hb, cudaMemcpyDeviceToHost, s);
+    if (cudaStreamSynchronize(s) != cudaSuccess) { err = "handle exchange failed"; return 1; }
+    cudaFree(d);
+    for (int k = 0; k < 2; ++k) {
+      peer_rec[k] = peer_flags[k] = nullptr;
+      if (peer[k] < 0) continue;
+      if (cudaIpcOpenMemHandle(&peer_rec[k], theirs[k][0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&peer_flags[k], theirs[k][1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        err = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
+        return 1;
+      }
+      opened.push_back(peer_rec[k]); opened.push_back(peer_flags[k]);
+    }
+    return 0;
+  }
 };
 
 // ---- in-process transport ---------------------------------------------------------------------
@@ -89,6 +122,7 @@ struct LocalHub {
   std::mutex mu;
   std::condition_variable cv;
   std::map<std::pair<int, int>, std::deque<Msg>> q;  // (src, dst) -> FIFO
+  std::map<int, std::pair<void*, void*>> ptrs;       // rank -> (record array, flag words): exchange_pointers
   int nranks = 0;
   static std::shared_ptr<LocalHub> get(int group, int nranks) {
     static std::mutex gmu;
@@ -134,6 +168,19 @@ struct LocalLink : Link {
         err = "local transport: copy from mailbox failed"; return 1;
       }
       cudaFree(m.dptr);
+    }
+    return 0;
+  }
+  int exchange_pointers(void* rec, void* flags, int left, int right, void* peer_rec[2], void* peer_flags[2], cudaStream_t) override {
+    std::unique_lock<std::mutex> l(hub->mu);
+    hub->ptrs[rank] = {rec, flags};
+    hub->cv.notify_all();
+    const int peer[2] = {left, right};
+    for (int k = 0; k < 2; ++k) {
+      peer_rec[k] = peer_flags[k] = nullptr;
+      if (peer[k] < 0) continue;
+      hub->cv.wait(l, [&] { return hub->ptrs.count(peer[k]) != 0; });
+      peer_rec[k] = hub->ptrs[peer[k]].first; peer_flags[k] = hub->ptrs[peer[k]].second;
     }
     return 0;
   }

@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   __shared__ __align__(16) double2 srec2[2][TILE * RS2];  // double-buffered tiles of source records
   __shared__ __align__(16) float spos[4][TILE];  // fp32 x, y, z relative to the pass origin, and x^2 + y^2 + z^2
   __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
+  __shared__ const double2* seg_base[kMaxSeg];  // record array of the segment: own, or a neighbour's (ghost column)
   __shared__ int s_nseg;
   __shared__ uint32_t s_next[NT / 32];
   const double* __restrict__ rec = P::records(dv);
@@ -450,11 +451,12 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
           if (x < 0 || x >= nx || y < 0 || y >= ((nz > 1) ? ny : 1)) continue;
           const uint32_t row = (nz > 1) ? (uint32_t)(x * ny + y) : (uint32_t)x;
           const uint32_t* cs = dv.cell_start;
+          const double2* base = rec2;
           uint32_t koff = 0;  // ghost columns have their own table, indexed from the column's first cell
-          if (x == dv.ghost_col[0]) { cs = dv.ghost_start[0]; koff = (uint32_t)x * ny * nz; }
-          else if (x == dv.ghost_col[1]) { cs = dv.ghost_start[1]; koff = (uint32_t)x * ny * nz; }
+          if (x == dv.ghost_col[0]) { cs = dv.ghost_start[0]; koff = (uint32_t)x * ny * nz; base = reinterpret_cast<const double2*>(dv.ghost_rec[0]); }
+          else if (x == dv.ghost_col[1]) { cs = dv.ghost_start[1]; koff = (uint32_t)x * ny * nz; base = reinterpret_cast<const double2*>(dv.ghost_rec[1]); }
           const uint32_t js = cs[row * F + f0 - koff], je = cs[row * F + f1 + 1 - koff];
-          if (je > js) { seg_start[ns] = js; seg_pref[ns] = C; C += je - js; ++ns; }
+          if (je > js) { seg_start[ns] = js; seg_pref[ns] = C; seg_base[ns] = base; C += je - js; ++ns; }
         }
       seg_pref[ns] = C;
       s_nseg = ns;
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
         int s = 0;
         while (cand >= seg_pref[s + 1]) ++s;
         const int64_t gidx = (int64_t)seg_start[s] + (cand - seg_pref[s]);
-        cp_async16(buf + r * RS2 + c, rec2 + gidx * CH + c);
+        cp_async16(buf + r * RS2 + c, seg_base[s] + gidx * CH + c);
       }
       cp_async_commit();
     };

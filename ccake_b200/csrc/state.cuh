@@ -55,6 +55,9 @@ struct DeviceView {
   // of cell c of that column (c = y * nz + z). ghost_col = -1: no neighbour on that side.
   int32_t ghost_col[2];
   const uint32_t* ghost_start[2];
+  // where the ghost records of each side live: behind the own records (halo exchanged by message: the own array again), or
+  // the NEIGHBOUR's record array itself, mapped over NVLink peer memory (ghost_start then holds the neighbour's own offsets)
+  const double* ghost_rec[2];
 };
 
 CCB_HD double& col(double* base, int64_t cap, int c, int64_t i) { return base[(int64_t)c * cap + i]; }

@@ -228,7 +228,9 @@ int ccb_grid_shape(ccb_ctx* ctx, int32_t ncell[3]);
  * One context per GPU / process, config.rank of config.nranks. Rank r owns the particles whose neighbour-grid cell
  * column along x lies in [col_lo, col_hi) (contiguous, ascending with the rank; the outermost slabs extend to the grid
  * edge). Every cell build then hands particles that left the slab to rank -+ 1 and appends the arrivals; every
- * gather is preceded by the exchange of the edge columns' packed records (the 2h-wide halo). Transport: NCCL
+ * gather reads the edge columns' packed records of its neighbours (the 2h-wide halo): straight out of their record arrays over
+ * NVLink peer memory (CUDA IPC, ordered by ready / done flag words; the default between processes) or as a message appended
+ * behind the own records (environment CCB_HALO_P2P=0). Transport of everything else: NCCL
  * send/recv (ccb_comm_init; rank 0 creates the id with ccb_comm_unique_id and the caller broadcasts it), or mailboxes
  * between contexts of ONE process, each driven by its own host thread (ccb_comm_init_local; used by the single-GPU tests).
  * Call order: ccb_create, ccb_comm_init*, ccb_set_slab, ccb_upload_ic (own rows + global ids). Host arrays in particle-id

@@ -148,3 +148,33 @@ def test_slabs_rk4_accumulators_follow_the_particles():
     for f in ("position", "u", "extensive", "extensive_shv"):
         ref = one.get(f)
         assert rel_err(run.gather(f), ref, max(np.max(np.abs(ref)), 1e-12)) < 1e-12, f
+
+
+@pytest.mark.gpu
+def test_peer_memory_halo_matches_halo_messages(tmp_path):
+    """CCB_HALO_P2P=1 with two in-process slabs: the boundary tasks read the neighbour's record array directly, ordered by the
+    ready / done flags, and give the single-context answer like the message path does. Run in a child process: the switch is read
+    at communicator creation, and the spinning wait kernels want every stream on its own hardware queue."""
+    job = tmp_path / "p2p_job.py"
+    job.write_text(r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from common import viscous_settings, charged_settings, gubser_ic, rel_err
+from ccake_b200 import SPHWorkstation
+from slab_harness import SlabRun
+for settings, ic in ((viscous_settings(dt=0.02), gubser_ic(dx=0.1, shear=True)), (charged_settings(dt=0.02), gubser_ic(dx=0.1, shear=True, charges=True))):
+    one = SPHWorkstation(settings)
+    one.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+    run = SlabRun(settings, ic, 2)
+    for _ in range(4):
+        one.advance_timestep(settings["dt"]); run.each(lambda r, w: w.advance_timestep(settings["dt"]))
+    one.synchronize(); run.each(lambda r, w: w.synchronize())
+    for f in ("position", "u", "extensive", "gradP", "du_dt"):
+        ref = one.get(f)
+        assert rel_err(run.gather(f), ref, max(np.max(np.abs(ref)), 1e-12)) < 1e-12, f
+    assert np.array_equal(run.gather_int("btrack"), one.get_int("btrack"))
+print("P2P OK")
+""" % (ROOT, os.path.join(ROOT, "tests")))
+    env = dict(os.environ, CCB_HALO_P2P="1", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    out = subprocess.run([sys.executable, str(job)], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0 and "P2P OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
