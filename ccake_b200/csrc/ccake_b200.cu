@@ -1450,6 +1450,18 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   if (rc) return rc;
   const int64_t n = ctx->n, cap = ctx->cap;
   ctx->t = ctx->cfg.t0;
+  if (ctx->comm && ctx->p2p && !std::getenv("CCB_HALO_P2P")) {
+    // Peer reads pay off while the halo is latency-bound. A large ghost column is re-read over NVLink by every boundary task
+    // that stages it, where one message lands it in local memory (and L2) once: measured 7 % slower on config 4 cut into 8
+    // slabs (56 MB per column) and 3 % faster on config 2 (0.9 MB). All ranks agree on the mean column size.
+    double est = (double)ctx->n / std::max(1, ctx->slab_hi - ctx->slab_lo) * sizeof(double) * REC_G_MAX;
+    double* d = reinterpret_cast<double*>(ctx->d_info + 8);
+    CUDA_OK(cudaMemcpyAsync(d, &est, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    COMM_OK(ctx->comm->allreduce_sum(d, 1, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(&est, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (est / ctx->cfg.nranks > 4.0e6) ctx->p2p = false;
+  }
   if (ctx->comm && ctx->p2p) {  // peer-memory halo: every rank shows its (new) record array and flag words to its neighbours
     CUDA_OK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(int) * 8, ctx->stream));
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
