@@ -1467,9 +1467,21 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     ctx->halo_epoch = 0;
     const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
-    if (ctx->comm->exchange_pointers(ctx->rec, ctx->d_flags, rank - 1, rank + 1 < nranks ? rank + 1 : -1, ctx->peer_rec, ctx->peer_flags, ctx->stream)) {
-      ctx->err = std::string(ctx->comm->name()) + " transport: peer-memory halo unavailable (" + ctx->comm->err + "); set CCB_HALO_P2P=0 for halo messages";
-      return CCB_ERR_COMM;
+    // ... and all ranks agree on whether that worked everywhere; if CUDA IPC is not available (container without a shared IPC
+    // namespace, no peer access) every rank falls back to halo messages together
+    double failed = ctx->comm->exchange_pointers(ctx->rec, ctx->d_flags, rank - 1, rank + 1 < nranks ? rank + 1 : -1, ctx->peer_rec, ctx->peer_flags,
+                                                 ctx->stream) ? 1.0 : 0.0;
+    double* d = reinterpret_cast<double*>(ctx->d_info + 8);
+    CUDA_OK(cudaMemcpyAsync(d, &failed, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    COMM_OK(ctx->comm->allreduce_sum(d, 1, ctx->stream));
+    CUDA_OK(cudaMemcpyAsync(&failed, d, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (failed > 0.0) {
+      if (std::getenv("CCB_HALO_P2P")) {
+        ctx->err = std::string(ctx->comm->name()) + " transport: peer-memory halo unavailable (" + ctx->comm->err + ")";
+        return CCB_ERR_COMM;
+      }
+      ctx->p2p = false;
     }
   }
   const int64_t mig0 = ctx->migrated_out + ctx->migrated_in;

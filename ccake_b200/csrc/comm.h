@@ -88,8 +88,16 @@ struct NcclLink : Link {
   int exchange_pointers(void* rec, void* flags, int left, int right, void* peer_rec[2], void* peer_flags[2], cudaStream_t s) override {
     for (void* p : opened) cudaIpcCloseMemHandle(p);
     opened.clear();
+    // A local failure must not leave a neighbour waiting in the handle exchange: the exchange always runs (zeroed handles on
+    // failure) and the caller agrees on the outcome across ranks before using the pointers.
+    int failed = 0;
     cudaIpcMemHandle_t mine[2], theirs[2][2];
-    if (cudaIpcGetMemHandle(&mine[0], rec) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], flags) != cudaSuccess) { err = "cudaIpcGetMemHandle failed"; return 1; }
+    std::memset(mine, 0, sizeof(mine));
+    if (cudaIpcGetMemHandle(&mine[0], rec) != cudaSuccess || cudaIpcGetMemHandle(&mine[1], flags) != cudaSuccess) {
+      err = std::string("cudaIpcGetMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
+      std::memset(mine, 0, sizeof(mine));
+      failed = 1;
+    }
     char* d = nullptr;
     const size_t hb = sizeof(mine);
     if (cudaMalloc(&d, 3 * hb) != cudaSuccess) { err = "cudaMalloc failed"; return 1; }
@@ -105,14 +113,16 @@ struct NcclLink : Link {
     for (int k = 0; k < 2; ++k) {
       peer_rec[k] = peer_flags[k] = nullptr;
       if (peer[k] < 0) continue;
+      if (failed) continue;
       if (cudaIpcOpenMemHandle(&peer_rec[k], theirs[k][0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
           cudaIpcOpenMemHandle(&peer_flags[k], theirs[k][1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
         err = std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(cudaGetLastError());
-        return 1;
+        failed = 1;
+        continue;
       }
       opened.push_back(peer_rec[k]); opened.push_back(peer_flags[k]);
     }
-    return 0;
+    return failed;
   }
 };
 
