@@ -5,25 +5,26 @@
 // neighbour list and issues 5 (fields) or 5D+D^2 [+6+3D] (gradients) atomic adds PER PAIR into
 // a 4.5 KB/particle AoSoA. Here (particles are already sorted by cell, phase 01):
 //
-//   * a CTA takes a task = NT consecutive particles of the cell-sorted order (one target per thread,
-//     its record and its sums in registers). Consecutive sorted particles lie in consecutive cells of
-//     one grid row, so their neighbours are the particles of the 3^D stencil around that short run
-//     of cells: 3 (2-D) or 9 (3-D) CONTIGUOUS ranges of the sorted records (a row of cells along the
-//     fastest grid axis is contiguous in memory). Every task is full, whatever the cell occupancies;
-//   * the candidate sources are streamed through shared memory in tiles of 128 records (128-bit
-//     loads). Tile k takes every ntiles-th candidate, so each tile is a uniform sample of the whole
-//     neighbourhood and every target finds about the same number of neighbours in it;
-//   * phase 1 (per tile): every thread tests its target against all 128 staged sources in fp32
-//     (coordinates relative to a nearby cell corner; cut-off widened by 1e-4 so that no true
-//     neighbour is missed) and keeps the hits as 4 x 32-bit masks. The reads are warp-uniform
+//   * a CTA takes a task = NT (64 fields, 128 gradients) consecutive particles of the cell-sorted order, one target per
+//     thread with its sums in registers. Consecutive sorted particles lie in consecutive cells of one grid row, so their
+//     neighbours are the particles of the 3^D stencil around that short run of cells: 3 (2-D) or 9 (3-D) CONTIGUOUS ranges
+//     of the sorted records (a row of cells along the fastest grid axis is contiguous in memory); in a slab run a ghost
+//     column is one more such range, in the neighbouring rank's record array (peer memory) or behind the own records;
+//   * the candidate sources are streamed through shared memory in tiles of 64 records, double-buffered with cp.async
+//     (tile k + 1 lands while tile k is processed). Tile k takes every ntiles-th candidate, so each tile is a uniform
+//     sample of the neighbourhood and every target finds about the same number of neighbours in it;
+//   * phase 1 (per tile): every thread tests its target against all staged sources in fp32, in the expanded form
+//     |b|^2 - 2 a.b <= R^2 - |a|^2 (coordinates relative to a nearby cell corner; the cut-off carries a bound on the
+//     rounding, so no true neighbour is missed), and keeps the hits as mask words. The reads are warp-uniform
 //     (shared-memory broadcast) and run on the fp32 pipe, off the fp64 pipe;
-//   * phase 2: every thread walks ITS OWN hit bits, re-tests exactly in fp64 (the reference's
-//     predicate dx*dx + dy*dy + dz*dz <= (2h)^2, unfused) and evaluates the pair term from the
-//     staged record. A warp iterates max-over-lanes(hits) times instead of once per candidate:
-//     only ~1/3 (2-D) to ~1/6 (3-D) of the candidates in the 3^D cells are neighbours, which is
-//     what a lane-per-target loop over all candidates wastes;
-//   * sums stay in registers and are written once: no atomics, reproducible run to run (the
-//     reference's atomic ordering is not).
+//   * phase 2: every thread walks ITS OWN hit bits, re-tests exactly in fp64 (the reference's predicate
+//     dx*dx + dy*dy + dz*dz <= (2h)^2, unfused) and evaluates the pair term from the staged record, 16 bytes at a time.
+//     A warp iterates max-over-lanes(hits) times instead of once per candidate: only ~1/3 (2-D) to ~1/6 (3-D) of the
+//     candidates in the 3^D cells are neighbours, which is what a lane-per-target loop over all candidates wastes;
+//   * the gradient sums are accumulated in moment form (GradPolicy), so the target's own record is read once, in the
+//     epilogue; parts of the records that are zero in every particle are skipped (DeviceView::qflag);
+//   * sums stay in registers and are written once: no atomics, reproducible run to run (the reference's atomic ordering
+//     is not).
 #pragma once
 
 #include "gather_params.cuh"
