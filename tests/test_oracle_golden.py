@@ -283,3 +283,24 @@ hydro:
     c = S.to_config(s)
     assert c.rk_order == 4 and c.eos_type == 2 and c.diffusion_mode == 2 and c.diffusion_relax_mode == 1
     assert c.diffusion_regulator_enabled == 1 and c.critical_scaling_diffusion == 1 and c.using_diffusion == 1
+
+
+@needs_ref
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path on a bounded window of the workload) prints ONE JSON line with the keys the
+    driver reads; no GPU involved."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-scale", "0.1"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "particle_steps_per_s" and d["unit"] == "particle-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["config"]["workload"] == "config2_viscous_gubser_bsq_2p1d"
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
