@@ -915,6 +915,15 @@ int upload_id_ordered(ccb_ctx* ctx, const double* host, double* dst_col) {
 
 }  // namespace
 
+namespace {
+// scratch device buffer of a host-query call: freed on every exit path
+template <class T> struct DevBuf {
+  T* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  cudaError_t alloc(int64_t count) { return cudaMalloc(&p, sizeof(T) * (size_t)count); }
+};
+}  // namespace
+
 // =================================================================================
 extern "C" {
 
@@ -1032,15 +1041,14 @@ int ccb_eos_full_thermo(ccb_ctx* ctx, int member, int64_t n, const double* point
   if (n == 0) return CCB_OK;
   if (ctx->use_chain && !ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
   if (member < 0 || member >= (ctx->use_chain ? ctx->chain.n : 1)) { ctx->err = "ccb_eos_full_thermo: no such member of chosen_EOSs"; return CCB_ERR_INVALID; }
-  double *d_in = nullptr, *d_out = nullptr;
-  CUDA_OK(cudaMalloc(&d_in, sizeof(double) * 4 * n));
-  CUDA_OK(cudaMalloc(&d_out, sizeof(double) * TH_N * n));
-  CUDA_OK(cudaMemcpyAsync(d_in, points, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  DevBuf<double> d_in, d_out;
+  CUDA_OK(d_in.alloc(4 * n));
+  CUDA_OK(d_out.alloc(TH_N * n));
+  CUDA_OK(cudaMemcpyAsync(d_in.p, points, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   const ConformalParams cp{ctx->cfg.conformal_c, ctx->cfg.conformal_T0, ctx->cfg.conformal_muB0, ctx->cfg.conformal_muS0, ctx->cfg.conformal_muQ0};
-  LAUNCHER("eos_query_kernel", launch_eos_query(ctx->stream, ctx->chain, ctx->use_chain ? nullptr : &cp, member, n, d_in, d_out));
-  CUDA_OK(cudaMemcpyAsync(out, d_out, sizeof(double) * TH_N * n, cudaMemcpyDeviceToHost, ctx->stream));
+  LAUNCHER("eos_query_kernel", launch_eos_query(ctx->stream, ctx->chain, ctx->use_chain ? nullptr : &cp, member, n, d_in.p, d_out.p));
+  CUDA_OK(cudaMemcpyAsync(out, d_out.p, sizeof(double) * TH_N * n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_in); cudaFree(d_out);
   return CCB_OK;
 }
 
@@ -1050,20 +1058,19 @@ int ccb_eos_locate(ccb_ctx* ctx, int energy, int64_t n, const double* dens, cons
   if (!energy && !seed && ctx->use_chain) { ctx->err = "ccb_eos_locate: update_s needs a seed point"; return CCB_ERR_INVALID; }
   if (energy && !ctx->use_chain) { ctx->err = "ccb_eos_locate: energy = 1 (s_out) is built for the chain equations of state only"; return CCB_ERR_INVALID; }
   if (ctx->use_chain && !ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
-  double *d_dens = nullptr, *d_seed = nullptr, *d_th = nullptr;
-  int32_t *d_start = nullptr, *d_eos = nullptr;
-  CUDA_OK(cudaMalloc(&d_dens, sizeof(double) * 4 * n));
-  CUDA_OK(cudaMalloc(&d_th, sizeof(double) * 16 * n));
-  CUDA_OK(cudaMalloc(&d_eos, sizeof(int32_t) * n));
-  CUDA_OK(cudaMemcpyAsync(d_dens, dens, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
-  if (seed) { CUDA_OK(cudaMalloc(&d_seed, sizeof(double) * 4 * n)); CUDA_OK(cudaMemcpyAsync(d_seed, seed, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream)); }
-  if (start) { CUDA_OK(cudaMalloc(&d_start, sizeof(int32_t) * n)); CUDA_OK(cudaMemcpyAsync(d_start, start, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream)); }
+  DevBuf<double> d_dens, d_seed, d_th;
+  DevBuf<int32_t> d_start, d_eos;
+  CUDA_OK(d_dens.alloc(4 * n));
+  CUDA_OK(d_th.alloc(16 * n));
+  CUDA_OK(d_eos.alloc(n));
+  CUDA_OK(cudaMemcpyAsync(d_dens.p, dens, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (seed) { CUDA_OK(d_seed.alloc(4 * n)); CUDA_OK(cudaMemcpyAsync(d_seed.p, seed, sizeof(double) * 4 * n, cudaMemcpyHostToDevice, ctx->stream)); }
+  if (start) { CUDA_OK(d_start.alloc(n)); CUDA_OK(cudaMemcpyAsync(d_start.p, start, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream)); }
   const ConformalParams cp{ctx->cfg.conformal_c, ctx->cfg.conformal_T0, ctx->cfg.conformal_muB0, ctx->cfg.conformal_muS0, ctx->cfg.conformal_muQ0};
-  LAUNCHER("eos_locate_kernel", launch_eos_locate(ctx->stream, ctx->chain, cp, ctx->use_chain ? 1 : 0, energy, n, d_dens, d_seed, d_start, d_th, d_eos));
-  CUDA_OK(cudaMemcpyAsync(thermo, d_th, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_OK(cudaMemcpyAsync(eos, d_eos, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  LAUNCHER("eos_locate_kernel", launch_eos_locate(ctx->stream, ctx->chain, cp, ctx->use_chain ? 1 : 0, energy, n, d_dens.p, d_seed.p, d_start.p, d_th.p, d_eos.p));
+  CUDA_OK(cudaMemcpyAsync(thermo, d_th.p, sizeof(double) * 16 * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(eos, d_eos.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_dens); cudaFree(d_seed); cudaFree(d_th); cudaFree(d_start); cudaFree(d_eos);
   return CCB_OK;
 }
 
