@@ -5,9 +5,10 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU implementation, oracle/_ref)
 
 One "step" = SPHWorkstation::advance_timestep (two derivative evaluations + RK2 updates) over the whole
-particle system. Workload at N = 1: BASELINE.json configs[1], the viscous-Gubser 2+1D run with the conformal
-BSQ equation of state (settings of input/config_visc_gubser.yaml) on the 401 x 401 lattice = 160 801 particles.
-Rank 0 prints ONE JSON line. See DESIGN.md "Measurement" for every field.
+particle system. Workload: BASELINE.json configs[3], the configuration the metric is quoted on ("3+1D Milne ... ~8M
+particles, slab-split 1-8 GPUs"): 7 989 930 particles with B, S, Q charges on the tabulated EoS; it fits one B200, so
+N = 1 runs it whole and N > 1 cuts the SAME system into N slabs (strong scaling). The other configs are --workload
+choices. Rank 0 prints ONE JSON line. See DESIGN.md "Measurement" for every field.
 """
 from __future__ import annotations
 
@@ -29,7 +30,7 @@ if ROOT not in sys.path:
 
 METRIC = "particle_steps_per_s"
 UNIT = "particle-steps/s"
-DEFAULT_WORKLOAD = "config2_viscous_gubser_bsq_2p1d"
+DEFAULT_WORKLOAD = "config4_milne_bsq_table_3p1d"
 # bounded CPU sample: fraction of the lattice extent (configs 1-4) or of the particle count (config 5) the reference's CPU
 # implementation runs, sized for 10-30 s of host work at the workload's own spacing, smoothing length and neighbour count
 CPU_SCALE = {"config1": 0.25, "config2": 0.5, "config3": 0.07, "config4": 0.1, "config5": 0.1}
@@ -157,16 +158,31 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-def time_reference(workload, scale, steps, warmup):
+def time_reference(workload, scale, steps, warmup, par04_steps=0):
     """The reference's own CPU implementation (oracle/_ref: its unmodified translation units compiled against the
-    shims of oracle/shim, OpenMP over all host cores) on a bounded sample of the workload."""
+    shims of oracle/shim, OpenMP over ALL host cores) on a bounded sample of the workload. Per-phase seconds come from
+    the reference's own CCAKE_PROFILE table (include/phase_profiler.h). `par04_steps` > 0 adds a second leg in which
+    phase 04 -- a serial host loop in the reference as shipped (src/sph_workstation.cpp:1737-1762) -- runs under OpenMP
+    (oracle/ref_driver.cpp: thermodynamics_openmp), everything else unchanged."""
+    os.environ["CCAKE_PROFILE"] = "1"                    # read once, when the PhaseProfiler singleton is first touched
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())  # torchrun exports 1 to its workers
     from oracle import ref
 
     if not ref.available():
         raise SystemExit("oracle/_ref/libccake_ref.so is missing: run __graft_entry__.build() where /root/reference exists")
+    ref.set_threads(os.cpu_count())
     settings, ic, desc = make_workload(workload, scale)
     if settings["eos_type"] == "table":
         settings["eos_path"] = eos_table(as_file=True)
+
+    def phases(before, after):
+        out = {}
+        for k, (tot, calls) in after.items():
+            t0, c0 = before.get(k, (0.0, 0))
+            if calls > c0:
+                out[k] = {"seconds": round(tot - t0, 4), "calls": calls - c0, "ms_per_call": round(1e3 * (tot - t0) / (calls - c0), 3)}
+        return out
+
     with stdout_to_stderr():
         keys = ref.SETTING_KEYS
         sim = ref.RefSim({k: v for k, v in settings.items() if k in keys or k.startswith("kappa_")})
@@ -180,27 +196,44 @@ def time_reference(workload, scale, steps, warmup):
         tw = (time.perf_counter() - tw) / max(warmup, 1)
         if steps is None:  # cpu_baseline leg of the own arm: about 15 s of host work, 2..20 steps
             steps = int(min(20, max(2, round(15.0 / max(tw, 1e-3)))))
+        p0 = ref.profile_table()
         t0 = time.perf_counter()
         for _ in range(steps):
             sim.advance(dt, 2)
         el = time.perf_counter() - t0
+        p1 = ref.profile_table()
+        par = None
+        if par04_steps > 0:
+            sim.advance_par04(dt, 2)        # builds the per-thread EquationOfState pool (table load): untimed
+            p2 = ref.profile_table()
+            t0 = time.perf_counter()
+            for _ in range(par04_steps):
+                sim.advance_par04(dt, 2)
+            el2 = time.perf_counter() - t0
+            par = {"value": n * par04_steps / el2, "unit": UNIT, "ms_per_step": 1e3 * el2 / par04_steps, "steps": par04_steps,
+                   "per_phase": phases(p2, ref.profile_table()),
+                   "what": "the same reference step with phase 04 (update_all_particle_thermodynamics, serial as shipped) run under "
+                           "OpenMP, one EquationOfState per thread; results bit-identical to the serial loop"}
     cores = ref.omp_threads()
-    return dict(value=n * steps / el, seconds=el, n=n, cores=cores, desc=desc, steps=steps)
+    return dict(value=n * steps / el, seconds=el, n=n, cores=cores, desc=desc, steps=steps, per_phase=phases(p0, p1), phase04_openmp=par)
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    r = time_reference(args.workload, args.cpu_scale, steps, warmup)
+    r = time_reference(args.workload, args.cpu_scale, steps, warmup, par04_steps=max(2, min(steps, 5)))
     out = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": 1e3 * r["seconds"] / steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": args.workload, "description": r["desc"], "particles": r["n"], "rk_order": 2},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
                          "sample": "%d of the workload's particles (same spacing, smoothing length and neighbour count; lattice extent x%.2f), "
-                                   "%d RK2 steps after %d warm-up" % (r["n"], args.cpu_scale, steps, warmup)},
+                                   "%d RK2 steps after %d warm-up" % (r["n"], args.cpu_scale, steps, warmup),
+                         "per_phase": r["per_phase"], "phase04_openmp": r["phase04_openmp"],
+                         "note": "value = the reference AS SHIPPED: every phase OpenMP over `cores` threads except 04_thermodynamics, which is a "
+                                 "serial host loop in the reference; phase04_openmp = the same step with that loop parallelised"},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(out), flush=True)
@@ -252,6 +285,88 @@ def gradient_pair_flop_executed(D, shear, diffusion, currents_zero=False):
     return float(3 * D - 1 + 19 + 3 * D + (1 if (shear or diffusion) else 0) + 2 * fma)
 
 
+def parity_check(rank, world, local_rank, table):
+    """N > 1, inside the driver's own scaling run: the slab-decomposed path exactly as the timed region uses it (per-stage
+    migration and column tables over NCCL; the 2h halo once by CUDA-IPC peer memory over NVLink, once by NCCL messages) against a
+    SINGLE-context run of the same system on rank 0's GPU. A 3e5-particle instance of the bench workload (same h / spacing, same
+    table, same switches), 4 RK2 steps. Integers (ids, neighbour counts) must be equal, the evolved state within 1e-11."""
+    import torch.distributed as dist
+
+    from ccake_b200 import SPHWorkstation, slabs, workloads as W
+
+    settings, ic = W.config4_milne_bsq(n_target=300_000)
+    settings["eos_table_data"] = table
+    dt, steps = settings["dt"], 4
+    fields = ("position", "u", "extensive", "extensive_bulk", "extensive_shv")
+    n_global = ic["r"].shape[0]
+    one = None
+    if rank == 0:
+        ws1 = SPHWorkstation(settings, device=local_rank)
+        ws1.upload_initial_conditions(ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"], ic["u"], ic["bulk"], ic["shv6"])
+        for _ in range(steps):
+            ws1.advance_timestep(dt)
+        ws1.synchronize()
+        one = {f: ws1.get(f) for f in fields}
+        one["btrack"] = ws1.get_int("btrack")
+        ws1.close()
+    out = {"workload": "config4_milne_bsq_table_3p1d:3e5", "particles": n_global, "steps": steps, "tolerance": 1e-11, "halo_modes": {}}
+    saved = os.environ.get("CCB_HALO_P2P")
+    for mode, env in (("peer_memory", "1"), ("nccl_message", "0")):
+        os.environ["CCB_HALO_P2P"] = env
+        res = {"ok": False}
+        try:
+            ws = SPHWorkstation(settings, device=local_rank, rank=rank, nranks=world)
+            mn, ed, nc = ws.grid_geometry()
+            ax = ws.slab_axis
+            cols = slabs.column_of(ic["r"][:, ax], mn[ax], ed[ax], int(nc[ax]))
+            ranges = slabs.partition_columns(cols, int(nc[ax]), world)
+            part = slabs.split_initial_conditions(ic, cols, ranges[rank])
+            ws.comm_init_nccl()
+            ws.set_slab(*ranges[rank])
+            ws.upload_initial_conditions(part["r"], part["e"], part["rhoB"], part["rhoS"], part["rhoQ"], part["u"], part["bulk"], part["shv6"],
+                                         ids=part["id"])
+            for _ in range(steps):
+                ws.advance_timestep(dt)
+            ws.synchronize()
+            mine = {f: ws.get_device_order(f) for f in fields}
+            mine["id"], mine["btrack"], mine["mig"] = ws.get_int_device_order("id"), ws.get_int_device_order("btrack"), ws.migration_counts()
+            ws.close()
+            err = None
+        except Exception as e:  # a rank that cannot run a mode (no CUDA IPC ...) reports it; the others are told by the gather
+            mine, err = None, repr(e)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (mine, err))
+        if rank == 0:
+            errs = [g[1] for g in gathered if g[1]]
+            if errs:
+                res = {"ok": False, "error": errs[0]}
+            else:
+                ids = np.concatenate([g[0]["id"] for g in gathered])
+                ids_ok = bool(np.array_equal(np.sort(ids), np.arange(n_global)))
+                worst = 0.0
+                for f in fields:
+                    got = np.full_like(one[f], np.nan)
+                    for g in gathered:
+                        got[g[0]["id"]] = g[0][f]
+                    worst = max(worst, float(np.max(np.abs(got - one[f])) / max(np.max(np.abs(one[f])), 1e-300)))
+                bt = np.full(n_global, -999, dtype=np.int64)
+                for g in gathered:
+                    bt[g[0]["id"]] = g[0]["btrack"]
+                bt_ok = bool(np.array_equal(bt, one["btrack"]))
+                res = {"ok": bool(ids_ok and bt_ok and worst < 1e-11), "worst_rel_err": worst, "btrack_equal": bt_ok, "ids_complete": ids_ok,
+                       "migrated_out_in": [list(g[0]["mig"]) for g in gathered]}
+        out["halo_modes"][mode] = res
+    if saved is None:
+        os.environ.pop("CCB_HALO_P2P", None)
+    else:
+        os.environ["CCB_HALO_P2P"] = saved
+    if rank == 0:
+        out["ok"] = all(m.get("ok") for m in out["halo_modes"].values())
+        out["worst_rel_err"] = max((m.get("worst_rel_err", float("inf")) for m in out["halo_modes"].values()), default=None)
+        out["btrack_equal"] = all(m.get("btrack_equal", False) for m in out["halo_modes"].values())
+    return out
+
+
 def committed_traffic(workload, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed `ncu --set full` capture of this
     workload (profiles/traffic.json, written from the .ncu-rep by scripts/ncu_summary.py --traffic); None if not captured."""
@@ -283,8 +398,9 @@ def own_arm(args, rank, world, local_rank):
         from ccake_b200 import slabs
 
         mn, ed, nc = ws.grid_geometry()
-        cols = slabs.column_of(ic["r"][:, 0], mn[0], ed[0], int(nc[0]))
-        ranges = slabs.partition_columns(cols, int(nc[0]), world)
+        ax = ws.slab_axis
+        cols = slabs.column_of(ic["r"][:, ax], mn[ax], ed[ax], int(nc[ax]))
+        ranges = slabs.partition_columns(cols, int(nc[ax]), world)
         part = slabs.split_initial_conditions(ic, cols, ranges[rank])
         ws.comm_init_nccl()
         ws.set_slab(*ranges[rank])
@@ -351,6 +467,10 @@ def own_arm(args, rank, world, local_rank):
     barrier()
     ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * t_host))
     assert np.all(np.isfinite(host[: w * ws.n_particles]))
+    del host
+    verify = None
+    if world > 1 and not args.no_verify:
+        verify = parity_check(rank, world, local_rank, eos_table(as_file=False))
 
     if rank != 0:
         return
@@ -390,10 +510,12 @@ def own_arm(args, rank, world, local_rank):
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = time_reference(args.workload, args.cpu_scale, None, 1)
+        r = time_reference(args.workload, args.cpu_scale, None, 1, par04_steps=2)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
                "sample": "%d particles (lattice extent x%.2f at the workload's spacing, smoothing length and neighbour count), %d RK2 steps "
-                         "after 1 warm-up, %.1f s" % (r["n"], args.cpu_scale, r["steps"], r["seconds"])}
+                         "after 1 warm-up, %.1f s" % (r["n"], args.cpu_scale, r["steps"], r["seconds"]),
+               "per_phase": r["per_phase"], "phase04_openmp": r["phase04_openmp"],
+               "note": "value = the reference as shipped (phase 04 is a serial host loop); phase04_openmp = the same step with that loop under OpenMP"}
 
     bytes_state = 8 * w * n_global
     out = {
@@ -402,28 +524,32 @@ def own_arm(args, rank, world, local_rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": desc, "particles": n_global, "particles_rank0": n, "rk_order": 2,
                    "mean_neighbours": float(np.mean(bt[bt >= 0])),
-                   "parallelism": "single GPU" if world == 1 else "%d slabs along x (%s), 2h halo + per-stage migration over NCCL" % (
-                       world, "one copy of the workload per GPU" if args.scaling == "weak" else "the one workload cut at particle-count quantiles"),
+                   "parallelism": "single GPU" if world == 1 else "%d slabs along %s (%s), 2h halo + per-stage migration over NCCL" % (
+                       world, "xyz"[ws.slab_axis] if ws.slab_axis < 2 or D == 2 else "eta", "one copy of the workload per GPU" if args.scaling == "weak" else "the one workload cut at particle-count quantiles"),
                    "l2": "no flush: per-step working set %.0f MB of particle columns per GPU > 126 MB L2" % (8e-6 * n * 190)},
         "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                 "d2h_bytes_per_step": bytes_state, "ms_per_step": ms_e2e / args.steps,
                 "api": "copy_host_to_device(pinned state) + advance_timestep + copy_device_to_host via the C ABI"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
     }
+    if verify is not None:
+        out["parity_check"] = verify
     print(json.dumps(out), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD)
     ap.add_argument("--cpu-scale", type=float, default=None, help="lattice-extent factor of the bounded CPU sample (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="N > 1: weak = one copy of the workload per GPU (the driver's scaling run), strong = the one workload over N slabs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong = the ONE workload cut into N slabs (default: the north star's 1 -> 8 GPU curve of the 3+1D config), "
+                         "weak = one copy of the workload per GPU side by side along x")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the slab-vs-single-context parity check")
     args = ap.parse_args()
 
     if args.cpu_scale is None:

@@ -48,7 +48,7 @@ class Config(C.Structure):
         ("conformal_muS0", C.c_double), ("conformal_muQ0", C.c_double),
         ("freeze_out_temperature_MeV", C.c_double),
         ("prohibit_unstable_cs2", C.c_int), ("prohibit_acausal_cs2", C.c_int), ("restrict_mu_T_ratios", C.c_int),
-        ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int),
+        ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("slab_axis", C.c_int),
     ]
 
 
@@ -142,6 +142,7 @@ def lib():
     L.ccb_migration_counts.argtypes = [ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ccb_get_field_device_order.argtypes = [ctx, C.c_int, dp]
     L.ccb_get_int_field_device_order.argtypes = [ctx, C.c_int, ip]
+    L.ccb_debug_neighbour_list.argtypes = [ctx, C.POINTER(C.c_int64), ip, C.c_int64]
     L.ccb_stream.argtypes = [ctx]
     L.ccb_stream.restype = C.c_void_p
     L.ccb_device_field.argtypes = [ctx, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
@@ -158,4 +159,4 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
             "ccb_measure_dfma_peak", "ccb_comm_unique_id", "ccb_comm_init", "ccb_comm_init_local", "ccb_set_slab",
             "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order",
-            "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]
+            "ccb_debug_neighbour_list", "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]

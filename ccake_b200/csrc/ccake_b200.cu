@@ -4,6 +4,7 @@
 //
 // There is deliberately NO host fallback: every entry point that computes launches
 // CUDA kernels on the context's stream and returns CCB_ERR_CUDA if no device is usable.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -53,7 +54,8 @@ struct ccb_ctx {
   double* d_stage = nullptr;    // staging for id-ordered transfers (16 columns) and reductions
   double* init_tmp = nullptr;
   double* d_reduce = nullptr;   // per-block partials of ccb_reduce
-  bool cells_valid = false;
+  bool cells_valid = false;   // the cell table and sort order match the current positions (gathers may run)
+  bool cells_built = false;   // a cell build has run on this particle set (dv.key matches the current order)
   bool have_state = false;
   std::string err;
   int64_t launches = 0;
@@ -72,7 +74,7 @@ struct ccb_ctx {
   ccb::EosChain chain;
   bool have_table = false;   // the EoS chain is ready: table loaded, or an analytic single-member chain (tanh_conformal, conformal_diagonal)
   bool use_chain = false;    // phase 04 runs through the chain kernels (every eos_type but the closed-form conformal one)
-  int chunk = 128, chunk_fields = 64;   // targets per gather task (= threads per CTA) of the gradient / field gather
+  ccb::GatherShape shape_grad{128, 64, 0}, shape_fields{64, 64, 0};   // launch shapes of the gradient / field gather
   int sms = 148;
   // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
   std::unique_ptr<ccb::Link> comm;
@@ -164,7 +166,8 @@ void resolve_phase_events(ccb_ctx* ctx) {
   ctx->ev_used = 0;
 }
 
-// The neighbour grid of the reference (src/system_state.cpp:651-700 + Cabana's Cartesian grid).
+// The neighbour grid of the reference (src/system_state.cpp:651-700 + Cabana's Cartesian grid), stored in KEY order
+// (CellGrid, state.cuh): the slab axis is the slowest digit of the cell key.
 void setup_grid(ccb_ctx* ctx) {
   const ccb_config& c = ctx->cfg;
   double min_pos[3] = {c.xmin, c.ymin, c.etamin};
@@ -175,18 +178,30 @@ void setup_grid(ccb_ctx* ctx) {
   const double radius = 2 * h;
   for (int d = ctx->D; d < 3; ++d) min_pos[d] = -h;
   CellGrid& g = ctx->grid;
+  int order[3], no = 0;
+  order[no++] = c.slab_axis;
+  for (int d = 0; d < 3; ++d) if (d != c.slab_axis) order[no++] = d;
   g.ncells = 1;
-  for (int d = 0; d < 3; ++d) {
+  for (int k = 0; k < 3; ++k) {
+    const int d = order[k];
     const double max_pos = -min_pos[d];
     const double delta = 1. * radius;
     int nc = (int)std::floor((max_pos - min_pos[d]) * (1.0 / delta));
     if (nc < 1) nc = 1;
     const double dx = (max_pos - min_pos[d]) / nc;
-    g.min[d] = min_pos[d];
-    g.rdx[d] = 1.0 / dx;
-    g.nc[d] = nc;
+    g.axis[k] = d;
+    g.min[k] = min_pos[d];
+    g.rdx[k] = 1.0 / dx;
+    g.nc[k] = nc;
     g.ncells *= nc;
   }
+}
+// cell key of the library (digits in key order) -> cell id in the reference's numbering (ix ny + iy) nz + iz
+int32_t reference_cell_id(const CellGrid& g, uint32_t key) {
+  int c[3], ncs[3];
+  uint32_t k = key;
+  for (int q = 2; q >= 0; --q) { c[g.axis[q]] = (int)(k % (uint32_t)g.nc[q]); ncs[g.axis[q]] = g.nc[q]; k /= (uint32_t)g.nc[q]; }
+  return (int32_t)((c[0] * ncs[1] + c[1]) * ncs[2] + c[2]);
 }
 
 int free_particles(ccb_ctx* ctx) {
@@ -280,6 +295,7 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   }
   if (n > 0) LAUNCH(iota_kernel, cdiv(n, 256), 256, dv.id, n);
   ctx->cells_valid = false;
+  ctx->cells_built = false;
   ctx->have_state = true;
   return CCB_OK;
 }
@@ -317,12 +333,14 @@ GatherParams make_gather(ccb_ctx* ctx) {
   gp.task_count = gp.task_n0 = gp.task_off0 = gp.task_off1 = 0;
 
   const CellGrid& g = ctx->grid;
-  gp.fast_axis = (g.nc[2] > 1) ? 2 : 1;
-  gp.fast_min = g.min[gp.fast_axis];
-  gp.fast_rdx = g.rdx[gp.fast_axis];
-  gp.fast_nc = g.nc[gp.fast_axis];
+  const int fast_digit = (g.nc[2] > 1) ? 2 : 1;
+  gp.fast_coord = g.axis[fast_digit];
+  gp.fast_min = g.min[fast_digit];
+  gp.fast_rdx = g.rdx[fast_digit];
+  gp.fast_nc = g.nc[fast_digit];
   gp.t = ctx->t;
   gp.milne = ctx->milne ? 1 : 0;
+  gp.nbr_off = nullptr; gp.nbr_idx = nullptr;
   return gp;
 }
 
@@ -427,7 +445,7 @@ int migrate(ccb_ctx* ctx, int64_t* n_sort, int64_t* n_drop) {
   int32_t* info = ctx->d_info;  // [0] out left, [1] out right, [2] in from left, [3] in from right
   uint32_t *list_l = ctx->key_b, *list_r = ctx->idx_b;  // free until the sort
   CUDA_OK(cudaMemsetAsync(info, 0, sizeof(int32_t) * 4, ctx->stream));
-  LAUNCH(find_leavers, cdiv(n, 256), 256, ctx->dv.f[CCB_F_POSITION], g.min[0], g.rdx[0], g.nc[0], ctx->slab_lo, ctx->slab_hi,
+  LAUNCH(find_leavers, cdiv(n, 256), 256, ctx->dv.f[CCB_F_POSITION] + (int64_t)g.axis[0] * ctx->cap, g.min[0], g.rdx[0], g.nc[0], ctx->slab_lo, ctx->slab_hi,
          left >= 0 ? 1 : 0, right >= 0 ? 1 : 0, n, list_l, list_r, info);
   COMM_OK(ctx->comm->group_begin());
   if (left >= 0) COMM_OK(ctx->comm->send(info + 0, sizeof(int32_t), left, ctx->stream));
@@ -497,10 +515,17 @@ int exchange_column_tables(ccb_ctx* ctx) {
   if (left >= 0) COMM_OK(ctx->comm->recv(tab + 2 * T, sizeof(uint32_t) * T, left, ctx->stream));
   if (right >= 0) COMM_OK(ctx->comm->recv(tab + 3 * T, sizeof(uint32_t) * T, right, ctx->stream));
   COMM_OK(ctx->comm->group_end());
-  uint32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // own first column [start, end], own last column, left table ends, right table ends
-  LAUNCH(table_ends, 1, 32, own_first, own_last, tab + 2 * T, tab + 3 * T, P, left >= 0 ? 1 : 0, right >= 0 ? 1 : 0, ctx->d_ends);
+  uint32_t h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // own first column [start, end], own last column, left table ends, right table ends, rows with a real key
+  LAUNCH(table_ends, 1, 32, own_first, own_last, tab + 2 * T, tab + 3 * T, P, left >= 0 ? 1 : 0, right >= 0 ? 1 : 0, dv.cell_start + g.ncells, ctx->d_ends);
   CUDA_OK(cudaMemcpyAsync(h, ctx->d_ends, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  // cell_start[ncells] = rows that carry a key inside this slab. It must equal the count the migration arithmetic arrived at: an
+  // arrival whose column lies outside the receiving slab (a particle that crossed a whole slab in one stage, or a slab changed
+  // after the upload) got the sentinel key too and would otherwise be lost silently.
+  if ((int64_t)h[8] != ctx->n) {
+    ctx->err = "slab migration: " + std::to_string(ctx->n - (int64_t)h[8]) + " particle(s) arrived outside the receiving slab (moved more than one slab per stage?)";
+    return CCB_ERR_STATE;
+  }
   ctx->send_start[0] = h[0]; ctx->send_n[0] = left >= 0 ? (int64_t)h[1] - h[0] : 0;
   ctx->send_start[1] = h[2]; ctx->send_n[1] = right >= 0 ? (int64_t)h[3] - h[2] : 0;
   ctx->ghost_n[0] = left >= 0 ? (int64_t)h[5] - h[4] : 0;
@@ -589,6 +614,7 @@ int do_build_cells(ccb_ctx* ctx) {
     if ((rc = sort_and_permute(ctx, ctx->n, 0))) return rc;
   }
   ctx->cells_valid = true;
+  ctx->cells_built = true;
   return CCB_OK;
 }
 
@@ -716,9 +742,9 @@ int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& laun
 int do_gather_fields(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
-  return slab_gather(ctx, REC_F, ctx->chunk_fields % 1000, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
-    if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->chunk_fields, st, ctx->dv, ctx->grid, gp));
-    else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->chunk_fields, st, ctx->dv, ctx->grid, gp));
+  return slab_gather(ctx, REC_F, ctx->shape_fields.nt, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
+    if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->shape_fields, st, ctx->dv, ctx->grid, gp));
+    else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->shape_fields, st, ctx->dv, ctx->grid, gp));
     return CCB_OK;
   });
 }
@@ -754,9 +780,10 @@ int do_gather_gradients(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_GRAD);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
-  return slab_gather(ctx, grad_record_doubles(ctx), ctx->chunk % 1000, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
-    if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->chunk, st, ctx->dv, ctx->grid, gp));
-    else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->chunk, st, ctx->dv, ctx->grid, gp));
+  return slab_gather(ctx, grad_record_doubles(ctx), ctx->shape_grad.nt, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
+    if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->shape_grad, st, ctx->dv, ctx->grid, gp));
+    else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->shape_grad, st, ctx->dv, ctx->grid, gp));
+    if (df) ctx->launches++;  // the two sparsity twins of a diffusion run
     return CCB_OK;
   });
 }
@@ -765,6 +792,7 @@ int do_eom(ccb_ctx* ctx, double h_stage, int do_update) {
   PhaseTimer pt(ctx, PH_TIME_DERIV);
   const StageParams sp = make_stage(ctx, h_stage, do_update);
   DISPATCH_DM("eom_rk_kernel", launch_eom_rk, ctx->stream, ctx->dv, sp);
+  if (do_update) ctx->cells_valid = false;   // positions moved: the sort order and cell table are stale
   return CCB_OK;
 }
 
@@ -956,6 +984,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
     ctx->have_table = true;
   }
   if (!(cfg->hT > 0.0)) { ctx->err = "hT must be positive"; return CCB_ERR_INVALID; }
+  if (cfg->slab_axis < 0 || cfg->slab_axis >= cfg->dim) { ctx->err = "slab_axis must be a spatial axis of the run (0 .. dim - 1)"; return CCB_ERR_INVALID; }
   ctx->D = cfg->dim;
   ctx->milne = cfg->coordinate_system == CCB_COORD_HYPERBOLIC;
   ctx->t = cfg->t0;
@@ -980,10 +1009,10 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   ctx->dv.ghost_start[0] = ctx->dv.ghost_start[1] = nullptr;
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, cfg->device);
   {  // gather launch shape: 128 (gradients) / 64 (fields) targets per task, 64 source records per shared-memory tile
-     // (measured best over the BASELINE configs, profiles/README.md r01c); environment overrides are for tuning runs only
-    ctx->chunk = 128; ctx->chunk_fields = 64;
-    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->chunk = ctx->chunk_fields = v; }
-    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) { ctx->chunk += 1000 * v; ctx->chunk_fields += 1000 * v; } }
+     // (measured best over the BASELINE configs, profiles/README.md); environment overrides are for tuning runs only
+    if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->shape_grad.nt = ctx->shape_fields.nt = v; }
+    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_grad.tile = ctx->shape_fields.tile = v; }
+    if (const char* e = std::getenv("CCB_GATHER_REGS")) ctx->shape_grad.regs = std::atoi(e) != 0;
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);
@@ -1091,7 +1120,7 @@ double ccb_time(ccb_ctx* ctx) { return ctx ? ctx->t : 0.0; }
 int ccb_set_time(ccb_ctx* ctx, double t) { if (!ctx) return CCB_ERR_INVALID; ctx->t = t; return CCB_OK; }
 int64_t ccb_kernel_launches(ccb_ctx* ctx) { return ctx ? ctx->launches : -1; }
 void* ccb_stream(ccb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-int ccb_grid_shape(ccb_ctx* ctx, int32_t nc[3]) { if (!ctx) return CCB_ERR_INVALID; for (int d = 0; d < 3; ++d) nc[d] = ctx->grid.nc[d]; return CCB_OK; }
+int ccb_grid_shape(ccb_ctx* ctx, int32_t nc[3]) { if (!ctx) return CCB_ERR_INVALID; for (int k = 0; k < 3; ++k) nc[ctx->grid.axis[k]] = ctx->grid.nc[k]; return CCB_OK; }
 
 int ccb_profile_enable(ccb_ctx* ctx, int on) {
   if (!ctx) return CCB_ERR_INVALID;
@@ -1168,11 +1197,13 @@ int ccb_get_int_field(ccb_ctx* ctx, int field, int32_t* host) {
   if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
   const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
                        : field == CCB_I_EOS ? ctx->dv.eos_id : reinterpret_cast<const int32_t*>(ctx->dv.key);
-  if (field == CCB_I_CELL && !ctx->cells_valid) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
+  if (field == CCB_I_CELL && !ctx->cells_built) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
   int32_t* stage = reinterpret_cast<int32_t*>(ctx->d_stage);
   LAUNCH(scatter_int_by_id, cdiv(ctx->n, 256), 256, src, stage, ctx->dv.id, ctx->n);
   CUDA_OK(cudaMemcpyAsync(host, stage, sizeof(int32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (field == CCB_I_CELL && ctx->grid.axis[0] != 0)   // the key's digits follow the slab axis: report the reference's numbering
+    for (int64_t i = 0; i < ctx->n; ++i) host[i] = reference_cell_id(ctx->grid, (uint32_t)host[i]);
   return CCB_OK;
 }
 
@@ -1276,7 +1307,7 @@ static int comm_buffers(ccb_ctx* ctx) {
   CUDA_OK(cudaMalloc(&ctx->ghost_tab, sizeof(uint32_t) * 4 * T));
   CUDA_OK(cudaMemset(ctx->ghost_tab, 0, sizeof(uint32_t) * 4 * T));
   CUDA_OK(cudaMalloc(&ctx->d_info, sizeof(int32_t) * 8 + sizeof(double) * 8));
-  CUDA_OK(cudaMalloc(&ctx->d_ends, sizeof(uint32_t) * 8));
+  CUDA_OK(cudaMalloc(&ctx->d_ends, sizeof(uint32_t) * 12));
   CUDA_OK(cudaMalloc(&ctx->d_flags, sizeof(int) * 8));
   CUDA_OK(cudaMemset(ctx->d_flags, 0, sizeof(int) * 8));
   return CCB_OK;
@@ -1327,7 +1358,7 @@ int ccb_set_slab(ccb_ctx* ctx, int32_t col_lo, int32_t col_hi) {
 }
 int ccb_grid_geometry(ccb_ctx* ctx, double min[3], double edge[3], int32_t nc[3]) {
   if (!ctx || !min || !edge || !nc) return CCB_ERR_INVALID;
-  for (int d = 0; d < 3; ++d) { min[d] = ctx->grid.min[d]; edge[d] = 1.0 / ctx->grid.rdx[d]; nc[d] = ctx->grid.nc[d]; }
+  for (int k = 0; k < 3; ++k) { const int d = ctx->grid.axis[k]; min[d] = ctx->grid.min[k]; edge[d] = 1.0 / ctx->grid.rdx[k]; nc[d] = ctx->grid.nc[k]; }
   return CCB_OK;
 }
 int ccb_migration_counts(ccb_ctx* ctx, int64_t* out, int64_t* in) {
@@ -1353,11 +1384,60 @@ int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
   if (field < 0 || field >= CCB_I_COUNT || !host) return CCB_ERR_INVALID;
-  if (field == CCB_I_CELL && !ctx->cells_valid) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
+  if (field == CCB_I_CELL && !ctx->cells_built) { ctx->err = "cell list not built"; return CCB_ERR_STATE; }
   const int32_t* src = field == CCB_I_ID ? ctx->dv.id : field == CCB_I_BTRACK ? ctx->dv.btrack : field == CCB_I_FREEZE ? ctx->dv.freeze
                        : field == CCB_I_EOS ? ctx->dv.eos_id : reinterpret_cast<const int32_t*>(ctx->dv.key);
   CUDA_OK(cudaMemcpyAsync(host, src, sizeof(int32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (field == CCB_I_CELL && ctx->grid.axis[0] != 0)
+    for (int64_t i = 0; i < ctx->n; ++i) host[i] = reference_cell_id(ctx->grid, (uint32_t)host[i]);
+  return CCB_OK;
+}
+
+// Debug / test entry point: the neighbour SETS the field gather visits, as a CSR list in particle-id order with ascending
+// neighbour ids -- what SystemState::reset_neighbour_list stores as its Verlet list (src/system_state.cpp:651-719). The product
+// path never materialises this list (2 GB for config 1); a twin of the field gather (FieldsPolicy EMIT) writes the id of every
+// neighbour it visits. Call after ccb_smooth_fields; offsets has ccb_n() + 1 entries, idx room for `cap` entries.
+int ccb_debug_neighbour_list(ccb_ctx* ctx, int64_t* offsets, int32_t* idx, int64_t cap) {
+  int rc = check_ready(ctx, true);
+  if (rc) return rc;
+  if (!offsets || !idx) return CCB_ERR_INVALID;
+  if (ctx->comm) { ctx->err = "ccb_debug_neighbour_list: single-context runs only"; return CCB_ERR_STATE; }
+  const int64_t n = ctx->n;
+  std::vector<int32_t> bt(n), ids(n);
+  CUDA_OK(cudaMemcpyAsync(bt.data(), ctx->dv.btrack, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(ids.data(), ctx->dv.id, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int64_t> off(n + 1, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    if (bt[i] < 0) { ctx->err = "ccb_debug_neighbour_list: btrack = -1 (sticky) hides a neighbour count"; return CCB_ERR_STATE; }
+    off[i + 1] = off[i] + bt[i];
+  }
+  const int64_t total = off[n];
+  if (total > cap) { ctx->err = "ccb_debug_neighbour_list: idx buffer too small"; return CCB_ERR_INVALID; }
+  DevBuf<int64_t> d_off;
+  DevBuf<int32_t> d_idx;
+  CUDA_OK(d_off.alloc(n + 1));
+  CUDA_OK(d_idx.alloc(std::max<int64_t>(total, 1)));
+  CUDA_OK(cudaMemcpyAsync(d_off.p, off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemsetAsync(d_idx.p, 0xff, sizeof(int32_t) * std::max<int64_t>(total, 1), ctx->stream));
+  GatherParams gp = make_gather(ctx);
+  gp.nbr_off = d_off.p; gp.nbr_idx = d_idx.p;
+  if (ctx->D == 2) LAUNCHER("gather_kernel<fields, emit>", launch_gather_fields<2>(false, ctx->shape_fields, ctx->stream, ctx->dv, ctx->grid, gp));
+  else LAUNCHER("gather_kernel<fields, emit>", launch_gather_fields<3>(false, ctx->shape_fields, ctx->stream, ctx->dv, ctx->grid, gp));
+  std::vector<int32_t> raw(std::max<int64_t>(total, 1));
+  CUDA_OK(cudaMemcpyAsync(raw.data(), d_idx.p, sizeof(int32_t) * std::max<int64_t>(total, 1), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  std::vector<int64_t> where(n);  // particle id -> sorted index
+  for (int64_t i = 0; i < n; ++i) where[ids[i]] = i;
+  offsets[0] = 0;
+  for (int64_t p = 0; p < n; ++p) offsets[p + 1] = offsets[p] + bt[where[p]];
+  for (int64_t p = 0; p < n; ++p) {
+    const int64_t i = where[p];
+    int32_t* dst = idx + offsets[p];
+    std::copy(raw.begin() + off[i], raw.begin() + off[i + 1], dst);
+    std::sort(dst, dst + bt[i]);
+  }
   return CCB_OK;
 }
 
@@ -1399,6 +1479,7 @@ int ccb_step(ccb_ctx* ctx, double dt) {
     }
     const RkCols c = rk_columns(ctx);
     LAUNCH(rk4_final_kernel, cdiv(ctx->n, 256), 256, c, dt, ctx->n, ctx->dv.freeze, ctx->dv.id, ctx->dv.err);
+    ctx->cells_valid = false;
     return CCB_OK;
   }
   // Evolver::advance_timestep_rk2 (src/evolver.cpp:494-507): midpoint rule

@@ -35,7 +35,7 @@ __global__ void cell_key_kernel(DeviceView dv, CellGrid g, uint32_t* __restrict_
   int c[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    const double x = dv.f[CCB_F_POSITION][(int64_t)d * dv.cap + i];
+    const double x = dv.f[CCB_F_POSITION][(int64_t)g.axis[d] * dv.cap + i];
     int ci = (int)floor((x - g.min[d]) * g.rdx[d]);
     // More than one cell outside the neighbour grid (NaN included): the clamped cell no longer bounds the particle's
     // neighbours. The reference indexes out of bounds there (src/system_state.cpp:636-638); here it is an error.
@@ -146,8 +146,10 @@ __global__ void p2p_wait(const int* flag_a, const int* flag_b, int epoch, int* g
 }
 // the eight record offsets exchange_column_tables needs on the host, gathered for ONE device-to-host copy
 __global__ void table_ends(const uint32_t* __restrict__ own_first, const uint32_t* __restrict__ own_last, const uint32_t* __restrict__ tab_left,
-                           const uint32_t* __restrict__ tab_right, int64_t P, int has_left, int has_right, uint32_t* __restrict__ out) {
+                           const uint32_t* __restrict__ tab_right, int64_t P, int has_left, int has_right, const uint32_t* __restrict__ n_keyed,
+                           uint32_t* __restrict__ out) {
   if (threadIdx.x != 0) return;
+  out[8] = n_keyed[0];
   out[0] = own_first[0]; out[1] = own_first[P]; out[2] = own_last[0]; out[3] = own_last[P];
   out[4] = has_left ? tab_left[0] : 0u; out[5] = has_left ? tab_left[P] : 0u;
   out[6] = has_right ? tab_right[0] : 0u; out[7] = has_right ? tab_right[P] : 0u;

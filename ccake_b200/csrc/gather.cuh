@@ -84,9 +84,11 @@ __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double
 
 // ------------------------------------------------------------------------------------------
 // smooth_fields: sigma_lab, smoothed s, rho_B, rho_S, rho_Q, neighbour count
-template <int D_, bool FACT>
+template <int D_, bool FACT, bool EMIT_ = false>
 struct FieldsPolicy {
-  static constexpr int D = D_, REC = REC_F, STRIDE = REC_F_STRIDE;
+  static constexpr int D = D_, REC = REC_F, STRIDE = REC_F_STRIDE, CH_STAGE = REC_F / 2, VARIANT = -1;
+  // EMIT: debug twin that also writes the ids of the neighbours it visits (ccb_debug_neighbour_list): GatherParams::nbr_off / nbr_idx
+  static constexpr bool EMIT = EMIT_;
   struct Target { double x[3]; int cf; };
   struct Acc { double sig, s, B, S, Q; int cnt; };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_fields; }
@@ -110,7 +112,7 @@ struct FieldsPolicy {
     // spacing commensurate with h): the reference's list searches +-1 cell and does not hold it. W = 0 there, so only
     // the neighbour count is at stake; the rare knife-edge pair re-derives the source's cell to decide.
     if (in && r2 >= gp.rsqr_edge) {
-      const double xf = (gp.fast_axis == 2) ? b1.x : b0.y;
+      const double xf = (gp.fast_coord == 2) ? b1.x : (gp.fast_coord == 1 ? b0.y : b0.x);
       int cj = (int)floor((xf - gp.fast_min) * gp.fast_rdx);
       cj = cj < 0 ? 0 : (cj > gp.fast_nc - 1 ? gp.fast_nc - 1 : cj);
       if (abs(cj - t.cf) > 1) in = false;
@@ -178,17 +180,27 @@ struct FieldsPolicy {
 // target's own record is not needed until the epilogue. Against the reference's per-pair expression this halves the
 // fp64 instructions per pair and frees the 20..36 registers that held the target record. The results differ from the
 // per-pair form by rounding only (the sums are re-associated), far inside the 1e-10 parity bar.
-template <int D_, bool SHEAR, bool DIFF, bool FACT>
+//
+// QNZ (diffusion runs only): compile-time twin of the run-time sparsity flag DeviceView::qflag[0..1]. QNZ = false is the
+// variant for "every record of this launch carries q^mu_a = 0" (kappa = 0 and no initial diffusion: the reference's own
+// config_visc_gubser.yaml / input_ampt.yaml): the six q-moment accumulators do not exist, and only the chunks below KQ of a
+// record are staged into shared memory. Both variants are launched; the one that does not match the flag exits at once.
+template <int D_, bool SHEAR, bool DIFF, bool FACT, bool QNZ = DIFF>
 struct GradPolicy {
   using R = GradRec<D_, DIFF>;
-  static constexpr int D = D_, REC = R::REC, STRIDE = R::STRIDE;
+  static constexpr int D = D_, REC = R::REC;
+  static constexpr int KQ = DIFF ? (R::Q0 + 1) / 2 : REC / 2;  // first chunk that holds nothing but q^mu_a entries
+  static constexpr int CH_STAGE = (DIFF && !QNZ) ? KQ : REC / 2;            // 16-byte chunks of a record staged per source
+  static constexpr int STRIDE = (CH_STAGE % 2 == 1) ? 2 * CH_STAGE : 2 * CH_STAGE + 2;  // shared-memory stride: odd number of chunks
+  static constexpr int VARIANT = DIFF ? (QNZ ? 1 : 0) : -1;  // -1: runs whatever the flag says
+  static constexpr bool EMIT = false;
   struct Target { double x[3]; double v[D]; int cf; };
   // fp64 accumulators live across the neighbour loop: decides the register budget of the launch (inst_gather.cu)
-  static constexpr int NACC = 4 * D + D * D + ((SHEAR || DIFF) ? 1 : 0) + (SHEAR ? 2 * D : 0) + (DIFF ? 6 + 3 * D : 0);
+  static constexpr int NACC = 4 * D + D * D + ((SHEAR || DIFF) ? 1 : 0) + (SHEAR ? 2 * D : 0) + (DIFF ? 3 * D : 0) + ((DIFF && QNZ) ? 6 : 0);
   struct Acc {
     double sA[D], mP[D], mB[D], mE[D], mV[D][D];
     double sKv, kS0[D], cSh[D];        // shear (sKv also feeds grad_qa)
-    double kQ0[3], cq[3], mAL[D][3];   // diffusion
+    double kQ0[3], cq[3], mAL[D][3];   // diffusion (kQ0, cq: QNZ only; otherwise never touched and optimised away)
   };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_grad; }
   __device__ static void init(Acc& a) {
@@ -249,11 +261,11 @@ struct GradPolicy {
 #pragma unroll
           for (int d = 0; d < D; ++d) a.mAL[d][c] = fma(A[d], val, a.mAL[d][c]);
         }
-    } else if (DIFF && idx >= R::Q0 && idx < R::Q0 + 3) {
+    } else if (DIFF && QNZ && idx >= R::Q0 && idx < R::Q0 + 3) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
         if (c == idx - R::Q0) a.kQ0[c] = fma(Kv, val, a.kQ0[c]);
-    } else if (DIFF && idx >= R::QI && idx < R::QI + 3 * D) {
+    } else if (DIFF && QNZ && idx >= R::QI && idx < R::QI + 3 * D) {
 #pragma unroll
       for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -283,11 +295,10 @@ struct GradPolicy {
     return in;
   }
   // the record is consumed 16 bytes at a time, in layout order: no more than one chunk is live at any point
-  // qnz = false: every record of this launch carries q^mu_a = 0 (DeviceView::qflag), so the chunks from Q0 on (Q0, QI,
-  // padding) contribute exact zeros and are neither loaded nor accumulated.
+  // QNZ = false: every record of this launch carries q^mu_a = 0 (DeviceView::qflag), so the chunks from Q0 on (Q0, QI,
+  // padding) contribute exact zeros and are neither staged, loaded nor accumulated.
   static constexpr int FLAG = 0;  // DeviceView::qflag[0..1]
-  static constexpr int KQ = DIFF ? (R::Q0 + 1) / 2 : REC / 2;  // first chunk that holds nothing but q^mu_a entries
-  __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool qnz) {
+  __device__ static void accum(const double2* sb, const Prep& p, Acc& a, bool) {
 #pragma unroll
     for (int d = 0; d < D; ++d) a.sA[d] += p.A[d];
     if (SHEAR || DIFF) a.sKv += p.Kv;
@@ -298,7 +309,7 @@ struct GradPolicy {
       consume(2 * k, v.x, p.A, p.Kv, a);
       consume(2 * k + 1, v.y, p.A, p.Kv, a);
     }
-    if (DIFF && qnz) {
+    if (DIFF && QNZ) {
 #pragma unroll
       for (int k = KQ; k < REC / 2; ++k) {
         const double2 v = sb[k];
@@ -337,7 +348,7 @@ struct GradPolicy {
         for (int c = 0; c < 3; ++c) gal[d][c] = inv_sig * (a.mAL[d][c] - ra[R::ALPHA + (DIFF ? c : 0)] * a.sA[d]);
       }
     }
-    if (DIFF) {
+    if (DIFF && QNZ) {  // !QNZ: every q^mu_a of the launch is zero, and so are these two sums
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         gq[c] = sig * (a.kQ0[c] + ra[R::Q0 + (DIFF ? c : 0)] * a.sKv);
@@ -381,7 +392,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 template <class P, int NT, int MINB, int TILE = kGatherTile>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
-  constexpr int D = P::D, NW = TILE / 32, CH = P::REC / 2, RS2 = P::STRIDE / 2;
+  constexpr int D = P::D, NW = TILE / 32, CH = P::CH_STAGE, RCH = P::REC / 2, RS2 = P::STRIDE / 2;
+  // compile-time sparsity variants (GradPolicy QNZ): only the launch that matches the run-time flag does the work
+  if (P::VARIANT >= 0) {
+    const bool nz = (dv.qflag[P::FLAG] | dv.qflag[P::FLAG + 1]) != 0;
+    if (nz != (P::VARIANT == 1)) return;
+  }
   __shared__ __align__(16) double2 srec2[2][TILE * RS2];  // double-buffered tiles of source records
   __shared__ __align__(16) float spos[4][TILE];  // fp32 x, y, z relative to the pass origin, and x^2 + y^2 + z^2
   __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
@@ -402,6 +418,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   tg.cf = (int)(dv.key[active ? i : first] % (uint32_t)((g.nc[2] > 1) ? g.nc[2] : g.nc[1]));
   typename P::Acc acc;
   P::init(acc);
+  int emitted = 0;  // EMIT only
   const bool qnz = (dv.qflag[P::FLAG] | dv.qflag[P::FLAG + 1]) != 0;  // sparsity flag of this gather's records: see P::accum
 
   // The cells of a grid row along the fastest axis are contiguous in the sorted order: F cells per row,
@@ -427,10 +444,14 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     double org[3];
     float tx[3];
     {
+      // grid arrays are in KEY order (slowest digit first); CellGrid::axis maps a digit to its spatial coordinate
       const int c3[3] = {rx, (nz > 1) ? ry : fa, (nz > 1) ? fa : 0};
+      double ok[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ok[k] = g.min[k] + c3[k] / g.rdx[k];
 #pragma unroll
       for (int d = 0; d < 3; ++d) {
-        org[d] = (d < D) ? g.min[d] + c3[d] / g.rdx[d] : 0.0;
+        org[d] = (d < D) ? (g.axis[0] == d ? ok[0] : (g.axis[1] == d ? ok[1] : ok[2])) : 0.0;
         tx[d] = (float)(tg.x[d] - org[d]);
       }
     }
@@ -477,7 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
         int s = 0;
         while (cand >= seg_pref[s + 1]) ++s;
         const int64_t gidx = (int64_t)seg_start[s] + (cand - seg_pref[s]);
-        cp_async16(buf + r * RS2 + c, seg_base[s] + gidx * CH + c);
+        cp_async16(buf + r * RS2 + c, seg_base[s] + gidx * RCH + c);
       }
       cp_async_commit();
     };
@@ -553,7 +574,16 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
           for (int w = 0; w < NW; ++w)
             if (base == w * 32) m[w] ^= low;
           typename P::Prep pp;
-          if (P::prep(gp, tg, srec + j * RS2, true, pp)) P::accum(srec + j * RS2, pp, acc, qnz);
+          if (P::prep(gp, tg, srec + j * RS2, true, pp)) {
+            P::accum(srec + j * RS2, pp, acc, qnz);
+            if (P::EMIT) {  // debug twin: the id of every neighbour visited (self excluded), in visiting order
+              const uint32_t cand = (uint32_t)j * ntiles + k;
+              int sg = 0;
+              while (cand >= seg_pref[sg + 1]) ++sg;
+              const int64_t gidx = (int64_t)seg_start[sg] + (cand - seg_pref[sg]);
+              if (gidx != i) gp.nbr_idx[gp.nbr_off[i] + emitted++] = dv.id[gidx];
+            }
+          }
         }
       }
     }

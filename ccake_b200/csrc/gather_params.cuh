@@ -43,14 +43,17 @@ struct GatherParams {
   double rsqr;       // (2 hT)^2: the neighbour cut-off of the reference (src/system_state.cpp:689)
   float rsqr_f;      // the same with a safety margin, for the fp32 pre-filter
   double rsqr_edge;  // rsqr (1 - 1e-12): pairs at or above it sit on the cut-off (knife edge, see FieldsPolicy::pair)
-  double fast_min, fast_rdx;  // the grid's fastest axis (z for a 3-D grid, y for a 2-D one): cell = floor((x - min) rdx)
-  int fast_axis, fast_nc;
+  double fast_min, fast_rdx;  // the fastest digit of the cell key that has more than one cell: cell = floor((x - min) rdx)
+  int fast_coord, fast_nc;    // fast_coord = the spatial coordinate (0 x, 1 y, 2 z / eta) that digit indexes
   // which tasks a launch covers: block b -> task (b < task_n0 ? task_off0 + b : task_off1 + b - task_n0); task_count = 0
   // means all of them. A slab run launches the interior tasks first and the two boundary ranges (the first and last cell
   // column, which need the ghost records) once the halo exchange has completed on the communication stream.
   int task_count, task_n0, task_off0, task_off1;
   double t;
   int milne;
+  // debug twin of the field gather (FieldsPolicy EMIT): CSR offsets per target (sorted order) and the id buffer it fills
+  const int64_t* nbr_off;
+  int32_t* nbr_idx;
 };
 
 }  // namespace ccb

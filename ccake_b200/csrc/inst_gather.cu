@@ -23,41 +23,43 @@ cudaError_t launch(cudaStream_t s, const DeviceView& dv, const CellGrid& g, cons
   gather_kernel<P, NT, MINB, TILE><<<ntasks, NT, 0, s>>>(dv, g, q);
   return cudaGetLastError();
 }
-// nt = targets per task (64 | 128) + 1000 x (source records per shared-memory tile: 32 | 64; default 64). Tiles are
-// double-buffered, so 128-record tiles of the largest record would not fit the 48 KB of static shared memory.
+// GatherShape: targets per task (64 | 128), source records per shared-memory tile (32 | 64; tiles are double-buffered), and the
+// register budget of the gradient variants (regs = 0: 128 registers per thread, MINB CTAs per SM as given; regs = 1: one CTA per
+// SM fewer, i.e. 168 registers at 128 threads).
 template <class P, int MINB64, int MINB128>
-cudaError_t launch_nt(int nt, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
-  const int tile = nt / 1000;
-  nt %= 1000;
-  if (tile == 32) return nt == 128 ? launch<P, 128, MINB128, 32>(s, dv, g, gp) : launch<P, 64, MINB64, 32>(s, dv, g, gp);
-  return nt == 128 ? launch<P, 128, MINB128, 64>(s, dv, g, gp) : launch<P, 64, MINB64, 64>(s, dv, g, gp);
+cudaError_t launch_shape(const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
+  if (sh.tile == 32) return sh.nt == 128 ? launch<P, 128, MINB128, 32>(s, dv, g, gp) : launch<P, 64, MINB64, 32>(s, dv, g, gp);
+  return sh.nt == 128 ? launch<P, 128, MINB128, 64>(s, dv, g, gp) : launch<P, 64, MINB64, 64>(s, dv, g, gp);
+}
+// a diffusion run launches both compile-time sparsity twins; the one that does not match DeviceView::qflag exits at once
+template <int D, bool S, bool F, bool X>
+cudaError_t launch_grad(const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
+  if (!F) return sh.regs ? launch_shape<GradPolicy<D, S, false, X, false>, 6, 3>(sh, s, dv, g, gp) : launch_shape<GradPolicy<D, S, false, X, false>, 8, 4>(sh, s, dv, g, gp);
+  cudaError_t e = sh.regs ? launch_shape<GradPolicy<D, S, F, X, false>, 6, 3>(sh, s, dv, g, gp) : launch_shape<GradPolicy<D, S, F, X, false>, 8, 4>(sh, s, dv, g, gp);
+  if (e != cudaSuccess) return e;
+  return sh.regs ? launch_shape<GradPolicy<D, S, F, X, true>, 6, 3>(sh, s, dv, g, gp) : launch_shape<GradPolicy<D, S, F, X, true>, 8, 4>(sh, s, dv, g, gp);
 }
 }  // namespace
 
 template <>
-cudaError_t launch_gather_fields<CCB_INST_D>(bool fact, int nt, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
+cudaError_t launch_gather_fields<CCB_INST_D>(bool fact, const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
                                              const GatherParams& gp) {
   constexpr int D = CCB_INST_D;
-  if (D == 3 && fact) return launch_nt<FieldsPolicy<D, (D == 3)>, 12, 6>(nt, s, dv, g, gp);
-  return launch_nt<FieldsPolicy<D, false>, 12, 6>(nt, s, dv, g, gp);
+  if (gp.nbr_idx) return launch<FieldsPolicy<D, false, true>, 64, 8, 64>(s, dv, g, gp);  // debug twin: neighbour ids (plain kernel)
+  if (D == 3 && fact) return launch_shape<FieldsPolicy<D, (D == 3)>, 12, 6>(sh, s, dv, g, gp);
+  return launch_shape<FieldsPolicy<D, false>, 12, 6>(sh, s, dv, g, gp);
 }
 
 template <>
-cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact, int nt, cudaStream_t s,
+cudaError_t launch_gather_gradients<CCB_INST_D>(bool shear, bool diff, bool fact, const GatherShape& sh, cudaStream_t s,
                                                 const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
   constexpr int D = CCB_INST_D;
-  // register budget: 128 per thread (16 warps per SM) for every variant. The largest one (D = 3, shear + diffusion: 43
-  // accumulators) then spills ~200 bytes inside the neighbour loop, which still measured 6 % faster than 168 registers
-  // without spills at 12 warps per SM (profiles/README.md, r01c).
-#define CCB_GG(S, F, X) return launch_nt<GradPolicy<D, S, F, X>, 8, 4>(nt, s, dv, g, gp)
   if (D == 3 && fact) {
-    if (shear) { if (diff) CCB_GG(true, true, (D == 3)); else CCB_GG(true, false, (D == 3)); }
-    else { if (diff) CCB_GG(false, true, (D == 3)); else CCB_GG(false, false, (D == 3)); }
-  } else {
-    if (shear) { if (diff) CCB_GG(true, true, false); else CCB_GG(true, false, false); }
-    else { if (diff) CCB_GG(false, true, false); else CCB_GG(false, false, false); }
+    if (shear) return diff ? launch_grad<D, true, true, (D == 3)>(sh, s, dv, g, gp) : launch_grad<D, true, false, (D == 3)>(sh, s, dv, g, gp);
+    return diff ? launch_grad<D, false, true, (D == 3)>(sh, s, dv, g, gp) : launch_grad<D, false, false, (D == 3)>(sh, s, dv, g, gp);
   }
-#undef CCB_GG
+  if (shear) return diff ? launch_grad<D, true, true, false>(sh, s, dv, g, gp) : launch_grad<D, true, false, false>(sh, s, dv, g, gp);
+  return diff ? launch_grad<D, false, true, false>(sh, s, dv, g, gp) : launch_grad<D, false, false, false>(sh, s, dv, g, gp);
 }
 
 }  // namespace ccb

@@ -8,10 +8,12 @@
 
 namespace ccb {
 
-// nt = targets (= threads) per task: 64 or 128.
-template <int D> cudaError_t launch_gather_fields(bool fact, int nt, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
+// launch shape of a gather: nt = targets (= threads) per task (64 | 128), tile = source records per shared-memory tile (32 | 64),
+// regs = register budget of the gradient variants (0: 128 per thread; 1: 168 per thread, one CTA per SM fewer)
+struct GatherShape { int nt, tile, regs; };
+template <int D> cudaError_t launch_gather_fields(bool fact, const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
                                                   const GatherParams& gp);
-template <int D> cudaError_t launch_gather_gradients(bool shear, bool diff, bool fact, int nt, cudaStream_t s, const DeviceView& dv,
+template <int D> cudaError_t launch_gather_gradients(bool shear, bool diff, bool fact, const GatherShape& sh, cudaStream_t s, const DeviceView& dv,
                                                      const CellGrid& g, const GatherParams& gp);
 template <int D, bool MILNE> cudaError_t launch_prologue(cudaStream_t s, const DeviceView& dv, double t);
 template <int D, bool MILNE> cudaError_t launch_eos_local(cudaStream_t s, const DeviceView& dv, const StageParams& sp);

@@ -28,9 +28,14 @@ static const int kEvolvedFields[] = {CCB_F_POSITION, CCB_F_U, CCB_F_EXTENSIVE, C
                                      CCB_F_EXTENSIVE_SHV, CCB_F_EXTENSIVE_DIFFUSION, CCB_F_EZ};
 static const int kNumEvolvedFields = 7;
 
+// Neighbour grid of the reference (src/system_state.cpp:651-700) with its arrays in KEY order: digit 0 is the slowest digit
+// of the cell key, digit 2 the fastest; axis[k] is the spatial coordinate (0 x, 1 y, 2 z / eta) digit k indexes. The slab
+// axis (ccb_config::slab_axis) is digit 0, so that a slab's edge column is one contiguous range of the cell-sorted order;
+// the other coordinates follow in ascending order (a 2-D run's unused third coordinate is always digit 2, one cell).
 struct CellGrid {
   double min[3], rdx[3];
   int nc[3];
+  int axis[3];
   int64_t ncells;
 };
 

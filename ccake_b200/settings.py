@@ -125,6 +125,7 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     c.prohibit_acausal_cs2 = int(bool(s["prohibit_acausal_cs2"]))
     c.restrict_mu_T_ratios = int(bool(s["restrict_mu_T_ratios"]))
     c.device, c.rank, c.nranks = int(device), int(rank), int(nranks)
+    c.slab_axis = int(s.get("slab_axis", 0))
     return c
 
 

@@ -128,6 +128,11 @@ class SPHWorkstation:
         self._check(self._L.ccb_grid_geometry(self._ctx, _dp(mn), _dp(ed), nc))
         return mn, ed, np.array(list(nc), dtype=np.int64)
 
+    @property
+    def slab_axis(self):
+        """Spatial axis the slab decomposition cuts (0 = x, 2 = eta): ccb_config::slab_axis."""
+        return int(self._cfg.slab_axis)
+
     def comm_init_local(self, group=0):
         """In-process transport between the contexts of one process (each driven by its own thread)."""
         self._check(self._L.ccb_comm_init_local(self._ctx, int(group)))
@@ -246,6 +251,18 @@ class SPHWorkstation:
     def set_int(self, field, values):
         a = np.ascontiguousarray(values, dtype=np.int32)
         self._check(self._L.ccb_set_int_field(self._ctx, _capi.INT_FIELDS[field], a.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def neighbours(self):
+        """The neighbour sets the field gather visits as a CSR list (offsets[n + 1], ascending ids), particle-id order: the
+        reference's Verlet list (SystemState::reset_neighbour_list). Debug / test only; call after smooth_all_particle_fields."""
+        n = self.n_particles
+        bt = self.get_int("btrack")
+        total = int(np.sum(bt[bt > 0]))
+        off = np.zeros(n + 1, dtype=np.int64)
+        idx = np.empty(max(total, 1), dtype=np.int32)
+        self._check(self._L.ccb_debug_neighbour_list(self._ctx, off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                     idx.ctypes.data_as(C.POINTER(C.c_int32)), int(idx.size)))
+        return off, idx[:total]
 
     def grid_shape(self):
         nc = (C.c_int32 * 3)()

@@ -80,6 +80,8 @@ typedef struct {
   /* runtime */
   int device;              /* CUDA device ordinal */
   int rank, nranks;        /* slab decomposition (1 process per GPU) */
+  int slab_axis;           /* spatial axis the slabs cut: 0 = x (default), 1 = y, 2 = eta / z (3+1D). The neighbour-grid cell key is
+                              ordered with this axis slowest, so that a slab's edge column is one contiguous range of the sorted order */
 } ccb_config;
 
 /* Initial-condition rows, one entry per particle, units as in the reference's IC
@@ -243,6 +245,12 @@ int ccb_grid_geometry(ccb_ctx* ctx, double min[3], double edge[3], int32_t ncell
 int ccb_migration_counts(ccb_ctx* ctx, int64_t* sent, int64_t* received);              /* running totals */
 int ccb_get_field_device_order(ccb_ctx* ctx, int field, double* host);          /* n x width, current (cell-sorted) order */
 int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host);
+
+/* debug / test: the neighbour sets the field gather visits, as the CSR list SystemState::reset_neighbour_list stores
+ * (src/system_state.cpp:651-719: VerletList, full neighbour tag, self excluded): offsets[ccb_n() + 1] in particle-id order,
+ * idx = neighbour ids, ascending within a particle; cap = entries idx can hold (sum of CCB_I_BTRACK). Call after
+ * ccb_smooth_fields. The product path never materialises this list. */
+int ccb_debug_neighbour_list(ccb_ctx* ctx, int64_t* offsets, int32_t* idx, int64_t cap);
 
 /* --- the ten phases of SPHWorkstation::get_time_derivatives (src/sph_workstation.cpp:1543-1583) --- */
 int ccb_build_cells(ccb_ctx* ctx);        /* 01 SystemState::reset_neighbour_list (src/system_state.cpp:651-719) */

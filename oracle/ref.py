@@ -112,6 +112,11 @@ def lib():
         L.ccake_ref_phase.argtypes = [C.c_void_p, C.c_int]
         L.ccake_ref_allocate_raw.argtypes = [C.c_void_p, C.c_long]
         L.ccake_ref_advance.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ccake_ref_advance_par04.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ccake_ref_set_threads.argtypes = [C.c_int]
+        L.ccake_ref_set_threads.restype = None
+        L.ccake_ref_profile_report.argtypes = [C.c_char_p, C.c_long]
+        L.ccake_ref_profile_report.restype = C.c_long
         L.ccake_ref_n.restype = C.c_long
         L.ccake_ref_n.argtypes = [C.c_void_p]
         L.ccake_ref_time.restype = C.c_double
@@ -136,6 +141,28 @@ def lib():
 def omp_threads() -> int:
     """Threads the reference's parallel loops run on (omp_get_max_threads of the build)."""
     return int(lib().ccake_ref_omp_threads())
+
+
+def set_threads(n: int) -> None:
+    """omp_set_num_threads for the reference's parallel loops (torchrun pins OMP_NUM_THREADS=1 in its workers)."""
+    lib().ccake_ref_set_threads(int(n))
+
+
+def profile_table() -> dict:
+    """The reference's own CCAKE_PROFILE table (include/phase_profiler.h) parsed into {phase: (total_s, calls)}.
+    Empty unless CCAKE_PROFILE was set in the environment before this library was loaded."""
+    need = lib().ccake_ref_profile_report(None, 0)
+    buf = C.create_string_buffer(int(need) + 8)
+    lib().ccake_ref_profile_report(buf, len(buf))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        f = line.split()
+        if len(f) == 5 and f[4].endswith("%"):
+            try:
+                out[f[0]] = (float(f[1]), int(f[2]))
+            except ValueError:
+                pass
+    return out
 
 
 def _dp(a):
@@ -199,6 +226,11 @@ class RefSim:
 
     def advance(self, dt, rk_order=2):
         lib().ccake_ref_advance(self.h, float(dt), int(rk_order))
+
+    def advance_par04(self, dt, rk_order=2):
+        """The same step with phase 04 OpenMP-parallelised (ref_driver.cpp: thermodynamics_openmp); everything else is the
+        unmodified reference."""
+        lib().ccake_ref_advance_par04(self.h, float(dt), int(rk_order))
 
     @property
     def n(self):

@@ -23,6 +23,7 @@
 #include "sph_workstation.h"
 #include "system_state.h"
 #include "settings.h"
+#include "phase_profiler.h"
 
 using namespace ccake;
 
@@ -37,6 +38,7 @@ struct RefBase {
   virtual int phase(int which) = 0;
   virtual int get_time_derivatives() = 0;
   virtual int advance(double dt, int rk) = 0;
+  virtual int advance_par04(double dt, int rk) = 0;
   virtual long n() = 0;
   virtual double time() = 0;
   virtual void set_time(double t) = 0;
@@ -135,6 +137,54 @@ struct Ref : RefBase {
   }
   int get_time_derivatives() override { ws->get_time_derivatives(st->dt); return 0; }
   int advance(double dt, int rk) override { ws->advance_timestep(dt, rk); return 0; }
+  // ---- the reference's step with phase 04 OpenMP-parallelised -------------------------------------
+  // As shipped, update_all_particle_thermodynamics (src/sph_workstation.cpp:1737-1762) is a SERIAL host loop over
+  // systemPtr->particles between copy_thermo_device_to_host / copy_thermo_host_to_device. This variant runs the same loop
+  // body (locate_phase_diagram_point_sBSQ, :659-741: tbqs + update_s + set_thermo) under `omp parallel for`, every thread
+  // on its OWN EquationOfState (the class carries the current phase-diagram point and the root-finder state), so that the
+  // CPU baseline can be quoted both ways. Everything else is the unmodified reference: the same Evolver class drives the
+  // same public phase methods in the order of get_time_derivatives (:1543-1583), timed under the same CCAKE_PROFILE names.
+  std::vector<std::unique_ptr<EquationOfState>> eos_pool;
+  std::unique_ptr<Evolver<D>> evolver2;
+  void thermodynamics_openmp() {
+    const int nt = omp_get_max_threads();
+    if ((int)eos_pool.size() != nt) {
+      eos_pool.resize(nt);
+#pragma omp parallel for schedule(static, 1)
+      for (int k = 0; k < nt; ++k) { eos_pool[k].reset(new EquationOfState()); eos_pool[k]->set_SettingsPtr(st); eos_pool[k]->init(); }
+    }
+    sys->copy_thermo_device_to_host();
+    const long np = (long)sys->particles.size();
+    int failed = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : failed)
+    for (long i = 0; i < np; ++i) {
+      EquationOfState& eos = *eos_pool[omp_get_thread_num()];
+      auto& p = sys->particles[i];
+      eos.tbqs(p.T(), p.muB(), p.muQ(), p.muS(), p.get_current_eos_name());
+      if (eos.update_s(p.thermo.s, p.thermo.rhoB, p.thermo.rhoS, p.thermo.rhoQ, false)) eos.set_thermo(p.thermo);
+      else failed++;
+    }
+    if (failed) std::fprintf(stderr, "ccake_ref: phase 04 (OpenMP variant): %d particles without a solution\n", failed);
+    sys->copy_thermo_host_to_device();
+  }
+  void get_time_derivatives_par04() {
+    const double t = sys->t, t2 = t * t;
+    { CCAKE_PHASE("01_neighbour_list"); sys->reset_neighbour_list(); }
+    { CCAKE_PHASE("02_gamma_velocity"); ws->calculate_gamma_and_velocities(); }
+    { CCAKE_PHASE("03_smooth_fields"); ws->smooth_all_particle_fields(t2); }
+    { CCAKE_PHASE("04_thermodynamics_openmp"); thermodynamics_openmp(); }
+    { CCAKE_PHASE("05_reset_pi_tensor"); ws->reset_pi_tensor(t2); }
+    { CCAKE_PHASE("06_regulate_diffusion"); ws->regulate_diffusion(); }
+    { CCAKE_PHASE("08_viscosities"); ws->update_all_particle_viscosities(); }
+    { CCAKE_PHASE("09_smooth_gradients"); ws->smooth_all_particle_gradients(t2); }
+    { CCAKE_PHASE("10_time_derivatives"); TEOM<D>::evaluate_time_derivatives(sys, st); }
+  }
+  int advance_par04(double dt, int rk) override {
+    if (!evolver2) { evolver2.reset(new Evolver<D>(st, sys)); evolver2->allocate_cache(); }
+    evolver2->execute_timestep(dt, rk, [this] { this->get_time_derivatives_par04(); });
+    sys->number_of_elapsed_timesteps++;
+    return 0;
+  }
   long n() override { return (long)sys->cabana_particles.size(); }
   double time() override { return sys->t; }
   void set_time(double t) override { sys->t = t; }
@@ -337,6 +387,18 @@ int ccake_ref_eos_names(void* h, int* out) { return static_cast<RefBase*>(h)->eo
 int ccake_ref_eos_thermo(void* h, const char* name, long n, const double* points, double* out17) {
   return static_cast<RefBase*>(h)->eos_thermo(name, n, points, out17);
 }
+int ccake_ref_advance_par04(void* h, double dt, int rk) { return static_cast<RefBase*>(h)->advance_par04(dt, rk); }
 int ccake_ref_omp_threads() { return omp_get_max_threads(); }
+// torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm asks for all host cores explicitly
+void ccake_ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+// The reference's own per-phase wall-time table (include/phase_profiler.h; needs CCAKE_PROFILE=1 in the environment BEFORE the
+// library is loaded): written into buf as text, returns the length needed.
+long ccake_ref_profile_report(char* buf, long cap) {
+  std::ostringstream os;
+  ccake::PhaseProfiler::instance().report(os);
+  const std::string s = os.str();
+  if (buf && cap > 0) { const long m = std::min<long>(cap - 1, (long)s.size()); std::memcpy(buf, s.data(), m); buf[m] = 0; }
+  return (long)s.size() + 1;
+}
 
 }  // extern "C"

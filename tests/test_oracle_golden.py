@@ -293,14 +293,18 @@ def test_bench_reference_arm_contract():
     import subprocess
     import sys
 
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-scale", "0.1"],
-                         capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--cpu-scale", "0.05"],
+                         capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))   # as torchrun exports it
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "particle_steps_per_s" and d["unit"] == "particle-steps/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None and d["dtype"] == "f64"
-    assert d["config"]["workload"] == "config2_viscous_gubser_bsq_2p1d"
-    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["workload"] == "config4_milne_bsq_table_3p1d" and d["scaling"] == "strong"   # the configuration the metric is quoted on
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["cores"] == os.cpu_count()   # all host cores, whatever OMP_NUM_THREADS the launcher exported
+    # per-phase seconds under the reference's CCAKE_PROFILE names, and the step with phase 04 OpenMP-parallelised next to it
+    assert {"01_neighbour_list", "03_smooth_fields", "04_thermodynamics", "09_smooth_gradients", "10_time_derivatives"} <= set(d["cpu_baseline"]["per_phase"])
+    assert d["cpu_baseline"]["phase04_openmp"]["value"] > 0 and "04_thermodynamics_openmp" in d["cpu_baseline"]["phase04_openmp"]["per_phase"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
