@@ -49,7 +49,9 @@ struct ccb_ctx {
            *scan_sums = nullptr;
   int64_t ncells_alloc = 0, hist_alloc = 0, sums_alloc = 0;
   double* rec = nullptr;        // gather records
-  int32_t* tasks = nullptr;
+  int32_t* tasks = nullptr;     // gather task list (cell order), one entry per chunk of <= task_nt particles of one cell
+  uint32_t* task_pos = nullptr; // cap + 1: task flags, then their exclusive scan
+  int32_t* d_taskinfo = nullptr;// [0..2] task counts (cells.cuh: task_scatter), [4] / [5] task counters of the interior / boundary launch
   int32_t* d_small = nullptr;   // [0] ntasks, [1..2] err
   double* d_stage = nullptr;    // staging for id-ordered transfers (16 columns) and reductions
   double* init_tmp = nullptr;
@@ -74,7 +76,9 @@ struct ccb_ctx {
   ccb::EosChain chain;
   bool have_table = false;   // the EoS chain is ready: table loaded, or an analytic single-member chain (tanh_conformal, conformal_diagonal)
   bool use_chain = false;    // phase 04 runs through the chain kernels (every eos_type but the closed-form conformal one)
-  ccb::GatherShape shape_grad{128, 64, 0}, shape_fields{64, 64, 0};   // launch shapes of the gradient / field gather
+  // launch shapes of the gradient / field gather. nt (targets = threads per task) is common to both: it is the chunk size of
+  // the task list
+  ccb::GatherShape shape_grad{64, 64, 0}, shape_fields{64, 64, 0};
   int sms = 148;
   // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
   std::unique_ptr<ccb::Link> comm;
@@ -208,7 +212,8 @@ int free_particles(ccb_ctx* ctx) {
   cudaFree(ctx->slab); cudaFree(ctx->y0_slab); cudaFree(ctx->alt_slab); cudaFree(ctx->ints);
   cudaFree(ctx->k_slab); cudaFree(ctx->alt_k_slab); ctx->k_slab = ctx->alt_k_slab = nullptr;
   cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
-  cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
+  cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->task_pos); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
+  ctx->task_pos = nullptr;
   for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); ctx->mig_d[k] = nullptr; ctx->mig_i[k] = nullptr; }
   cudaFree(ctx->mig_list); ctx->mig_list = nullptr;
   ctx->mig_cap = 0;
@@ -281,13 +286,14 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   CUDA_OK(cudaMalloc(&ctx->rec, sizeof(double) * REC_G_MAX * cap));
   ctx->rec_cap = cap;
   CUDA_OK(cudaMalloc(&ctx->tasks, sizeof(int32_t) * cap));
+  CUDA_OK(cudaMalloc(&ctx->task_pos, sizeof(uint32_t) * (cap + 1)));
   CUDA_OK(cudaMalloc(&ctx->d_stage, sizeof(double) * kStageCols * cap));
   dv.key = ctx->key_a;
   dv.cell_start = ctx->cell_count;
   dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
   dv.ghost_rec[0] = dv.ghost_rec[1] = ctx->rec;
-  dv.tasks = ctx->tasks; dv.ntasks = ctx->d_small; dv.err = ctx->d_small + 1;
-  const int64_t need_sums = cdiv(std::max<int64_t>(ctx->hist_alloc, ctx->grid.ncells + 1), kScanTile) + 1;
+  dv.tasks = ctx->tasks; dv.ntasks = ctx->d_taskinfo; dv.err = ctx->d_small + 1;
+  const int64_t need_sums = cdiv(std::max<int64_t>(std::max<int64_t>(ctx->hist_alloc, ctx->grid.ncells + 1), cap + 1), kScanTile) + 1;
   if (need_sums > ctx->sums_alloc) {
     cudaFree(ctx->scan_sums);
     CUDA_OK(cudaMalloc(&ctx->scan_sums, sizeof(uint32_t) * need_sums));
@@ -330,7 +336,7 @@ GatherParams make_gather(ccb_ctx* ctx) {
   gp.rsqr = radius * radius;
   gp.rsqr_f = (float)(gp.rsqr * (1.0 + 1e-4));  // fp32 pre-filter: never misses a true neighbour (gather.cuh)
   gp.rsqr_edge = gp.rsqr * (1.0 - 1e-12);
-  gp.task_count = gp.task_n0 = gp.task_off0 = gp.task_off1 = 0;
+  gp.task_sel = 0; gp.task_info = ctx->d_taskinfo; gp.task_counter = ctx->d_taskinfo + 4;
 
   const CellGrid& g = ctx->grid;
   const int fast_digit = (g.nc[2] > 1) ? 2 : 1;
@@ -578,24 +584,25 @@ int exchange_halo(ccb_ctx* ctx, int rec_doubles) {
   return CCB_OK;
 }
 
-// Task ranges of a slab gather with `nt` targets per task: interior = tasks that lie wholly outside the first / last cell
-// column (no ghost records needed), boundary = the rest, at the two ends of the sorted order.
-struct TaskSplit { int64_t ntasks, i0, i1; };
-TaskSplit split_tasks(ccb_ctx* ctx, int nt) {
-  const int rank = ctx->cfg.rank, nranks = ctx->cfg.nranks;
-  TaskSplit ts;
-  ts.ntasks = cdiv(ctx->n, nt);
-  const int64_t b0 = rank > 0 ? ctx->send_start[0] + ctx->send_n[0] : 0;
-  const int64_t b1 = rank + 1 < nranks ? ctx->send_start[1] : ctx->n;
-  ts.i0 = std::min<int64_t>(cdiv(b0, nt), ts.ntasks);
-  ts.i1 = std::max<int64_t>(std::min<int64_t>(b1 / nt, ts.ntasks), ts.i0);
-  return ts;
-}
-
 int grad_record_doubles(ccb_ctx* ctx) {
   const bool df = ctx->cfg.using_diffusion;
   if (ctx->D == 2) return df ? GradRec<2, true>::REC : GradRec<2, false>::REC;
   return df ? GradRec<3, true>::REC : GradRec<3, false>::REC;
+}
+
+// The task list of the gathers (cells.cuh): chunks of <= task_nt particles of one cell, in cell order.
+int build_task_list(ccb_ctx* ctx) {
+  const CellGrid& g = ctx->grid;
+  DeviceView& dv = ctx->dv;
+  const int64_t n = ctx->n, P = (int64_t)g.nc[1] * g.nc[2];
+  LAUNCH(task_flag, cdiv(n, 256), 256, dv.key, dv.cell_start, ctx->task_pos, n, (uint32_t)ctx->shape_grad.nt);
+  int rc = exclusive_scan(ctx, ctx->task_pos, ctx->task_pos, n, 1);
+  if (rc) return rc;
+  const bool has_l = ctx->comm && ctx->cfg.rank > 0, has_r = ctx->comm && ctx->cfg.rank + 1 < ctx->cfg.nranks;
+  const uint32_t* lo = has_l ? dv.cell_start + (int64_t)(ctx->slab_lo + 1) * P : nullptr;   // end of the first own column
+  const uint32_t* hi = has_r ? dv.cell_start + (int64_t)(ctx->slab_hi - 1) * P : nullptr;   // start of the last own column
+  LAUNCH(task_scatter, cdiv(n, 256), 256, ctx->task_pos, ctx->tasks, n, lo, hi, ctx->d_taskinfo);
+  return CCB_OK;
 }
 
 int do_build_cells(ccb_ctx* ctx) {
@@ -613,6 +620,7 @@ int do_build_cells(ccb_ctx* ctx) {
     ctx->dv.n = ctx->n;
     if ((rc = sort_and_permute(ctx, ctx->n, 0))) return rc;
   }
+  if ((rc = build_task_list(ctx))) return rc;
   ctx->cells_valid = true;
   ctx->cells_built = true;
   return CCB_OK;
@@ -683,20 +691,16 @@ int slab_gather_p2p(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& 
   CUDA_OK(cudaStreamWaitEvent(cs, ctx->ev_pack, 0));
   p2p_wait<<<1, 1, 0, cs>>>(has_l ? ctx->d_flags + 0 : nullptr, has_r ? ctx->d_flags + 1 : nullptr, e, gflag, ctx->dv.err);
   ctx->launches++;
-  const TaskSplit ts = split_tasks(ctx, nt);
-  const int64_t nb = ts.i0 + (ts.ntasks - ts.i1);
-  if (nb > 0) {
+  {  // boundary tasks: the slab's first and last cell column (task counts and ranges live on the device)
     GatherParams gb = gp;
-    gb.task_count = (int)nb; gb.task_n0 = (int)ts.i0; gb.task_off0 = 0; gb.task_off1 = (int)ts.i1;
+    gb.task_sel = 2; gb.task_counter = ctx->d_taskinfo + 5;
     if ((rc = launch(gb, cs))) return rc;
   }
   p2p_signal<<<1, 1, 0, cs>>>(has_l ? pl + 3 : nullptr, has_r ? pr + 2 : nullptr, e, (const int*)nullptr);
   ctx->launches++;
   CUDA_OK(cudaEventRecord(ctx->ev_halo, cs));
-  if (ts.i1 > ts.i0) {
-    gp.task_count = gp.task_n0 = (int)(ts.i1 - ts.i0); gp.task_off0 = (int)ts.i0; gp.task_off1 = 0;
-    if ((rc = launch(gp, ctx->stream))) return rc;
-  }
+  gp.task_sel = 1;
+  if ((rc = launch(gp, ctx->stream))) return rc;
   CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
   return CCB_OK;
 }
@@ -705,6 +709,7 @@ int slab_gather_p2p(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& 
 // the interior tasks next to them on the compute stream, which then waits for the boundary tasks.
 template <class F>
 int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& launch) {
+  CUDA_OK(cudaMemsetAsync(ctx->d_taskinfo + 4, 0, 2 * sizeof(int32_t), ctx->stream));  // task counters of this gather's launches
   if (!ctx->comm) return launch(gp, ctx->stream);
   if (ctx->p2p) return slab_gather_p2p(ctx, rec_doubles, nt, gp, launch);
   // do the ghost records carry what the own records may lack (q^mu_a != 0 for the gradient gather, charges for the fields)?
@@ -723,18 +728,14 @@ int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& laun
       ctx->launches++;
     }
   }
-  const TaskSplit ts = split_tasks(ctx, nt);
-  const int64_t nb = ts.i0 + (ts.ntasks - ts.i1);
-  if (nb > 0) {
+  {
     GatherParams gb = gp;
-    gb.task_count = (int)nb; gb.task_n0 = (int)ts.i0; gb.task_off0 = 0; gb.task_off1 = (int)ts.i1;
+    gb.task_sel = 2; gb.task_counter = ctx->d_taskinfo + 5;
     if ((rc = launch(gb, ctx->comm_stream))) return rc;
   }
   CUDA_OK(cudaEventRecord(ctx->ev_halo, ctx->comm_stream));
-  if (ts.i1 > ts.i0) {
-    gp.task_count = gp.task_n0 = (int)(ts.i1 - ts.i0); gp.task_off0 = (int)ts.i0; gp.task_off1 = 0;
-    if ((rc = launch(gp, ctx->stream))) return rc;
-  }
+  gp.task_sel = 1;
+  if ((rc = launch(gp, ctx->stream))) return rc;
   CUDA_OK(cudaStreamWaitEvent(ctx->stream, ctx->ev_halo, 0));
   return CCB_OK;
 }
@@ -995,6 +996,8 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   CUDA_OK(cudaMalloc(&ctx->d_small, sizeof(int32_t) * 8));
   CUDA_OK(cudaMemsetAsync(ctx->d_small, 0, sizeof(int32_t) * 8, ctx->stream));
   CUDA_OK(cudaMalloc(&ctx->d_reduce, sizeof(double) * 7 * 296));
+  CUDA_OK(cudaMalloc(&ctx->d_taskinfo, sizeof(int32_t) * 16));
+  CUDA_OK(cudaMemsetAsync(ctx->d_taskinfo, 0, sizeof(int32_t) * 16, ctx->stream));
   {
     CUDA_OK(cudaMalloc(&ctx->d_qflag, sizeof(int) * 4));
     const int one_zero[4] = {1, 0, 1, 0};  // until the first local update has looked: assume non-zero currents
@@ -1008,10 +1011,11 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
   ctx->dv.ghost_col[0] = ctx->dv.ghost_col[1] = -1;
   ctx->dv.ghost_start[0] = ctx->dv.ghost_start[1] = nullptr;
   cudaDeviceGetAttribute(&ctx->sms, cudaDevAttrMultiProcessorCount, cfg->device);
-  {  // gather launch shape: 128 (gradients) / 64 (fields) targets per task, 64 source records per shared-memory tile
-     // (measured best over the BASELINE configs, profiles/README.md); environment overrides are for tuning runs only
+  {  // gather launch shape: 64 targets per task, 64 source records per shared-memory tile (measured best over the BASELINE
+     // configs, profiles/README.md); environment overrides are for tuning runs only
     if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->shape_grad.nt = ctx->shape_fields.nt = v; }
-    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_grad.tile = ctx->shape_fields.tile = v; }
+    if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_grad.tile = v; }
+    if (const char* e = std::getenv("CCB_FIELDS_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_fields.tile = v; }
     if (const char* e = std::getenv("CCB_GATHER_REGS")) ctx->shape_grad.regs = std::atoi(e) != 0;
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
@@ -1033,7 +1037,7 @@ int ccb_destroy(ccb_ctx* ctx) {
   if (!ctx) return CCB_ERR_INVALID;
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_particles(ctx);
-  cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce);
+  cudaFree(ctx->cell_count); cudaFree(ctx->scan_sums); cudaFree(ctx->d_small); cudaFree(ctx->d_reduce); cudaFree(ctx->d_taskinfo);
   cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends); cudaFree(ctx->d_qflag); cudaFree(ctx->d_flags);
   if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_halo); }
   cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
@@ -1421,8 +1425,11 @@ int ccb_debug_neighbour_list(ccb_ctx* ctx, int64_t* offsets, int32_t* idx, int64
   CUDA_OK(d_idx.alloc(std::max<int64_t>(total, 1)));
   CUDA_OK(cudaMemcpyAsync(d_off.p, off.data(), sizeof(int64_t) * (n + 1), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(cudaMemsetAsync(d_idx.p, 0xff, sizeof(int32_t) * std::max<int64_t>(total, 1), ctx->stream));
+  // the field records share their buffer with the gradient records: pack them again (phase 02 is idempotent)
+  if ((rc = do_prologue(ctx))) return rc;
   GatherParams gp = make_gather(ctx);
   gp.nbr_off = d_off.p; gp.nbr_idx = d_idx.p;
+  CUDA_OK(cudaMemsetAsync(ctx->d_taskinfo + 4, 0, 2 * sizeof(int32_t), ctx->stream));
   if (ctx->D == 2) LAUNCHER("gather_kernel<fields, emit>", launch_gather_fields<2>(false, ctx->shape_fields, ctx->stream, ctx->dv, ctx->grid, gp));
   else LAUNCHER("gather_kernel<fields, emit>", launch_gather_fields<3>(false, ctx->shape_fields, ctx->stream, ctx->dv, ctx->grid, gp));
   std::vector<int32_t> raw(std::max<int64_t>(total, 1));

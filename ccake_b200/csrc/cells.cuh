@@ -354,13 +354,31 @@ __global__ void permute_columns(PermuteList pl, const uint32_t* __restrict__ per
   for (int c = 0; c < pl.nints; ++c) pl.idst[c][i] = pl.isrc[c][j];
 }
 
-// first particle of every chunk of <= `chunk` targets that share a cell -> work list of the gathers
-__global__ void build_tasks(const uint32_t* __restrict__ key, const uint32_t* __restrict__ cell_start, int32_t* __restrict__ tasks,
-                            int32_t* __restrict__ ntasks, int64_t n, uint32_t chunk) {
+// ---- task list of the gathers ------------------------------------------------------------------------------------------
+// A task = up to `chunk` consecutive particles of ONE cell (a cell with more particles is cut into chunks), so that every
+// target of a gather CTA has the same 3^D-cell stencil. task_flag marks the first particle of every task, an exclusive scan
+// numbers them, task_scatter writes the list in cell order and the three counts the gather kernels read:
+// info[0] = tasks, info[1] = tasks before particle b_lo (= the slab's first cell column), info[2] = tasks before b_hi.
+__global__ void task_flag(const uint32_t* __restrict__ key, const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ flag, int64_t n,
+                          uint32_t chunk) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t rank = (uint32_t)i - cell_start[key[i]];
-  if ((rank % chunk) == 0u) tasks[atomicAdd(ntasks, 1)] = (int32_t)i;
+  flag[i] = (rank % chunk) == 0u ? 1u : 0u;
+}
+// pos = exclusive scan of the flags (n + 1 entries). lo / hi point at the cell-table entries that bound the interior of a slab
+// (nullptr = no neighbour on that side = no boundary column): they are read on the device, the host never sees them.
+__global__ void task_scatter(const uint32_t* __restrict__ pos, int32_t* __restrict__ tasks, int64_t n, const uint32_t* __restrict__ lo,
+                             const uint32_t* __restrict__ hi, int32_t* __restrict__ info) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    int64_t b_lo = lo ? (int64_t)lo[0] : 0, b_hi = hi ? (int64_t)hi[0] : n;
+    if (b_hi < b_lo) b_hi = b_lo;  // a slab of one column with a neighbour on either side: every task is a boundary task
+    info[0] = (int32_t)pos[n];
+    info[1] = (int32_t)pos[b_lo < n ? b_lo : n];
+    info[2] = (int32_t)pos[b_hi < n ? b_hi : n];
+  }
+  if (i < n && pos[i + 1] != pos[i]) tasks[pos[i]] = (int32_t)i;
 }
 
 // whole blocks of columns at once (ccb_upload_state / ccb_download_state): blockIdx.y = column

@@ -5,11 +5,11 @@
 // neighbour list and issues 5 (fields) or 5D+D^2 [+6+3D] (gradients) atomic adds PER PAIR into
 // a 4.5 KB/particle AoSoA. Here (particles are already sorted by cell, phase 01):
 //
-//   * a CTA takes a task = NT (64 fields, 128 gradients) consecutive particles of the cell-sorted order, one target per
-//     thread with its sums in registers. Consecutive sorted particles lie in consecutive cells of one grid row, so their
-//     neighbours are the particles of the 3^D stencil around that short run of cells: 3 (2-D) or 9 (3-D) CONTIGUOUS ranges
-//     of the sorted records (a row of cells along the fastest grid axis is contiguous in memory); in a slab run a ghost
-//     column is one more such range, in the neighbouring rank's record array (peer memory) or behind the own records;
+//   * a CTA takes a task = up to NT consecutive particles of ONE cell of the cell-sorted order (task list: cells.cuh), one
+//     target per thread with its sums in registers. Their neighbours are the particles of the 3^D stencil around that cell:
+//     3 (2-D) or 9 (3-D) CONTIGUOUS ranges of the sorted records (a row of cells along the fastest grid axis is contiguous
+//     in memory); in a slab run a ghost column is one more such range, in the neighbouring rank's record array (peer
+//     memory) or behind the own records. CTAs are persistent and pull tasks from a device-side counter;
 //   * the candidate sources are streamed through shared memory in tiles of 64 records, double-buffered with cp.async
 //     (tile k + 1 lands while tile k is processed). Tile k takes every ntiles-th candidate, so each tile is a uniform
 //     sample of the neighbourhood and every target finds about the same number of neighbours in it;
@@ -38,9 +38,17 @@ __device__ __forceinline__ double dist_sqr_exact(double dx, double dy, double dz
   return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
-// r and 1/r from r^2 with one rsqrt (2 ulp) instead of sqrt + divisions; r2 == 0 (self) is handled by the callers
+// 1 / sqrt(x) for a positive NORMAL x (a squared pair distance inside the cut-off): the hardware seed (MUFU.RSQ64H, 2^-22) and
+// one third-order correction -- the sequence rsqrt() itself runs, without its range check and slow-path call (2 ulp).
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-(y * y), x, 1.0);
+  return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+// r and 1/r from r^2 with one rsqrt instead of sqrt + divisions; r2 == 0 (self) is handled by the callers
 __device__ __forceinline__ void r_and_inv(double r2, double& r, double& ir) {
-  ir = rsqrt(r2);
+  ir = rsqrt_pos(r2);
   r = r2 * ir;
 }
 // W(r, h) of src/kernel.cpp:36-48 with q = r * (1/h)
@@ -274,7 +282,7 @@ struct GradPolicy {
     }
   }
   struct Prep { double A[D], Kv; };
-  // exact predicate + A_b = m_b grad_a W_ab (zero for a pair that is not in the neighbour list, or `valid` = false)
+  // exact predicate + A_b = m_b grad_a W_ab; false for a pair that is not in the neighbour list (nothing else is computed then)
   __device__ static bool prep(const GatherParams& gp, const Target& t, const double2* sb, bool valid, Prep& p) {
     const double2 b0 = sb[0], b1 = sb[1];
     double rel[3];
@@ -282,17 +290,24 @@ struct GradPolicy {
     rel[2] = (D == 3) ? t.x[2] - b1.x : 0.0;
     const double r2 = (D == 3) ? dist_sqr_exact(rel[0], rel[1], rel[2]) : __dadd_rn(__dmul_rn(rel[0], rel[0]), __dmul_rn(rel[1], rel[1]));
     // outside the neighbour list, or coincident (self): grad W(0) = 0 and every pair term carries grad W
-    const bool in = valid && (r2 <= gp.rsqr) && r2 != 0.0;
-    double gK[D];
-    grad_kernel<D, FACT>(gp, rel, in ? r2 : gp.rsqr, gK);
+    if (!(valid && (r2 <= gp.rsqr) && r2 != 0.0)) return false;
     const double m_b = (R::M == 2) ? b1.x : b1.y;
+    if (FACT) {
+      double gK[D];
+      grad_kernel<D, FACT>(gp, rel, r2, gK);
+#pragma unroll
+      for (int d = 0; d < D; ++d) p.A[d] = m_b * gK[d];
+    } else {
+      double r, ir;
+      r_and_inv(r2, r, ir);
+      const double g = m_b * sph_gradw_factor_fast(gp.kD, r, ir);
+#pragma unroll
+      for (int d = 0; d < D; ++d) p.A[d] = g * rel[d];
+    }
     p.Kv = 0.;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      p.A[d] = in ? m_b * gK[d] : 0.0;
-      p.Kv = fma(p.A[d], t.v[d], p.Kv);
-    }
-    return in;
+    for (int d = 0; d < D; ++d) p.Kv = fma(p.A[d], t.v[d], p.Kv);
+    return true;
   }
   // the record is consumed 16 bytes at a time, in layout order: no more than one chunk is live at any point
   // QNZ = false: every record of this launch carries q^mu_a = 0 (DeviceView::qflag), so the chunks from Q0 on (Q0, QI,
@@ -399,48 +414,50 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     if (nz != (P::VARIANT == 1)) return;
   }
   __shared__ __align__(16) double2 srec2[2][TILE * RS2];  // double-buffered tiles of source records
-  __shared__ __align__(16) float spos[4][TILE];  // fp32 x, y, z relative to the pass origin, and x^2 + y^2 + z^2
+  __shared__ __align__(16) float spos[4][TILE];  // fp32 x, y, z relative to the task origin, and x^2 + y^2 + z^2
   __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
   __shared__ const double2* seg_base[kMaxSeg];  // record array of the segment: own, or a neighbour's (ghost column)
-  __shared__ int s_nseg;
-  __shared__ uint32_t s_next[NT / 32];
+  __shared__ int s_nseg, s_task;
   const double* __restrict__ rec = P::records(dv);
   const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(rec);
   const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
-
-  const int64_t task = (int)blockIdx.x < gp.task_n0 ? (int64_t)gp.task_off0 + blockIdx.x : (int64_t)gp.task_off1 + (blockIdx.x - gp.task_n0);
-  const int64_t first = task * NT;
-  const int64_t last = min(first + NT, dv.n) - 1;
-  const int64_t i = first + threadIdx.x;
-  const bool active = i <= last;
-  typename P::Target tg;
-  P::load_target(rec + (active ? i : first) * P::REC, tg);
-  tg.cf = (int)(dv.key[active ? i : first] % (uint32_t)((g.nc[2] > 1) ? g.nc[2] : g.nc[1]));
-  typename P::Acc acc;
-  P::init(acc);
-  int emitted = 0;  // EMIT only
-  const bool qnz = (dv.qflag[P::FLAG] | dv.qflag[P::FLAG + 1]) != 0;  // sparsity flag of this gather's records: see P::accum
-
-  // The cells of a grid row along the fastest axis are contiguous in the sorted order: F cells per row,
-  // row index rho = key / F. A task's particles lie in the rows rho_f .. rho_l (almost always one row; two when
-  // the task straddles a row end; more only where rows hold a handful of particles). The task is processed
-  // in passes, one per row that holds targets: in a pass the lanes of that row are live and the sources are
-  // the 3^(D-1) neighbouring rows restricted to the cells [fa - 1, fb + 1] around the targets' cells [fa, fb].
   const int F = (nz > 1) ? nz : ny;
-  const uint32_t my_key = dv.key[active ? i : first];
-  const uint32_t my_rho = active ? my_key / F : 0xffffffffu;
-  const uint32_t key_f = dv.key[first], key_l = dv.key[last];
-  const uint32_t rho_f = key_f / F, rho_l = key_l / F;
-  uint32_t rho = rho_f;
+  const bool qnz = (dv.qflag[P::FLAG] | dv.qflag[P::FLAG + 1]) != 0;  // run-time sparsity flag of the field records (FieldsPolicy::accum)
+
+  // Tasks (cells.cuh: task list): a task = up to NT consecutive particles of ONE cell, so that every target of a CTA has the same
+  // 3^D-cell stencil; the list is in cell order: [tasks of the slab's first cell column | interior | last column]. The CTAs of a
+  // launch are persistent and pull tasks from a counter, neighbouring tasks running at the same time (their candidates share L2).
+  const int* __restrict__ ti = gp.task_info;
+  int a0 = 0, a1 = ti[0], b0 = 0, b1 = 0;
+  if (gp.task_sel == 1) { a0 = ti[1]; a1 = ti[2]; }                      // interior
+  else if (gp.task_sel == 2) { a1 = ti[1]; b0 = ti[2]; b1 = ti[0]; }     // the two boundary columns
+  const int na = a1 - a0, count = na + (b1 - b0);
+
   for (;;) {
-    const bool in_pass = active && my_rho == rho;
-    const int fa = (rho == rho_f) ? (int)(key_f % F) : 0, fb = (rho == rho_l) ? (int)(key_l % F) : F - 1;
-    const int f0 = max(fa - 1, 0), f1 = min(fb + 1, F - 1);
+    __syncthreads();  // the previous task's tiles, segment table and s_task are no longer in use
+    if (threadIdx.x == 0) s_task = atomicAdd(gp.task_counter, 1);
+    __syncthreads();
+    const int q = s_task;
+    if (q >= count) break;
+    const int64_t first = dv.tasks[q < na ? a0 + q : b0 + (q - na)];
+    const uint32_t key_f = dv.key[first];
+    const int64_t last = min(first + (int64_t)NT, (int64_t)dv.cell_start[key_f + 1]) - 1;
+    const int64_t i = first + threadIdx.x;
+    const bool active = i <= last;
+    typename P::Target tg;
+    P::load_target(rec + (active ? i : first) * P::REC, tg);
+    const int fa = (int)(key_f % (uint32_t)F);
+    const uint32_t rho = key_f / (uint32_t)F;  // row of cells along the fastest digit: contiguous in the sorted order
+    tg.cf = fa;
+    typename P::Acc acc;
+    P::init(acc);
+    int emitted = 0;  // EMIT only
+    const int f0 = max(fa - 1, 0), f1 = min(fa + 1, F - 1);
     // neighbouring rows: (x +- 1, y +- 1) for a 3-D grid (rho = x ny + y), x +- 1 for a 2-D one (rho = x)
     const int ry = (nz > 1) ? (int)(rho % ny) : 0, rx = (nz > 1) ? (int)(rho / ny) : (int)rho;
     const int nrow_y = (nz > 1) ? 3 : 1;
-    // frame of the fp32 pre-filter: coordinates relative to the corner of the pass's first target cell, so that
-    // every coordinate in play is a few cell edges at most
+    // frame of the fp32 pre-filter: coordinates relative to the corner of the task's cell, so that every coordinate in
+    // play is two cell edges at most
     double org[3];
     float tx[3];
     {
@@ -455,15 +472,12 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
         tx[d] = (float)(tg.x[d] - org[d]);
       }
     }
-    // squared extent of the pass's candidates and targets about `org` (cells f0 .. f1 along the fastest axis, +-1 cell across)
+    // squared extent of the candidates and targets about `org` (+-1 cell along every axis in use, +1 for the cell itself)
     float ext2;
     {
-      const int fa_ax = (nz > 1) ? 2 : 1;
-      const float ef = (float)((max(f1 - fa, fa - f0) + 1) / g.rdx[fa_ax]);
       const float e0 = (float)(2.0 / g.rdx[0]), e1 = (float)(2.0 / g.rdx[1]), e2 = (D == 3) ? (float)(2.0 / g.rdx[2]) : 0.f;
-      ext2 = ef * ef + e0 * e0 + e1 * e1 + e2 * e2;
+      ext2 = e0 * e0 + e1 * e1 + e2 * e2;
     }
-    __syncthreads();  // the previous pass's tiles and segment table are no longer in use
     if (threadIdx.x == 0) {
       int ns = 0;
       uint32_t C = 0;
@@ -490,15 +504,19 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     // tile k = candidates k, k + ntiles, ... < C: a uniform sample of the neighbourhood, so that every lane finds about
     // the same number of hits in it (contiguous tiles [k TILE, (k + 1) TILE) measured 1.7x slower: the walk of phase 2
     // costs max-over-lanes(hits) per tile). Tile k + 1 is in flight (cp.async) while tile k is processed.
+    // Staging: record r of tile k is candidate r * ntiles + k. NT / TILE threads share a record and copy alternating 16-byte
+    // chunks of it, so that the segment search and the address arithmetic run once per thread and tile.
     auto stage = [&](uint32_t k, double2* buf) {
+      constexpr int TPR = (NT >= TILE) ? NT / TILE : 1;
       const int nt = (int)((C - k + ntiles - 1) / ntiles);
-      for (int q = threadIdx.x; q < nt * CH; q += NT) {
-        const int r = q / CH, c = q - r * CH;
+      for (int r = threadIdx.x / TPR; r < nt; r += NT / TPR) {
         const uint32_t cand = (uint32_t)r * ntiles + k;
-        int s = 0;
-        while (cand >= seg_pref[s + 1]) ++s;
-        const int64_t gidx = (int64_t)seg_start[s] + (cand - seg_pref[s]);
-        cp_async16(buf + r * RS2 + c, seg_base[s] + gidx * RCH + c);
+        int sg = 0;
+        while (cand >= seg_pref[sg + 1]) ++sg;
+        const double2* src = seg_base[sg] + ((int64_t)seg_start[sg] + (cand - seg_pref[sg])) * RCH;
+        double2* dst = buf + r * RS2;
+#pragma unroll
+        for (int c = threadIdx.x % TPR; c < CH; c += TPR) cp_async16(dst + c, src + c);
       }
       cp_async_commit();
     };
@@ -527,7 +545,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
       //   |b|^2 - 2 a.b <= R^2 - |a|^2   (|b|^2 staged per source, the right-hand side formed once per lane):
       // D FMAs + 1 compare per candidate instead of D subtractions, D multiply-adds and a compare. The expansion
       // cancels, so the cut-off carries an absolute margin for the fp32 rounding of coordinates up to `ext` (the
-      // extent of the pass around its origin): no true neighbour is missed; a false positive costs one exact test.
+      // extent of the stencil around its origin): no true neighbour is missed; a false positive costs one exact test.
       uint32_t m[NW];
       const float ax = -2.f * tx[0], ay = -2.f * tx[1], az = -2.f * tx[2];
       const float thr = (gp.rsqr_f + 4.0e-6f * ext2) - fmaf(tx[0], tx[0], fmaf(tx[1], tx[1], tx[2] * tx[2]));
@@ -553,7 +571,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
             }
           }
         }
-        m[w] = in_pass ? mw : 0u;
+        m[w] = active ? mw : 0u;
       }
       // ---- phase 2: every lane walks its own hits (a software-pipelined, branch-free variant of this loop measured
       // 5-10 % slower: the loop is bound by shared-memory gather bandwidth, not by per-warp latency)
@@ -587,18 +605,8 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
         }
       }
     }
-    // next row that holds targets of this task
-    uint32_t nxt = (active && my_rho > rho) ? my_rho : 0xffffffffu;
-    nxt = __reduce_min_sync(0xffffffffu, nxt);
-    if ((threadIdx.x & 31) == 0) s_next[threadIdx.x >> 5] = nxt;
-    __syncthreads();
-    nxt = s_next[0];
-#pragma unroll
-    for (int w = 1; w < NT / 32; ++w) nxt = min(nxt, s_next[w]);
-    if (nxt == 0xffffffffu) break;
-    rho = nxt;
+    if (active) P::store(dv, gp, i, acc);
   }
-  if (active) P::store(dv, gp, i, acc);
 }
 
 }  // namespace ccb

@@ -45,10 +45,13 @@ struct GatherParams {
   double rsqr_edge;  // rsqr (1 - 1e-12): pairs at or above it sit on the cut-off (knife edge, see FieldsPolicy::pair)
   double fast_min, fast_rdx;  // the fastest digit of the cell key that has more than one cell: cell = floor((x - min) rdx)
   int fast_coord, fast_nc;    // fast_coord = the spatial coordinate (0 x, 1 y, 2 z / eta) that digit indexes
-  // which tasks a launch covers: block b -> task (b < task_n0 ? task_off0 + b : task_off1 + b - task_n0); task_count = 0
-  // means all of them. A slab run launches the interior tasks first and the two boundary ranges (the first and last cell
-  // column, which need the ghost records) once the halo exchange has completed on the communication stream.
-  int task_count, task_n0, task_off0, task_off1;
+  // which tasks a launch covers (DeviceView::tasks is in cell order): task_sel 0 = all, 1 = interior, 2 = the slab's first and
+  // last cell column (the targets that need ghost records; launched once the halo has arrived / the neighbours are ready).
+  // task_info (device): [0] number of tasks, [1] first interior task, [2] first task of the last column.
+  // task_counter (device): the next task of this launch; zeroed before the launch.
+  int task_sel;
+  const int* task_info;
+  int* task_counter;
   double t;
   int milne;
   // debug twin of the field gather (FieldsPolicy EMIT): CSR offsets per target (sorted order) and the id buffer it fills

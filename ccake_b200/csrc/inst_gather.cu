@@ -9,18 +9,21 @@
 namespace ccb {
 
 namespace {
-// one CTA per task of NT consecutive sorted particles; the hardware block scheduler balances the SMs
+// persistent CTAs, as many as fit the device at once; they pull tasks (cells.cuh: task list) from GatherParams::task_counter
 template <class P, int NT, int MINB, int TILE>
 cudaError_t launch(cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
-  static bool configured = false;
-  if (!configured) {
+  static int grid = 0;
+  if (!grid) {
     cudaFuncSetAttribute(gather_kernel<P, NT, MINB, TILE>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_kernel<P, NT, MINB, TILE>, NT, 0);
+    grid = sms * (per_sm > 0 ? per_sm : 1);
   }
-  GatherParams q = gp;
-  unsigned ntasks = (unsigned)q.task_count;
-  if (q.task_count <= 0) { ntasks = (unsigned)((dv.n + NT - 1) / NT); q.task_n0 = (int)ntasks; q.task_off0 = q.task_off1 = 0; }
-  gather_kernel<P, NT, MINB, TILE><<<ntasks, NT, 0, s>>>(dv, g, q);
+  // no more CTAs than there can be tasks (small systems): every particle starts at most one task
+  const int64_t most = dv.n > 0 ? dv.n : 1;
+  gather_kernel<P, NT, MINB, TILE><<<(unsigned)(most < grid ? most : grid), NT, 0, s>>>(dv, g, gp);
   return cudaGetLastError();
 }
 // GatherShape: targets per task (64 | 128), source records per shared-memory tile (32 | 64; tiles are double-buffered), and the
@@ -45,7 +48,7 @@ template <>
 cudaError_t launch_gather_fields<CCB_INST_D>(bool fact, const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
                                              const GatherParams& gp) {
   constexpr int D = CCB_INST_D;
-  if (gp.nbr_idx) return launch<FieldsPolicy<D, false, true>, 64, 8, 64>(s, dv, g, gp);  // debug twin: neighbour ids (plain kernel)
+  if (gp.nbr_idx) return launch_shape<FieldsPolicy<D, false, true>, 8, 4>(sh, s, dv, g, gp);  // debug twin: neighbour ids (plain kernel)
   if (D == 3 && fact) return launch_shape<FieldsPolicy<D, (D == 3)>, 12, 6>(sh, s, dv, g, gp);
   return launch_shape<FieldsPolicy<D, false>, 12, 6>(sh, s, dv, g, gp);
 }

@@ -52,7 +52,7 @@ struct DeviceView {
   double* rec_grad;            // REC_GRAD doubles / particle, see gather kernels
   int* qflag;                  // [0] some own gradient record carries a non-zero diffusion current q^mu_a, [1] some ghost record does;
                                // [2], [3] likewise for a non-zero B, S or Q entry of the field records
-  int32_t* tasks;              // first particle of every (cell, 32-target chunk)
+  int32_t* tasks;              // gather tasks in cell order: first particle of every chunk of <= NT particles of one cell
   int32_t* ntasks;
   int32_t* err;                // [0] status code, [1] first offending particle id
   // slab decomposition: the cell columns (index along x) just outside this rank's slab hold GHOST records,

@@ -249,7 +249,9 @@ int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host);
 /* debug / test: the neighbour sets the field gather visits, as the CSR list SystemState::reset_neighbour_list stores
  * (src/system_state.cpp:651-719: VerletList, full neighbour tag, self excluded): offsets[ccb_n() + 1] in particle-id order,
  * idx = neighbour ids, ascending within a particle; cap = entries idx can hold (sum of CCB_I_BTRACK). Call after
- * ccb_smooth_fields. The product path never materialises this list. */
+ * ccb_smooth_fields (any later phase may have run too: phase 02 is repeated to re-pack the field records, which
+ * invalidates the gradient records -- run ccb_local_update before the next ccb_smooth_gradients). The product path never
+ * materialises this list. */
 int ccb_debug_neighbour_list(ccb_ctx* ctx, int64_t* offsets, int32_t* idx, int64_t cap);
 
 /* --- the ten phases of SPHWorkstation::get_time_derivatives (src/sph_workstation.cpp:1543-1583) --- */

@@ -1,0 +1,7 @@
+TAG=r02b
+mkdir -p gpurun_out
+(time timeout 3000 python -m pytest tests -m gpu -q 2>&1 | tail -80) > gpurun_out/${TAG}_pytest.log 2>&1
+tail -15 gpurun_out/${TAG}_pytest.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gather_kernel" -s 14 -c 3 -o gpurun_out/${TAG}_prof_gather_config4 -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu.log 2>&1
+tail -3 gpurun_out/${TAG}_ncu.log
+ls -la gpurun_out/
