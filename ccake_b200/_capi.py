@@ -48,7 +48,7 @@ class Config(C.Structure):
         ("conformal_muS0", C.c_double), ("conformal_muQ0", C.c_double),
         ("freeze_out_temperature_MeV", C.c_double),
         ("prohibit_unstable_cs2", C.c_int), ("prohibit_acausal_cs2", C.c_int), ("restrict_mu_T_ratios", C.c_int),
-        ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("slab_axis", C.c_int),
+        ("device", C.c_int), ("rank", C.c_int), ("nranks", C.c_int), ("particlization_enabled", C.c_int), ("dt", C.c_double), ("online_inverter_enabled", C.c_int), ("slab_axis", C.c_int),
     ]
 
 
@@ -56,6 +56,20 @@ class EosTable(C.Structure):
     """``ccb_eos_table``."""
 
     _fields_ = [("n", C.c_int32 * 4), ("grid", C.POINTER(C.c_double)), ("fields", C.POINTER(C.c_double)), ("normalize_by_T", C.c_int)]
+
+
+class PreTile(C.Structure):
+    """``ccb_preinverted_tile``."""
+
+    _fields_ = [("slot", C.c_int32 * 4), ("min", C.c_double * 4), ("step", C.c_double * 4), ("N", C.c_int32 * 4),
+                ("log_spacing", C.c_int32 * 4), ("vars", C.POINTER(C.c_double))]
+
+
+class PreFlat(C.Structure):
+    """``ccb_preinverted_flat``."""
+
+    _fields_ = [("Ns", C.c_int32), ("NB", C.c_int32)] + [(k, C.POINTER(C.c_double)) for k in
+                                                           ("s", "nB", "T", "muB", "muS", "muQ", "e", "p", "cs2", "chiTT", "chiTB", "chiBB")]
 
 
 class IC(C.Structure):
@@ -142,6 +156,11 @@ def lib():
     L.ccb_migration_counts.argtypes = [ctx, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.ccb_get_field_device_order.argtypes = [ctx, C.c_int, dp]
     L.ccb_get_int_field_device_order.argtypes = [ctx, C.c_int, ip]
+    L.ccb_set_preinverted_table.argtypes = [ctx, C.c_int32, C.POINTER(PreTile)]
+    L.ccb_set_preinverted_flat.argtypes = [ctx, C.POINTER(PreFlat)]
+    L.ccb_generate_preinverted_tile.argtypes = [ctx, ip, C.c_int32, dp, ip]
+    L.ccb_freeze_out.argtypes = [ctx, C.POINTER(C.c_int64)]
+    L.ccb_freeze_out_results.argtypes = [ctx, dp, ip]
     L.ccb_debug_neighbour_list.argtypes = [ctx, C.POINTER(C.c_int64), ip, C.c_int64]
     L.ccb_stream.argtypes = [ctx]
     L.ccb_stream.restype = C.c_void_p
@@ -159,4 +178,4 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
             "ccb_measure_dfma_peak", "ccb_comm_unique_id", "ccb_comm_init", "ccb_comm_init_local", "ccb_set_slab",
             "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order",
-            "ccb_debug_neighbour_list", "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]
+            "ccb_debug_neighbour_list", "ccb_freeze_out", "ccb_freeze_out_results", "ccb_set_preinverted_table", "ccb_set_preinverted_flat", "ccb_generate_preinverted_tile", "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]

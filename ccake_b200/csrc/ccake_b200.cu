@@ -14,7 +14,9 @@
 
 #include "cells.cuh"
 #include "comm.h"
+#include "eos_preinverted.cuh"
 #include "eos_table_host.h"
+#include "freeze_out.cuh"
 #include "launchers.h"
 
 using namespace ccb;
@@ -74,6 +76,19 @@ struct ccb_ctx {
   std::unique_ptr<ccb::HostTable> table;
   double *d_hot_s = nullptr, *d_hot_e = nullptr, *d_full = nullptr;
   ccb::EosChain chain;
+  // pre-inverted EoS (online_inverter_enabled = 0): device copies of the tiles / the flat table, and the flat table's host copy
+  std::vector<double*> pre_alloc;
+  ccb::PreTile* d_pre_tiles = nullptr;
+  ccb::PreTable pre_table{nullptr, 0};
+  ccb::PreFlat pre_flat_dev{};
+  std::vector<std::vector<double>> pre_flat_host;   // s_axis, nB_axis, T, muB, muS, muQ, e, p, cs2, dwds, dwdB (fm units)
+  bool have_pre = false;
+  // freeze-out (freeze_out.cuh): snapshot / results rows by particle id; FreezeOut::frzc, taup, taupp; SystemState::number_part_fo
+  ccb::FreezeArrays frz{};
+  double* frz_slab = nullptr;
+  int frzc = 0;
+  double taup = 0.0, taupp = 0.0;
+  int64_t number_part_fo = 0;
   bool have_table = false;   // the EoS chain is ready: table loaded, or an analytic single-member chain (tanh_conformal, conformal_diagonal)
   bool use_chain = false;    // phase 04 runs through the chain kernels (every eos_type but the closed-form conformal one)
   // launch shapes of the gradient / field gather. nt (targets = threads per task) is common to both: it is the chunk size of
@@ -213,6 +228,8 @@ int free_particles(ccb_ctx* ctx) {
   cudaFree(ctx->k_slab); cudaFree(ctx->alt_k_slab); ctx->k_slab = ctx->alt_k_slab = nullptr;
   cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
   cudaFree(ctx->rec); cudaFree(ctx->tasks); cudaFree(ctx->task_pos); cudaFree(ctx->d_stage); cudaFree(ctx->init_tmp);
+  cudaFree(ctx->frz_slab); cudaFree(ctx->frz.print); cudaFree(ctx->frz.count);
+  ctx->frz_slab = nullptr; ctx->frz = FreezeArrays{};
   ctx->task_pos = nullptr;
   for (int k = 0; k < 2; ++k) { cudaFree(ctx->mig_d[k]); cudaFree(ctx->mig_i[k]); ctx->mig_d[k] = nullptr; ctx->mig_i[k] = nullptr; }
   cudaFree(ctx->mig_list); ctx->mig_list = nullptr;
@@ -300,6 +317,23 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
     ctx->sums_alloc = need_sums;
   }
   if (n > 0) LAUNCH(iota_kernel, cdiv(n, 256), 256, dv.id, n);
+  dv.eos_type_is_table = ctx->cfg.eos_type == CCB_EOS_TABLE ? 1 : 0;
+  {  // freeze-out: the counter always (the initial status check runs in every run); the snapshot and results rows when particlization is on
+    CUDA_OK(cudaMalloc(&ctx->frz.count, sizeof(unsigned long long)));
+    ctx->frzc = 0; ctx->taup = ctx->taupp = 0.0; ctx->number_part_fo = 0;
+    if (ctx->cfg.particlization_enabled) {
+      if (ctx->cfg.nranks > 1) { ctx->err = "particlization_enabled: freeze-out runs on single-context systems (the snapshot rows do not migrate between slabs)"; return CCB_ERR_INVALID; }
+      const size_t rows = (size_t)cap * (6 * FZ_ROW + FR_ROW);
+      CUDA_OK(cudaMalloc(&ctx->frz_slab, sizeof(double) * rows));
+      CUDA_OK(cudaMemsetAsync(ctx->frz_slab, 0, sizeof(double) * rows, ctx->stream));
+      double* q = ctx->frz_slab;
+      double** six[6] = {&ctx->frz.frz1, &ctx->frz.frz2, &ctx->frz.fback, &ctx->frz.fback2, &ctx->frz.fback3, &ctx->frz.fback4};
+      for (int k = 0; k < 6; ++k) { *six[k] = q; q += (size_t)cap * FZ_ROW; }
+      ctx->frz.results = q;
+      CUDA_OK(cudaMalloc(&ctx->frz.print, sizeof(int32_t) * cap));
+      CUDA_OK(cudaMemsetAsync(ctx->frz.print, 0, sizeof(int32_t) * cap, ctx->stream));
+    }
+  }
   ctx->cells_valid = false;
   ctx->cells_built = false;
   ctx->have_state = true;
@@ -335,15 +369,8 @@ GatherParams make_gather(ccb_ctx* ctx) {
   const double radius = 2 * ctx->cfg.hT;
   gp.rsqr = radius * radius;
   gp.rsqr_f = (float)(gp.rsqr * (1.0 + 1e-4));  // fp32 pre-filter: never misses a true neighbour (gather.cuh)
-  gp.rsqr_edge = gp.rsqr * (1.0 - 1e-12);
   gp.task_sel = 0; gp.task_info = ctx->d_taskinfo; gp.task_counter = ctx->d_taskinfo + 4;
 
-  const CellGrid& g = ctx->grid;
-  const int fast_digit = (g.nc[2] > 1) ? 2 : 1;
-  gp.fast_coord = g.axis[fast_digit];
-  gp.fast_min = g.min[fast_digit];
-  gp.fast_rdx = g.rdx[fast_digit];
-  gp.fast_nc = g.nc[fast_digit];
   gp.t = ctx->t;
   gp.milne = ctx->milne ? 1 : 0;
   gp.nbr_off = nullptr; gp.nbr_idx = nullptr;
@@ -752,6 +779,22 @@ int do_gather_fields(ccb_ctx* ctx) {
 
 int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
   StageParams sp = make_stage(ctx, 0.0, 0);
+  if (!ctx->cfg.online_inverter_enabled) {
+    // pre-inverted EoS: phase 04 is a table lookup (EoS_Interpolator::fill_thermodynamics), then the streaming local update
+    if (!ctx->have_pre) { ctx->err = "online_inverter_enabled = 0: no pre-inverted table (ccb_set_preinverted_table / ccb_set_preinverted_flat)"; return CCB_ERR_STATE; }
+    if (do_eos) {
+      PhaseTimer pt(ctx, PH_THERMO);
+      LAUNCHER("pre_fill_kernel", launch_pre_fill(ctx->stream, ctx->dv, ctx->pre_table));
+    }
+    if (do_local) {
+      PhaseTimer pt(ctx, PH_LOCAL);
+      { const int rc = p2p_wait_readers(ctx); if (rc) return rc; }
+      sp.do_eos = 0; sp.do_local = 1;
+      CUDA_OK(cudaMemsetAsync(ctx->d_qflag, 0, sizeof(int), ctx->stream));
+      DISPATCH_DM("eos_local_kernel", launch_eos_local, ctx->stream, ctx->dv, sp);
+    }
+    return CCB_OK;
+  }
   if (ctx->use_chain) {
     // tabulated / chain EoS: the root search has its own kernel (register-heavy, divergent); the streaming
     // local update then reads the thermodynamics it stored
@@ -857,6 +900,41 @@ RkCols rk_columns(ccb_ctx* ctx) {
   return c;
 }
 
+// FreezeOut::check_freeze_out_status (include/freeze_out.h:462-541); *count = particles that are freezing out (status 3) now
+int do_freeze_check_status(ccb_ctx* ctx, int64_t* count) {
+  CUDA_OK(cudaMemsetAsync(ctx->frz.count, 0, sizeof(unsigned long long), ctx->stream));
+  LAUNCHER("freeze_check_status_kernel", launch_freeze_check_status(ctx->stream, ctx->dv, ctx->frz, ctx->t, ctx->efcheck));
+  unsigned long long h = 0;
+  CUDA_OK(cudaMemcpyAsync(&h, ctx->frz.count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->number_part_fo += (int64_t)h;
+  if (count) *count = (int64_t)h;
+  return CCB_OK;
+}
+// SPHWorkstation::freeze_out_particles (src/sph_workstation.cpp:1475-1485) = check_freeze_out_status + FreezeOut::bsqsvfreezeout (:550-641)
+int do_freeze_out(ccb_ctx* ctx, int64_t* n_freezing_out) {
+  if (!ctx->frz.frz1) { ctx->err = "ccb_freeze_out: the context was created with particlization_enabled = 0"; return CCB_ERR_STATE; }
+  int64_t curfrz = 0;
+  int rc = do_freeze_check_status(ctx, &curfrz);
+  if (rc) return rc;
+  if (n_freezing_out) *n_freezing_out = curfrz;
+  if (ctx->frzc == 0) {          // first time step: current -> frz2
+    ctx->taupp = ctx->t; ctx->frzc = 1;
+    DISPATCH_DM("freeze_snapshot_kernel", launch_freeze_snapshot, ctx->stream, ctx->dv, ctx->frz, 2);
+  } else if (ctx->frzc == 1) {   // second time step: current -> frz1
+    ctx->taup = ctx->t; ctx->frzc = 2;
+    DISPATCH_DM("freeze_snapshot_kernel", launch_freeze_snapshot, ctx->stream, ctx->dv, ctx->frz, 1);
+    if (curfrz > 0) DISPATCH_DM("freeze_interpolate_kernel", launch_freeze_interpolate, ctx->stream, ctx->dv, ctx->frz, ctx->efcheck, ctx->taup, ctx->taupp, ctx->cfg.dt);
+  } else {
+    DISPATCH_DM("freeze_evo_kernel", launch_freeze_evo, ctx->stream, ctx->dv, ctx->frz);
+    const double tau = ctx->t;
+    if (curfrz > 0) DISPATCH_DM("freeze_interpolate_kernel", launch_freeze_interpolate, ctx->stream, ctx->dv, ctx->frz, ctx->efcheck, ctx->taup, ctx->taupp, ctx->cfg.dt);
+    DISPATCH_DM("freeze_advance_kernel", launch_freeze_advance, ctx->stream, ctx->dv, ctx->frz);
+    ctx->taupp = ctx->taup; ctx->taup = tau;
+  }
+  return CCB_OK;
+}
+
 int snapshot_y0(ccb_ctx* ctx) {
   for (int k = 0; k < kNumEvolvedFields; ++k) {
     const int f = kEvolvedFields[k];
@@ -882,6 +960,15 @@ int surface_device_error(ccb_ctx* ctx) {
 
 int do_init_particles(ccb_ctx* ctx, const StageParams& sp) {
   int eos_done = 0;
+  if (!ctx->cfg.online_inverter_enabled) {
+    // SPHWorkstation::initialize_entropy_and_charge_densities with use_preinverted (src/sph_workstation.cpp:260-320): flat table only
+    if (!ctx->have_pre || !ctx->pre_table.flat) {
+      ctx->err = "online_inverter_enabled = 0: the initialisation needs the flat (s, nB) pre-inverted table (ccb_set_preinverted_flat), as in the reference";
+      return CCB_ERR_STATE;
+    }
+    LAUNCHER("pre_init_kernel", launch_pre_init(ctx->stream, ctx->dv, ctx->pre_flat_dev, ctx->init_tmp, ctx->cfg.input_as_entropy));
+    eos_done = 1;
+  } else
   if (ctx->use_chain) {
     if (!ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
     LAUNCHER("eos_chain_init_kernel", launch_eos_chain_init(ctx->stream, ctx->dv, ctx->chain, ctx->init_tmp, ctx->cfg.input_as_entropy));
@@ -1041,6 +1128,8 @@ int ccb_destroy(ccb_ctx* ctx) {
   cudaFree(ctx->ghost_tab); cudaFree(ctx->d_info); cudaFree(ctx->d_ends); cudaFree(ctx->d_qflag); cudaFree(ctx->d_flags);
   if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->ev_pack); cudaEventDestroy(ctx->ev_halo); }
   cudaFree(ctx->d_hot_s); cudaFree(ctx->d_hot_e); cudaFree(ctx->d_full);
+  for (double* q : ctx->pre_alloc) cudaFree(q);
+  cudaFree(ctx->d_pre_tiles);
   ctx->comm.reset();
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1069,6 +1158,143 @@ int ccb_load_eos_table_dat(ccb_ctx* ctx, const char* path, int normalize_by_T) {
   if (!read_thermo_dat(path, *ctx->table, ctx->err)) return CCB_ERR_INVALID;
   return install_table(ctx, normalize_by_T != 0);
 }
+// ---- pre-inverted equation of state ------------------------------------------------------------------------------------
+static int pre_reset(ccb_ctx* ctx) {
+  for (double* q : ctx->pre_alloc) cudaFree(q);
+  ctx->pre_alloc.clear();
+  ctx->have_pre = false;
+  if (!ctx->d_pre_tiles) CUDA_OK(cudaMalloc(&ctx->d_pre_tiles, sizeof(PreTile) * kPreTileCount));
+  return CCB_OK;
+}
+static int pre_upload(ccb_ctx* ctx, const double* host, size_t count, double** dev) {
+  CUDA_OK(cudaMalloc(dev, sizeof(double) * count));
+  ctx->pre_alloc.push_back(*dev);
+  CUDA_OK(cudaMemcpy(*dev, host, sizeof(double) * count, cudaMemcpyHostToDevice));
+  return CCB_OK;
+}
+int ccb_set_preinverted_table(ccb_ctx* ctx, int32_t ntiles, const ccb_preinverted_tile* tiles) {
+  if (!ctx || ntiles < 1 || !tiles) return CCB_ERR_INVALID;
+  if (!ctx->stream) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
+  int rc = pre_reset(ctx);
+  if (rc) return rc;
+  std::vector<PreTile> h(kPreTileCount);
+  for (auto& t : h) std::memset(&t, 0, sizeof(t));
+  for (int k = 0; k < ntiles; ++k) {
+    const ccb_preinverted_tile& in = tiles[k];
+    const int lim[4] = {5, 4, 4, 4};
+    size_t count = PRE_NVAR;
+    for (int i = 0; i < 4; ++i) {
+      if (in.slot[i] < 0 || in.slot[i] >= lim[i] || in.N[i] < 1) { ctx->err = "ccb_set_preinverted_table: tile slot or axis size out of range"; return CCB_ERR_INVALID; }
+      count *= (size_t)in.N[i];
+    }
+    if (!in.vars) return CCB_ERR_INVALID;
+    PreTile& t = h[((in.slot[0] * 4 + in.slot[1]) * 4 + in.slot[2]) * 4 + in.slot[3]];
+    for (int i = 0; i < 4; ++i) { t.min[i] = in.min[i]; t.step[i] = in.step[i]; t.N[i] = in.N[i]; t.log_spacing[i] = in.log_spacing[i]; }
+    double* d = nullptr;
+    if ((rc = pre_upload(ctx, in.vars, count, &d))) return rc;
+    t.vars = d;
+  }
+  CUDA_OK(cudaMemcpy(ctx->d_pre_tiles, h.data(), sizeof(PreTile) * kPreTileCount, cudaMemcpyHostToDevice));
+  ctx->pre_table.tiles = ctx->d_pre_tiles;
+  ctx->pre_table.flat = 0;
+  ctx->have_pre = true;
+  return CCB_OK;
+}
+// EoS_Interpolator::load_flat_table (src/eos_interpolator.cpp:262-521) from arrays: unit conversion, log-uniformity check of the
+// axes, dw/ds and dw/dB from the chi tensor (baryon-only Schur complement), host copies for the initialisation queries
+int ccb_set_preinverted_flat(ccb_ctx* ctx, const ccb_preinverted_flat* in) {
+  if (!ctx || !in || in->Ns < 2 || in->NB < 2) return CCB_ERR_INVALID;
+  const double* req[] = {in->s, in->nB, in->T, in->muB, in->muS, in->muQ, in->e, in->p, in->cs2, in->chiTT, in->chiTB, in->chiBB};
+  for (const double* q : req) if (!q) return CCB_ERR_INVALID;
+  if (!ctx->stream) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
+  int rc = pre_reset(ctx);
+  if (rc) return rc;
+  const int Ns = in->Ns, NB = in->NB;
+  const size_t Ntot = (size_t)Ns * NB;
+  const double hc1 = 1.0 / kHbarcMeVfm, hc2 = hc1 * hc1, hc3 = hc2 * hc1, hc4 = hc2 * hc2;
+  std::vector<std::vector<double>>& H = ctx->pre_flat_host;
+  H.assign(11, std::vector<double>());
+  enum { HS = 0, HNB, HT, HMUB, HMUS, HMUQ, HE, HP, HCS2, HDWDS, HDWDB };
+  H[HS].resize(Ns); H[HNB].resize(NB);
+  for (int is = 0; is < Ns; ++is) H[HS][is] = in->s[(size_t)is * NB] * hc3;
+  for (int iB = 0; iB < NB; ++iB) H[HNB][iB] = in->nB[iB] * hc3;
+  double lmin[2], lstep[2];
+  for (int a = 0; a < 2; ++a) {
+    const std::vector<double>& ax = H[a];
+    const double l0 = std::log10(ax.front()), l1 = std::log10(ax.back()), step = (l1 - l0) / (ax.size() - 1);
+    double dev = 0.0;
+    for (size_t i = 1; i + 1 < ax.size(); ++i) dev = std::max(dev, std::fabs(std::log10(ax[i + 1]) - std::log10(ax[i]) - step));
+    if (!(dev <= 1e-6)) { ctx->err = std::string("ccb_set_preinverted_flat: axis ") + (a ? "nB" : "s") + " is not uniformly log-spaced"; return CCB_ERR_INVALID; }
+    lmin[a] = l0; lstep[a] = step;
+  }
+  for (int k = HT; k <= HDWDB; ++k) H[k].resize(Ntot);
+  const double EPS = 1e-30;
+  for (int is = 0; is < Ns; ++is)
+    for (int iB = 0; iB < NB; ++iB) {
+      const size_t i = (size_t)is * NB + iB;
+      const double T = in->T[i] * hc1, muB = in->muB[i] * hc1;
+      const double chiTT = in->chiTT[i] * hc2, chiTB = in->chiTB[i] * hc2, chiBB = in->chiBB[i] * hc2;
+      const double s_c = H[HS][is], nB_c = H[HNB][iB];
+      const double dentr_dt = chiTT - (chiTB * chiTB) / (chiBB + EPS), dentr_dmub = chiTB - (chiTT * chiBB) / (chiTB + EPS);
+      const double db_dt = chiTB - (chiBB * chiTT) / (chiTB + EPS), db_dmub = chiBB - (chiTB * chiTB) / (chiTT + EPS);
+      double dwds = T + s_c / dentr_dt;
+      if (std::fabs(nB_c) > kTiny) dwds += nB_c / dentr_dmub;
+      double dwdB = muB;
+      if (std::fabs(nB_c) > kTiny) dwdB += s_c / db_dt + nB_c / db_dmub;
+      H[HT][i] = T; H[HMUB][i] = muB; H[HMUS][i] = in->muS[i] * hc1; H[HMUQ][i] = in->muQ[i] * hc1;
+      H[HE][i] = in->e[i] * hc4; H[HP][i] = in->p[i] * hc4; H[HCS2][i] = in->cs2[i];
+      H[HDWDS][i] = dwds; H[HDWDB][i] = dwdB;
+    }
+  // device: the tile in slot [0][0][0][0] (11 fields, eos_variables order; dwdS = dwdQ = 0) and the flat arrays of the init queries
+  std::vector<double> vars((size_t)PRE_NVAR * Ntot, 0.0);
+  const int src[PRE_NVAR] = {HT, HMUB, HMUQ, HMUS, HE, HP, HCS2, HDWDS, HDWDB, -1, -1};
+  for (int v = 0; v < PRE_NVAR; ++v) if (src[v] >= 0) std::copy(H[src[v]].begin(), H[src[v]].end(), vars.begin() + (size_t)v * Ntot);
+  std::vector<PreTile> h(kPreTileCount);
+  for (auto& t : h) std::memset(&t, 0, sizeof(t));
+  PreTile& t = h[0];
+  t.min[0] = lmin[0]; t.step[0] = lstep[0]; t.N[0] = Ns; t.log_spacing[0] = 1;
+  t.min[1] = lmin[1]; t.step[1] = lstep[1]; t.N[1] = NB; t.log_spacing[1] = 1;
+  t.N[2] = t.N[3] = 1;
+  double* d = nullptr;
+  if ((rc = pre_upload(ctx, vars.data(), vars.size(), &d))) return rc;
+  t.vars = d;
+  CUDA_OK(cudaMemcpy(ctx->d_pre_tiles, h.data(), sizeof(PreTile) * kPreTileCount, cudaMemcpyHostToDevice));
+  ctx->pre_table.tiles = ctx->d_pre_tiles;
+  ctx->pre_table.flat = 1;
+  PreFlat& f = ctx->pre_flat_dev;
+  f.Ns = Ns; f.NB = NB; f.log_s_min = lmin[0]; f.dlog_s = lstep[0]; f.log_nB_min = lmin[1]; f.dlog_nB = lstep[1];
+  const double** dst[11] = {&f.s_axis, &f.nB_axis, &f.T, &f.muB, &f.muS, &f.muQ, &f.e, &f.p, &f.cs2, &f.dwds, &f.dwdB};
+  for (int k = 0; k < 11; ++k) {
+    double* q = nullptr;
+    if ((rc = pre_upload(ctx, H[k].data(), H[k].size(), &q))) return rc;
+    *dst[k] = q;
+  }
+  // efcheck = EoS_Interpolator::efreeze_at_T(T_FO) (SPHWorkstation::initialize, src/sph_workstation.cpp:75-79), on the host copy
+  PreFlat hf = f;
+  hf.s_axis = H[HS].data(); hf.nB_axis = H[HNB].data(); hf.T = H[HT].data(); hf.muB = H[HMUB].data(); hf.muS = H[HMUS].data();
+  hf.muQ = H[HMUQ].data(); hf.e = H[HE].data(); hf.p = H[HP].data(); hf.cs2 = H[HCS2].data(); hf.dwds = H[HDWDS].data(); hf.dwdB = H[HDWDB].data();
+  ctx->efcheck = pre_efreeze_at_T(hf, ctx->cfg.freeze_out_temperature_MeV / kHbarcMeVfm);
+  ctx->have_pre = true;
+  return CCB_OK;
+}
+// utilities/generate_eos_table.cpp on the device: one decade tile located with the run's own inversion kernel
+int ccb_generate_preinverted_tile(ccb_ctx* ctx, const int32_t exponent[4], int32_t N, double* vars, int32_t* eos) {
+  if (!ctx || !exponent || N < 2 || N > 64 || !vars || !eos) return CCB_ERR_INVALID;
+  if (!ctx->stream) { ctx->err = "no CUDA device available (this library has no CPU path)"; return CCB_ERR_CUDA; }
+  if (ctx->use_chain && !ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
+  const int64_t total = (int64_t)N * N * N * N;
+  DevBuf<double> d_vars;
+  DevBuf<int32_t> d_eos;
+  CUDA_OK(d_vars.alloc(PRE_NVAR * total));
+  CUDA_OK(d_eos.alloc(total));
+  const ConformalParams cp{ctx->cfg.conformal_c, ctx->cfg.conformal_T0, ctx->cfg.conformal_muB0, ctx->cfg.conformal_muS0, ctx->cfg.conformal_muQ0};
+  LAUNCHER("pre_generate_kernel", launch_pre_generate(ctx->stream, ctx->chain, cp, ctx->use_chain ? 1 : 0, exponent, N, d_vars.p, d_eos.p));
+  CUDA_OK(cudaMemcpyAsync(vars, d_vars.p, sizeof(double) * PRE_NVAR * total, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(eos, d_eos.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return CCB_OK;
+}
+
 int ccb_eos_full_thermo(ccb_ctx* ctx, int member, int64_t n, const double* points, double* out) {
   if (!ctx || n < 0 || (n && (!points || !out))) return CCB_ERR_INVALID;
   if (n == 0) return CCB_OK;
@@ -1448,6 +1674,17 @@ int ccb_debug_neighbour_list(ccb_ctx* ctx, int64_t* offsets, int32_t* idx, int64
   return CCB_OK;
 }
 
+int ccb_freeze_out(ccb_ctx* ctx, int64_t* n_freezing_out) { int rc = check_ready(ctx, false); return rc ? rc : do_freeze_out(ctx, n_freezing_out); }
+int ccb_freeze_out_results(ccb_ctx* ctx, double* results, int32_t* print) {
+  int rc = check_ready(ctx, false);
+  if (rc) return rc;
+  if (!results || !print) return CCB_ERR_INVALID;
+  if (!ctx->frz.results) { ctx->err = "ccb_freeze_out_results: the context was created with particlization_enabled = 0"; return CCB_ERR_STATE; }
+  CUDA_OK(cudaMemcpyAsync(results, ctx->frz.results, sizeof(double) * FR_ROW * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(print, ctx->frz.print, sizeof(int32_t) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return CCB_OK;
+}
 int ccb_build_cells(ccb_ctx* ctx) { int rc = check_ready(ctx, false); return rc ? rc : do_build_cells(ctx); }
 int ccb_smooth_fields(ccb_ctx* ctx) {
   int rc = check_ready(ctx, true);
@@ -1487,6 +1724,8 @@ int ccb_step(ccb_ctx* ctx, double dt) {
     const RkCols c = rk_columns(ctx);
     LAUNCH(rk4_final_kernel, cdiv(ctx->n, 256), 256, c, dt, ctx->n, ctx->dv.freeze, ctx->dv.id, ctx->dv.err);
     ctx->cells_valid = false;
+    ctx->t = t0 + dt;
+    if (ctx->cfg.particlization_enabled) return do_freeze_out(ctx, nullptr);
     return CCB_OK;
   }
   // Evolver::advance_timestep_rk2 (src/evolver.cpp:494-507): midpoint rule
@@ -1494,6 +1733,7 @@ int ccb_step(ccb_ctx* ctx, double dt) {
   ctx->t = t0 + 0.5 * dt;
   if ((rc = derivative_evaluation(ctx, dt, 1))) return rc;
   ctx->t = t0 + dt;
+  if (ctx->cfg.particlization_enabled) return do_freeze_out(ctx, nullptr);   // SPHWorkstation::advance_timestep, src/sph_workstation.cpp:2063
   return CCB_OK;
 }
 
@@ -1627,7 +1867,9 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   if ((rc = do_prologue(ctx))) return rc;
   if ((rc = do_gather_fields(ctx))) return rc;
   if ((rc = do_eos_local(ctx, 1, 1))) return rc;
-  rc = surface_device_error(ctx);
+  // the initial freeze-out check of SPHWorkstation::initial_smoothing (src/sph_workstation.cpp:450-452), unconditional there
+  if (!rc) rc = do_freeze_check_status(ctx, nullptr);
+  if (!rc) rc = surface_device_error(ctx);
   cudaFree(ctx->init_tmp);
   ctx->init_tmp = nullptr;
   if (rc) return rc;

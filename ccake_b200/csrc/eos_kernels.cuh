@@ -5,6 +5,7 @@
 // table, which is sized to stay L2-resident); the 17-field table is touched once per particle, after convergence.
 #pragma once
 
+#include "eos_preinverted.cuh"
 #include "local.cuh"
 #include "physics_eos_chain.cuh"
 
@@ -105,6 +106,78 @@ __global__ void eos_locate_kernel(EosChain ch, ConformalParams conf, int use_cha
   const double v[16] = {th.T, th.muB, th.muS, th.muQ, th.e, th.s, th.rhoB, th.rhoS, th.rhoQ, th.p, th.cs2, th.w, th.dwds, th.dwdB, th.dwdS, th.dwdQ};
   for (int k = 0; k < 16; ++k) thermo[i * 16 + k] = ok ? v[k] : nan("");
   eos_out[i] = eos;
+}
+
+// ---- pre-inverted equation of state (eos_preinverted.cuh) ---------------------------------------------------------------
+// Phase 04 with Settings::online_inverter_enabled = false: EoS_Interpolator::fill_thermodynamics (src/eos_interpolator.cpp:531-627).
+// Writes T, muB, muS, muQ, e, p, cs2, w = e + p and dw/d(s, B, S, Q); s and the charge densities stay what the field gather stored.
+__global__ void __launch_bounds__(128) pre_fill_kernel(DeviceView dv, PreTable tb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  double* T = dv.f[CCB_F_THERMO];
+  double o[PRE_NVAR];
+  if (!pre_fill(tb, col(T, dv.cap, 5, i), col(T, dv.cap, 6, i), col(T, dv.cap, 7, i), col(T, dv.cap, 8, i), o)) {
+    raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]);
+    return;
+  }
+  col(T, dv.cap, 0, i) = o[PRE_T]; col(T, dv.cap, 1, i) = o[PRE_MUB]; col(T, dv.cap, 2, i) = o[PRE_MUS]; col(T, dv.cap, 3, i) = o[PRE_MUQ];
+  col(T, dv.cap, 4, i) = o[PRE_E]; col(T, dv.cap, 9, i) = o[PRE_P]; col(T, dv.cap, 10, i) = o[PRE_CS2]; col(T, dv.cap, 11, i) = o[PRE_E] + o[PRE_P];
+  col(T, dv.cap, 12, i) = o[PRE_DWDS]; col(T, dv.cap, 13, i) = o[PRE_DWDB]; col(T, dv.cap, 14, i) = o[PRE_DWDSS]; col(T, dv.cap, 15, i) = o[PRE_DWDQ];
+  col(dv.f[CCB_F_TSEED], dv.cap, 0, i) = o[PRE_T]; col(dv.f[CCB_F_TSEED], dv.cap, 1, i) = o[PRE_MUB];
+  col(dv.f[CCB_F_TSEED], dv.cap, 2, i) = o[PRE_MUS]; col(dv.f[CCB_F_TSEED], dv.cap, 3, i) = o[PRE_MUQ];
+}
+// Initial location on the flat (s, nB) table (SPHWorkstation::initialize_entropy_and_charge_densities with use_preinverted,
+// src/sph_workstation.cpp:260-320): query_thermo_host for entropy input, invert_e_to_s_host for energy input.
+__global__ void __launch_bounds__(128) pre_init_kernel(DeviceView dv, PreFlat fl, const double* __restrict__ tmp, int input_as_entropy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n) return;
+  const int64_t cap = dv.cap;
+  const double rhoB = tmp[1 * cap + i];
+  PreThermo q;
+  const bool ok = input_as_entropy ? pre_query_thermo(fl, tmp[i], rhoB, q) : pre_invert_e_to_s(fl, tmp[i] / kHbarcGeVfm, rhoB, q);
+  if (!ok) { raise_error(dv, CCB_ERR_EOS_NO_ROOT, dv.id[i]); return; }
+  Thermo th;
+  th.T = q.T; th.muB = q.muB; th.muS = q.muS; th.muQ = q.muQ; th.e = q.e; th.s = q.s; th.rhoB = q.rhoB; th.rhoS = 0.0; th.rhoQ = 0.0;
+  th.p = q.p; th.cs2 = q.cs2; th.w = q.w; th.dwds = q.dwds; th.dwdB = q.dwdB; th.dwdS = 0.0; th.dwdQ = 0.0;
+  for (int a = 0; a < 3; ++a) for (int x = 0; x < 4; ++x) th.dalpha[a][x] = 0.0;
+  th.chiBB = 0.0; th.chiBB0 = 0.0;
+  store_thermo(dv, i, th);
+  dv.eos_id[i] = 0;
+}
+// One tile of the pre-inverted table (utilities/generate_eos_table.cpp:223-330): node (is, iB, iS, iQ) of the decade tile
+// `exponent` is x = 10^e + i * 10^(e + 1) / N per axis; every node is located from the generator's seed (T = 750 / 197 fm^-1,
+// mu = 0) with the run's own inversion (update_s through the chain, or the closed-form conformal inversion).
+// vars: [PRE_NVAR][N^4]; eos: answering member per node, -1 (and NaN) where the reference aborts ("root-finding failed").
+__global__ void __launch_bounds__(128) pre_generate_kernel(EosChain ch, ConformalParams conf, int use_chain, int e0, int e1, int e2, int e3, int N,
+                                                           double* __restrict__ vars, int32_t* __restrict__ eos_out) {
+  const int64_t total = (int64_t)N * N * N * N;
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  const int iQ = (int)(k % N), iS = (int)((k / N) % N), iB = (int)((k / ((int64_t)N * N)) % N), is = (int)(k / ((int64_t)N * N * N));
+  const int ex[4] = {e0, e1, e2, e3}, ii[4] = {is, iB, iS, iQ};
+  double x[4];
+  for (int j = 0; j < 4; ++j) { const double xmin = pow(10., (double)ex[j]), xmax = pow(10., (double)(ex[j] + 1)); x[j] = xmin + ii[j] * (xmax / N); }
+  Thermo th;
+  int eos = -1;
+  bool ok;
+  if (use_chain) {
+    const double pos[4] = {750. / 197., 0.0, 0.0, 0.0};
+    ChainResult res;
+    ok = chain_update_s(ch, 0, pos, x[0], x[1], x[2], x[3], res);
+    if (ok) { chain_thermo(ch, res, th); eos = res.eos; }
+  } else {
+    double T, muB, muS, muQ;
+    ok = conformal_invert_s(conf, x[0], x[1], x[2], x[3], T, muB, muS, muQ);
+    if (ok) {
+      double r[TH_N];
+      conformal_full_thermo(conf, T, muB, muQ, muS, r);
+      thermo_from_forward(T, muB, muQ, muS, r, 0, th);
+      eos = 0;
+    }
+  }
+  const double v[PRE_NVAR] = {th.T, th.muB, th.muQ, th.muS, th.e, th.p, th.cs2, th.dwds, th.dwdB, th.dwdQ, th.dwdS};
+  for (int q = 0; q < PRE_NVAR; ++q) vars[(int64_t)q * total + k] = ok ? v[q] : nan("");
+  eos_out[k] = eos;
 }
 
 }  // namespace ccb

@@ -97,7 +97,7 @@ struct FieldsPolicy {
   static constexpr int D = D_, REC = REC_F, STRIDE = REC_F_STRIDE, CH_STAGE = REC_F / 2, VARIANT = -1;
   // EMIT: debug twin that also writes the ids of the neighbours it visits (ccb_debug_neighbour_list): GatherParams::nbr_off / nbr_idx
   static constexpr bool EMIT = EMIT_;
-  struct Target { double x[3]; int cf; };
+  struct Target { double x[3]; };
   struct Acc { double sig, s, B, S, Q; int cnt; };
   __device__ static const double* records(const DeviceView& dv) { return dv.rec_fields; }
   __device__ static void init(Acc& a) { a.sig = a.s = a.B = a.S = a.Q = 0.; a.cnt = 0; }
@@ -114,23 +114,17 @@ struct FieldsPolicy {
     const double dx = t.x[0] - b0.x, dy = t.x[1] - b0.y, dz = (D == 3) ? t.x[2] - b1.x : 0.0;
     // D = 2: z = 0 for every particle, and adding the exact zero dz*dz does not change the sum: skipped
     const double r2 = (D == 3) ? dist_sqr_exact(dx, dy, dz) : __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    bool in = valid && r2 <= gp.rsqr;  // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523)
-    // A task scans the cells [fa - 1, fb + 1] of its row, wider than the 3-cell stencil of one target. A source further
-    // than one cell away can only pass the cut-off when it sits EXACTLY on it (cell edge = 2h to rounding, lattice
-    // spacing commensurate with h): the reference's list searches +-1 cell and does not hold it. W = 0 there, so only
-    // the neighbour count is at stake; the rare knife-edge pair re-derives the source's cell to decide.
-    if (in && r2 >= gp.rsqr_edge) {
-      const double xf = (gp.fast_coord == 2) ? b1.x : (gp.fast_coord == 1 ? b0.y : b0.x);
-      int cj = (int)floor((xf - gp.fast_min) * gp.fast_rdx);
-      cj = cj < 0 ? 0 : (cj > gp.fast_nc - 1 ? gp.fast_nc - 1 : cj);
-      if (abs(cj - t.cf) > 1) in = false;
-    }
+    // the self term W(0) is part of the sum (reset_fields, src/sph_workstation.cpp:514-523). The candidates of a task are exactly
+    // the 3^D cells around the targets' cell, the cells the reference's list searches: a pair on the cut-off needs no special care
+    const bool in = valid && r2 <= gp.rsqr;
+    if (!in) { p.w = 0.0; p.hit = 0; return false; }
     double w;
     if (FACT) {
       const double rp = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
       w = sph_w(gp.k2, rp) * sph_w(gp.k1, fabs(dz));
     } else {
-      w = sph_w_fast(gp.kD, sqrt(r2));
+      const double r = r2 > 0.0 ? r2 * rsqrt_pos(r2) : 0.0;
+      w = sph_w_fast(gp.kD, r);
     }
     p.w = in ? w : 0.0;
     p.hit = in ? 1 : 0;
@@ -197,12 +191,12 @@ template <int D_, bool SHEAR, bool DIFF, bool FACT, bool QNZ = DIFF>
 struct GradPolicy {
   using R = GradRec<D_, DIFF>;
   static constexpr int D = D_, REC = R::REC;
-  static constexpr int KQ = DIFF ? (R::Q0 + 1) / 2 : REC / 2;  // first chunk that holds nothing but q^mu_a entries
+  static constexpr int KQ = DIFF ? (R::SIGLAB + 1) / 2 : REC / 2;  // first chunk that holds nothing a source contributes when q^mu_a = 0
   static constexpr int CH_STAGE = (DIFF && !QNZ) ? KQ : REC / 2;            // 16-byte chunks of a record staged per source
   static constexpr int STRIDE = (CH_STAGE % 2 == 1) ? 2 * CH_STAGE : 2 * CH_STAGE + 2;  // shared-memory stride: odd number of chunks
   static constexpr int VARIANT = DIFF ? (QNZ ? 1 : 0) : -1;  // -1: runs whatever the flag says
   static constexpr bool EMIT = false;
-  struct Target { double x[3]; double v[D]; int cf; };
+  struct Target { double x[3]; double v[D]; };
   // fp64 accumulators live across the neighbour loop: decides the register budget of the launch (inst_gather.cu)
   static constexpr int NACC = 4 * D + D * D + ((SHEAR || DIFF) ? 1 : 0) + (SHEAR ? 2 * D : 0) + (DIFF ? 3 * D : 0) + ((DIFF && QNZ) ? 6 : 0);
   struct Acc {
@@ -448,7 +442,6 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     P::load_target(rec + (active ? i : first) * P::REC, tg);
     const int fa = (int)(key_f % (uint32_t)F);
     const uint32_t rho = key_f / (uint32_t)F;  // row of cells along the fastest digit: contiguous in the sorted order
-    tg.cf = fa;
     typename P::Acc acc;
     P::init(acc);
     int emitted = 0;  // EMIT only

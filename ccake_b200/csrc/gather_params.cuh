@@ -25,13 +25,15 @@ template <int D, bool DIFF> struct GradRec {
   static constexpr int S0 = 2 * D + 4;        // pi^{0i} / sigma_lab^2, D doubles
   static constexpr int SM = 3 * D + 4;        // pi^{ij} / sigma_lab^2, i <= j, D(D+1)/2 doubles
   static constexpr int NSM = D * (D + 1) / 2;
-  static constexpr int SIGLAB = SM + NSM;     // sigma_lab (used of the TARGET only)
-  static constexpr int BASE = SIGLAB + 1;     // 14 (D = 2), 20 (D = 3)
-  static constexpr int ALPHA = BASE;          // mu_a / T, 3 doubles
-  static constexpr int Q0 = BASE + 3;         // q^0_a / sigma_lab^2, 3 doubles
-  static constexpr int QI = BASE + 6;         // q^i_a / sigma_lab^2, [a][i], 3 D doubles
-  static constexpr int FULL = BASE + 6 + 3 * D;
-  static constexpr int REC = DIFF ? ((FULL + 1) / 2) * 2 : BASE;           // doubles per record in global memory (even)
+  // everything a SOURCE contributes comes first (the gather stages only that part when the diffusion currents are zero);
+  // sigma_lab is used of the TARGET only and sits behind it
+  static constexpr int ALPHA = SM + NSM;                // mu_a / T, 3 doubles (DIFF only)
+  static constexpr int SIGLAB = DIFF ? ALPHA + 3 : SM + NSM;   // sigma_lab: 14 | 20 without diffusion, 16 | 22 with it (D = 2 | 3)
+  static constexpr int BASE = SIGLAB + 1;
+  static constexpr int Q0 = BASE;                       // q^0_a / sigma_lab^2, 3 doubles
+  static constexpr int QI = BASE + 3;                   // q^i_a / sigma_lab^2, [a][i], 3 D doubles
+  static constexpr int FULL = BASE + 3 + 3 * D;
+  static constexpr int REC = DIFF ? ((FULL + 1) / 2) * 2 : ((BASE + 1) / 2) * 2;   // doubles per record in global memory (even)
   static constexpr int STRIDE = ((REC / 2) % 2 == 1) ? REC : REC + 2;      // shared-memory stride: odd number of 16-byte units
   __host__ __device__ static constexpr int sym(int d, int e) { return d <= e ? d * D - d * (d - 1) / 2 + (e - d) : e * D - e * (e - 1) / 2 + (d - e); }
 };
@@ -42,9 +44,6 @@ struct GatherParams {
   KernelNorm k2, k1; // factorised variant: W_2D(r_perp, hT) * W_1D(|d eta|, hEta)
   double rsqr;       // (2 hT)^2: the neighbour cut-off of the reference (src/system_state.cpp:689)
   float rsqr_f;      // the same with a safety margin, for the fp32 pre-filter
-  double rsqr_edge;  // rsqr (1 - 1e-12): pairs at or above it sit on the cut-off (knife edge, see FieldsPolicy::pair)
-  double fast_min, fast_rdx;  // the fastest digit of the cell key that has more than one cell: cell = floor((x - min) rdx)
-  int fast_coord, fast_nc;    // fast_coord = the spatial coordinate (0 x, 1 y, 2 z / eta) that digit indexes
   // which tasks a launch covers (DeviceView::tasks is in cell order): task_sel 0 = all, 1 = interior, 2 = the slab's first and
   // last cell column (the targets that need ghost records; launched once the halo has arrived / the neighbours are ready).
   // task_info (device): [0] number of tasks, [1] first interior task, [2] first task of the last column.

@@ -25,4 +25,19 @@ cudaError_t launch_eos_locate(cudaStream_t s, const EosChain& ch, const Conforma
   return cudaGetLastError();
 }
 
+cudaError_t launch_pre_fill(cudaStream_t s, const DeviceView& dv, const PreTable& tb) {
+  pre_fill_kernel<<<(unsigned)((dv.n + 127) / 128), 128, 0, s>>>(dv, tb);
+  return cudaGetLastError();
+}
+cudaError_t launch_pre_init(cudaStream_t s, const DeviceView& dv, const PreFlat& fl, const double* tmp, int input_as_entropy) {
+  pre_init_kernel<<<(unsigned)((dv.n + 127) / 128), 128, 0, s>>>(dv, fl, tmp, input_as_entropy);
+  return cudaGetLastError();
+}
+cudaError_t launch_pre_generate(cudaStream_t s, const EosChain& ch, const ConformalParams& conf, int use_chain, const int32_t exponent[4], int N,
+                                double* vars, int32_t* eos) {
+  const int64_t total = (int64_t)N * N * N * N;
+  pre_generate_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(ch, conf, use_chain, exponent[0], exponent[1], exponent[2], exponent[3], N, vars, eos);
+  return cudaGetLastError();
+}
+
 }  // namespace ccb

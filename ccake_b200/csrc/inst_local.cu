@@ -1,5 +1,6 @@
 // Instantiations of the per-particle kernels for one (dimension, metric) pair
 // (-DCCB_INST_D=2|3 -DCCB_INST_MILNE=0|1).
+#include "freeze_out.cuh"
 #include "local.cuh"
 #include "launchers.h"
 
@@ -32,6 +33,30 @@ cudaError_t launch_init_particles<D_, M_>(cudaStream_t s, const DeviceView& dv, 
                                                                           bulk_from_trace, efcheck, eos_done);
   return cudaGetLastError();
 }
+// freeze-out (freeze_out.cuh)
+template <> cudaError_t launch_freeze_snapshot<D_, M_>(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa, int which) {
+  freeze_snapshot_kernel<D_><<<(unsigned)cdiv(dv.n, 128), 128, 0, s>>>(dv, fa, which);
+  return cudaGetLastError();
+}
+template <> cudaError_t launch_freeze_evo<D_, M_>(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa) {
+  freeze_evo_kernel<D_><<<(unsigned)cdiv(dv.n, 128), 128, 0, s>>>(dv, fa);
+  return cudaGetLastError();
+}
+template <> cudaError_t launch_freeze_advance<D_, M_>(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa) {
+  freeze_advance_kernel<D_><<<(unsigned)cdiv(dv.n, 128), 128, 0, s>>>(dv, fa);
+  return cudaGetLastError();
+}
+template <> cudaError_t launch_freeze_interpolate<D_, M_>(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa, double efcheck, double taup,
+                                                          double taupp, double dt) {
+  freeze_interpolate_kernel<D_, M_><<<(unsigned)cdiv(dv.n, 128), 128, 0, s>>>(dv, fa, efcheck, taup, taupp, dt);
+  return cudaGetLastError();
+}
+#if CCB_INST_D == 2 && CCB_INST_MILNE == 1
+cudaError_t launch_freeze_check_status(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa, double time_in, double efcheck) {
+  freeze_check_status_kernel<0><<<(unsigned)cdiv(dv.n, 128), 128, 0, s>>>(dv, fa, time_in, efcheck);
+  return cudaGetLastError();
+}
+#endif
 #if CCB_INST_D == 2
 template <>
 cudaError_t launch_reduce_totals<M_>(int nblocks, cudaStream_t s, const DeviceView& dv, double t, double* out,

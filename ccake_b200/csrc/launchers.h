@@ -29,6 +29,21 @@ cudaError_t launch_eos_chain_init(cudaStream_t s, const DeviceView& dv, const Eo
 cudaError_t launch_eos_query(cudaStream_t s, const EosChain& ch, const ConformalParams* conf, int member, int64_t n, const double* pts, double* out);
 cudaError_t launch_eos_locate(cudaStream_t s, const EosChain& ch, const ConformalParams& conf, int use_chain, int energy, int64_t n,
                               const double* dens, const double* seed, const int32_t* start, double* thermo, int32_t* eos_out);
+// pre-inverted EoS (eos_preinverted.cuh): phase 04 lookup, initial location on the flat table, tile generator
+struct PreTable;
+struct PreFlat;
+cudaError_t launch_pre_fill(cudaStream_t s, const DeviceView& dv, const PreTable& tb);
+cudaError_t launch_pre_init(cudaStream_t s, const DeviceView& dv, const PreFlat& fl, const double* tmp, int input_as_entropy);
+cudaError_t launch_pre_generate(cudaStream_t s, const EosChain& ch, const ConformalParams& conf, int use_chain, const int32_t exponent[4], int N,
+                                double* vars, int32_t* eos);
+// freeze-out (freeze_out.cuh)
+struct FreezeArrays;
+cudaError_t launch_freeze_check_status(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa, double time_in, double efcheck);
+template <int D, bool MILNE> cudaError_t launch_freeze_snapshot(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa, int which);
+template <int D, bool MILNE> cudaError_t launch_freeze_evo(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa);
+template <int D, bool MILNE> cudaError_t launch_freeze_advance(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa);
+template <int D, bool MILNE>
+cudaError_t launch_freeze_interpolate(cudaStream_t s, const DeviceView& dv, const FreezeArrays& fa, double efcheck, double taup, double taupp, double dt);
 template <bool MILNE>
 cudaError_t launch_reduce_totals(int nblocks, cudaStream_t s, const DeviceView& dv, double t, double* out,
                                  unsigned long long* nfrozen);

@@ -55,6 +55,7 @@ struct DeviceView {
   int32_t* tasks;              // gather tasks in cell order: first particle of every chunk of <= NT particles of one cell
   int32_t* ntasks;
   int32_t* err;                // [0] status code, [1] first offending particle id
+  int eos_type_is_table;       // the run's EoS chain starts with the table (thermodynamic_info::eos_type_is_table of member 0)
   // slab decomposition: the cell columns (index along x) just outside this rank's slab hold GHOST records,
   // appended to rec_fields / rec_grad behind the n own records; ghost_start[s][c] .. [c + 1] is the record range
   // of cell c of that column (c = y * nz + z). ghost_col = -1: no neighbour on that side.

@@ -125,6 +125,9 @@ def to_config(settings: dict, device: int = 0, rank: int = 0, nranks: int = 1) -
     c.prohibit_acausal_cs2 = int(bool(s["prohibit_acausal_cs2"]))
     c.restrict_mu_T_ratios = int(bool(s["restrict_mu_T_ratios"]))
     c.device, c.rank, c.nranks = int(device), int(rank), int(nranks)
+    c.particlization_enabled = int(bool(s.get("particlization_enabled", False)))
+    c.dt = float(s["dt"])
+    c.online_inverter_enabled = int(bool(s.get("online_inverter_enabled", True)))
     c.slab_axis = int(s.get("slab_axis", 0))
     return c
 

@@ -62,6 +62,47 @@ class SPHWorkstation:
                 path = os.path.join(str(self.settings["eos_path"]), "thermo.dat")
                 self._check(self._L.ccb_load_eos_table_dat(self._ctx, path.encode(), int(bool(self.settings["normalize_by_T"]))))
 
+        if not self.settings.get("online_inverter_enabled", True):
+            # SPHWorkstation::initialize -> EoS_Interpolator(preinverted_eos_path), src/sph_workstation.cpp:47-58
+            flat, tiles = self.settings.get("preinverted_flat"), self.settings.get("preinverted_tiles")
+            if flat is not None:
+                self.set_preinverted_flat(flat)
+            elif tiles is not None:
+                self.set_preinverted_table(tiles)
+
+    # -- pre-inverted EoS (EoS_Interpolator) --------------------------------------------
+    def set_preinverted_table(self, tiles):
+        """TILED table: list of dicts exponent[4], min[4], step[4], vars (11, N0, N1, N2, N3) (ccake_b200.eos_preinverted)."""
+        arr = (_capi.PreTile * len(tiles))()
+        keep = []
+        for k, t in enumerate(tiles):
+            v = np.ascontiguousarray(t["vars"], dtype=np.float64)
+            keep.append(v)
+            for i in range(4):
+                arr[k].slot[i] = int(t["exponent"][i]) + 3
+                arr[k].min[i], arr[k].step[i] = float(t["min"][i]), float(t["step"][i])
+                arr[k].N[i] = int(v.shape[1 + i])
+                arr[k].log_spacing[i] = int(bool(t.get("log_spacing", (0, 0, 0, 0))[i]))
+            arr[k].vars = _dp(v)
+        self._check(self._L.ccb_set_preinverted_table(self._ctx, len(tiles), arr))
+
+    def set_preinverted_flat(self, flat):
+        """FLAT (s, nB) table as the file holds it (MeV units): dict of (Ns, NB) arrays s nB T muB muS muQ e p cs2 chiTT chiTB chiBB."""
+        f = _capi.PreFlat()
+        keep = {k: np.ascontiguousarray(flat[k], dtype=np.float64) for k in ("s", "nB", "T", "muB", "muS", "muQ", "e", "p", "cs2", "chiTT", "chiTB", "chiBB")}
+        f.Ns, f.NB = keep["s"].shape
+        for k, v in keep.items():
+            setattr(f, k, _dp(v))
+        self._check(self._L.ccb_set_preinverted_flat(self._ctx, C.byref(f)))
+
+    def generate_preinverted_tile(self, exponent, N=20):
+        """utilities/generate_eos_table.cpp for one decade tile, on the device: ((11, N, N, N, N) fields, (N, N, N, N) answering EoS)."""
+        ex = (C.c_int32 * 4)(*[int(e) for e in exponent])
+        v = np.empty((11, N, N, N, N), dtype=np.float64)
+        eos = np.empty((N, N, N, N), dtype=np.int32)
+        self._check(self._L.ccb_generate_preinverted_tile(self._ctx, ex, int(N), _dp(v), eos.ctypes.data_as(C.POINTER(C.c_int32))))
+        return v, eos
+
     def eos_chain_parameters(self):
         """Matched parameters of the fall-back EoSs + efcheck (table runs; EquationOfState::set_up_chosen_EOSs)."""
         out = np.zeros(18)
@@ -303,6 +344,20 @@ class SPHWorkstation:
         if rk_order is not None and rk_order != self._cfg.rk_order:
             raise ValueError("rk_order is fixed at context creation")
         self._check(self._L.ccb_step(self._ctx, float(dt)))
+
+    def freeze_out_particles(self):
+        """SPHWorkstation::freeze_out_particles: status machine + hypersurface interpolation; returns the particles frozen out now.
+        (advance_timestep calls it itself when settings['particlization_enabled'].)"""
+        k = C.c_int64()
+        self._check(self._L.ccb_freeze_out(self._ctx, C.byref(k)))
+        return k.value
+
+    def freeze_out_results(self):
+        """FreezeOut::results of every particle ((n, 64) at the CCB_FO_* offsets, particle-id order) and the print flags (n,)."""
+        n = self.n_particles
+        res = np.zeros((n, 64)); pr = np.zeros(n, dtype=np.int32)
+        self._check(self._L.ccb_freeze_out_results(self._ctx, _dp(res), pr.ctypes.data_as(C.POINTER(C.c_int32))))
+        return res, pr.astype(bool)
 
     def synchronize(self):
         self._check(self._L.ccb_synchronize(self._ctx))

@@ -80,6 +80,11 @@ typedef struct {
   /* runtime */
   int device;              /* CUDA device ordinal */
   int rank, nranks;        /* slab decomposition (1 process per GPU) */
+  int particlization_enabled; /* Settings::particlization_enabled: ccb_step ends with SPHWorkstation::freeze_out_particles (src/sph_workstation.cpp:2063) */
+  double dt;               /* Settings::dt: the freeze-out interpolation steps back by it for particles without neighbours (include/freeze_out.h:717) */
+  int online_inverter_enabled; /* Settings::online_inverter_enabled (include/defaults.h:15): 1 = phase 04 inverts the EoS per particle
+                              (conformal closed form / table root search); 0 = phase 04 is a lookup in a PRE-INVERTED table
+                              (EoS_Interpolator::fill_thermodynamics), set with ccb_set_preinverted_table / ccb_set_preinverted_flat */
   int slab_axis;           /* spatial axis the slabs cut: 0 = x (default), 1 = y, 2 = eta / z (3+1D). The neighbour-grid cell key is
                               ordered with this axis slowest, so that a slab's edge column is one contiguous range of the sorted order */
 } ccb_config;
@@ -186,6 +191,35 @@ int ccb_load_eos_table_dat(ccb_ctx* ctx, const char* path, int normalize_by_T);
  * conformal, out[12..16] conformal_diagonal; out[17] = efcheck (src/sph_workstation.cpp:66-81) */
 int ccb_eos_chain_parameters(ccb_ctx* ctx, double out[18]);
 
+/* --- pre-inverted equation of state (online_inverter_enabled = 0; EoS_Interpolator, include/eos_interpolator.h:45-163) ----------
+ * The reference reads these tables from HDF5 (src/eos_interpolator.cpp:16-521); here they arrive as arrays, and
+ * ccb_generate_preinverted_tile produces them on the device with the run's own inversion kernel (utilities/generate_eos_table.cpp).
+ * TILED format: one tile per decade of (s, |rhoB|, |rhoS|, |rhoQ|), slot = exponent + 3 in [0,5) x [0,4)^3; every tile has its own
+ * axes (min, step, N; a log-spaced axis stores log10 of the physical value) and 11 fields in the order of ccake::eos_variables
+ * (T muB muQ muS e p cs2 dwds dwdB dwdQ dwdS), each N[0] x N[1] x N[2] x N[3] with the rhoQ index fastest.
+ * FLAT format (src/eos_interpolator.cpp:262-521): ONE (s, nB) table, log-spaced in both, S and Q degenerate, handed over as the
+ * file holds it (MeV units; s, nB as 2-D arrays [Ns][NB]); the library applies the loader's unit conversion and derives dw/ds,
+ * dw/dB from chiTT, chiTB, chiBB as the loader does. Only the flat format serves a whole run (initialisation and efcheck:
+ * query_thermo_host, invert_e_to_s_host, efreeze_at_T are flat-only in the reference); tiles serve ccb_update_thermodynamics. */
+typedef struct {
+  int32_t slot[4];
+  double min[4], step[4];
+  int32_t N[4];
+  int32_t log_spacing[4];
+  const double* vars;      /* 11 x N[0] x N[1] x N[2] x N[3] */
+} ccb_preinverted_tile;
+typedef struct {
+  int32_t Ns, NB;
+  const double *s, *nB;                               /* [Ns][NB], MeV^3 */
+  const double *T, *muB, *muS, *muQ, *e, *p, *cs2;    /* MeV, MeV^4, dimensionless */
+  const double *chiTT, *chiTB, *chiBB;                /* MeV^2 */
+} ccb_preinverted_flat;
+int ccb_set_preinverted_table(ccb_ctx* ctx, int32_t ntiles, const ccb_preinverted_tile* tiles);
+int ccb_set_preinverted_flat(ccb_ctx* ctx, const ccb_preinverted_flat* table);
+/* one decade tile of N^4 nodes (the reference generator uses N = 20): vars[11][N^4] as ccb_preinverted_tile::vars wants them, eos[N^4] =
+ * answering member of chosen_EOSs, -1 (and NaN fields) where the reference's generator aborts ("EoS root-finding failed") */
+int ccb_generate_preinverted_tile(ccb_ctx* ctx, const int32_t exponent[4], int32_t N, double* vars, int32_t* eos);
+
 /* --- host queries of the equation of state (EquationOfState / EoS_base surface, include/eos.h:62-210, include/eos_base.h:12-50) ---
  * Batched and evaluated on the device; all arrays are caller-owned HOST arrays, row-major; both calls synchronise.
  * ccb_eos_full_thermo: EoS_base::get_full_thermo of member `member` of chosen_EOSs (0 = the run's default EoS) at n points
@@ -270,6 +304,24 @@ int ccb_get_time_derivatives(ccb_ctx* ctx); /* all of the above in order */
 int ccb_step(ccb_ctx* ctx, double dt);
 int ccb_synchronize(ccb_ctx* ctx);        /* waits for the stream and surfaces device-side error flags */
 int ccb_reduce(ccb_ctx* ctx, ccb_totals* out);
+
+/* --- freeze-out (include/freeze_out.h:165-933) ---------------------------------------------------------------------------------
+ * ccb_freeze_out = SPHWorkstation::freeze_out_particles (src/sph_workstation.cpp:1475-1485): FreezeOut::check_freeze_out_status (the
+ * 0 -> 1 -> 3 status machine on e <= efcheck) + FreezeOut::bsqsvfreezeout (snapshot bookkeeping of the last two time steps and of the
+ * back-up steps of particles that are losing their neighbours; hypersurface interpolation of every particle that reached status 3,
+ * which then becomes 4). ccb_step calls it itself when particlization_enabled; ccb_upload_ic runs the initial status check
+ * (SPHWorkstation::initial_smoothing, :450-452). n_freezing_out = particles frozen out by this call.
+ * ccb_freeze_out_results: the reference's `results` record (ResultsTypes, include/freeze_out.h:35-49) of every particle, particle-id
+ * order, CCB_FO_ROW doubles per particle at the CCB_FO_* offsets; print[id] = 1 for the particles frozen out by the LAST call (the rows
+ * Output::print_freeze_out writes). Single-context runs only. */
+enum {
+  CCB_FO_SHEARSUB = 0, CCB_FO_DIFFOUT = 16, CCB_FO_DIVT = 28, CCB_FO_DIVE = 31, CCB_FO_DIVP = 34, CCB_FO_RSUB = 37, CCB_FO_UOUT = 40,
+  CCB_FO_DIVTTEMP = 43, CCB_FO_DIVPPRESS, CCB_FO_DIVEENER, CCB_FO_GSUB, CCB_FO_BULKSUB, CCB_FO_THETASUB, CCB_FO_SWSUB, CCB_FO_SHEAR33SUB,
+  CCB_FO_TLIST, CCB_FO_SFO, CCB_FO_EFLUC, CCB_FO_TFLUC, CCB_FO_MUBFLUC, CCB_FO_MUSFLUC, CCB_FO_MUQFLUC, CCB_FO_CS2FZFLUC, CCB_FO_WFZFLUC,
+  CCB_FO_RHOBFLUC, CCB_FO_RHOSFLUC, CCB_FO_RHOQFLUC, CCB_FO_EOS_TYPE, CCB_FO_ROW = 64
+};
+int ccb_freeze_out(ccb_ctx* ctx, int64_t* n_freezing_out);
+int ccb_freeze_out_results(ccb_ctx* ctx, double* results, int32_t* print);
 
 /* --- instrumentation ------------------------------------------------------ */
 /* number of kernels launched by this context since creation, and device time (ms) per

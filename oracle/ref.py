@@ -88,7 +88,8 @@ SETTING_KEYS = frozenset([
     "lambda_Pipi_mode", "phi1_mode", "phi3_mode", "diffusionMode", "diffusionRelaxMode", "print_conservation_status",
     "prohibit_unstable_cs2", "prohibit_acausal_cs2", "restrict_mu_T_ratios", "C_B", "critical_scaling_bulk", "critical_scaling_diffusion",
     "critical_point_T", "critical_point_muB", "critical_gaussian_width_T", "critical_gaussian_width_muB", "diffusion_regulator_enabled",
-    "diffusion_regulator_chi0", "diffusion_regulator_e0", "diffusion_regulator_xi0", "diffusion_regulator_rq_max"])
+    "diffusion_regulator_chi0", "diffusion_regulator_e0", "diffusion_regulator_xi0", "diffusion_regulator_rq_max",
+    "online_inverter_enabled", "preinverted_eos_path", "particlization_enabled"])
 
 
 def available() -> bool:
@@ -113,6 +114,15 @@ def lib():
         L.ccake_ref_allocate_raw.argtypes = [C.c_void_p, C.c_long]
         L.ccake_ref_advance.argtypes = [C.c_void_p, C.c_double, C.c_int]
         L.ccake_ref_advance_par04.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.ccake_ref_h5_reset.argtypes = [C.c_char_p]
+        L.ccake_ref_h5_reset.restype = None
+        L.ccake_ref_h5_put_dataset.argtypes = [C.c_char_p, C.c_char_p, dp, C.c_int, lp]
+        L.ccake_ref_h5_put_attr.argtypes = [C.c_char_p, C.c_char_p, C.c_double]
+        L.ccake_ref_interp_fill.argtypes = [C.c_char_p, C.c_long, dp, dp]
+        L.ccake_ref_interp_query.argtypes = [C.c_char_p, C.c_int, C.c_long, dp, dp, dp, ip, C.c_double, dp]
+        L.ccake_ref_eos_update_s.argtypes = [C.c_void_p, C.c_long, dp, dp, dp, ip]
+        L.ccake_ref_freeze_out.argtypes = [C.c_void_p]
+        L.ccake_ref_freeze_results.argtypes = [C.c_void_p, dp, ip]
         L.ccake_ref_set_threads.argtypes = [C.c_int]
         L.ccake_ref_set_threads.restype = None
         L.ccake_ref_profile_report.argtypes = [C.c_char_p, C.c_long]
@@ -163,6 +173,57 @@ def profile_table() -> dict:
             except ValueError:
                 pass
     return out
+
+
+# ---- pre-inverted EoS tables for the reference's EoS_Interpolator (in-memory HDF5 stand-in, oracle/shim/H5Cpp.h) ----------
+PRE_VARS = ["T", "muB", "muQ", "muS", "e", "p", "cs2", "dwds", "dwdB", "dwdQ", "dwdS"]   # ccake::eos_variables order
+
+
+def _put(path, name, arr):
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    dims = (C.c_long * a.ndim)(*a.shape)
+    assert lib().ccake_ref_h5_put_dataset(path.encode(), name.encode(), _dp(a), a.ndim, dims) == 0
+
+
+def h5_put_tiles(path, tiles):
+    """Register a TILED pre-inverted table (the groups utilities/generate_eos_table.cpp writes: table_<es>_<eB>_<eS>_<eQ> with the
+    axis attributes and one dataset per field) under `path`. tiles: list of dicts exponent[4], min[4], max[4], step[4], vars[11, N0..N3]."""
+    lib().ccake_ref_h5_reset(path.encode())
+    for t in tiles:
+        g = "table_%d_%d_%d_%d" % tuple(t["exponent"])
+        for k, ax in enumerate(("s", "rhoB", "rhoS", "rhoQ")):
+            for what, key in (("%s_min" % ax, "min"), ("%s_max" % ax, "max"), (("ds" if ax == "s" else "d" + ax), "step")):
+                assert lib().ccake_ref_h5_put_attr(path.encode(), ("%s@%s" % (g, what)).encode(), float(t[key][k])) == 0
+            assert lib().ccake_ref_h5_put_attr(path.encode(), ("%s@%s_Axis" % (g, ax)).encode(), float(k)) == 0
+        for v, name in enumerate(PRE_VARS):
+            _put(path, g + "/" + name, t["vars"][v])
+
+
+def h5_put_flat(path, flat):
+    """Register a FLAT (s, nB) table (src/eos_interpolator.cpp:262-340): /dimensions + /data/<field> 2-D datasets, MeV units."""
+    lib().ccake_ref_h5_reset(path.encode())
+    Ns, NB = flat["s"].shape
+    _put(path, "dimensions", np.array([Ns, NB], dtype=np.float64))
+    for k in ("s", "nB", "T", "muB", "muS", "muQ", "e", "p", "cs2", "chiTT", "chiTB", "chiBB"):
+        _put(path, "data/" + k, flat[k])
+
+
+def interp_fill(path, dens):
+    """EoS_Interpolator::fill_thermodynamics on probe particles: dens (n, 4) = s, rhoB, rhoS, rhoQ -> thermo (n, 31)."""
+    d = np.ascontiguousarray(dens, dtype=np.float64).reshape(-1, 4)
+    out = np.zeros((d.shape[0], 31))
+    lib().ccake_ref_interp_fill(path.encode(), d.shape[0], _dp(d), _dp(out))
+    return out
+
+
+def interp_query(path, a, rhoB, energy=False, T_fo=150.0 / 197.3269804):
+    """query_thermo_host (a = s) / invert_e_to_s_host (a = e) of the flat table -> ((n, 12) T muB muS muQ e p cs2 s rhoB w dwds dwdB,
+    ok (n,), efreeze_at_T(T_fo))."""
+    a = np.ascontiguousarray(a, dtype=np.float64); b = np.ascontiguousarray(rhoB, dtype=np.float64)
+    out = np.zeros((a.size, 12)); ok = np.zeros(a.size, dtype=np.int32); ef = C.c_double()
+    lib().ccake_ref_interp_query(path.encode(), int(bool(energy)), a.size, _dp(a), _dp(b), _dp(out), ok.ctypes.data_as(C.POINTER(C.c_int)),
+                                 float(T_fo), C.byref(ef))
+    return out, ok.astype(bool), ef.value
 
 
 def _dp(a):
@@ -304,6 +365,25 @@ class RefSim:
         if rc:
             raise KeyError(name)
         return out
+
+    def eos_update_s(self, dens, seed):
+        """EquationOfState::tbqs(seed, "default") + update_s(dens) + set_thermo per row, as utilities/generate_eos_table.cpp:295-311
+        does per node: dens (n, 4) = s, rhoB, rhoS, rhoQ; seed (n, 4) = T, muB, muQ, muS -> (thermo (n, 31), ok (n,))."""
+        d = np.ascontiguousarray(dens, dtype=np.float64).reshape(-1, 4)
+        sd = np.ascontiguousarray(seed, dtype=np.float64).reshape(-1, 4)
+        out = np.zeros((d.shape[0], 31)); ok = np.zeros(d.shape[0], dtype=np.int32)
+        lib().ccake_ref_eos_update_s(self.h, d.shape[0], _dp(d), _dp(sd), _dp(out), ok.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, ok.astype(bool)
+
+    def freeze_out(self):
+        """SPHWorkstation::freeze_out_particles (advance() calls it itself when particlization_enabled)."""
+        lib().ccake_ref_freeze_out(self.h)
+
+    def freeze_results(self):
+        """FreezeOut::results: (n, 64) rows in ResultsTypes member order (= the CCB_FO_* offsets), print flags (n,)."""
+        out = np.zeros((self.n, 64)); pr = np.zeros(self.n, dtype=np.int32)
+        lib().ccake_ref_freeze_results(self.h, _dp(out), pr.ctypes.data_as(C.POINTER(C.c_int)))
+        return out, pr.astype(bool)
 
     def totals(self):
         out = np.zeros(6)

@@ -24,6 +24,9 @@
 #include "system_state.h"
 #include "settings.h"
 #include "phase_profiler.h"
+#include "eos_interpolator.h"
+
+#include <fstream>
 
 using namespace ccake;
 
@@ -51,6 +54,9 @@ struct RefBase {
   virtual int totals(double* out) = 0;
   virtual int eos_names(int* out) = 0;
   virtual int eos_thermo(const char* name, long n, const double* points, double* out17) = 0;
+  virtual int eos_update_s(long n, const double* dens, const double* seed, double* thermo31, int* ok) = 0;
+  virtual int freeze_out() = 0;
+  virtual int freeze_results(double* out64, int* print) = 0;
 };
 
 template <unsigned int D, template <unsigned int> class TEOM>
@@ -137,6 +143,41 @@ struct Ref : RefBase {
   }
   int get_time_derivatives() override { ws->get_time_derivatives(st->dt); return 0; }
   int advance(double dt, int rk) override { ws->advance_timestep(dt, rk); return 0; }
+  // SPHWorkstation::freeze_out_particles (src/sph_workstation.cpp:1475-1485) and FreezeOut::results (include/freeze_out.h:35-49),
+  // one row of 64 doubles per particle in the member order of ResultsTypes, + the print flags
+  int freeze_out() override { ws->freeze_out_particles(); return 0; }
+  int freeze_results(double* out, int* print) override {
+    auto& r = ws->freezePtr->results;
+    FRZ_RESULTS_VIEW(r_, r);
+    const long np = n();
+    for (long i = 0; i < np; ++i) {
+      double* o = out + 64 * i;
+      for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) o[a * 4 + b] = r_shearsub(i, a, b);
+      for (int c = 0; c < 3; ++c) for (int m = 0; m < 4; ++m) o[16 + c * 4 + m] = r_diffout(i, c, m);
+      for (int d = 0; d < 3; ++d) { o[28 + d] = r_divT(i, d); o[31 + d] = r_divE(i, d); o[34 + d] = r_divP(i, d); o[37 + d] = r_rsub(i, d); o[40 + d] = r_uout(i, d); }
+      o[43] = r_divTtemp(i); o[44] = r_divPpress(i); o[45] = r_divEener(i); o[46] = r_gsub(i); o[47] = r_bulksub(i); o[48] = r_thetasub(i);
+      o[49] = r_swsub(i); o[50] = r_shear33sub(i); o[51] = r_tlist(i); o[52] = r_sFO(i); o[53] = r_Efluc(i); o[54] = r_Tfluc(i);
+      o[55] = r_muBfluc(i); o[56] = r_muSfluc(i); o[57] = r_muQfluc(i); o[58] = r_cs2fzfluc(i); o[59] = r_wfzfluc(i);
+      o[60] = r_rhoBfluc(i); o[61] = r_rhoSfluc(i); o[62] = r_rhoQfluc(i); o[63] = r_eos_type(i);
+      print[i] = r_print(i) ? 1 : 0;
+    }
+    return 0;
+  }
+  // One node of utilities/generate_eos_table.cpp:295-311: tbqs(seed, "default"), update_s(densities), set_thermo
+  int eos_update_s(long n, const double* dens, const double* seed, double* thermo31, int* ok) override {
+    if (!eos_probe) { eos_probe.reset(new EquationOfState()); eos_probe->set_SettingsPtr(st); eos_probe->init(); }
+    for (long i = 0; i < n; ++i) {
+      eos_probe->tbqs(seed[4 * i], seed[4 * i + 1], seed[4 * i + 2], seed[4 * i + 3], "default");
+      ok[i] = eos_probe->update_s(dens[4 * i], dens[4 * i + 1], dens[4 * i + 2], dens[4 * i + 3], false) ? 1 : 0;
+      thermodynamic_info t;
+      if (ok[i]) eos_probe->set_thermo(t);
+      const double v[31] = {t.T, t.muB, t.muS, t.muQ, t.e, t.s, t.rhoB, t.rhoS, t.rhoQ, t.p, t.cs2, t.w, t.dwds, t.dwdB, t.dwdS, t.dwdQ,
+                            t.dalpha_Bds, t.dalpha_BdB, t.dalpha_BdS, t.dalpha_BdQ, t.dalpha_Sds, t.dalpha_SdB, t.dalpha_SdS, t.dalpha_SdQ,
+                            t.dalpha_Qds, t.dalpha_QdB, t.dalpha_QdS, t.dalpha_QdQ, t.chiBB, t.chiBB0, t.eos_type_is_table};
+      for (int k = 0; k < 31; ++k) thermo31[31 * i + k] = v[k];
+    }
+    return 0;
+  }
   // ---- the reference's step with phase 04 OpenMP-parallelised -------------------------------------
   // As shipped, update_all_particle_thermodynamics (src/sph_workstation.cpp:1737-1762) is a SERIAL host loop over
   // systemPtr->particles between copy_thermo_device_to_host / copy_thermo_host_to_device. This variant runs the same loop
@@ -293,6 +334,9 @@ std::shared_ptr<Settings> parse_settings(const char* kv) {
     else if (k == "eos_type") s->eos_type = v;
     else if (k == "eos_path") s->eos_path = v;
     else if (k == "normalize_by_T") s->normalize_by_T = to_bool(v);
+    else if (k == "online_inverter_enabled") s->online_inverter_enabled = to_bool(v);
+    else if (k == "particlization_enabled") s->particlization_enabled = to_bool(v);
+    else if (k == "preinverted_eos_path") s->preinverted_eos_path = v;
     else if (k == "Freeze_Out_Temperature") s->Freeze_Out_Temperature = std::stod(v);
     else if (k == "baryon_charge_enabled") s->baryon_charge_enabled = to_bool(v);
     else if (k == "strange_charge_enabled") s->strange_charge_enabled = to_bool(v);
@@ -386,6 +430,60 @@ int ccake_ref_totals(void* h, double* out) { return static_cast<RefBase*>(h)->to
 int ccake_ref_eos_names(void* h, int* out) { return static_cast<RefBase*>(h)->eos_names(out); }
 int ccake_ref_eos_thermo(void* h, const char* name, long n, const double* points, double* out17) {
   return static_cast<RefBase*>(h)->eos_thermo(name, n, points, out17);
+}
+// ---- pre-inverted EoS (EoS_Interpolator, src/eos_interpolator.cpp): tables are handed over as arrays into the in-memory HDF5
+// stand-in of oracle/shim/H5Cpp.h; the reference's own loader, interpolator and host queries then run unmodified -------------
+void ccake_ref_h5_reset(const char* path) {
+  h5shim::registry()[path] = std::make_shared<h5shim::File>();
+  std::ofstream touch(path);   // EoS_Interpolator's constructor checks std::filesystem::exists(path)
+}
+int ccake_ref_h5_put_dataset(const char* path, const char* name, const double* data, int ndim, const long* dims) {
+  auto it = h5shim::registry().find(path);
+  if (it == h5shim::registry().end()) return 1;
+  size_t n = 1;
+  std::vector<hsize_t> d;
+  for (int k = 0; k < ndim; ++k) { n *= (size_t)dims[k]; d.push_back((hsize_t)dims[k]); }
+  it->second->dsets[name].assign(data, data + n);
+  it->second->dims[name] = d;
+  return 0;
+}
+int ccake_ref_h5_put_attr(const char* path, const char* group_at_name, double value) {
+  auto it = h5shim::registry().find(path);
+  if (it == h5shim::registry().end()) return 1;
+  it->second->attrs[group_at_name] = value;
+  return 0;
+}
+// EoS_Interpolator::fill_thermodynamics on n probe particles: dens[n][4] = (s, rhoB, rhoS, rhoQ) -> thermo[n][31] (thermo_info order)
+int ccake_ref_interp_fill(const char* path, long n, const double* dens, double* thermo) {
+  ccake::EoS_Interpolator interp{std::filesystem::path(path)};
+  Cabana::AoSoA<ccake::CabanaParticle, DeviceType, VECTOR_LENGTH> p("probe", (size_t)n);
+  auto th = Cabana::slice<ccake::particle_info::thermo_scalar_info>(p);
+  for (long i = 0; i < n; ++i) {
+    for (int k = 0; k < 31; ++k) th(i, k) = 0.0;
+    th(i, ccake::thermo_info::s) = dens[4 * i]; th(i, ccake::thermo_info::rhoB) = dens[4 * i + 1];
+    th(i, ccake::thermo_info::rhoS) = dens[4 * i + 2]; th(i, ccake::thermo_info::rhoQ) = dens[4 * i + 3];
+  }
+  interp.fill_thermodynamics(p, 1.0);
+  for (long i = 0; i < n; ++i) for (int k = 0; k < 31; ++k) thermo[31 * i + k] = th(i, k);
+  return 0;
+}
+// host queries of the flat table: mode 0 = query_thermo_host(a = s, rhoB), 1 = invert_e_to_s_host(a = e, rhoB);
+// out[n][12] = T muB muS muQ e p cs2 s rhoB w dwds dwdB, ok[n]; *efreeze = efreeze_at_T(T_fo)
+int ccake_ref_interp_query(const char* path, int mode, long n, const double* a, const double* rhoB, double* out, int* ok, double T_fo, double* efreeze) {
+  ccake::EoS_Interpolator interp{std::filesystem::path(path)};
+  for (long i = 0; i < n; ++i) {
+    ccake::thermodynamic_info t;
+    ok[i] = mode ? interp.invert_e_to_s_host(a[i], rhoB[i], t) : interp.query_thermo_host(a[i], rhoB[i], t);
+    const double v[12] = {t.T, t.muB, t.muS, t.muQ, t.e, t.p, t.cs2, t.s, t.rhoB, t.w, t.dwds, t.dwdB};
+    for (int k = 0; k < 12; ++k) out[12 * i + k] = v[k];
+  }
+  if (efreeze) *efreeze = interp.efreeze_at_T(T_fo);
+  return 0;
+}
+int ccake_ref_freeze_out(void* h) { return static_cast<RefBase*>(h)->freeze_out(); }
+int ccake_ref_freeze_results(void* h, double* out64, int* print) { return static_cast<RefBase*>(h)->freeze_results(out64, print); }
+int ccake_ref_eos_update_s(void* h, long n, const double* dens, const double* seed, double* thermo31, int* ok) {
+  return static_cast<RefBase*>(h)->eos_update_s(n, dens, seed, thermo31, ok);
 }
 int ccake_ref_advance_par04(void* h, double dt, int rk) { return static_cast<RefBase*>(h)->advance_par04(dt, rk); }
 int ccake_ref_omp_threads() { return omp_get_max_threads(); }

@@ -53,7 +53,7 @@ inline void fence(const std::string&) {}
 
 // math
 using std::sqrt; using std::pow; using std::fabs; using std::abs; using std::exp;
-using std::log; using std::floor; using std::tanh; using std::isfinite;
+using std::log; using std::log10; using std::floor; using std::tanh; using std::isfinite;
 inline float sqrtf(float x) { return std::sqrt(x); }
 template <class T> inline T max(const T& a, const T& b) { return a < b ? b : a; }
 template <class T> inline T min(const T& a, const T& b) { return b < a ? b : a; }
@@ -128,6 +128,19 @@ template <class T, class... P> class View<T*, P...> {
   View(const std::string&, size_t n) : d(std::make_shared<std::vector<T>>(n)) {}
   T& operator()(size_t i) const { return (*d)[i]; }
   size_t extent(int) const { return d->size(); }
+  T* data() const { return d->data(); }
+};
+// rank-4 View (EoS_Interpolator's tables, include/eos_interpolator.h:32-34): LayoutRight, shared storage
+template <class T, class... P> class View<T****, P...> {
+  std::shared_ptr<std::vector<T>> d;
+  size_t n[4] = {0, 0, 0, 0};
+ public:
+  View() : d(std::make_shared<std::vector<T>>()) {}
+  View(const std::string&, size_t n0, size_t n1, size_t n2, size_t n3) : d(std::make_shared<std::vector<T>>(n0 * n1 * n2 * n3)) {
+    n[0] = n0; n[1] = n1; n[2] = n2; n[3] = n3;
+  }
+  T& operator()(size_t i, size_t j, size_t k, size_t l) const { return (*d)[((i * n[1] + j) * n[2] + k) * n[3] + l]; }
+  size_t extent(int a) const { return n[a]; }
   T* data() const { return d->data(); }
 };
 template <class V> inline V create_mirror_view(const V& v) { return v; }

@@ -1,19 +1,17 @@
 // TEST INFRASTRUCTURE ONLY (oracle). Not part of the product path.
 //
 // Force-included (-include) ahead of the reference sources when building
-// oracle/_ref/. It pre-defines the include guards of four reference headers that
-// are OUT OF SCOPE for the hot path (SURVEY.md section 2 rows 10b, 14, 15:
-// freeze_out.h, jets.h, source.h, eos_interpolator.h) and declares inert
+// oracle/_ref/. It pre-defines the include guards of three reference headers that
+// are OUT OF SCOPE for the hot path (SURVEY.md section 2 rows 14, 15:
+// freeze_out.h, jets.h, source.h) and declares inert
 // stand-ins with just the members src/sph_workstation.cpp names, so the hot-path
 // translation units compile unchanged without dragging HDF5 / jets / sources in.
 // Every stand-in aborts if it is ever reached.
 #ifndef CCAKE_ORACLE_OUT_OF_SCOPE_STUBS_H
 #define CCAKE_ORACLE_OUT_OF_SCOPE_STUBS_H
 
-#define FREEZEOUT_H
 #define BBMG_H
 #define SOURCE_H
-#define EOS_INTERPOLATOR_H
 
 #include <Cabana_Core.hpp>
 
@@ -32,16 +30,6 @@ namespace ccake {
   std::abort();
 }
 
-template <unsigned int D> class FreezeOut {
- public:
-  FreezeOut(std::shared_ptr<Settings>, std::shared_ptr<SystemState<D>>) {}
-  // Called unconditionally at the end of initial_smoothing (sph_workstation.cpp:452).
-  // It only moves per-particle freeze flags, which no hot-path field reads, so it
-  // is a no-op here rather than an abort.
-  void check_freeze_out_status(int& count) { count = 0; }
-  void bsqsvfreezeout(int) { oracle_out_of_scope("FreezeOut::bsqsvfreezeout"); }
-};
-
 template <unsigned int D> class BBMG {
  public:
   BBMG() {}
@@ -58,13 +46,5 @@ template <unsigned int D> class Source {
   void advance_sources() { oracle_out_of_scope("Source::advance_sources"); }
 };
 
-class EoS_Interpolator {
- public:
-  explicit EoS_Interpolator(std::filesystem::path) { oracle_out_of_scope("EoS_Interpolator"); }
-  double efreeze_at_T(double) { oracle_out_of_scope("EoS_Interpolator::efreeze_at_T"); }
-  bool query_thermo_host(double, double, thermodynamic_info&) { oracle_out_of_scope("EoS_Interpolator"); }
-  bool invert_e_to_s_host(double, double, thermodynamic_info&) { oracle_out_of_scope("EoS_Interpolator"); }
-  template <class A> void fill_thermodynamics(A&, double) { oracle_out_of_scope("EoS_Interpolator::fill_thermodynamics"); }
-};
 }  // namespace ccake
 #endif

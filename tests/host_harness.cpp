@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "../ccake_b200/csrc/eos_preinverted.cuh"
 #include "../ccake_b200/csrc/stage_params.h"
 
 using namespace ccb;
@@ -214,4 +215,42 @@ int hh_chain_solve(void* hv, int energy, int64_t n, const double* targets, const
   return failures;
 }
 
+}  // extern "C"
+
+// ---- pre-inverted EoS (eos_preinverted.cuh) on the host: the arithmetic of pre_fill_kernel / pre_init_kernel -----------------
+extern "C" {
+// tiles: ntiles x {slot[4], N[4], log[4]} ints, {min[4], step[4]} doubles, vars pointers; dens[n][4] -> out[n][11], ok[n]
+int hh_pre_fill(int ntiles, const int* tile_ints, const double* tile_doubles, const double* const* tile_vars, int flat, int64_t n, const double* dens,
+                double* out, int* ok) {
+  std::vector<PreTile> tiles(kPreTileCount);
+  for (auto& t : tiles) std::memset(&t, 0, sizeof(t));
+  for (int k = 0; k < ntiles; ++k) {
+    const int* ti = tile_ints + 12 * k;
+    PreTile& t = tiles[((ti[0] * 4 + ti[1]) * 4 + ti[2]) * 4 + ti[3]];
+    for (int i = 0; i < 4; ++i) { t.N[i] = ti[4 + i]; t.log_spacing[i] = ti[8 + i]; t.min[i] = tile_doubles[8 * k + i]; t.step[i] = tile_doubles[8 * k + 4 + i]; }
+    t.vars = tile_vars[k];
+  }
+  const PreTable tb{tiles.data(), flat};
+  for (int64_t i = 0; i < n; ++i) ok[i] = pre_fill(tb, dens[4 * i], dens[4 * i + 1], dens[4 * i + 2], dens[4 * i + 3], out + PRE_NVAR * i) ? 1 : 0;
+  return 0;
+}
+// flat-table initialisation queries: arrays[11] = s_axis nB_axis T muB muS muQ e p cs2 dwds dwdB (fm units);
+// mode 0 query_thermo(a = s), 1 invert_e_to_s(a = e) -> out[n][12] = T muB muS muQ e p cs2 s rhoB w dwds dwdB
+int hh_pre_flat_query(int Ns, int NB, const double* const* arrays, int mode, int64_t n, const double* a, const double* rhoB, double* out, int* ok,
+                      double T_fo, double* efreeze) {
+  PreFlat f;
+  f.Ns = Ns; f.NB = NB;
+  f.s_axis = arrays[0]; f.nB_axis = arrays[1]; f.T = arrays[2]; f.muB = arrays[3]; f.muS = arrays[4]; f.muQ = arrays[5];
+  f.e = arrays[6]; f.p = arrays[7]; f.cs2 = arrays[8]; f.dwds = arrays[9]; f.dwdB = arrays[10];
+  f.log_s_min = std::log10(f.s_axis[0]); f.dlog_s = (std::log10(f.s_axis[Ns - 1]) - f.log_s_min) / (Ns - 1);
+  f.log_nB_min = std::log10(f.nB_axis[0]); f.dlog_nB = (std::log10(f.nB_axis[NB - 1]) - f.log_nB_min) / (NB - 1);
+  for (int64_t i = 0; i < n; ++i) {
+    PreThermo q{};
+    ok[i] = (mode ? pre_invert_e_to_s(f, a[i], rhoB[i], q) : pre_query_thermo(f, a[i], rhoB[i], q)) ? 1 : 0;
+    const double v[12] = {q.T, q.muB, q.muS, q.muQ, q.e, q.p, q.cs2, q.s, q.rhoB, q.w, q.dwds, q.dwdB};
+    for (int k = 0; k < 12; ++k) out[12 * i + k] = v[k];
+  }
+  if (efreeze) *efreeze = pre_efreeze_at_T(f, T_fo);
+  return 0;
+}
 }  // extern "C"
