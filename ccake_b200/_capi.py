@@ -97,7 +97,7 @@ _FIELD_NAMES = [
 FIELDS = {name: (i, w) for i, (name, w) in enumerate(_FIELD_NAMES)}
 INT_FIELDS = {"id": 0, "btrack": 1, "freeze": 2, "cell": 3, "eos": 4}
 PHASE_NAMES = ["01_neighbour_list", "02_gamma_velocity", "03_smooth_fields", "04_thermodynamics",
-               "05_08_local_update", "09_smooth_gradients", "10_time_derivatives", "other"]
+               "05_06_08_local_update", "09_smooth_gradients", "10_time_derivatives", "other"]
 
 _lib = None
 
@@ -159,6 +159,15 @@ def lib():
     L.ccb_set_preinverted_table.argtypes = [ctx, C.c_int32, C.POINTER(PreTile)]
     L.ccb_set_preinverted_flat.argtypes = [ctx, C.POINTER(PreFlat)]
     L.ccb_generate_preinverted_tile.argtypes = [ctx, ip, C.c_int32, dp, ip]
+    L.ccb_ic_read.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    L.ccb_ic_file_view.argtypes = [C.c_void_p]
+    L.ccb_ic_file_view.restype = C.POINTER(IC)
+    L.ccb_ic_file_header.argtypes = [C.c_void_p, dp]
+    L.ccb_ic_file_free.argtypes = [C.c_void_p]
+    L.ccb_ic_file_free.restype = None
+    L.ccb_efcheck.argtypes = [ctx, dp]
+    L.ccb_profile_phase_name.argtypes = [C.c_int]
+    L.ccb_profile_phase_name.restype = C.c_char_p
     L.ccb_freeze_out.argtypes = [ctx, C.POINTER(C.c_int64)]
     L.ccb_freeze_out_results.argtypes = [ctx, dp, ip]
     L.ccb_debug_neighbour_list.argtypes = [ctx, C.POINTER(C.c_int64), ip, C.c_int64]
@@ -178,4 +187,4 @@ EXPORTED = ["ccb_create", "ccb_destroy", "ccb_last_error", "ccb_field_width", "c
             "ccb_stream", "ccb_device_field", "ccb_state_width", "ccb_upload_state", "ccb_download_state",
             "ccb_measure_dfma_peak", "ccb_comm_unique_id", "ccb_comm_init", "ccb_comm_init_local", "ccb_set_slab",
             "ccb_grid_geometry", "ccb_migration_counts", "ccb_get_field_device_order", "ccb_get_int_field_device_order",
-            "ccb_debug_neighbour_list", "ccb_freeze_out", "ccb_freeze_out_results", "ccb_set_preinverted_table", "ccb_set_preinverted_flat", "ccb_generate_preinverted_tile", "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]
+            "ccb_debug_neighbour_list", "ccb_profile_phase_count", "ccb_profile_phase_name", "ccb_ic_read", "ccb_ic_file_view", "ccb_ic_file_header", "ccb_ic_file_free", "ccb_efcheck", "ccb_freeze_out", "ccb_freeze_out_results", "ccb_set_preinverted_table", "ccb_set_preinverted_flat", "ccb_generate_preinverted_tile", "ccb_set_eos_table", "ccb_load_eos_table_dat", "ccb_eos_chain_parameters", "ccb_eos_full_thermo", "ccb_eos_locate"]

@@ -1021,14 +1021,6 @@ int install_table(ccb_ctx* ctx, bool normalize_by_T) {
   return CCB_OK;
 }
 
-int upload_id_ordered(ccb_ctx* ctx, const double* host, double* dst_col) {
-  // host (id order) -> staging -> current order
-  CUDA_OK(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
-  LAUNCH(gather_by_id, cdiv(ctx->n, 256), 256, ctx->d_stage, dst_col, ctx->dv.id, ctx->n);
-  CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  return CCB_OK;
-}
-
 }  // namespace
 
 namespace {
@@ -1367,6 +1359,13 @@ int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls) {
   return CCB_OK;
 }
 
+int ccb_profile_phase_count(void) { return PH_COUNT; }
+const char* ccb_profile_phase_name(int phase) {
+  static const char* kName[PH_COUNT] = {"01_neighbour_list", "02_gamma_velocity", "03_smooth_fields", "04_thermodynamics", "05_06_08_local_update",
+                                        "09_smooth_gradients", "10_time_derivatives", "other"};
+  return phase >= 0 && phase < PH_COUNT ? kName[phase] : nullptr;
+}
+
 int ccb_allocate(ccb_ctx* ctx, int64_t n) {
   if (!ctx || n <= 0) return CCB_ERR_INVALID;
   int rc = allocate_particles(ctx, n);
@@ -1381,11 +1380,9 @@ int ccb_set_field(ccb_ctx* ctx, int field, const double* host) {
   if (ctx->comm) { ctx->err = "ccb_set_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
   const int w = kFieldWidth[field];
-  std::vector<double> colbuf(ctx->n);
-  for (int c = 0; c < w; ++c) {
-    for (int64_t i = 0; i < ctx->n; ++i) colbuf[i] = host[i * w + c];
-    if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->dv.f[field] + (int64_t)c * ctx->cap))) return rc;
-  }
+  CUDA_OK(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyHostToDevice, ctx->stream));
+  LAUNCH(gather_rows_by_id, cdiv(ctx->n, 256), 256, ctx->d_stage, w, 0, 1, w, ctx->dv.f[field], ctx->cap, ctx->dv.id, ctx->n);
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));   // the caller's buffer may be pageable and reused at once
   if (field == CCB_F_POSITION) ctx->cells_valid = false;
   return CCB_OK;
 }
@@ -1396,14 +1393,9 @@ int ccb_get_field(ccb_ctx* ctx, int field, double* host) {
   if (ctx->comm) { ctx->err = "ccb_get_field: particle-id ordered access is per GPU; with a slab decomposition use the *_device_order getters and CCB_I_ID"; return CCB_ERR_STATE; }
   if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
   const int w = kFieldWidth[field];
-  std::vector<double> buf((size_t)ctx->n * w);
-  for (int c = 0; c < w; ++c)
-    LAUNCH(scatter_by_id, cdiv(ctx->n, 256), 256, ctx->dv.f[field] + (int64_t)c * ctx->cap, ctx->d_stage + (int64_t)c * ctx->cap, ctx->dv.id, ctx->n);
-  for (int c = 0; c < w; ++c)
-    CUDA_OK(cudaMemcpyAsync(buf.data() + (size_t)c * ctx->n, ctx->d_stage + (int64_t)c * ctx->cap, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  LAUNCH(scatter_rows_by_id, cdiv(ctx->n, 256), 256, ctx->dv.f[field], ctx->cap, w, ctx->d_stage, ctx->dv.id, ctx->n);
+  CUDA_OK(cudaMemcpyAsync(host, ctx->d_stage, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  for (int c = 0; c < w; ++c)
-    for (int64_t i = 0; i < ctx->n; ++i) host[i * w + c] = buf[(size_t)c * ctx->n + i];
   return CCB_OK;
 }
 
@@ -1602,12 +1594,9 @@ int ccb_get_field_device_order(ccb_ctx* ctx, int field, double* host) {
   if (rc) return rc;
   if (field < 0 || field >= CCB_F_COUNT || !host) return CCB_ERR_INVALID;
   const int w = kFieldWidth[field];
-  std::vector<double> buf((size_t)ctx->n * w);
-  for (int c = 0; c < w; ++c)
-    CUDA_OK(cudaMemcpyAsync(buf.data() + (size_t)c * ctx->n, ctx->dv.f[field] + (int64_t)c * ctx->cap, sizeof(double) * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
+  LAUNCH(scatter_rows_by_id, cdiv(ctx->n, 256), 256, ctx->dv.f[field], ctx->cap, w, ctx->d_stage, (const int32_t*)nullptr, ctx->n);
+  CUDA_OK(cudaMemcpyAsync(host, ctx->d_stage, sizeof(double) * (size_t)w * ctx->n, cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  for (int c = 0; c < w; ++c)
-    for (int64_t i = 0; i < ctx->n; ++i) host[i * w + c] = buf[(size_t)c * ctx->n + i];
   return CCB_OK;
 }
 int ccb_get_int_field_device_order(ccb_ctx* ctx, int field, int32_t* host) {
@@ -1674,6 +1663,7 @@ int ccb_debug_neighbour_list(ccb_ctx* ctx, int64_t* offsets, int32_t* idx, int64
   return CCB_OK;
 }
 
+int ccb_efcheck(ccb_ctx* ctx, double* efcheck) { if (!ctx || !efcheck) return CCB_ERR_INVALID; *efcheck = ctx->efcheck; return CCB_OK; }
 int ccb_freeze_out(ccb_ctx* ctx, int64_t* n_freezing_out) { int rc = check_ready(ctx, false); return rc ? rc : do_freeze_out(ctx, n_freezing_out); }
 int ccb_freeze_out_results(ccb_ctx* ctx, double* results, int32_t* print) {
   int rc = check_ready(ctx, false);
@@ -1821,16 +1811,15 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   }
   const int64_t mig0 = ctx->migrated_out + ctx->migrated_in;
   DeviceView& dv = ctx->dv;
-  std::vector<double> colbuf(n);
+  // row-major host arrays go to the device as they are (one copy each) and are split into columns there
+  auto stage_rows = [&](const double* host, int w, int c0, int cstep, int ncols, double* dst, const int32_t* id) -> int {
+    CUDA_OK(cudaMemcpyAsync(ctx->d_stage, host, sizeof(double) * (size_t)w * n, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(gather_rows_by_id, cdiv(n, 256), 256, ctx->d_stage, w, c0, cstep, ncols, dst, cap, id, n);
+    return CCB_OK;
+  };
   // positions, velocities; sph_mass = extensive = 1 (process_initial_conditions, src/sph_workstation.cpp:1229-1340)
-  for (int d = 0; d < ctx->D; ++d) {
-    for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->r[i * 3 + d];
-    CUDA_OK(cudaMemcpyAsync(dv.f[CCB_F_POSITION] + (int64_t)d * cap, colbuf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->u ? ic->u[i * 3 + d] : 0.0;
-    CUDA_OK(cudaMemcpyAsync(dv.f[CCB_F_U] + (int64_t)d * cap, colbuf.data(), sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-  }
+  if ((rc = stage_rows(ic->r, 3, 0, 1, ctx->D, dv.f[CCB_F_POSITION], nullptr))) return rc;
+  if (ic->u) { if ((rc = stage_rows(ic->u, 3, 0, 1, ctx->D, dv.f[CCB_F_U], nullptr))) return rc; }
   for (int c = 0; c < 4; ++c) {
     LAUNCH(fill_kernel, cdiv(n, 256), 256, dv.f[CCB_F_SPH_MASS] + (int64_t)c * cap, 1.0, n);
     LAUNCH(fill_kernel, cdiv(n, 256), 256, dv.f[CCB_F_EXTENSIVE] + (int64_t)c * cap, 1.0, n);
@@ -1844,21 +1833,13 @@ int ccb_upload_ic(ccb_ctx* ctx, const ccb_ic* ic) {
   CUDA_OK(cudaMemsetAsync(ctx->init_tmp, 0, sizeof(double) * 19 * cap, ctx->stream));
   const double* src1[5] = {ic->e_or_s, ic->rhoB, ic->rhoS, ic->rhoQ, ic->bulk};
   for (int k = 0; k < 5; ++k)
-    if (src1[k] && (rc = upload_id_ordered(ctx, src1[k], ctx->init_tmp + (int64_t)k * cap))) return rc;
-  if (ic->shv6) {
-    const int pick[5] = {0, 1, 2, 3, 4};  // xx, xy, x-eta, yy, y-eta of the six-component row
-    for (int c = 0; c < 5; ++c) {
-      for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->shv6[i * 6 + pick[c]];
-      if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->init_tmp + (int64_t)(5 + c) * cap))) return rc;
-    }
-  }
+    if (src1[k] && (rc = stage_rows(src1[k], 1, 0, 1, 1, ctx->init_tmp + (int64_t)k * cap, dv.id))) return rc;
+  // xx, xy, x-eta, yy, y-eta of the six-component row
+  if (ic->shv6 && (rc = stage_rows(ic->shv6, 6, 0, 1, 5, ctx->init_tmp + (int64_t)5 * cap, dv.id))) return rc;
   ctx->init_diffusion = ic->diffusion != nullptr && ctx->cfg.using_diffusion;
-  if (ctx->init_diffusion) {
+  if (ctx->init_diffusion) {   // q^i_a, i = 1..3 of the [charge][mu] rows
     for (int c = 0; c < 3; ++c)
-      for (int d = 0; d < 3; ++d) {
-        for (int64_t i = 0; i < n; ++i) colbuf[i] = ic->diffusion[i * 12 + c * 4 + d + 1];
-        if ((rc = upload_id_ordered(ctx, colbuf.data(), ctx->init_tmp + (int64_t)(10 + c * 3 + d) * cap))) return rc;
-      }
+      if ((rc = stage_rows(ic->diffusion, 12, c * 4 + 1, 1, 3, ctx->init_tmp + (int64_t)(10 + c * 3) * cap, dv.id))) return rc;
   }
   const StageParams sp = make_stage(ctx, 0.0, 0);
   if ((rc = do_init_particles(ctx, sp))) return rc;

@@ -395,6 +395,24 @@ __global__ void scatter_columns_by_id(ColumnList cl, double* __restrict__ stage,
   if (i < n) stage[(int64_t)blockIdx.y * n + id[i]] = cl.col[blockIdx.y][i];
 }
 
+// rows of a row-major host array (staged on the device as src[n][w]) -> `ncols` columns dst + k * stride, in the current particle
+// order: dst[k][i] = src[id[i]][c0 + k * cstep] (id == nullptr: identity). Replaces per-column transposes on the host.
+__global__ void gather_rows_by_id(const double* __restrict__ src, int w, int c0, int cstep, int ncols, double* __restrict__ dst, int64_t stride,
+                                  const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t row = id ? id[i] : i;
+  for (int k = 0; k < ncols; ++k) dst[(int64_t)k * stride + i] = src[row * w + c0 + k * cstep];
+}
+
+// the reverse: `w` columns in the current order -> row-major dst[n][w] in particle-id order
+__global__ void scatter_rows_by_id(const double* __restrict__ src, int64_t stride, int w, double* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t row = id ? id[i] : i;
+  for (int k = 0; k < w; ++k) dst[row * w + k] = src[(int64_t)k * stride + i];
+}
+
 // 16 independent fp64 FMA chains per thread: the DFMA issue-rate ceiling (ccb_measure_dfma_peak)
 __global__ void dfma_peak_kernel(double* out, int iters, double m) {
   double a[16];

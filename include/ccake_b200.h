@@ -110,6 +110,18 @@ typedef struct {
                               holds them (BSQHydro::read_ccake, src/BSQHydro.cpp:261-372); NULL = zeros */
 } ccb_ic;
 
+/* Initial-condition TEXT files at scale (host code, no device involved): BSQHydro::read_ccake (src/BSQHydro.cpp:207-425; format 0:
+ * header "# <ignored> stepx stepy stepEta <ignored> xmin ymin etamin", rows x y eta e|s rhoB rhoS rhoQ ux uy ueta bulk pixx pixy pixeta
+ * piyy piyeta pietaeta [+ 12 currents when with_diffusion]) and BSQHydro::read_ICCING (:84-145; format 1: header "<ignored> stepx stepy
+ * <ignored> xmin ymin", rows x y e rhoB rhoS rhoQ). Parsed in parallel straight into the arrays of a ccb_ic, no Particle objects;
+ * rows at or below e_cutoff [GeV/fm^3] are dropped and disabled charges zeroed as the reference does. The ccb_ic_file owns the arrays. */
+typedef struct ccb_ic_file ccb_ic_file;
+int ccb_ic_read(const char* path, int format, int input_as_entropy, double e_cutoff_GeV, int baryon_charge_enabled, int strange_charge_enabled,
+                int electric_charge_enabled, int with_diffusion, ccb_ic_file** out);
+const ccb_ic* ccb_ic_file_view(const ccb_ic_file* f);
+int ccb_ic_file_header(const ccb_ic_file* f, double header[6]);   /* stepx, stepy, stepEta, xmin, ymin, etamin */
+void ccb_ic_file_free(ccb_ic_file* f);
+
 /* Per-particle fields addressable through ccb_get_field / ccb_set_field.
  * Width = doubles per particle. Names follow the reference members. */
 typedef enum {
@@ -320,6 +332,7 @@ enum {
   CCB_FO_TLIST, CCB_FO_SFO, CCB_FO_EFLUC, CCB_FO_TFLUC, CCB_FO_MUBFLUC, CCB_FO_MUSFLUC, CCB_FO_MUQFLUC, CCB_FO_CS2FZFLUC, CCB_FO_WFZFLUC,
   CCB_FO_RHOBFLUC, CCB_FO_RHOSFLUC, CCB_FO_RHOQFLUC, CCB_FO_EOS_TYPE, CCB_FO_ROW = 64
 };
+int ccb_efcheck(ccb_ctx* ctx, double* efcheck);   /* SystemState::efcheck = e(T_FO, mu = 0) [fm^-4] (SPHWorkstation::initialize, src/sph_workstation.cpp:66-81) */
 int ccb_freeze_out(ccb_ctx* ctx, int64_t* n_freezing_out);
 int ccb_freeze_out_results(ccb_ctx* ctx, double* results, int32_t* print);
 
@@ -329,6 +342,8 @@ int ccb_freeze_out_results(ccb_ctx* ctx, double* results, int32_t* print);
 int64_t ccb_kernel_launches(ccb_ctx* ctx);
 int ccb_profile_enable(ccb_ctx* ctx, int on);
 int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls);
+int ccb_profile_phase_count(void);
+const char* ccb_profile_phase_name(int phase);   /* the CCAKE_PHASE labels of src/sph_workstation.cpp:1543-1582; NULL past the last phase */
 /* fp64 FMA peak (TFLOP/s) of a device from a DFMA micro-benchmark: roofline denominator of the gathers */
 int ccb_measure_dfma_peak(int device, double* tflops);
 void* ccb_stream(ccb_ctx* ctx);           /* cudaStream_t of the context */

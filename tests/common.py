@@ -138,6 +138,45 @@ def harness():
     return C.CDLL(HARNESS_LIB)
 
 
+DROPIN_SRC = os.path.join(ROOT, "tests", "cpp", "dropin_bsqhydro.cpp")
+DROPIN_LIB = os.path.join(ROOT, "tests", "libdropin_bsqhydro.so")
+REFERENCE = "/root/reference"
+
+
+def build_dropin():
+    """The reference's unmodified src/BSQHydro.cpp compiled against include/ccake_dropin/ (tests/cpp/dropin_bsqhydro.cpp).
+    Needs /root/reference; on the GPU box the prebuilt tests/libdropin_bsqhydro.so is used. The include path is an overlay
+    directory: the drop-in headers + links to the reference headers they do not replace (a quoted #include looks next to the
+    including file first, so the reference's own include/ cannot simply come second on the path)."""
+    if not os.path.isdir(os.path.join(REFERENCE, "src")):
+        return os.path.exists(DROPIN_LIB)
+    dropin = os.path.join(ROOT, "include", "ccake_dropin")
+    lib = os.path.join(ROOT, "ccake_b200", "libccake_b200.so")
+    srcs = [DROPIN_SRC, lib, os.path.join(ROOT, "include", "ccake_b200.h"), os.path.join(ROOT, "oracle", "settings_kv.h")] + \
+        [os.path.join(dropin, f) for f in os.listdir(dropin)]
+    if os.path.exists(DROPIN_LIB) and all(os.path.getmtime(x) <= os.path.getmtime(DROPIN_LIB) for x in srcs):
+        return True
+    overlay = os.path.join(ROOT, "tests", "cpp", "build", "include")
+    if os.path.isdir(overlay):
+        for f in os.listdir(overlay):
+            os.unlink(os.path.join(overlay, f))
+    os.makedirs(overlay, exist_ok=True)
+    ours = set(os.listdir(dropin))
+    for f in os.listdir(os.path.join(REFERENCE, "include")):
+        if f not in ours:
+            os.symlink(os.path.join(REFERENCE, "include", f), os.path.join(overlay, f))
+    for f in ours:
+        os.symlink(os.path.join(dropin, f), os.path.join(overlay, f))
+    src_link = os.path.join(ROOT, "tests", "cpp", "build", "src")   # vector.h / matrix.h include "../src/vector.cpp"
+    if not os.path.islink(src_link):
+        os.symlink(os.path.join(REFERENCE, "src"), src_link)
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-w", "-I", overlay, "-I", os.path.join(REFERENCE, "src"),
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "oracle"), "-I", os.path.join(ROOT, "oracle", "shim"),
+                           DROPIN_SRC, os.path.join(REFERENCE, "src", "formatted_output.cpp"), os.path.join(REFERENCE, "src", "particle.cpp"),
+                           "-o", DROPIN_LIB, "-L", os.path.dirname(lib), "-lccake_b200", "-Wl,-rpath,$ORIGIN/../ccake_b200"])
+    return True
+
+
 class EomArrays(C.Structure):
     _fields_ = [(k, C.POINTER(C.c_double)) for k in
                 ("u", "v", "gamma", "sigma", "sigma_lab", "mass_s", "bulk", "shv", "q", "thermo", "dalpha", "gradP",

@@ -53,3 +53,42 @@ def test_synthetic_table_is_thermodynamically_consistent():
     # reference's prohibit_unstable_cs2 / prohibit_acausal_cs2 switches hand the particle to the fall-back EoS)
     core = (T >= 100.0) & (np.abs(B) <= 150.0) & (np.abs(Q) <= 150.0) & (np.abs(S) <= 150.0)
     assert np.all(t["fields"][core, 6] > 0) and np.all(t["fields"][core, 6] < 1.0)
+
+
+def test_parallel_ic_reader_matches_the_line_by_line_reader(tmp_path):
+    """ccb_ic_read (csrc/ic_reader.cpp, host code) against the per-line Python twin of BSQHydro::read_ccake: header, energy cut-off,
+    disabled charges, the twelve diffusion columns, blank and comment lines; and read_ICCING's six-column format."""
+    rng = np.random.default_rng(5)
+    s, ic = W.config2_viscous_gubser_bsq(dx=0.1, xmax=2.0)
+    n = ic["r"].shape[0]
+    ic["diffusion"] = rng.standard_normal((n, 3, 4))
+    ic["bulk"] = rng.standard_normal(n) * 0.01
+    s = dict(s, e_cutoff=float(np.median(ic["e"])), input_initial_diffusion=True, strange_charge_enabled=False)
+    path = tmp_path / "ic.dat"
+    W.write_ccake(str(path), s, ic)
+    txt = open(path).read().splitlines()
+    txt.insert(5, "")
+    txt.insert(9, "# a comment between rows")
+    open(path, "w").write("\n".join(txt))   # no trailing newline
+    s_py, ic_py = W.read_ccake_python(str(path), s)
+    s_c, ic_c = W.read_ccake(str(path), s)
+    assert 0 < ic_py["r"].shape[0] < n, "the cut-off must drop some rows"
+    for k in ("stepx", "stepy", "stepEta", "xmin", "ymin", "etamin"):
+        assert s_py[k] == s_c[k]
+    for k in ("r", "e", "rhoB", "rhoQ", "u", "bulk", "shv6"):
+        assert np.array_equal(ic_py[k], ic_c[k]), k
+    assert np.array_equal(ic_py["diffusion"][:, [0, 2]], ic_c["diffusion"][:, [0, 2]])
+    assert np.all(ic_c["rhoS"] == 0.0) and np.all(ic_c["diffusion"][:, 1, :] == 0.0)   # disabled charge (src/BSQHydro.cpp:340-372)
+    # entropy input: the cut-off acts on the ideal-gas energy estimate (src/BSQHydro.cpp:383-398)
+    s_e = dict(s, input_as_entropy=True, e_cutoff=0.12 * float(np.median(ic["e"])) ** (4.0 / 3.0), input_initial_diffusion=False)
+    a, b = W.read_ccake_python(str(path), s_e)[1], W.read_ccake(str(path), s_e)[1]
+    assert 0 < a["e"].size < n and np.array_equal(a["e"], b["e"]) and np.array_equal(a["r"], b["r"])
+    # ICCING: header "<ignored> stepx stepy <ignored> xmin ymin", rows x y e rhoB rhoS rhoQ (src/BSQHydro.cpp:84-145)
+    p2 = tmp_path / "iccing.dat"
+    rows = np.column_stack([ic["r"], ic["e"], ic["rhoB"], ic["rhoS"], ic["rhoQ"]])
+    with open(p2, "w") as f:
+        f.write("0 0.1 0.1 0 -2.0 -2.0\n")
+        np.savetxt(f, rows, fmt="%.17g")
+    s_i, ic_i = W.read_ccake(str(p2), dict(s, e_cutoff=0.0, strange_charge_enabled=True), fmt="iccing")
+    assert s_i["stepx"] == 0.1 and s_i["xmin"] == -2.0 and np.array_equal(ic_i["r"], ic["r"]) and np.array_equal(ic_i["e"], ic["e"])
+    assert np.array_equal(ic_i["rhoS"], ic["rhoS"]) and np.all(ic_i["u"] == 0.0) and np.all(ic_i["shv6"] == 0.0)
