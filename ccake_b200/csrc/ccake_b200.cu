@@ -491,7 +491,9 @@ int migrate(ccb_ctx* ctx, int64_t* n_sort, int64_t* n_drop) {
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   const int64_t outL = h[0], outR = h[1], inL = h[2], inR = h[3];
   if (outL + outR + inL + inR == 0) return CCB_OK;
-  if (n + inL + inR > ctx->cap) { ctx->err = "slab overflow: more arrivals than the particle capacity holds"; return CCB_ERR_STATE; }
+  // A slab that cannot hold its arrivals still takes part in the payload exchange below (the rows land in the migration buffers,
+  // not in the particle columns), so that no neighbour is left blocked in a receive; the error is returned after it.
+  const bool overflow = n + inL + inR > ctx->cap;
   MigrateList ml;
   migrate_list(ctx, ml);
   const int64_t need = std::max<int64_t>(std::max(outL + outR, inL + inR), 1);
@@ -522,6 +524,12 @@ int migrate(ccb_ctx* ctx, int64_t* n_sort, int64_t* n_drop) {
   if (left >= 0 && inL) { COMM_OK(ctx->comm->recv(rd, sizeof(double) * ml.ncols * inL, left, ctx->stream)); COMM_OK(ctx->comm->recv(ri, sizeof(int32_t) * 4 * inL, left, ctx->stream)); }
   if (right >= 0 && inR) { COMM_OK(ctx->comm->recv(rd + ml.ncols * inL, sizeof(double) * ml.ncols * inR, right, ctx->stream)); COMM_OK(ctx->comm->recv(ri + 4 * inL, sizeof(int32_t) * 4 * inR, right, ctx->stream)); }
   COMM_OK(ctx->comm->group_end());
+  if (overflow) {
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->err = "slab overflow: " + std::to_string(n + inL + inR) + " particles after migration, capacity " + std::to_string(ctx->cap) +
+               " (the slab decomposition is static: cut the slabs again, or upload with fewer particles per rank)";
+    return CCB_ERR_STATE;
+  }
   if (inL) LAUNCH(unpack_rows, cdiv(inL, 128), 128, ml, n, inL, rd, ri);
   if (inR) LAUNCH(unpack_rows, cdiv(inR, 128), 128, ml, n + inL, inR, rd + ml.ncols * inL, ri + 4 * inL);
   *n_sort = n + inL + inR;

@@ -113,6 +113,31 @@ def config2_viscous_gubser_bsq(dx=0.025, xmax=5.0, seed=7):
     return settings, ic
 
 
+def viscous_gubser_check(initial):
+    """The reference's own physics check (misc/Gubser_checks/ac, README.txt there): Israel-Stewart hydrodynamics in Gubser flow from
+    the semi-analytic tau = 1 fm profile on the 201 x 201, dx = 0.05 fm grid, eta/s = 0.2, tau_R = 5 eta / (e + P), conformal e = 3 P, no
+    charges. `initial` = rows x y T[GeV] u^x u^y pi^xx pi^yy pi^xy tau^2 pi^etaeta [GeV/fm^3] (tests/golden/viscous_gubser_ac.npz);
+    converted to the ccake IC columns exactly as utilities/gubser_ic_converter.py does. Settings: input/config_visc_gubser.yaml
+    without its charges (h = 0.1 fm)."""
+    a = np.asarray(initial, dtype=np.float64)
+    x, y, T = a[:, 0], a[:, 1], a[:, 2]
+    eps = HBARC_GEVFM * 3.0 * CONFORMAL_C * T ** 4 / HBARC_GEVFM ** 4
+    z = np.zeros_like(x)
+    dx = 0.05
+    settings = dict(_COMMON, dt=0.01, hT=0.1, hEta=0.1, stepx=dx, stepy=dx, stepEta=0.1, xmin=-5.0, ymin=-5.0, etamin=-0.1,
+                    Freeze_Out_Temperature=153.334025, baryon_charge_enabled=False, strange_charge_enabled=False, electric_charge_enabled=False,
+                    etaMode="constant", constant_eta_over_s=0.2, shearRelaxMode="Gubser", use_vorticity=False,
+                    delta_pipi_mode="default", tau_pipi_mode="disabled", lambda_piPi_mode="disabled", phi6_mode="disabled",
+                    phi7_mode="disabled", input_initial_shear=True,
+                    zetaMode="constant", constant_zeta_over_s=0.0, cs2_dependent_zeta_A=1.67552, cs2_dependent_zeta_p=2.0,
+                    bulk_from_trace=False, bulkRelaxMode="default", modulate_zeta_with_tanh=False,
+                    delta_PiPi_mode="israel-stewart", lambda_Pipi_mode="default", phi1_mode="disabled", phi3_mode="disabled",
+                    diffusionMode="disabled", diffusionRelaxMode="constant_over_T")
+    ic = dict(r=np.stack([x, y], 1), e=eps, u=np.stack([a[:, 3], a[:, 4]], 1), rhoB=None, rhoS=None, rhoQ=None, bulk=None,
+              shv6=np.stack([a[:, 5], a[:, 7], z, a[:, 6], z, a[:, 8]], 1))
+    return settings, ic
+
+
 def config5_cartesian_blob(n_target=1_000_000, sigma=3.0, seed=11):
     """BASELINE config 5: 3+1D Cartesian Gaussian blob on a cubic lattice inside radius 3 sigma, h = 2 dx
     (N_ngb ~ 268), conformal EoS, ideal fluid at rest."""
