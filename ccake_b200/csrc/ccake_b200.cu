@@ -59,6 +59,11 @@ struct ccb_ctx {
   double* init_tmp = nullptr;
   double* d_reduce = nullptr;   // per-block partials of ccb_reduce
   bool cells_valid = false;   // the cell table and sort order match the current positions (gathers may run)
+  // the neighbour list of the stage as tile bitmasks (GatherParams::hitmask): stored by the field gather, read by the gradient gather
+  unsigned long long* hitmask = nullptr;
+  int hit_kmax = 0;
+  int64_t hit_cap = 0;
+  bool hit_valid = false, hit_off = false;
   bool cells_built = false;   // a cell build has run on this particle set (dv.key matches the current order)
   bool have_state = false;
   std::string err;
@@ -224,6 +229,8 @@ int32_t reference_cell_id(const CellGrid& g, uint32_t key) {
 }
 
 int free_particles(ccb_ctx* ctx) {
+  if (ctx->hitmask) { cudaFree(ctx->hitmask); ctx->hitmask = nullptr; }
+  ctx->hit_valid = false; ctx->hit_cap = 0; ctx->hit_kmax = 0;
   cudaFree(ctx->slab); cudaFree(ctx->y0_slab); cudaFree(ctx->alt_slab); cudaFree(ctx->ints);
   cudaFree(ctx->k_slab); cudaFree(ctx->alt_k_slab); ctx->k_slab = ctx->alt_k_slab = nullptr;
   cudaFree(ctx->key_a); cudaFree(ctx->key_b); cudaFree(ctx->idx_a); cudaFree(ctx->idx_b); cudaFree(ctx->hist);
@@ -374,7 +381,32 @@ GatherParams make_gather(ccb_ctx* ctx) {
   gp.t = ctx->t;
   gp.milne = ctx->milne ? 1 : 0;
   gp.nbr_off = nullptr; gp.nbr_idx = nullptr;
+  gp.hitmask = nullptr; gp.hit_kmax = 0; gp.hit_stride = 0;
   return gp;
+}
+
+// Room for the hit masks of one stage: hit_kmax tiles of 64 candidates per target (tiles beyond that fall back to the pre-filter in
+// the gradient gather). A quarter of the free device memory at most; both gathers must cut their tiles the same way.
+int ensure_hitmask(ccb_ctx* ctx) {
+  if (ctx->hit_off) return CCB_OK;
+  const ccb::GatherShape &a = ctx->shape_fields, &b = ctx->shape_grad;
+  if (a.nt != b.nt || a.tile != b.tile) { ctx->hit_off = true; return CCB_OK; }
+  if (ctx->hitmask && ctx->hit_cap == ctx->cap) return CCB_OK;
+  if (ctx->hitmask) { cudaFree(ctx->hitmask); ctx->hitmask = nullptr; }
+  ctx->hit_valid = false;
+  size_t free_b = 0, total_b = 0;
+  CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_tile = sizeof(unsigned long long) * (size_t)ctx->cap;
+  size_t budget = free_b / 4;
+  if (budget > ((size_t)32 << 30)) budget = (size_t)32 << 30;
+  int64_t kmax = (int64_t)(budget / per_tile);
+  if (kmax > 1024) kmax = 1024;
+  if (kmax < 4) { ctx->hit_off = true; return CCB_OK; }
+  // a stage needs ceil(candidates / tile) tiles per task: 27 for a 3-D lattice at h = 2 d, ~140 for the 2-D h = 0.4 Gubser run
+  if (cudaMalloc(&ctx->hitmask, per_tile * (size_t)kmax) != cudaSuccess) { cudaGetLastError(); ctx->hitmask = nullptr; ctx->hit_off = true; return CCB_OK; }
+  ctx->hit_kmax = (int)kmax;
+  ctx->hit_cap = ctx->cap;
+  return CCB_OK;
 }
 
 constexpr int kReduceBlocks = 296;
@@ -643,6 +675,7 @@ int build_task_list(ccb_ctx* ctx) {
 int do_build_cells(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_NEIGHBOUR);
   int rc;
+  ctx->hit_valid = false;
   if (ctx->comm) {
     int64_t n_sort = ctx->n, n_drop = 0;
     if ((rc = migrate(ctx, &n_sort, &n_drop))) return rc;
@@ -778,11 +811,18 @@ int slab_gather(ccb_ctx* ctx, int rec_doubles, int nt, GatherParams gp, F&& laun
 int do_gather_fields(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_FIELDS);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
-  return slab_gather(ctx, REC_F, ctx->shape_fields.nt, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
+  int rc = ensure_hitmask(ctx);
+  if (rc) return rc;
+  GatherParams g0 = make_gather(ctx);
+  ctx->hit_valid = false;
+  if (ctx->hitmask) { g0.hitmask = ctx->hitmask; g0.hit_kmax = ctx->hit_kmax; g0.hit_stride = ctx->hit_cap; }
+  rc = slab_gather(ctx, REC_F, ctx->shape_fields.nt, g0, [&](const GatherParams& gp, cudaStream_t st) -> int {
     if (ctx->D == 2) LAUNCHER("gather_kernel<fields>", launch_gather_fields<2>(false, ctx->shape_fields, st, ctx->dv, ctx->grid, gp));
     else LAUNCHER("gather_kernel<fields>", launch_gather_fields<3>(fact, ctx->shape_fields, st, ctx->dv, ctx->grid, gp));
     return CCB_OK;
   });
+  if (!rc && ctx->hitmask) ctx->hit_valid = true;   // valid until the cells are rebuilt (do_build_cells)
+  return rc;
 }
 
 int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
@@ -832,7 +872,9 @@ int do_gather_gradients(ccb_ctx* ctx) {
   PhaseTimer pt(ctx, PH_SMOOTH_GRAD);
   const bool fact = ctx->D == 3 && ctx->cfg.factorized_kernel;
   const bool sh = ctx->cfg.using_shear, df = ctx->cfg.using_diffusion;
-  return slab_gather(ctx, grad_record_doubles(ctx), ctx->shape_grad.nt, make_gather(ctx), [&](const GatherParams& gp, cudaStream_t st) -> int {
+  GatherParams g0 = make_gather(ctx);
+  if (ctx->hit_valid && ctx->hitmask && ctx->hit_cap == ctx->cap) { g0.hitmask = ctx->hitmask; g0.hit_kmax = ctx->hit_kmax; g0.hit_stride = ctx->hit_cap; }
+  return slab_gather(ctx, grad_record_doubles(ctx), ctx->shape_grad.nt, g0, [&](const GatherParams& gp, cudaStream_t st) -> int {
     if (ctx->D == 2) LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<2>(sh, df, false, ctx->shape_grad, st, ctx->dv, ctx->grid, gp));
     else LAUNCHER("gather_kernel<gradients>", launch_gather_gradients<3>(sh, df, fact, ctx->shape_grad, st, ctx->dv, ctx->grid, gp));
     if (df) ctx->launches++;  // the two sparsity twins of a diffusion run
@@ -1104,6 +1146,7 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
     if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_grad.tile = v; }
     if (const char* e = std::getenv("CCB_FIELDS_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_fields.tile = v; }
     if (const char* e = std::getenv("CCB_GATHER_REGS")) ctx->shape_grad.regs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("CCB_HITMASK")) ctx->hit_off = std::atoi(e) == 0;
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }
   ctx->kD = make_kernel_norm(ctx->D, cfg->hT);

@@ -95,6 +95,7 @@ __device__ __forceinline__ bool grad_kernel(const GatherParams& gp, const double
 template <int D_, bool FACT, bool EMIT_ = false>
 struct FieldsPolicy {
   static constexpr int D = D_, REC = REC_F, STRIDE = REC_F_STRIDE, CH_STAGE = REC_F / 2, VARIANT = -1;
+  static constexpr int MASK_MODE = 1;  // stores the exact hit masks of its tiles (GatherParams::hitmask)
   // EMIT: debug twin that also writes the ids of the neighbours it visits (ccb_debug_neighbour_list): GatherParams::nbr_off / nbr_idx
   static constexpr bool EMIT = EMIT_;
   struct Target { double x[3]; };
@@ -195,6 +196,7 @@ struct GradPolicy {
   static constexpr int CH_STAGE = (DIFF && !QNZ) ? KQ : REC / 2;            // 16-byte chunks of a record staged per source
   static constexpr int STRIDE = (CH_STAGE % 2 == 1) ? 2 * CH_STAGE : 2 * CH_STAGE + 2;  // shared-memory stride: odd number of chunks
   static constexpr int VARIANT = DIFF ? (QNZ ? 1 : 0) : -1;  // -1: runs whatever the flag says
+  static constexpr int MASK_MODE = 2;  // reads the hit masks the field gather of the stage stored
   static constexpr bool EMIT = false;
   struct Target { double x[3]; double v[D]; };
   // fp64 accumulators live across the neighbour loop: decides the register budget of the launch (inst_gather.cu)
@@ -514,58 +516,75 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
       cp_async_commit();
     };
     if (ntiles) stage(0, srec2[0]);
+    // hit masks of the stage (GatherParams::hitmask): written by the field gather, read back by the gradient gather
+    const int kmask = gp.hitmask ? gp.hit_kmax : 0;
+    unsigned long long* hm = gp.hitmask + (active ? i : first);
+    unsigned long long mnext = 0ull;  // MASK_MODE 2: the mask of the next tile, loaded one tile ahead
+    if (P::MASK_MODE == 2 && kmask > 0 && ntiles) mnext = active ? __ldg(hm) : 0ull;
     for (uint32_t k = 0; k < ntiles; ++k) {
       const int nt = (int)((C - k + ntiles - 1) / ntiles);
       const double2* srec = srec2[k & 1];
+      const bool reuse = P::MASK_MODE == 2 && (int)k < kmask;  // CTA-uniform
       cp_async_wait_all();
       __syncthreads();  // tile k has landed for every thread, and tile k - 1 (buffer (k + 1) & 1, spos) is fully consumed
       if (k + 1 < ntiles) stage(k + 1, srec2[(k + 1) & 1]);
-      for (int r = threadIdx.x; r < TILE; r += NT) {  // fp32 relative positions of tile k
-        if (r < nt) {
-          const double2 v0 = srec[r * RS2];
-          const float xf = (float)(v0.x - org[0]), yf = (float)(v0.y - org[1]);
-          float zf = 0.f;
-          if (D == 3) zf = (float)(srec[r * RS2 + 1].x - org[2]);
-          spos[0][r] = xf; spos[1][r] = yf;
-          if (D == 3) spos[2][r] = zf;
-          spos[3][r] = fmaf(xf, xf, fmaf(yf, yf, zf * zf));
-        } else {
-          spos[0][r] = 0.f; spos[1][r] = 0.f; spos[2][r] = 0.f; spos[3][r] = 3.0e38f;
-        }
-      }
-      __syncthreads();
-      // ---- phase 1: fp32 pre-filter, hit masks. |a - b|^2 <= R^2 is tested in the expanded form
-      //   |b|^2 - 2 a.b <= R^2 - |a|^2   (|b|^2 staged per source, the right-hand side formed once per lane):
-      // D FMAs + 1 compare per candidate instead of D subtractions, D multiply-adds and a compare. The expansion
-      // cancels, so the cut-off carries an absolute margin for the fp32 rounding of coordinates up to `ext` (the
-      // extent of the stencil around its origin): no true neighbour is missed; a false positive costs one exact test.
       uint32_t m[NW];
-      const float ax = -2.f * tx[0], ay = -2.f * tx[1], az = -2.f * tx[2];
-      const float thr = (gp.rsqr_f + 4.0e-6f * ext2) - fmaf(tx[0], tx[0], fmaf(tx[1], tx[1], tx[2] * tx[2]));
-#pragma unroll
-      for (int w = 0; w < NW; ++w) {
-        uint32_t mw = 0u;
-        if (w * 32 < nt) {
-#pragma unroll
-          for (int b4 = 0; b4 < 8; ++b4) {
-            const float4 X = reinterpret_cast<const float4*>(&spos[0][w * 32])[b4];
-            const float4 Y = reinterpret_cast<const float4*>(&spos[1][w * 32])[b4];
-            const float4 S = reinterpret_cast<const float4*>(&spos[3][w * 32])[b4];
-            float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (D == 3) Z = reinterpret_cast<const float4*>(&spos[2][w * 32])[b4];
-            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-            const float ss[4] = {S.x, S.y, S.z, S.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float v = ss[e];
-              if (D == 3) v = fmaf(az, zs[e], v);
-              v = fmaf(ax, xs[e], fmaf(ay, ys[e], v));
-              if (v <= thr) mw |= (1u << (b4 * 4 + e));
-            }
+      if (reuse) {
+        m[0] = (uint32_t)mnext;
+        if (NW > 1) m[NW - 1] = (uint32_t)(mnext >> 32);
+        mnext = 0ull;
+        if ((int)(k + 1) < kmask && k + 1 < ntiles && active) mnext = __ldg(hm + (int64_t)(k + 1) * gp.hit_stride);
+      } else {
+        for (int r = threadIdx.x; r < TILE; r += NT) {  // fp32 relative positions of tile k
+          if (r < nt) {
+            const double2 v0 = srec[r * RS2];
+            const float xf = (float)(v0.x - org[0]), yf = (float)(v0.y - org[1]);
+            float zf = 0.f;
+            if (D == 3) zf = (float)(srec[r * RS2 + 1].x - org[2]);
+            spos[0][r] = xf; spos[1][r] = yf;
+            if (D == 3) spos[2][r] = zf;
+            spos[3][r] = fmaf(xf, xf, fmaf(yf, yf, zf * zf));
+          } else {
+            spos[0][r] = 0.f; spos[1][r] = 0.f; spos[2][r] = 0.f; spos[3][r] = 3.0e38f;
           }
         }
-        m[w] = active ? mw : 0u;
+        __syncthreads();
+        // ---- phase 1: fp32 pre-filter, hit masks. |a - b|^2 <= R^2 is tested in the expanded form
+        //   |b|^2 - 2 a.b <= R^2 - |a|^2   (|b|^2 staged per source, the right-hand side formed once per lane):
+        // D FMAs + 1 compare per candidate instead of D subtractions, D multiply-adds and a compare. The expansion
+        // cancels, so the cut-off carries an absolute margin for the fp32 rounding of coordinates up to `ext` (the
+        // extent of the stencil around its origin): no true neighbour is missed; a false positive costs one exact test.
+        const float ax = -2.f * tx[0], ay = -2.f * tx[1], az = -2.f * tx[2];
+        const float thr = (gp.rsqr_f + 4.0e-6f * ext2) - fmaf(tx[0], tx[0], fmaf(tx[1], tx[1], tx[2] * tx[2]));
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          uint32_t mw = 0u;
+          if (w * 32 < nt) {
+#pragma unroll
+            for (int b4 = 0; b4 < 8; ++b4) {
+              const float4 X = reinterpret_cast<const float4*>(&spos[0][w * 32])[b4];
+              const float4 Y = reinterpret_cast<const float4*>(&spos[1][w * 32])[b4];
+              const float4 S = reinterpret_cast<const float4*>(&spos[3][w * 32])[b4];
+              float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (D == 3) Z = reinterpret_cast<const float4*>(&spos[2][w * 32])[b4];
+              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+              const float ss[4] = {S.x, S.y, S.z, S.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float v = ss[e];
+                if (D == 3) v = fmaf(az, zs[e], v);
+                v = fmaf(ax, xs[e], fmaf(ay, ys[e], v));
+                if (v <= thr) mw |= (1u << (b4 * 4 + e));
+              }
+            }
+          }
+          m[w] = active ? mw : 0u;
+        }
       }
+      // MASK_MODE 1: the exact mask of this tile = the pre-filter's hits minus those the fp64 predicate rejects below
+      uint32_t mex[NW];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) mex[w] = m[w];
       // ---- phase 2: every lane walks its own hits (a software-pipelined, branch-free variant of this loop measured
       // 5-10 % slower: the loop is bound by shared-memory gather bandwidth, not by per-warp latency)
       int mine = 0;
@@ -594,9 +613,15 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
               const int64_t gidx = (int64_t)seg_start[sg] + (cand - seg_pref[sg]);
               if (gidx != i) gp.nbr_idx[gp.nbr_off[i] + emitted++] = dv.id[gidx];
             }
+          } else if (P::MASK_MODE == 1) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+              if (base == w * 32) mex[w] &= ~low;
           }
         }
       }
+      if (P::MASK_MODE == 1 && (int)k < kmask && active)
+        hm[(int64_t)k * gp.hit_stride] = (unsigned long long)mex[0] | (NW > 1 ? ((unsigned long long)mex[NW - 1] << 32) : 0ull);
     }
     if (active) P::store(dv, gp, i, acc);
   }

@@ -53,6 +53,13 @@ struct GatherParams {
   int* task_counter;
   double t;
   int milne;
+  // The neighbour list of the stage as tile bitmasks: the field gather (phase 03) stores, per target and tile, the mask of the
+  // sources that passed the EXACT predicate; the gradient gather (phase 09) of the same stage runs over the same tasks and tiles and
+  // reads the masks back instead of repeating the fp32 pre-filter (216 B per particle at 27 tiles of 64, against ~1 KB for a CSR
+  // list of 245 neighbours). hitmask[k * hit_stride + i] for tile k < hit_kmax of target i; nullptr = off.
+  unsigned long long* hitmask;
+  int hit_kmax;
+  int64_t hit_stride;
   // debug twin of the field gather (FieldsPolicy EMIT): CSR offsets per target (sorted order) and the id buffer it fills
   const int64_t* nbr_off;
   int32_t* nbr_idx;
