@@ -391,6 +391,14 @@ def own_arm(args, rank, world, local_rank):
     if settings["eos_type"] == "table":
         settings["eos_table_data"] = eos_table(as_file=False)
     dt = settings["dt"]
+    if world > 1 and args.scaling == "strong" and "slab_axis" not in settings and os.environ.get("CCB_SLAB_AXIS", "auto") == "auto":
+        # cut along the axis that balances best (config 4 is long and flat in eta: largest slab 1.02x the mean there, 1.09x along x)
+        from ccake_b200 import slabs as _slabs
+
+        D_ = ic["r"].shape[1]
+        settings["slab_axis"], _ = _slabs.best_axis(ic["r"], [2.0 * settings["hT"]] * D_, world)
+    elif os.environ.get("CCB_SLAB_AXIS", "auto") != "auto":
+        settings["slab_axis"] = int(os.environ["CCB_SLAB_AXIS"])
     ws = SPHWorkstation(settings, device=local_rank, rank=rank, nranks=world)
     n_global = ic["r"].shape[0]
     if world > 1:
@@ -400,7 +408,9 @@ def own_arm(args, rank, world, local_rank):
         mn, ed, nc = ws.grid_geometry()
         ax = ws.slab_axis
         cols = slabs.column_of(ic["r"][:, ax], mn[ax], ed[ax], int(nc[ax]))
-        ranges = slabs.partition_columns(cols, int(nc[ax]), world)
+        # strong scaling: cut at quantiles of the estimated cost (the gathers' work grows with the local density), not of the count
+        cost = slabs.particle_cost(ic["r"], mn, ed) if args.scaling == "strong" and os.environ.get("CCB_SLAB_CUT", "cost") == "cost" else None
+        ranges = slabs.partition_columns(cols, int(nc[ax]), world, weights=cost)
         part = slabs.split_initial_conditions(ic, cols, ranges[rank])
         ws.comm_init_nccl()
         ws.set_slab(*ranges[rank])
@@ -499,7 +509,7 @@ def own_arm(args, rank, world, local_rank):
     flop_pair = PAIR_FLOP.get(dom) or gradient_pair_flop_executed(D, sw["using_shear"], sw["using_diffusion"], currents_zero)
     fp64_achieved = pairs * flop_pair / t_dom / 1e12 if dom in ("03_smooth_fields", "09_smooth_gradients") else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": committed_traffic(args.workload, dom), "peak_source": peak_src, "algorithmic_bytes_per_particle": alg.get(dom),
+                "traffic": committed_traffic(args.workload, dom) if world == 1 else None, "peak_source": peak_src, "algorithmic_bytes_per_particle": alg.get(dom),
                 "ms_per_launch": per_kernel[dom]["ms_per_launch"],
                 "fp64": {"achieved": fp64_achieved, "peak": tf.value, "unit": "TFLOP/s",
                          "frac": (fp64_achieved / tf.value) if (fp64_achieved and tf.value) else None,
@@ -525,7 +535,7 @@ def own_arm(args, rank, world, local_rank):
         "config": {"workload": args.workload, "description": desc, "particles": n_global, "particles_rank0": n, "rk_order": 2,
                    "mean_neighbours": float(np.mean(bt[bt >= 0])),
                    "parallelism": "single GPU" if world == 1 else "%d slabs along %s (%s), 2h halo + per-stage migration over NCCL" % (
-                       world, "xyz"[ws.slab_axis] if ws.slab_axis < 2 or D == 2 else "eta", "one copy of the workload per GPU" if args.scaling == "weak" else "the one workload cut at particle-count quantiles"),
+                       world, "xyz"[ws.slab_axis] if ws.slab_axis < 2 or D == 2 else "eta", "one copy of the workload per GPU" if args.scaling == "weak" else "the one workload cut into contiguous cell-column ranges that minimise the largest slab"),
                    "l2": "no flush: per-step working set %.0f MB of particle columns per GPU > 126 MB L2" % (8e-6 * n * 190)},
         "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
                 "d2h_bytes_per_step": bytes_state, "ms_per_step": ms_e2e / args.steps,

@@ -64,6 +64,9 @@ struct ccb_ctx {
   int hit_kmax = 0;
   int64_t hit_cap = 0;
   bool hit_valid = false, hit_off = false;
+  // ccb_step: the RK snapshot y0 = y(t_n) is taken BY the first sort of the step (permute_columns writes the sorted evolved
+  // columns twice) instead of copying 26 columns and then permuting both copies
+  bool y0_pending = false;
   bool cells_built = false;   // a cell build has run on this particle set (dv.key matches the current order)
   bool have_state = false;
   std::string err;
@@ -444,16 +447,25 @@ int sort_and_permute(ccb_ctx* ctx, int64_t n, int drop_outside) {
   // gather every persistent column (and the RK snapshot) through the permutation
   PermuteList pl;
   pl.ncols = 0; pl.nints = 0;
+  const bool take_y0 = ctx->y0_pending;   // first sort of a step: y0 := the sorted evolved columns, its old content is dead
+  ctx->y0_pending = false;
   for (int f = 0; f < kNumPersistentFields; ++f) {
     if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
-    for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = dv.f[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt[f] + (int64_t)c * dv.cap; pl.ncols++; }
+    bool evolved = false;
+    for (int k = 0; k < kNumEvolvedFields; ++k) evolved = evolved || kEvolvedFields[k] == f;
+    for (int c = 0; c < kFieldWidth[f]; ++c) {
+      pl.src[pl.ncols] = dv.f[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt[f] + (int64_t)c * dv.cap;
+      pl.dst2[pl.ncols] = (take_y0 && evolved) ? ctx->alt_y0[f] + (int64_t)c * dv.cap : nullptr;
+      pl.ncols++;
+    }
   }
   for (int k = 0; k < kNumEvolvedFields; ++k) {
     const int f = kEvolvedFields[k];
     if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
-    for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = dv.y0[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_y0[f] + (int64_t)c * dv.cap; pl.ncols++; }
+    if (!take_y0)
+      for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = dv.y0[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_y0[f] + (int64_t)c * dv.cap; pl.dst2[pl.ncols] = nullptr; pl.ncols++; }
     if (ctx->k_slab)
-      for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = ctx->kacc[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_k[f] + (int64_t)c * dv.cap; pl.ncols++; }
+      for (int c = 0; c < kFieldWidth[f]; ++c) { pl.src[pl.ncols] = ctx->kacc[f] + (int64_t)c * dv.cap; pl.dst[pl.ncols] = ctx->alt_k[f] + (int64_t)c * dv.cap; pl.dst2[pl.ncols] = nullptr; pl.ncols++; }
   }
   int32_t* icur[4] = {dv.id, dv.btrack, dv.freeze, dv.eos_id};
   for (int k = 0; k < 4; ++k) { pl.isrc[k] = icur[k]; pl.idst[k] = ctx->alt_int[k]; pl.nints++; }
@@ -981,15 +993,6 @@ int do_freeze_out(ccb_ctx* ctx, int64_t* n_freezing_out) {
     if (curfrz > 0) DISPATCH_DM("freeze_interpolate_kernel", launch_freeze_interpolate, ctx->stream, ctx->dv, ctx->frz, ctx->efcheck, ctx->taup, ctx->taupp, ctx->cfg.dt);
     DISPATCH_DM("freeze_advance_kernel", launch_freeze_advance, ctx->stream, ctx->dv, ctx->frz);
     ctx->taupp = ctx->taup; ctx->taup = tau;
-  }
-  return CCB_OK;
-}
-
-int snapshot_y0(ccb_ctx* ctx) {
-  for (int k = 0; k < kNumEvolvedFields; ++k) {
-    const int f = kEvolvedFields[k];
-    if (f == CCB_F_EXTENSIVE_DIFFUSION && !ctx->cfg.using_diffusion) continue;
-    CUDA_OK(cudaMemcpyAsync(ctx->dv.y0[f], ctx->dv.f[f], sizeof(double) * kFieldWidth[f] * ctx->cap, cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return CCB_OK;
 }
@@ -1742,7 +1745,7 @@ int ccb_get_time_derivatives(ccb_ctx* ctx) { int rc = check_ready(ctx, false); r
 int ccb_step(ccb_ctx* ctx, double dt) {
   int rc = check_ready(ctx, false);
   if (rc) return rc;
-  if ((rc = snapshot_y0(ctx))) return rc;
+  ctx->y0_pending = true;   // the snapshot y0 = y(t_n) is written by the first sort of the step (sort_and_permute)
   const double t0 = ctx->t;
   if (ctx->cfg.rk_order == 4) {
     // Evolver::advance_timestep_rk4 (src/evolver.cpp:508-561), stage for stage AS THE REFERENCE RUNS IT: five derivative

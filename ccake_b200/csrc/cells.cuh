@@ -342,6 +342,7 @@ struct PermuteList {
   int ncols;
   const double* src[96];
   double* dst[96];
+  double* dst2[96];   // second destination of a column (the RK snapshot y0 taken with the first sort of a step), or nullptr
   int nints;
   const int32_t* isrc[4];
   int32_t* idst[4];
@@ -350,7 +351,11 @@ __global__ void permute_columns(PermuteList pl, const uint32_t* __restrict__ per
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const uint32_t j = perm[i];
-  for (int c = 0; c < pl.ncols; ++c) pl.dst[c][i] = pl.src[c][j];
+  for (int c = 0; c < pl.ncols; ++c) {
+    const double v = pl.src[c][j];
+    pl.dst[c][i] = v;
+    if (pl.dst2[c]) pl.dst2[c][i] = v;
+  }
   for (int c = 0; c < pl.nints; ++c) pl.idst[c][i] = pl.isrc[c][j];
 }
 

@@ -48,17 +48,22 @@ __device__ __forceinline__ void raise_error(DeviceView& dv, int code, int id) {
   if (atomicCAS(&dv.err[0], 0, code) == 0) dv.err[1] = id;
 }
 
+// Read of an input column that is streamed once (or re-read from L2): ld.global.cg, cached in L2 only. The per-particle kernels
+// with a register-heavy body (eom_rk_kernel: 254 registers + 672 B of stack) keep their stack in L1 this way instead of having it
+// evicted by ~130 input columns passing through.
+__device__ __forceinline__ double colr(const double* p, int64_t cap, int c, int64_t i) { return __ldcg(p + (int64_t)c * cap + i); }
+
 __device__ __forceinline__ void load_thermo(const DeviceView& dv, int64_t i, Thermo& th) {
   double* T = dv.f[CCB_F_THERMO];
-  th.T = col(T, dv.cap, 0, i); th.muB = col(T, dv.cap, 1, i); th.muS = col(T, dv.cap, 2, i); th.muQ = col(T, dv.cap, 3, i);
-  th.e = col(T, dv.cap, 4, i); th.s = col(T, dv.cap, 5, i); th.rhoB = col(T, dv.cap, 6, i); th.rhoS = col(T, dv.cap, 7, i);
-  th.rhoQ = col(T, dv.cap, 8, i); th.p = col(T, dv.cap, 9, i); th.cs2 = col(T, dv.cap, 10, i); th.w = col(T, dv.cap, 11, i);
-  th.dwds = col(T, dv.cap, 12, i); th.dwdB = col(T, dv.cap, 13, i); th.dwdS = col(T, dv.cap, 14, i); th.dwdQ = col(T, dv.cap, 15, i);
+  th.T = colr(T, dv.cap, 0, i); th.muB = colr(T, dv.cap, 1, i); th.muS = colr(T, dv.cap, 2, i); th.muQ = colr(T, dv.cap, 3, i);
+  th.e = colr(T, dv.cap, 4, i); th.s = colr(T, dv.cap, 5, i); th.rhoB = colr(T, dv.cap, 6, i); th.rhoS = colr(T, dv.cap, 7, i);
+  th.rhoQ = colr(T, dv.cap, 8, i); th.p = colr(T, dv.cap, 9, i); th.cs2 = colr(T, dv.cap, 10, i); th.w = colr(T, dv.cap, 11, i);
+  th.dwds = colr(T, dv.cap, 12, i); th.dwdB = colr(T, dv.cap, 13, i); th.dwdS = colr(T, dv.cap, 14, i); th.dwdQ = colr(T, dv.cap, 15, i);
 #pragma unroll
   for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int x = 0; x < 4; ++x) th.dalpha[a][x] = col(dv.f[CCB_F_DALPHA], dv.cap, a * 4 + x, i);
-  th.chiBB = col(dv.f[CCB_F_CHIBB], dv.cap, 0, i); th.chiBB0 = col(dv.f[CCB_F_CHIBB], dv.cap, 1, i);
+    for (int x = 0; x < 4; ++x) th.dalpha[a][x] = colr(dv.f[CCB_F_DALPHA], dv.cap, a * 4 + x, i);
+  th.chiBB = colr(dv.f[CCB_F_CHIBB], dv.cap, 0, i); th.chiBB0 = colr(dv.f[CCB_F_CHIBB], dv.cap, 1, i);
 }
 __device__ __forceinline__ void store_thermo(const DeviceView& dv, int64_t i, const Thermo& th) {
   double* T = dv.f[CCB_F_THERMO];
@@ -192,10 +197,10 @@ __global__ void eos_local_kernel(DeviceView dv, StageParams sp) {
 // the 13 transport scalars phase 08 stored (column order of CCB_F_TRANSPORT, include/ccake_b200.h)
 __device__ __forceinline__ void load_transport(const DeviceView& dv, int64_t i, Transport& tc) {
   const double* TC = dv.f[CCB_F_TRANSPORT];
-  tc.eta_pi = TC[i]; tc.tau_pi = TC[dv.cap + i]; tc.zeta_Pi = TC[2 * dv.cap + i]; tc.tau_Pi = TC[3 * dv.cap + i];
-  tc.delta_PiPi = TC[4 * dv.cap + i]; tc.delta_pipi = TC[5 * dv.cap + i]; tc.lambda_piPi = TC[6 * dv.cap + i];
-  tc.lambda_Pipi = TC[7 * dv.cap + i]; tc.phi1 = TC[8 * dv.cap + i]; tc.phi3 = TC[9 * dv.cap + i]; tc.phi6 = TC[10 * dv.cap + i];
-  tc.phi7 = TC[11 * dv.cap + i]; tc.tau_pipi = TC[12 * dv.cap + i];
+  tc.eta_pi = colr(TC, dv.cap, 0, i); tc.tau_pi = colr(TC, dv.cap, 1, i); tc.zeta_Pi = colr(TC, dv.cap, 2, i); tc.tau_Pi = colr(TC, dv.cap, 3, i);
+  tc.delta_PiPi = colr(TC, dv.cap, 4, i); tc.delta_pipi = colr(TC, dv.cap, 5, i); tc.lambda_piPi = colr(TC, dv.cap, 6, i);
+  tc.lambda_Pipi = colr(TC, dv.cap, 7, i); tc.phi1 = colr(TC, dv.cap, 8, i); tc.phi3 = colr(TC, dv.cap, 9, i); tc.phi6 = colr(TC, dv.cap, 10, i);
+  tc.phi7 = colr(TC, dv.cap, 11, i); tc.tau_pipi = colr(TC, dv.cap, 12, i);
 }
 
 // inputs of the equations of motion for particle i, from the SoA columns
@@ -203,32 +208,32 @@ template <int D>
 __device__ __forceinline__ void load_eom_inputs(const DeviceView& dv, const StageParams& sp, int64_t i, EomIn<D>& in) {
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    in.u[d] = col(dv.f[CCB_F_U], dv.cap, d, i);
-    in.v[d] = col(dv.f[CCB_F_V], dv.cap, d, i);
-    in.gradP[d] = col(dv.f[CCB_F_GRADP], dv.cap, d, i);
-    in.gradBulk[d] = col(dv.f[CCB_F_GRADBULK], dv.cap, d, i);
-    in.gradshear[d] = col(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i);
-    in.divshear[d] = col(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i);
+    in.u[d] = colr(dv.f[CCB_F_U], dv.cap, d, i);
+    in.v[d] = colr(dv.f[CCB_F_V], dv.cap, d, i);
+    in.gradP[d] = colr(dv.f[CCB_F_GRADP], dv.cap, d, i);
+    in.gradBulk[d] = colr(dv.f[CCB_F_GRADBULK], dv.cap, d, i);
+    in.gradshear[d] = colr(dv.f[CCB_F_GRADSHEAR], dv.cap, d, i);
+    in.divshear[d] = colr(dv.f[CCB_F_DIVSHEAR], dv.cap, d, i);
 #pragma unroll
-    for (int e = 0; e < D; ++e) in.gradV[d][e] = col(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i);
+    for (int e = 0; e < D; ++e) in.gradV[d][e] = colr(dv.f[CCB_F_GRADV], dv.cap, d * 3 + e, i);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) in.grad_alpha[d][c] = sp.fl.diffusion ? col(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) : 0.0;
+    for (int c = 0; c < 3; ++c) in.grad_alpha[d][c] = sp.fl.diffusion ? colr(dv.f[CCB_F_GRAD_ALPHA], dv.cap, d * 3 + c, i) : 0.0;
   }
-  in.gamma = dv.f[CCB_F_GAMMA][i];
-  in.sigma = dv.f[CCB_F_SIGMA][i];
-  in.sigma_lab = dv.f[CCB_F_SIGMA_LAB][i];
-  in.mass_s = col(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
-  in.bulk = dv.f[CCB_F_BULK][i];
+  in.gamma = colr(dv.f[CCB_F_GAMMA], dv.cap, 0, i);
+  in.sigma = colr(dv.f[CCB_F_SIGMA], dv.cap, 0, i);
+  in.sigma_lab = colr(dv.f[CCB_F_SIGMA_LAB], dv.cap, 0, i);
+  in.mass_s = colr(dv.f[CCB_F_SPH_MASS], dv.cap, 0, i);
+  in.bulk = colr(dv.f[CCB_F_BULK], dv.cap, 0, i);
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) in.shv[a][b] = col(dv.f[CCB_F_SHV], dv.cap, a * 4 + b, i);
+    for (int b = 0; b < 4; ++b) in.shv[a][b] = colr(dv.f[CCB_F_SHV], dv.cap, a * 4 + b, i);
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
 #pragma unroll
-    for (int mu = 0; mu < 4; ++mu) in.q[c][mu] = sp.fl.diffusion ? col(dv.f[CCB_F_DIFFUSION], dv.cap, c * 4 + mu, i) : 0.0;
-    in.div_qa[c] = sp.fl.diffusion ? col(dv.f[CCB_F_DIV_QA], dv.cap, c, i) : 0.0;
-    in.grad_qa[c] = sp.fl.diffusion ? col(dv.f[CCB_F_GRAD_QA], dv.cap, c, i) : 0.0;
+    for (int mu = 0; mu < 4; ++mu) in.q[c][mu] = sp.fl.diffusion ? colr(dv.f[CCB_F_DIFFUSION], dv.cap, c * 4 + mu, i) : 0.0;
+    in.div_qa[c] = sp.fl.diffusion ? colr(dv.f[CCB_F_DIV_QA], dv.cap, c, i) : 0.0;
+    in.grad_qa[c] = sp.fl.diffusion ? colr(dv.f[CCB_F_GRAD_QA], dv.cap, c, i) : 0.0;
   }
 }
 

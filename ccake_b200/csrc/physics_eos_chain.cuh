@@ -171,6 +171,33 @@ CCB_HD double table_field(const TableView& tb, const double x[4], int field) {
   return r;
 }
 
+// Gaussian elimination with partial pivoting of the 4 x 5 augmented system A, every index a compile-time constant after unrolling
+// (a row addressed by a run-time pivot index would put the whole matrix into local memory: the Newton loop then issues ~20
+// local stores per iterate). Rows are exchanged with the arg-max row only, as a single swap, so the arithmetic is that of the
+// textbook algorithm. Returns false for a singular matrix. On success x solves the system.
+CCB_HD bool solve4_pivoted(double A[4][5], double x[4]) {
+  CCB_UNROLL for (int j = 0; j < 4; ++j) {
+    int piv = j;
+    double amax = fabs(A[j][j]);
+    CCB_UNROLL for (int i = j + 1; i < 4; ++i) { const double v = fabs(A[i][j]); if (v > amax) { amax = v; piv = i; } }
+    if (!(amax > 0.0)) return false;
+    CCB_UNROLL for (int i = j + 1; i < 4; ++i) {
+      const bool sw = piv == i;
+      CCB_UNROLL for (int c = 0; c < 5; ++c) { const double a = A[j][c], b = A[i][c]; A[j][c] = sw ? b : a; A[i][c] = sw ? a : b; }
+    }
+    const double ip = 1.0 / A[j][j];
+    CCB_UNROLL for (int i = j + 1; i < 4; ++i) {
+      const double m = A[i][j] * ip;
+      CCB_UNROLL for (int c = j; c < 5; ++c) A[i][c] -= m * A[j][c];
+    }
+  }
+  x[3] = A[3][4] / A[3][3];
+  x[2] = (A[2][4] - A[2][3] * x[3]) / A[2][2];
+  x[1] = (A[1][4] - A[1][2] * x[2] - A[1][3] * x[3]) / A[1][1];
+  x[0] = (A[0][4] - A[0][1] * x[1] - A[0][2] * x[2] - A[0][3] * x[3]) / A[0][0];
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // tanh-modulated conformal EoS: p = t(T) * c T0^4 x^2, t = (1 + tanh((T - Tc)/Ts))/2 (include/eos_tanh_conformal.h:22-29, 215-262)
 CCB_HD void tanh_full_thermo(const AnalyticParams& P, double T, double muB, double muQ, double muS, double* r) {
@@ -197,15 +224,8 @@ CCB_HD void tanh_full_thermo(const AnalyticParams& P, double T, double muB, doub
                     {r[TH_TQ], r[TH_BQ], r[TH_Q2], r[TH_QS], r[TH_Q]},
                     {r[TH_TS], r[TH_BS], r[TH_QS], r[TH_S2], r[TH_SS]}};
   const double n[4] = {r[TH_S], r[TH_B], r[TH_Q], r[TH_SS]};
-  for (int j = 0; j < 4; ++j) {
-    int piv = j;
-    for (int i = j + 1; i < 4; ++i) if (fabs(H[i][j]) > fabs(H[piv][j])) piv = i;
-    if (piv != j) for (int k = 0; k < 5; ++k) { const double t = H[j][k]; H[j][k] = H[piv][k]; H[piv][k] = t; }
-    const double ip = 1.0 / H[j][j];
-    for (int i = j + 1; i < 4; ++i) { const double f = H[i][j] * ip; for (int k = j; k < 5; ++k) H[i][k] -= f * H[j][k]; }
-  }
   double y[4];
-  for (int i = 3; i >= 0; --i) { double s = H[i][4]; for (int k = i + 1; k < 4; ++k) s -= H[i][k] * y[k]; y[i] = s / H[i][i]; }
+  if (!solve4_pivoted(H, y)) { y[0] = y[1] = y[2] = y[3] = nan(""); }
   const double w = T * r[TH_S] + muB * r[TH_B] + muQ * r[TH_Q] + muS * r[TH_SS];
   r[TH_CS2] = (n[0] * y[0] + n[1] * y[1] + n[2] * y[2] + n[3] * y[3]) / w;
 }
@@ -300,25 +320,8 @@ CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const
     // Newton step: J dx = -f, elimination with partial pivoting
     double A[4][5];
     CCB_UNROLL for (int r = 0; r < 4; ++r) { CCB_UNROLL for (int d = 0; d < 4; ++d) A[r][d] = J[r][d]; A[r][4] = -f[r]; }
-    bool singular = false;
-    CCB_UNROLL for (int j = 0; j < 4; ++j) {
-      int piv = j;
-      double amax = fabs(A[j][j]);
-      CCB_UNROLL for (int i = j + 1; i < 4; ++i) if (fabs(A[i][j]) > amax) { amax = fabs(A[i][j]); piv = i; }
-      if (!(amax > 0.0)) { singular = true; break; }
-      if (piv != j) { CCB_UNROLL for (int c = 0; c < 5; ++c) { const double t = A[j][c]; A[j][c] = A[piv][c]; A[piv][c] = t; } }
-      const double ip = 1.0 / A[j][j];
-      CCB_UNROLL for (int i = j + 1; i < 4; ++i) {
-        const double m = A[i][j] * ip;
-        CCB_UNROLL for (int c = j; c < 5; ++c) A[i][c] -= m * A[j][c];
-      }
-    }
-    if (singular) return false;  // GSL_ENOPROGJ
     double dx[4];
-    dx[3] = A[3][4] / A[3][3];
-    dx[2] = (A[2][4] - A[2][3] * dx[3]) / A[2][2];
-    dx[1] = (A[1][4] - A[1][2] * dx[2] - A[1][3] * dx[3]) / A[1][1];
-    dx[0] = (A[0][4] - A[0][1] * dx[1] - A[0][2] * dx[2] - A[0][3] * dx[3]) / A[0][0];
+    if (!solve4_pivoted(A, dx)) return false;  // GSL_ENOPROGJ
     // A step that would leave the EoS's range is shortened to stop just inside it; an iterate that keeps pressing
     // against the boundary is the reference's "out-of-bounds" failure (src/rootfinder.cpp:283-337).
     double scale = 1.0;
@@ -392,21 +395,23 @@ CCB_HD bool find_root(const EosChain& ch, int k, bool energy, double t0_, double
   CCB_TRY()
   const double base[4] = {pos[0], pos[1], pos[2], pos[3]};
   // Rootfinder::tbqs keeps the previous position when the proposed one is out of range (src/rootfinder.cpp:172-203)
+  // (arrays are addressed with compile-time indices only -- a run-time index would move them to local memory for good)
+  auto at = [](const double* v, int d) { return d == 0 ? v[0] : (d == 1 ? v[1] : (d == 2 ? v[2] : v[3])); };
   auto propose = [&](int d, double v) {
-    double q[4] = {base[0], base[1], base[2], base[3]};
-    q[d] = v;
+    double q[4];
+    CCB_UNROLL for (int e = 0; e < 4; ++e) q[e] = (e == d) ? v : base[e];
     if (in_range(q, lo, hi)) { CCB_UNROLL for (int e = 0; e < 4; ++e) pos[e] = q[e]; }
   };
   // order of the reference: T, muB, muS, muQ (indices 0, 1, 3, 2 of x)
-  const int order[4] = {0, 1, 3, 2};
   for (int a = 0; a < 4; ++a) {
-    const int d = order[a];
+    const int d = (a == 2) ? 3 : (a == 3 ? 2 : a);
     if (d == 1 && t_only) continue;
     if (d >= 2 && (t_only || b_only)) continue;
-    const double step = 0.2 * base[d];
-    propose(d, (base[d] + step > hi[d]) ? hi[d] - 1.0 : base[d] + step);
+    const double bd = at(base, d), hd = at(hi, d), ld = at(lo, d);
+    const double step = 0.2 * bd;
+    propose(d, (bd + step > hd) ? hd - 1.0 : bd + step);
     CCB_TRY()
-    propose(d, (base[d] - step < lo[d]) ? lo[d] + 1.0 : base[d] - step);
+    propose(d, (bd - step < ld) ? ld + 1.0 : bd - step);
     CCB_TRY()
   }
   {

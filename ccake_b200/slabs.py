@@ -15,23 +15,65 @@ def column_of(x, grid_min_x, edge_x, ncols):
     return np.clip(c, 0, ncols - 1)
 
 
-def partition_columns(columns, ncols, nranks):
-    """Column ranges [lo, hi) per rank with (nearly) equal particle counts; every rank gets at least one column
-    and the ranges tile [0, ncols)."""
+def particle_cost(r, grid_min, edge, gather_share=0.7):
+    """Relative cost of a particle per step: the two neighbour gathers (`gather_share` of a step at mean density) scan the
+    particles of the 3^D cells around the target's cell, so their cost grows with the local cell occupancy; everything else
+    is per particle. r: (n, D) positions; grid_min, edge: the neighbour grid (ccb_grid_geometry). Mean cost = 1."""
+    r = np.asarray(r, dtype=np.float64)
+    D = r.shape[1]
+    c = np.floor((r - np.asarray(grid_min[:D])) / np.asarray(edge[:D])).astype(np.int64)
+    c -= c.min(0)
+    dims = c.max(0) + 1
+    key = np.ravel_multi_index(tuple(c[:, d] for d in range(D)), tuple(int(x) for x in dims))
+    occ = np.bincount(key)[key].astype(np.float64)
+    return (1.0 - gather_share) + gather_share * occ / occ.mean()
+
+
+def partition_columns(columns, ncols, nranks, weights=None):
+    """Column ranges [lo, hi) per rank with (nearly) equal particle counts -- or, with per-particle `weights` (particle_cost),
+    equal summed cost; every rank gets at least one column and the ranges tile [0, ncols)."""
     if nranks > ncols:
         raise ValueError("more ranks (%d) than cell columns (%d)" % (nranks, ncols))
-    counts = np.bincount(columns, minlength=ncols)
-    cum = np.concatenate([[0], np.cumsum(counts)])
-    total = cum[-1]
-    bounds = [0]
-    for r in range(1, nranks):
-        target = total * r / nranks
-        b = int(np.searchsorted(cum, target, side="left"))
-        b = max(b, bounds[-1] + 1)            # at least one column per rank
-        b = min(b, ncols - (nranks - r))      # leave one column for each remaining rank
-        bounds.append(b)
-    bounds.append(ncols)
+    counts = np.bincount(columns, weights=weights, minlength=ncols).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(counts)])
+    # contiguous ranges that minimise the LARGEST load (the step runs at the pace of the fullest slab): dynamic programme over
+    # (ranks used, columns covered); a column is the unit, so with few columns per rank the plain quantile cut can be 5-10 % worse
+    INF = float("inf")
+    best = np.full((nranks + 1, ncols + 1), INF)
+    arg = np.zeros((nranks + 1, ncols + 1), dtype=np.int64)
+    best[0, 0] = 0.0
+    for r in range(1, nranks + 1):
+        for j in range(r, ncols - (nranks - r) + 1):
+            i = np.arange(r - 1, j)                      # the last range is [i, j): at least one column
+            cand = np.maximum(best[r - 1, i], cum[j] - cum[i])
+            k = int(np.argmin(cand))
+            best[r, j], arg[r, j] = cand[k], i[k]
+    bounds = [ncols]
+    for r in range(nranks, 0, -1):
+        bounds.append(int(arg[r, bounds[-1]]))
+    bounds = bounds[::-1]
     return [(bounds[r], bounds[r + 1]) for r in range(nranks)]
+
+
+def best_axis(r, edge, nranks):
+    """The spatial axis whose cell columns cut into `nranks` slabs with the smallest largest slab (an event that is long and flat
+    in rapidity balances far better along eta than along x): (axis, largest slab / mean slab). r: (n, D); edge: cell edge per axis."""
+    r = np.asarray(r, dtype=np.float64)
+    out = None
+    for ax in range(r.shape[1]):
+        lo = r[:, ax].min() - 1e-9 * edge[ax]
+        ncols = int(np.floor((r[:, ax].max() - lo) / edge[ax])) + 1
+        if ncols < nranks:
+            continue
+        cols = column_of(r[:, ax], lo, edge[ax], ncols)
+        counts = np.bincount(cols, minlength=ncols)
+        ranges = partition_columns(cols, ncols, nranks)
+        worst = max(counts[a:b].sum() for a, b in ranges) * nranks / float(r.shape[0])
+        if out is None or worst < out[1] - 1e-3:
+            out = (ax, float(worst))
+    if out is None:
+        raise ValueError("no axis has %d cell columns" % nranks)
+    return out
 
 
 def split_initial_conditions(ic, columns, col_range):
