@@ -285,7 +285,7 @@ def gradient_pair_flop_executed(D, shear, diffusion, currents_zero=False):
     return float(3 * D - 1 + 19 + 3 * D + (1 if (shear or diffusion) else 0) + 2 * fma)
 
 
-def parity_check(rank, world, local_rank, table):
+def parity_check(rank, world, local_rank, table, slab_axis=0):
     """N > 1, inside the driver's own scaling run: the slab-decomposed path exactly as the timed region uses it (per-stage
     migration and column tables over NCCL; the 2h halo once by CUDA-IPC peer memory over NVLink, once by NCCL messages) against a
     SINGLE-context run of the same system on rank 0's GPU. A 3e5-particle instance of the bench workload (same h / spacing, same
@@ -296,6 +296,7 @@ def parity_check(rank, world, local_rank, table):
 
     settings, ic = W.config4_milne_bsq(n_target=300_000)
     settings["eos_table_data"] = table
+    settings["slab_axis"] = slab_axis   # the axis the timed run cuts
     dt, steps = settings["dt"], 4
     fields = ("position", "u", "extensive", "extensive_bulk", "extensive_shv")
     n_global = ic["r"].shape[0]
@@ -309,7 +310,7 @@ def parity_check(rank, world, local_rank, table):
         one = {f: ws1.get(f) for f in fields}
         one["btrack"] = ws1.get_int("btrack")
         ws1.close()
-    out = {"workload": "config4_milne_bsq_table_3p1d:3e5", "particles": n_global, "steps": steps, "tolerance": 1e-11, "halo_modes": {}}
+    out = {"workload": "config4_milne_bsq_table_3p1d:3e5", "particles": n_global, "steps": steps, "tolerance": 1e-11, "slab_axis": slab_axis, "halo_modes": {}}
     saved = os.environ.get("CCB_HALO_P2P")
     for mode, env in (("peer_memory", "1"), ("nccl_message", "0")):
         os.environ["CCB_HALO_P2P"] = env
@@ -396,7 +397,7 @@ def own_arm(args, rank, world, local_rank):
         from ccake_b200 import slabs as _slabs
 
         D_ = ic["r"].shape[1]
-        settings["slab_axis"], _ = _slabs.best_axis(ic["r"], [2.0 * settings["hT"]] * D_, world)
+        settings["slab_axis"], _ = _slabs.best_axis(ic["r"], [2.0 * settings["hT"]] * D_, world, axes=sorted({0, D_ - 1}))   # x or eta: the two axes the NCCL tests cut
     elif os.environ.get("CCB_SLAB_AXIS", "auto") != "auto":
         settings["slab_axis"] = int(os.environ["CCB_SLAB_AXIS"])
     ws = SPHWorkstation(settings, device=local_rank, rank=rank, nranks=world)
@@ -410,7 +411,7 @@ def own_arm(args, rank, world, local_rank):
         cols = slabs.column_of(ic["r"][:, ax], mn[ax], ed[ax], int(nc[ax]))
         # strong scaling: cut at quantiles of the estimated cost (the gathers' work grows with the local density), not of the count
         cost = slabs.particle_cost(ic["r"], mn, ed) if args.scaling == "strong" and os.environ.get("CCB_SLAB_CUT", "cost") == "cost" else None
-        ranges = slabs.partition_columns(cols, int(nc[ax]), world, weights=cost)
+        ranges = slabs.partition_columns(cols, int(nc[ax]), world, weights=cost, halo_cost=float(os.environ.get("CCB_SLAB_HALO_COST", "0.33")) if args.scaling == "strong" else 0.0)
         part = slabs.split_initial_conditions(ic, cols, ranges[rank])
         ws.comm_init_nccl()
         ws.set_slab(*ranges[rank])
@@ -480,7 +481,18 @@ def own_arm(args, rank, world, local_rank):
     del host
     verify = None
     if world > 1 and not args.no_verify:
-        verify = parity_check(rank, world, local_rank, eos_table(as_file=False))
+        verify = parity_check(rank, world, local_rank, eos_table(as_file=False), slab_axis=int(settings.get("slab_axis", 0)))
+    # per-rank view of the timed region: device time in the phases that do not wait for a neighbour (compute), and in the two slab
+    # exchanges at the head of every stage, where a rank that finished its stage early waits for its neighbours (load imbalance)
+    per_rank = None
+    if world > 1:
+        mine_ = {"particles": int(ws.n_particles),
+                 "compute_ms_per_step": sum(v[0] for k, v in phases.items() if not k.startswith(("01a", "01b", "other"))) / args.steps
+                 - sum(v[0] for k, v in phases.items() if k.startswith(("01a", "01b"))) / args.steps,
+                 "slab_exchange_ms_per_step": sum(v[0] for k, v in phases.items() if k.startswith(("01a", "01b"))) / args.steps}
+        gathered_ = [None] * world
+        dist.all_gather_object(gathered_, mine_)
+        per_rank = gathered_
 
     if rank != 0:
         return
@@ -503,6 +515,13 @@ def own_arm(args, rank, world, local_rank):
     achieved = alg.get(dom, 0) * n / t_dom / 1e9
     n = ws.n_particles
     bt = ws.get_int_device_order("btrack") if world > 1 else ws.get_int("btrack")
+    # which member of the EoS fall-back chain located each particle at the end of the run (rank 0's particles): a population that
+    # drifts away from the table would show here (EquationOfState::chosen_EOSs order, src/eos_initialization.cpp:249-455)
+    eos_members = None
+    if settings["eos_type"] == "table":
+        em = ws.get_int_device_order("eos") if world > 1 else ws.get_int("eos")
+        cnt = np.bincount(np.clip(em, 0, 3), minlength=4)
+        eos_members = {k: int(c) for k, c in zip(("table", "tanh_conformal", "conformal", "conformal_diagonal"), cnt)}
     pairs = float(np.sum(bt[bt > 0])) + n
     flop_ref = PAIR_FLOP.get(dom) or gradient_pair_flop(D, sw["using_shear"], sw["using_diffusion"])
     currents_zero = all(float(settings.get("kappa_%d%d" % (a, b), 0.0)) == 0.0 for a in range(3) for b in range(3))
@@ -531,9 +550,9 @@ def own_arm(args, rank, world, local_rank):
     out = {
         "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64", "data": "synthetic", "per_rank": per_rank,
         "config": {"workload": args.workload, "description": desc, "particles": n_global, "particles_rank0": n, "rk_order": 2,
-                   "mean_neighbours": float(np.mean(bt[bt >= 0])),
+                   "mean_neighbours": float(np.mean(bt[bt >= 0])), "eos_chain_members_rank0": eos_members,
                    "parallelism": "single GPU" if world == 1 else "%d slabs along %s (%s), 2h halo + per-stage migration over NCCL" % (
                        world, "xyz"[ws.slab_axis] if ws.slab_axis < 2 or D == 2 else "eta", "one copy of the workload per GPU" if args.scaling == "weak" else "the one workload cut into contiguous cell-column ranges that minimise the largest slab"),
                    "l2": "no flush: per-step working set %.0f MB of particle columns per GPU > 126 MB L2" % (8e-6 * n * 190)},

@@ -97,7 +97,7 @@ _FIELD_NAMES = [
 FIELDS = {name: (i, w) for i, (name, w) in enumerate(_FIELD_NAMES)}
 INT_FIELDS = {"id": 0, "btrack": 1, "freeze": 2, "cell": 3, "eos": 4}
 PHASE_NAMES = ["01_neighbour_list", "02_gamma_velocity", "03_smooth_fields", "04_thermodynamics",
-               "05_06_08_local_update", "09_smooth_gradients", "10_time_derivatives", "other"]
+               "05_06_08_local_update", "09_smooth_gradients", "10_time_derivatives", "other", "01a_slab_migration", "01b_slab_column_tables"]
 
 _lib = None
 

@@ -22,7 +22,7 @@
 using namespace ccb;
 
 namespace {
-enum { PH_NEIGHBOUR = 0, PH_GAMMA, PH_SMOOTH_FIELDS, PH_THERMO, PH_LOCAL, PH_SMOOTH_GRAD, PH_TIME_DERIV, PH_OTHER, PH_COUNT };
+enum { PH_NEIGHBOUR = 0, PH_GAMMA, PH_SMOOTH_FIELDS, PH_THERMO, PH_LOCAL, PH_SMOOTH_GRAD, PH_TIME_DERIV, PH_OTHER, PH_SLAB_MIGRATE, PH_SLAB_TABLES, PH_COUNT };
 }
 
 struct ccb_ctx {
@@ -690,12 +690,14 @@ int do_build_cells(ccb_ctx* ctx) {
   ctx->hit_valid = false;
   if (ctx->comm) {
     int64_t n_sort = ctx->n, n_drop = 0;
-    if ((rc = migrate(ctx, &n_sort, &n_drop))) return rc;
+    { PhaseTimer pm(ctx, PH_SLAB_MIGRATE); rc = migrate(ctx, &n_sort, &n_drop); }
+    if (rc) return rc;
     ctx->dv.n = n_sort;
     if ((rc = sort_and_permute(ctx, n_sort, 1))) return rc;   // leavers -> sentinel key -> sorted last -> dropped
     ctx->n = n_sort - n_drop;
     ctx->dv.n = ctx->n;
-    if ((rc = exchange_column_tables(ctx))) return rc;
+    { PhaseTimer pc(ctx, PH_SLAB_TABLES); rc = exchange_column_tables(ctx); }
+    if (rc) return rc;
   } else {
     ctx->dv.n = ctx->n;
     if ((rc = sort_and_permute(ctx, ctx->n, 0))) return rc;
@@ -1415,8 +1417,9 @@ int ccb_profile_get(ccb_ctx* ctx, int phase, double* ms, int64_t* calls) {
 
 int ccb_profile_phase_count(void) { return PH_COUNT; }
 const char* ccb_profile_phase_name(int phase) {
+  // the two slab entries are PARTS of 01_neighbour_list in a multi-GPU run (they include waiting for the neighbouring ranks)
   static const char* kName[PH_COUNT] = {"01_neighbour_list", "02_gamma_velocity", "03_smooth_fields", "04_thermodynamics", "05_06_08_local_update",
-                                        "09_smooth_gradients", "10_time_derivatives", "other"};
+                                        "09_smooth_gradients", "10_time_derivatives", "other", "01a_slab_migration", "01b_slab_column_tables"};
   return phase >= 0 && phase < PH_COUNT ? kName[phase] : nullptr;
 }
 

@@ -306,8 +306,10 @@ CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const
   double f[4], J[4][4], val[4], jac[4][4];
   double fnorm = 0.0;
   int clamped = 0;
+  bool have = false;  // val / jac already hold the evaluation at x (the accepted trial point of the previous iterate)
   for (int it = 0; it <= kNewtonMaxIter; ++it) {
-    if (!chain_densities(ch, k, energy, x, val, jac)) return false;
+    if (!have && !chain_densities(ch, k, energy, x, val, jac)) return false;
+    have = false;
     // residuals in the reference's order: (s, B, Q, S)
     f[0] = val[0] - target[0]; f[1] = val[1] - target[1]; f[2] = val[3] - target[3]; f[3] = val[2] - target[2];
     CCB_UNROLL for (int d = 0; d < 4; ++d) { J[0][d] = jac[0][d]; J[1][d] = jac[1][d]; J[2][d] = jac[3][d]; J[3][d] = jac[2][d]; }
@@ -332,14 +334,13 @@ CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const
     }
     if (scale < 1.0) { if (++clamped > 12 || !(scale > 1e-6)) return false; } else clamped = 0;
     // backtracking on sum|f| (the interpolant is only piecewise smooth)
-    double xt[4], ft = 0.0;
+    // The trial point is evaluated WITH its Jacobian: when it is accepted it is the next iterate, and the same 16 vertex loads
+    // would otherwise be repeated at the top of the loop (a third of all table evaluations of a converging search).
+    double xt[4], ft = 0.0, v2[4], j2[4][4];
     bool accepted = false;
     for (int bt = 0; bt < 8; ++bt) {
       CCB_UNROLL for (int d = 0; d < 4; ++d) xt[d] = x[d] + scale * dx[d];
-      double v2[4];
-      bool ok;
-      if (ch.kind[k] == EOS_KIND_TABLE) ok = table_densities(ch.table, energy ? ch.table.hot_e : ch.table.hot_s, xt, v2, nullptr);
-      else { double jj[4][4]; ok = chain_densities(ch, k, energy, xt, v2, jj); }
+      const bool ok = chain_densities(ch, k, energy, xt, v2, j2);
       if (ok) {
         double g[4] = {v2[0] - target[0], v2[1] - target[1], v2[3] - target[3], v2[2] - target[2]};
         if (mode == 1) { g[1] = xt[1]; g[2] = xt[2]; g[3] = xt[3]; }
@@ -350,7 +351,11 @@ CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const
       scale *= 0.5;
     }
     if (!accepted) return false;  // GSL_ENOPROG
-    CCB_UNROLL for (int d = 0; d < 4; ++d) x[d] = xt[d];
+    CCB_UNROLL for (int d = 0; d < 4; ++d) {
+      x[d] = xt[d]; val[d] = v2[d];
+      CCB_UNROLL for (int e = 0; e < 4; ++e) jac[d][e] = j2[d][e];
+    }
+    have = true;
   }
   return false;
 }

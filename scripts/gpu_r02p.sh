@@ -1,0 +1,20 @@
+TAG=r02p
+mkdir -p gpurun_out
+nvidia-smi -L | wc -l
+run() { # name nproc env...
+  name=$1; np=$2; shift; shift
+  env "$@" timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $np --master-addr 127.0.0.1 --master-port 295$np$np bench.py --gpus $np --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_config4_$name.json 2> gpurun_out/${TAG}_bench_config4_$name.err
+  python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/${TAG}_bench_config4_$name.json").read().strip().splitlines()[-1])
+    pk=d["roofline"]["per_kernel"]
+    print("$name: %.2f ms/step  %.3e p-steps/s e2e %.3e" % (d["ms_per_step"], d["value"], d["e2e"]["value"]), {k[:2]: round(v["ms_per_launch"],2) for k,v in pk.items()}, d["config"]["parallelism"][:40], "parity", d.get("parity_check",{}).get("ok"), d.get("parity_check",{}).get("worst_rel_err"))
+except Exception as e:
+    print("$name failed", e); print(open("gpurun_out/${TAG}_bench_config4_$name.err").read()[-1500:])
+PY
+}
+run n8_strong 8 A=1
+run n8_strong_xaxis 8 CCB_SLAB_AXIS=0
+run n4_strong 4 A=1
+run n2_strong 2 A=1

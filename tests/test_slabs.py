@@ -178,3 +178,31 @@ print("P2P OK")
     env = dict(os.environ, CCB_HALO_P2P="1", CUDA_DEVICE_MAX_CONNECTIONS="32")
     out = subprocess.run([sys.executable, str(job)], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "P2P OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_min_max_partition_and_axis_choice():
+    """partition_columns minimises the largest slab over all contiguous cuts (brute force on a small case), charges ghost columns when
+    asked to, and best_axis prefers the axis along which the system is flat."""
+    import itertools
+
+    from ccake_b200 import slabs
+
+    rng = np.random.default_rng(3)
+    counts = rng.integers(1, 50, 12)
+    cols = np.repeat(np.arange(12), counts)
+    for nr in (2, 3, 4):
+        rg = slabs.partition_columns(cols, 12, nr)
+        got = max(counts[a:b].sum() for a, b in rg)
+        best = min(max(counts[a:b].sum() for a, b in zip((0,) + cut, cut + (12,))) for cut in itertools.combinations(range(1, 12), nr - 1))
+        assert got == best and rg[0][0] == 0 and rg[-1][1] == 12 and all(rg[i][1] == rg[i + 1][0] for i in range(nr - 1))
+    # ghost columns charged: the interior slab of three gives way to the edge slabs
+    flat = np.repeat(np.arange(12), 10)
+    assert slabs.partition_columns(flat, 12, 3) == [(0, 4), (4, 8), (8, 12)]
+    a, b = slabs.partition_columns(flat, 12, 3, halo_cost=1.0)[1]
+    assert b - a < 4
+    # a system that is a flat slab along z and a narrow Gaussian along x cuts better along z
+    r = np.stack([rng.normal(0.0, 0.5, 200000), rng.normal(0.0, 0.5, 200000), rng.uniform(-4.0, 4.0, 200000)], 1)
+    ax, worst = slabs.best_axis(r, [0.25, 0.25, 0.25], 8, halo_cost=0.0)
+    assert ax == 2 and worst < 1.1
+    w = slabs.particle_cost(r, r.min(0), [0.25, 0.25, 0.25])
+    assert abs(w.mean() - 1.0) < 1e-12 and w.min() >= 0.3
