@@ -401,6 +401,15 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Packed fp32 FMA of sm_100 (FFMA2): two candidates of the pre-filter per instruction. Each half is an IEEE fp32 fma, so the masks
+// are those of the scalar form bit for bit.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a); rb = *reinterpret_cast<unsigned long long*>(&b); rc = *reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 template <class P, int NT, int MINB, int TILE = kGatherTile>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
   constexpr int D = P::D, NW = TILE / 32, CH = P::CH_STAGE, RCH = P::REC / 2, RS2 = P::STRIDE / 2;
@@ -555,6 +564,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
         // cancels, so the cut-off carries an absolute margin for the fp32 rounding of coordinates up to `ext` (the
         // extent of the stencil around its origin): no true neighbour is missed; a false positive costs one exact test.
         const float ax = -2.f * tx[0], ay = -2.f * tx[1], az = -2.f * tx[2];
+        const float2 ax2 = make_float2(ax, ax), ay2 = make_float2(ay, ay), az2 = make_float2(az, az);
         const float thr = (gp.rsqr_f + 4.0e-6f * ext2) - fmaf(tx[0], tx[0], fmaf(tx[1], tx[1], tx[2] * tx[2]));
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -567,15 +577,15 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
               const float4 S = reinterpret_cast<const float4*>(&spos[3][w * 32])[b4];
               float4 Z = make_float4(0.f, 0.f, 0.f, 0.f);
               if (D == 3) Z = reinterpret_cast<const float4*>(&spos[2][w * 32])[b4];
-              const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
-              const float ss[4] = {S.x, S.y, S.z, S.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float v = ss[e];
-                if (D == 3) v = fmaf(az, zs[e], v);
-                v = fmaf(ax, xs[e], fmaf(ay, ys[e], v));
-                if (v <= thr) mw |= (1u << (b4 * 4 + e));
-              }
+              // v = |b|^2 + az z + ay y + ax x for four candidates, two per FFMA2, in the order of the scalar expression
+              float2 lo = make_float2(S.x, S.y), hi = make_float2(S.z, S.w);
+              if (D == 3) { lo = ffma2(az2, make_float2(Z.x, Z.y), lo); hi = ffma2(az2, make_float2(Z.z, Z.w), hi); }
+              lo = ffma2(ax2, make_float2(X.x, X.y), ffma2(ay2, make_float2(Y.x, Y.y), lo));
+              hi = ffma2(ax2, make_float2(X.z, X.w), ffma2(ay2, make_float2(Y.z, Y.w), hi));
+              if (lo.x <= thr) mw |= (1u << (b4 * 4 + 0));
+              if (lo.y <= thr) mw |= (1u << (b4 * 4 + 1));
+              if (hi.x <= thr) mw |= (1u << (b4 * 4 + 2));
+              if (hi.y <= thr) mw |= (1u << (b4 * 4 + 3));
             }
           }
           m[w] = active ? mw : 0u;
