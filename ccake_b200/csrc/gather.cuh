@@ -391,14 +391,38 @@ struct GradPolicy {
 // register allocation is bounded for.
 constexpr int kMaxSeg = 9;
 
-// Ampere-style asynchronous copies (LDGSTS): 16 bytes global -> shared without a register round trip. Used to land tile
-// k + 1 of the source records while tile k is being processed (the tiles are too small and too scattered for TMA boxes:
-// every record of a tile comes from a different 112..288-byte row of the record array).
+// Ampere-style asynchronous copies (LDGSTS): 16 bytes global -> shared without a register round trip. The fall-back staging path
+// (CCB_STAGE_BULK=0); the default path is the bulk copy below. Neither is a TMA *tensor* box: the records of a tile are an
+// interleaved sample of the candidates (every ntiles-th), each a separate 64..304-byte row of the record array.
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+// Bulk asynchronous copies (the TMA engine, UBLKCP): ONE instruction moves a whole staged record (64 .. 304 contiguous bytes)
+// global -> shared and reports its bytes to an mbarrier; the tile is complete when the barrier's transaction count is met.
+// Replaces 4 .. 19 LDGSTS per record and the cp.async group wait. Built with -DCCB_STAGE_BULK=1; NOT the default: measured on
+// all five configs (profiles/r02u_bulk_staging_experiment.txt) the engine's per-operation cost loses against LDGSTS for records
+// this small -- field gather (64-byte records) +9..13 %, gradient gather -1.6 % (192-byte records) to +4 % (112-byte records).
+#ifndef CCB_STAGE_BULK
+#define CCB_STAGE_BULK 0
+#endif
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)),
+               "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 // Packed fp32 FMA of sm_100 (FFMA2): two candidates of the pre-filter per instruction. Each half is an IEEE fp32 fma, so the masks
@@ -423,6 +447,15 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
   __shared__ uint32_t seg_start[kMaxSeg], seg_pref[kMaxSeg + 1];
   __shared__ const double2* seg_base[kMaxSeg];  // record array of the segment: own, or a neighbour's (ghost column)
   __shared__ int s_nseg, s_task;
+#if CCB_STAGE_BULK
+  __shared__ __align__(8) unsigned long long tile_bar[2];  // one transaction barrier per tile buffer
+  if (threadIdx.x == 0) {
+    mbar_init(&tile_bar[0], 1); mbar_init(&tile_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  uint32_t staged = 0;  // tiles this CTA has staged so far: tile number g lives in buffer g & 1 and completes phase (g >> 1) & 1 of its barrier
+  __syncthreads();
+#endif
   const double* __restrict__ rec = P::records(dv);
   const double2* __restrict__ rec2 = reinterpret_cast<const double2*>(rec);
   const int nx = g.nc[0], ny = g.nc[1], nz = g.nc[2];
@@ -510,6 +543,24 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     // costs max-over-lanes(hits) per tile). Tile k + 1 is in flight (cp.async) while tile k is processed.
     // Staging: record r of tile k is candidate r * ntiles + k. NT / TILE threads share a record and copy alternating 16-byte
     // chunks of it, so that the segment search and the address arithmetic run once per thread and tile.
+#if CCB_STAGE_BULK
+    const uint32_t g0 = staged;   // global number of this task's tile 0
+    auto stage = [&](uint32_t k) {
+      const uint32_t slot = (g0 + k) & 1u;
+      double2* buf = srec2[slot];
+      const int nt = (int)((C - k + ntiles - 1) / ntiles);
+      if (threadIdx.x == 0) mbar_expect_tx(&tile_bar[slot], (unsigned)nt * (unsigned)(CH * 16));
+      for (int r = threadIdx.x; r < nt; r += NT) {
+        const uint32_t cand = (uint32_t)r * ntiles + k;
+        int sg = 0;
+        while (cand >= seg_pref[sg + 1]) ++sg;
+        const double2* src = seg_base[sg] + ((int64_t)seg_start[sg] + (cand - seg_pref[sg])) * RCH;
+        bulk_g2s(buf + r * RS2, src, CH * 16, &tile_bar[slot]);
+      }
+    };
+    if (ntiles) stage(0);
+    staged += ntiles;
+#else
     auto stage = [&](uint32_t k, double2* buf) {
       constexpr int TPR = (NT >= TILE) ? NT / TILE : 1;
       const int nt = (int)((C - k + ntiles - 1) / ntiles);
@@ -525,6 +576,7 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
       cp_async_commit();
     };
     if (ntiles) stage(0, srec2[0]);
+#endif
     // hit masks of the stage (GatherParams::hitmask): written by the field gather, read back by the gradient gather
     const int kmask = gp.hitmask ? gp.hit_kmax : 0;
     unsigned long long* hm = gp.hitmask + (active ? i : first);
@@ -532,11 +584,18 @@ __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGri
     if (P::MASK_MODE == 2 && kmask > 0 && ntiles) mnext = active ? __ldg(hm) : 0ull;
     for (uint32_t k = 0; k < ntiles; ++k) {
       const int nt = (int)((C - k + ntiles - 1) / ntiles);
-      const double2* srec = srec2[k & 1];
       const bool reuse = P::MASK_MODE == 2 && (int)k < kmask;  // CTA-uniform
+#if CCB_STAGE_BULK
+      const double2* srec = srec2[(g0 + k) & 1u];
+      mbar_wait(&tile_bar[(g0 + k) & 1u], ((g0 + k) >> 1) & 1u);   // every byte of tile k has landed
+      __syncthreads();  // tile k - 1 (the other buffer, spos) is fully consumed by every thread
+      if (k + 1 < ntiles) stage(k + 1);
+#else
+      const double2* srec = srec2[k & 1];
       cp_async_wait_all();
       __syncthreads();  // tile k has landed for every thread, and tile k - 1 (buffer (k + 1) & 1, spos) is fully consumed
       if (k + 1 < ntiles) stage(k + 1, srec2[(k + 1) & 1]);
+#endif
       uint32_t m[NW];
       if (reuse) {
         m[0] = (uint32_t)mnext;
