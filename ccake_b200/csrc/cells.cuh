@@ -127,7 +127,9 @@ __global__ void p2p_signal(int* peer_a, int* peer_b, int epoch, const int* spars
   __threadfence_system();
 }
 // One thread waits until both own flag words (nullptr = no neighbour) carry at least `epoch`; the neighbours' sparsity bits are
-// OR-ed into *ghost_flag (nullptr = not wanted). Gives up with CCB_ERR_COMM after ~10 s of polling rather than hanging the GPU.
+// OR-ed into *ghost_flag (nullptr = not wanted). Gives up with CCB_ERR_COMM after ~60 s of polling rather than hanging the GPU (a
+// neighbour that is merely slow -- first-touch IPC mapping, a profiler, heavy imbalance -- stays well inside that); the boundary
+// launch of the gather that follows on the same stream sees the error word and does no work (gather_kernel).
 __global__ void p2p_wait(const int* flag_a, const int* flag_b, int epoch, int* ghost_flag, int32_t* err) {
   int bits = 0;
   const int* f[2] = {flag_a, flag_b};
@@ -137,7 +139,7 @@ __global__ void p2p_wait(const int* flag_a, const int* flag_b, int epoch, int* g
     int v;
     while (((v = *reinterpret_cast<const volatile int*>(f[k])) >> 1) < epoch) {
       __nanosleep(200);
-      if (++spins > 50000000LL) { atomicCAS(&err[0], 0, (int)CCB_ERR_COMM); return; }
+      if (++spins > 300000000LL) { atomicCAS(&err[0], 0, (int)CCB_ERR_COMM); return; }
     }
     if ((v >> 1) == epoch) bits |= v & 1; else bits |= 1;  // a later epoch already: assume the general case
   }

@@ -133,6 +133,7 @@ struct LocalHub {
   std::condition_variable cv;
   std::map<std::pair<int, int>, std::deque<Msg>> q;  // (src, dst) -> FIFO
   std::map<int, std::pair<void*, void*>> ptrs;       // rank -> (record array, flag words): exchange_pointers
+  std::map<int, int> ptr_gen;                        // rank -> number of times it has published: a second exchange (re-upload) must not read the first one's pointers
   int nranks = 0;
   static std::shared_ptr<LocalHub> get(int group, int nranks) {
     static std::mutex gmu;
@@ -184,12 +185,13 @@ struct LocalLink : Link {
   int exchange_pointers(void* rec, void* flags, int left, int right, void* peer_rec[2], void* peer_flags[2], cudaStream_t) override {
     std::unique_lock<std::mutex> l(hub->mu);
     hub->ptrs[rank] = {rec, flags};
+    const int gen = ++hub->ptr_gen[rank];
     hub->cv.notify_all();
     const int peer[2] = {left, right};
     for (int k = 0; k < 2; ++k) {
       peer_rec[k] = peer_flags[k] = nullptr;
       if (peer[k] < 0) continue;
-      hub->cv.wait(l, [&] { return hub->ptrs.count(peer[k]) != 0; });
+      hub->cv.wait(l, [&] { return hub->ptr_gen.count(peer[k]) != 0 && hub->ptr_gen[peer[k]] >= gen; });
       peer_rec[k] = hub->ptrs[peer[k]].first; peer_flags[k] = hub->ptrs[peer[k]].second;
     }
     return 0;

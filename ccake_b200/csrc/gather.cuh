@@ -437,6 +437,9 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 template <class P, int NT, int MINB, int TILE = kGatherTile>
 __global__ void __launch_bounds__(NT, MINB) gather_kernel(DeviceView dv, CellGrid g, GatherParams gp) {
   constexpr int D = P::D, NW = TILE / 32, CH = P::CH_STAGE, RCH = P::REC / 2, RS2 = P::STRIDE / 2;
+  // boundary launch of a slab run: a failed wait for the neighbours (p2p_wait -> CCB_ERR_COMM) must not be followed by reads of
+  // ghost records that never became ready
+  if (gp.task_sel == 2 && dv.err[0] != 0) return;
   // compile-time sparsity variants (GradPolicy QNZ): only the launch that matches the run-time flag does the work
   if (P::VARIANT >= 0) {
     const bool nz = (dv.qflag[P::FLAG] | dv.qflag[P::FLAG + 1]) != 0;

@@ -70,3 +70,28 @@ def conformal_flat_table(Ns=121, NB=81, s_range=(1e-3, 1e3), nB_range=(1e-7, 10.
     z = np.zeros_like(S)
     return dict(s=S * hc ** 3, nB=B * hc ** 3, T=T * hc, muB=mu * hc, muS=z, muQ=z, e=3 * p * hc ** 4, p=p * hc ** 4, cs2=z + 1.0 / 3.0,
                 chiTT=4 * c * (3 * T * T + mu * mu) * hc ** 2, chiTB=8 * c * T * mu * hc ** 2, chiBB=4 * c * (T * T + 3 * mu * mu) * hc ** 2)
+
+
+def save_ccbpre(path, tiles=None, flat=None):
+    """The binary file the drop-in ``EoS_Interpolator(fs::path)`` reads (``include/ccake_dropin/eos_interpolator.h``; HDF5 is absent
+    from this image): magic ``CCBPRE01``, int32 flat, int32 ntiles, then either Ns, NB + the twelve (Ns, NB) arrays of the flat table
+    in ccb_preinverted_flat order, or per tile slot[4], N[4], log_spacing[4] (int32), min[4], step[4] (float64) and vars (11, N0..N3)."""
+    import struct
+
+    with open(path, "wb") as f:
+        f.write(b"CCBPRE01")
+        if flat is not None:
+            Ns, NB = flat["s"].shape
+            f.write(struct.pack("<iiii", 1, 0, Ns, NB))
+            for k in ("s", "nB", "T", "muB", "muS", "muQ", "e", "p", "cs2", "chiTT", "chiTB", "chiBB"):
+                f.write(np.ascontiguousarray(flat[k], dtype=np.float64).tobytes())
+        else:
+            f.write(struct.pack("<ii", 0, len(tiles)))
+            for t in tiles:
+                v = np.ascontiguousarray(t["vars"], dtype=np.float64)
+                f.write(struct.pack("<4i", *[int(e) + 3 for e in t["exponent"]]))   # slot = decade exponent + 3 (ccb_preinverted_tile)
+                f.write(struct.pack("<4i", *v.shape[1:]))
+                f.write(struct.pack("<4i", *[int(x) for x in t.get("log_spacing", (0, 0, 0, 0))]))
+                f.write(struct.pack("<4d", *[float(x) for x in t["min"]]))
+                f.write(struct.pack("<4d", *[float(x) for x in t["step"]]))
+                f.write(v.tobytes())

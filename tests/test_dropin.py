@@ -139,3 +139,37 @@ def test_unmodified_bsqhydro_with_particlization_writes_the_hypersurface(tmp_pat
     assert np.array_equal(rows[:, 21], sim.ints("freeze").astype(float))
     fo = open(out / "freeze_out.dat").read().splitlines()
     assert fo[0].startswith("#") and len(fo) - 1 == printed
+
+
+@pytest.mark.gpu
+def test_unmodified_bsqhydro_on_a_preinverted_table(tmp_path):
+    """eos.online_inverter_enabled: false (the reference's default): SPHWorkstation::initialize constructs EoS_Interpolator from
+    Settings::preinverted_eos_path -- the drop-in one reads the CCBPRE01 file eos_preinverted.save_ccbpre writes (no HDF5 here) -- and the
+    run initialises and evolves on the flat (s, n_B) table; against the reference running its own EoS_Interpolator on the same table."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    from ccake_b200 import eos_preinverted as P
+    from oracle import ref
+
+    flat = P.conformal_flat_table()
+    P.save_ccbpre(str(tmp_path / "flat.ccbpre"), flat=flat)
+    h5 = str(tmp_path / "flat.h5")
+    ref.h5_put_flat(h5, flat)
+    settings = viscous_settings(online_inverter_enabled=False, baryon_charge_enabled=True, dt=0.05, max_tau=1.07)
+    ic = gubser_ic(dx=0.1, shear=True, charges=True)
+    ic["rhoS"], ic["rhoQ"] = None, None
+    rows, t, steps, out = _run_dropin(settings, ic, tmp_path, preinverted_eos_path=str(tmp_path / "flat.ccbpre"))
+    sim = make_ref(dict(settings, preinverted_eos_path=h5), ic)
+    sim.initialize()
+    k = 0
+    while sim.t <= settings["max_tau"]:
+        sim.advance(settings["dt"], 2)
+        k += 1
+    assert steps == k == 2 and rows.shape[0] == sim.n
+    ref_rows = _ref_rows(sim)
+    assert np.array_equal(rows[:, 21], ref_rows[:, 21])
+    pmax = float(np.max(np.abs(ref_rows[:, 8])))
+    for name in ("r", "u", "T", "e", "p", "s", "bulk", "shv", "sigma", "gamma", "extensive_s"):
+        lo, hi = COLS[name]
+        scale = pmax if name in ("bulk", "shv") else None   # Pi and pi^{mu nu} on the scale of the pressure (Pi is ~1e-12 here)
+        assert common.rel_err(rows[:, lo:hi], ref_rows[:, lo:hi], scale) <= 3 * TOL * (k + 1), name

@@ -144,3 +144,23 @@ def test_flat_table_lookup_and_init_queries_match_the_reference():
         for k in range(12):
             assert np.max(np.abs(out[:, k] - want_q[:, k])) <= 1e-12 * max(np.max(np.abs(want_q[:, k])), 1.0), (energy, k)
         assert abs(efh.value - ef) <= 1e-13 * abs(ef)
+
+
+def test_ccbpre_file_layout(tmp_path):
+    """eos_preinverted.save_ccbpre writes what include/ccake_dropin/eos_interpolator.h reads: magic, flat flag, tile count, then the
+    flat arrays in ccb_preinverted_flat order or per tile slot (= exponent + 3), N, log_spacing, min, step, vars."""
+    import struct
+
+    from ccake_b200 import eos_preinverted as P
+
+    flat = P.conformal_flat_table(Ns=5, NB=4)
+    p = tmp_path / "f.ccbpre"
+    P.save_ccbpre(str(p), flat=flat)
+    b = open(p, "rb").read()
+    assert b[:8] == b"CCBPRE01" and struct.unpack("<iiii", b[8:24]) == (1, 0, 5, 4) and len(b) == 24 + 12 * 5 * 4 * 8
+    assert np.array_equal(np.frombuffer(b[24:24 + 160]), flat["s"].ravel()) and np.array_equal(np.frombuffer(b[-160:]), flat["chiBB"].ravel())
+    tiles = [dict(exponent=(-1, 0, -2, -3), min=[1, 2, 3, 4], step=[.1, .2, .3, .4], vars=np.arange(11 * 16, dtype=float).reshape(11, 2, 2, 2, 2))]
+    P.save_ccbpre(str(p), tiles=tiles)
+    b = open(p, "rb").read()
+    assert struct.unpack("<ii", b[8:16]) == (0, 1) and struct.unpack("<4i", b[16:32]) == (2, 3, 1, 0) and struct.unpack("<4i", b[32:48]) == (2, 2, 2, 2)
+    assert struct.unpack("<4d", b[64:96]) == (1.0, 2.0, 3.0, 4.0) and len(b) == 16 + 48 + 64 + 11 * 16 * 8
