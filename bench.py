@@ -248,7 +248,9 @@ def algorithmic_bytes(D, shear, diffusion):
     persistent = 3 + 3 + 4 + 4 + 1 + 5 + (9 if diffusion else 0) + 1 + 4
     evolved = 3 + 3 + 4 + 1 + 5 + (9 if diffusion else 0) + 1
     return {
-        "01_neighbour_list": 8 * (3 + 2 * (persistent + evolved)) + 4 * (2 + 4 * 2 * 3 + 8),
+        # keys + sort + permute of the persistent columns and the RK snapshot. Averaged over the two stages of an RK2 step: the first
+        # sort of a step WRITES y0 (the sorted evolved columns stored twice), the second permutes it (read + write)
+        "01_neighbour_list": 8 * (3 + 2 * persistent + 1.5 * evolved) + 4 * (2 + 4 * 2 * 3 + 8),
         "02_gamma_velocity": 8 * ((D + 3 + 8) + (1 + D + 8)),
         "03_smooth_fields": 8 * (8 + 1 + 10) + 8,
         "04_thermodynamics": 8 * (4 + D + 3 + 1 + 5 + (9 if diffusion else 0) + 3 + 4) + 8 * (16 + 12 + 4 + 1 + 16 + 12 + 13 + rec_g),
@@ -458,6 +460,9 @@ def own_arm(args, rank, world, local_rank):
     phases = ws.profile_table()
     ws.profile(False)
     clocks = sampler.stop()
+    # neighbour counts of the last timed stage (the pair count of the roofline): read here, before the end-to-end leg evolves the
+    # system further (an expanding fireball loses neighbours: 245 -> 220 per particle over 40 more steps of config 4)
+    bt = ws.get_int_device_order("btrack") if world > 1 else ws.get_int("btrack")
 
     # ---- end to end through the public API with HOST buffers --------------------------------
     w = ws.state_width
@@ -514,7 +519,6 @@ def own_arm(args, rank, world, local_rank):
     t_dom = per_kernel[dom]["ms_per_launch"] * 1e-3
     achieved = alg.get(dom, 0) * n / t_dom / 1e9
     n = ws.n_particles
-    bt = ws.get_int_device_order("btrack") if world > 1 else ws.get_int("btrack")
     # which member of the EoS fall-back chain located each particle at the end of the run (rank 0's particles): a population that
     # drifts away from the table would show here (EquationOfState::chosen_EOSs order, src/eos_initialization.cpp:249-455)
     eos_members = None

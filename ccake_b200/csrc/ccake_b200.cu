@@ -54,7 +54,7 @@ struct ccb_ctx {
   int32_t* tasks = nullptr;     // gather task list (cell order), one entry per chunk of <= task_nt particles of one cell
   uint32_t* task_pos = nullptr; // cap + 1: task flags, then their exclusive scan
   int32_t* d_taskinfo = nullptr;// [0..2] task counts (cells.cuh: task_scatter), [4] / [5] task counters of the interior / boundary launch
-  int32_t* d_small = nullptr;   // [0] ntasks, [1..2] err
+  int32_t* d_small = nullptr;   // [1..2] error code and first offending particle id
   double* d_stage = nullptr;    // staging for id-ordered transfers (16 columns) and reductions
   double* init_tmp = nullptr;
   double* d_reduce = nullptr;   // per-block partials of ccb_reduce
@@ -319,7 +319,7 @@ int allocate_particles(ccb_ctx* ctx, int64_t n) {
   dv.cell_start = ctx->cell_count;
   dv.rec_fields = ctx->rec; dv.rec_grad = ctx->rec;
   dv.ghost_rec[0] = dv.ghost_rec[1] = ctx->rec;
-  dv.tasks = ctx->tasks; dv.ntasks = ctx->d_taskinfo; dv.err = ctx->d_small + 1;
+  dv.tasks = ctx->tasks; dv.err = ctx->d_small + 1;
   const int64_t need_sums = cdiv(std::max<int64_t>(std::max<int64_t>(ctx->hist_alloc, ctx->grid.ncells + 1), cap + 1), kScanTile) + 1;
   if (need_sums > ctx->sums_alloc) {
     cudaFree(ctx->scan_sums);

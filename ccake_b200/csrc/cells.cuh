@@ -59,12 +59,6 @@ struct MigrateList {
   double* col[96];
   int32_t* icol[4];
 };
-__global__ void pack_rows(MigrateList ml, int64_t start, int64_t count, double* __restrict__ dbuf, int32_t* __restrict__ ibuf) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= count) return;
-  for (int c = 0; c < ml.ncols; ++c) dbuf[(int64_t)c * count + k] = ml.col[c][start + k];
-  for (int c = 0; c < 4; ++c) ibuf[(int64_t)c * count + k] = ml.icol[c][start + k];
-}
 __global__ void unpack_rows(MigrateList ml, int64_t start, int64_t count, const double* __restrict__ dbuf, const int32_t* __restrict__ ibuf) {
   const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= count) return;
@@ -435,15 +429,7 @@ __global__ void dfma_peak_kernel(double* out, int iters, double m) {
   if (s == 123.456) out[threadIdx.x] = s;
 }
 
-// scatter a column (current order) into id order for download, and the reverse for upload
-__global__ void scatter_by_id(const double* __restrict__ src, double* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[id[i]] = src[i];
-}
-__global__ void gather_by_id(const double* __restrict__ src, double* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) dst[i] = src[id[i]];
-}
+// integer columns (current order) <-> particle-id order
 __global__ void scatter_int_by_id(const int32_t* __restrict__ src, int32_t* __restrict__ dst, const int32_t* __restrict__ id, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[id[i]] = src[i];

@@ -53,7 +53,6 @@ struct DeviceView {
   int* qflag;                  // [0] some own gradient record carries a non-zero diffusion current q^mu_a, [1] some ghost record does;
                                // [2], [3] likewise for a non-zero B, S or Q entry of the field records
   int32_t* tasks;              // gather tasks in cell order: first particle of every chunk of <= NT particles of one cell
-  int32_t* ntasks;
   int32_t* err;                // [0] status code, [1] first offending particle id
   int eos_type_is_table;       // the run's EoS chain starts with the table (thermodynamic_info::eos_type_is_table of member 0)
   // slab decomposition: the cell columns (index along x) just outside this rank's slab hold GHOST records,
