@@ -1363,7 +1363,6 @@ int ccb_eos_locate(ccb_ctx* ctx, int energy, int64_t n, const double* dens, cons
   if (!ctx || n < 0 || (n && (!dens || !thermo || !eos))) return CCB_ERR_INVALID;
   if (n == 0) return CCB_OK;
   if (!energy && !seed && ctx->use_chain) { ctx->err = "ccb_eos_locate: update_s needs a seed point"; return CCB_ERR_INVALID; }
-  if (energy && !ctx->use_chain) { ctx->err = "ccb_eos_locate: energy = 1 (s_out) is built for the chain equations of state only"; return CCB_ERR_INVALID; }
   if (ctx->use_chain && !ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
   DevBuf<double> d_dens, d_seed, d_th;
   DevBuf<int32_t> d_start, d_eos;

@@ -95,7 +95,8 @@ __global__ void eos_locate_kernel(EosChain ch, ConformalParams conf, int use_cha
     if (ok) { chain_thermo(ch, res, th); eos = res.eos; }
   } else {
     double T, muB, muS, muQ;
-    ok = energy ? false : conformal_invert_s(conf, a, B, S, Q, T, muB, muS, muQ);
+    // closed-form conformal EoS: (s | e, rho) -> (T, mu) (EoS_conformal::get_tbqs_seed_from_{s,e}BSQ are exact inverses there)
+    ok = energy ? conformal_invert_e(conf, a, B, S, Q, T, muB, muS, muQ) : conformal_invert_s(conf, a, B, S, Q, T, muB, muS, muQ);
     if (ok) {
       double r[TH_N];
       conformal_full_thermo(conf, T, muB, muQ, muS, r);

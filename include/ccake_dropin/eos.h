@@ -67,6 +67,11 @@ class EquationOfState {
     return solution_found ? th16[5] : 0.0;
   }
   double s_out(double ein, bool& solution_found) { return s_out(ein, 0.0, 0.0, 0.0, solution_found); }
+  // the same for n density vectors (e, rhoB, rhoS, rhoQ) at once: thermo[n][16] in CCB_F_THERMO order, eos[n] = answering member of
+  // chosen_EOSs or -1 where s_out reports no solution. One device call (SPHWorkstation::freeze_in_match iterates over all cells).
+  void s_out_batch(int64_t n, const double* dens, double* thermo, int32_t* eos) {
+    if (n > 0) device->check(ccb_eos_locate(device->ctx, 1, n, dens, nullptr, nullptr, thermo, eos));
+  }
 
   double T() const { return point[0]; }
   double muB() const { return point[1]; }

@@ -8,6 +8,8 @@
 #ifndef SPH_WORKSTATION_H
 #define SPH_WORKSTATION_H
 
+#include <algorithm>
+#include <cmath>
 #include <iostream>
 #include <memory>
 #include <string>
@@ -90,6 +92,7 @@ class SPHWorkstation {
   // the host half of process_initial_conditions (src/sph_workstation.cpp:1229-1340): gamma, unit extensive densities and SPH
   // masses, the root-finder's seed, particle ids
   void process_initial_conditions() {
+    if (settingsPtr->IC_type == "freezein") freeze_in_match();   // src/sph_workstation.cpp:1236-1237
     systemPtr->n_particles = (int)systemPtr->particles.size();
     const double t = settingsPtr->t0, t2 = t * t;
     for (auto& p : systemPtr->particles) {
@@ -105,7 +108,91 @@ class SPHWorkstation {
     }
     for (int i = 0; i < systemPtr->n_particles; i++) { systemPtr->particles[i].ID = i; systemPtr->particles[i].hydro.ID = i; }
   }
-  void freeze_in_match() { throw std::runtime_error("IC_type freezein is out of scope (SURVEY.md section 2)"); }
+  // IC_type "freezein" (SPHWorkstation::freeze_in_match, src/sph_workstation.cpp:1024-1221): the raw T^{tau mu}, j_a^tau that
+  // BSQHydro::read_freezein stored on every particle -> (epsilon, u^mu, rho_a) by the fixed-point iteration v <- |M| / (M^0 + P(eps, n))
+  // with the pressure closed by the EoS. The reference iterates particle by particle with one host root search per iterate; here
+  // all unconverged cells advance together and each iterate is ONE batched device query (the per-particle arithmetic and the
+  // convergence test are the reference's, so every cell takes the same iterates).
+  void freeze_in_match() {
+    if (D < 2) throw std::runtime_error("Freeze-in IC requires D >= 2 (raw T^{mu nu} grids are 2D/3D).");
+    const double hc = constants::hbarc_GeVfm;
+    const double tau = settingsPtr->t0;
+    const bool hyper = settingsPtr->coordinate_system == "hyperbolic";
+    const double t2 = (D == 3 && hyper) ? tau * tau : 1.0;
+    const double tol = settingsPtr->freezein_tol, v_cap = 1.0 - 1e-12, e_floor = settingsPtr->e_cutoff / hc;
+    const int maxit = settingsPtr->freezein_max_iter;
+    const bool use[3] = {settingsPtr->baryon_charge_enabled, settingsPtr->strange_charge_enabled, settingsPtr->electric_charge_enabled};
+    auto& ps = systemPtr->particles;
+    const size_t n = ps.size();
+    std::vector<double> M0(n), Mx(n), My(n), Mn(n), Mmag(n), v(n), P(n, 0.0), j0(3 * n);
+    std::vector<char> done(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+      const Particle<D>& p = ps[i];
+      M0[i] = p.freezein_Ttau[0] / hc; Mx[i] = p.freezein_Ttau[1] / hc; My[i] = p.freezein_Ttau[2] / hc;
+      Mn[i] = (D == 3) ? p.freezein_Ttau[3] / hc : 0.0;
+      Mmag[i] = std::sqrt(Mx[i] * Mx[i] + My[i] * My[i] + t2 * Mn[i] * Mn[i]);
+      j0[3 * i] = p.freezein_jB[0]; j0[3 * i + 1] = p.freezein_jS[0]; j0[3 * i + 2] = p.freezein_jQ[0];
+      v[i] = (M0[i] > 0.0) ? std::min(Mmag[i] / M0[i], v_cap) : 0.0;
+    }
+    std::vector<size_t> idx;
+    std::vector<double> dens, th;
+    std::vector<int32_t> member;
+    for (int it = 0; it < maxit; ++it) {
+      idx.clear(); dens.clear();
+      for (size_t i = 0; i < n; ++i) {
+        if (done[i]) continue;
+        const double eps = std::max(M0[i] - v[i] * Mmag[i], 0.0), gamma = 1.0 / std::sqrt(1.0 - v[i] * v[i]);
+        if (eps > e_floor) {
+          idx.push_back(i);
+          dens.push_back(eps);
+          for (int a = 0; a < 3; ++a) dens.push_back(use[a] ? j0[3 * i + a] / gamma : 0.0);
+        } else P[i] = 0.0;   // near-vacuum cell
+      }
+      th.assign(16 * idx.size(), 0.0); member.assign(idx.size(), -1);
+      eos.s_out_batch((int64_t)idx.size(), dens.data(), th.data(), member.data());
+      // locate_phase_diagram_point_eBSQ: a cell without a solution is located again without its charges (src/sph_workstation.cpp:1808-1832)
+      std::vector<size_t> again;
+      std::vector<double> dens0;
+      for (size_t k = 0; k < idx.size(); ++k)
+        if (member[k] < 0) { again.push_back(k); dens0.insert(dens0.end(), {dens[4 * k], 0.0, 0.0, 0.0}); }
+      if (!again.empty()) {
+        std::vector<double> th0(16 * again.size());
+        std::vector<int32_t> m0(again.size());
+        eos.s_out_batch((int64_t)again.size(), dens0.data(), th0.data(), m0.data());
+        for (size_t q = 0; q < again.size(); ++q)
+          if (m0[q] >= 0) { member[again[q]] = m0[q]; for (int c = 0; c < 16; ++c) th[16 * again[q] + c] = th0[16 * q + c]; }
+      }
+      for (size_t k = 0; k < idx.size(); ++k) if (member[k] >= 0) P[idx[k]] = th[16 * k + 9];   // else: the pressure of the last successful location
+      bool all = true;
+      for (size_t i = 0; i < n; ++i) {
+        if (done[i]) continue;
+        const double denom = M0[i] + P[i];
+        const double v_new = (denom > 0.0) ? std::min(Mmag[i] / denom, v_cap) : 0.0;
+        if (std::abs(v_new - v[i]) < tol) done[i] = 1; else all = false;
+        v[i] = v_new;
+      }
+      if (all) break;
+    }
+    std::vector<Particle<D>> kept;
+    kept.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+      const double gamma = 1.0 / std::sqrt(1.0 - v[i] * v[i]);
+      const double eps = std::max(M0[i] - v[i] * Mmag[i], 0.0);
+      if (eps <= e_floor) continue;   // the decisive cut, on the rest-frame energy density
+      Particle<D> p = ps[i];
+      const double s = Mmag[i] > 0.0 ? gamma * v[i] / Mmag[i] : 0.0;
+      p.input.e = eps;
+      p.input.rhoB = use[0] ? j0[3 * i] / gamma : 0.0; p.input.rhoS = use[1] ? j0[3 * i + 1] / gamma : 0.0; p.input.rhoQ = use[2] ? j0[3 * i + 2] / gamma : 0.0;
+      p.hydro.u(0) = s * Mx[i];
+      if (D >= 2) p.hydro.u(1) = s * My[i];
+      if (D == 3) p.hydro.u(2) = s * Mn[i];
+      p.hydro.bulk = 0.0; p.hydro.shv = 0.0; p.hydro.diffusion = 0.0;   // ideal IC: the residual stress is discarded
+      p.thermo.T = 580.0 / constants::hbarc_MeVfm; p.thermo.muB = p.thermo.muS = p.thermo.muQ = 0.0; p.thermo.eos_name = "default";
+      p.Freeze = 0;
+      kept.push_back(p);
+    }
+    systemPtr->particles = std::move(kept);
+  }
 
   // The rows BSQHydro::read_ccake stored in `particles` (src/BSQHydro.cpp:262-403, fm units) go to the device in the units of the
   // IC file, and the library runs initialize_entropy_and_charge_densities + calculate_intial_sigma + initial_smoothing

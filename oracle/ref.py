@@ -89,7 +89,7 @@ SETTING_KEYS = frozenset([
     "prohibit_unstable_cs2", "prohibit_acausal_cs2", "restrict_mu_T_ratios", "C_B", "critical_scaling_bulk", "critical_scaling_diffusion",
     "critical_point_T", "critical_point_muB", "critical_gaussian_width_T", "critical_gaussian_width_muB", "diffusion_regulator_enabled",
     "diffusion_regulator_chi0", "diffusion_regulator_e0", "diffusion_regulator_xi0", "diffusion_regulator_rq_max",
-    "online_inverter_enabled", "preinverted_eos_path", "particlization_enabled"])
+    "online_inverter_enabled", "preinverted_eos_path", "particlization_enabled", "IC_type", "freezein_tol", "freezein_max_iter"])
 
 
 def available() -> bool:
@@ -108,6 +108,7 @@ def lib():
         L.ccake_ref_create.argtypes = [C.c_char_p]
         L.ccake_ref_destroy.argtypes = [C.c_void_p]
         L.ccake_ref_add_particles.argtypes = [C.c_void_p, C.c_long] + [dp] * 9
+        L.ccake_ref_add_freezein.argtypes = [C.c_void_p, C.c_long] + [dp] * 5
         for f in ("initialize", "get_time_derivatives"):
             getattr(L, "ccake_ref_" + f).argtypes = [C.c_void_p]
         L.ccake_ref_phase.argtypes = [C.c_void_p, C.c_int]
@@ -269,6 +270,15 @@ class RefSim:
         arrs.append(np.zeros((n, 6)) if shv6 is None else np.ascontiguousarray(shv6, dtype=np.float64))
         q = None if diffusion is None else np.ascontiguousarray(np.asarray(diffusion, dtype=np.float64).reshape(n, 12))
         lib().ccake_ref_add_particles(self.h, n, *[_dp(a) for a in arrs], None if q is None else _dp(q))
+
+    def add_freezein(self, r, Ttau, jB, jS, jQ):
+        """IC_type "freezein": per cell the position and the raw T^{tau mu} [GeV/fm^3], j_B^mu, j_S^mu, j_Q^mu [1/fm^3] (n x 4 each), as
+        BSQHydro::read_freezein stages them; initialize() then runs SPHWorkstation::freeze_in_match."""
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        n = r.shape[0]
+        r3 = np.zeros((n, 3)); r3[:, : r.shape[1]] = r
+        arrs = [r3] + [np.ascontiguousarray(a, dtype=np.float64).reshape(n, 4) for a in (Ttau, jB, jS, jQ)]
+        lib().ccake_ref_add_freezein(self.h, n, *[_dp(a) for a in arrs])
 
     def initialize(self):
         lib().ccake_ref_initialize(self.h)

@@ -37,6 +37,7 @@ struct RefBase {
   virtual ~RefBase() {}
   virtual int add_particles(long n, const double* r, const double* e_or_s, const double* rhoB, const double* rhoS,
                             const double* rhoQ, const double* u, const double* bulk, const double* shv6, const double* q12) = 0;
+  virtual int add_freezein(long n, const double* r, const double* Ttau, const double* jB, const double* jS, const double* jQ) = 0;
   virtual int initialize() = 0;
   virtual int allocate_raw(long n) = 0;
   virtual int phase(int which) = 0;
@@ -98,6 +99,21 @@ struct Ref : RefBase {
         const double e_check = (3. * C) * pow(1. / (4. * C), 4. / 3.) * pow(e_or_s[i], 4. / 3.);
         if (e_check > st->e_cutoff / hc) sys->add_particle(p);
       } else if (e > st->e_cutoff / hc) sys->add_particle(p);
+    }
+    return 0;
+  }
+
+  // The per-row work of BSQHydro::read_freezein (src/BSQHydro.cpp:449-544): raw T^{tau mu} [GeV/fm^3] and j_a^mu [1/fm^3] staged on
+  // the particle, with its safe pre-filter on T^{tau tau}; SPHWorkstation::freeze_in_match then runs inside process_initial_conditions.
+  int add_freezein(long n, const double* r, const double* Ttau, const double* jB, const double* jS, const double* jQ) override {
+    for (long i = 0; i < n; ++i) {
+      if (Ttau[4 * i] <= st->e_cutoff) continue;
+      Particle<D> p;
+      for (unsigned d = 0; d < D; ++d) p.r(d) = r[3 * i + d];
+      for (int k = 0; k < 4; ++k) {
+        p.freezein_Ttau[k] = Ttau[4 * i + k]; p.freezein_jB[k] = jB[4 * i + k]; p.freezein_jS[k] = jS[4 * i + k]; p.freezein_jQ[k] = jQ[4 * i + k];
+      }
+      sys->add_particle(p);
     }
     return 0;
   }
@@ -311,6 +327,9 @@ int ccake_ref_add_particles(void* h, long n, const double* r, const double* e_or
                             const double* rhoS, const double* rhoQ, const double* u, const double* bulk,
                             const double* shv6, const double* q12) {
   return static_cast<RefBase*>(h)->add_particles(n, r, e_or_s, rhoB, rhoS, rhoQ, u, bulk, shv6, q12);
+}
+int ccake_ref_add_freezein(void* h, long n, const double* r, const double* Ttau, const double* jB, const double* jS, const double* jQ) {
+  return static_cast<RefBase*>(h)->add_freezein(n, r, Ttau, jB, jS, jQ);
 }
 int ccake_ref_initialize(void* h) { return static_cast<RefBase*>(h)->initialize(); }
 int ccake_ref_allocate_raw(void* h, long n) { return static_cast<RefBase*>(h)->allocate_raw(n); }

@@ -103,6 +103,9 @@ inline std::shared_ptr<Settings> parse_settings(const char* kv) {
     else if (k == "diffusionRelaxMode") s->diffusionRelaxMode = v;
     else if (k == "IC_type") s->IC_type = v;
     else if (k == "IC_file") s->IC_file = v;
+    else if (k == "freezein_input_file") s->freezein_input_file = v;
+    else if (k == "freezein_tol") s->freezein_tol = std::stod(v);
+    else if (k == "freezein_max_iter") s->freezein_max_iter = std::stoi(v);
     else if (k == "results_directory") s->results_directory = v;
     else if (k == "txt_evolution") s->txt_evolution = to_bool(v);
     else if (k == "evolution_stride") s->evolution_stride = std::stoi(v);

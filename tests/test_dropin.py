@@ -173,3 +173,57 @@ def test_unmodified_bsqhydro_on_a_preinverted_table(tmp_path):
         lo, hi = COLS[name]
         scale = pmax if name in ("bulk", "shv") else None   # Pi and pi^{mu nu} on the scale of the pressure (Pi is ~1e-12 here)
         assert common.rel_err(rows[:, lo:hi], ref_rows[:, lo:hi], scale) <= 3 * TOL * (k + 1), name
+
+
+@pytest.mark.gpu
+def test_unmodified_bsqhydro_freezein_initial_conditions(tmp_path):
+    """IC_type "freezein": the reference's own read_freezein (unmodified BSQHydro.cpp) stages the raw T^{tau mu}, j_a^mu of every cell,
+    the drop-in SPHWorkstation::freeze_in_match closes them with the EoS in batched device queries, and the run proceeds; against the
+    reference's freeze_in_match (one host root search per cell and iterate) fed the same cells, and against the fluid the file was
+    made from (conformal EoS: P = eps / 3, so T^{tau tau} = (4 gamma^2 - 1) eps / 3, T^{tau i} = 4 eps gamma u^i / 3, j^tau = n gamma)."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    hc = 0.1973269804
+    ic = gubser_ic(dx=0.1, shear=False, charges=True)
+    n = ic["r"].shape[0]
+    eps, u = ic["e"], ic["u"]                       # GeV/fm^3, u^x u^y
+    gamma = np.sqrt(1.0 + np.sum(u * u, 1))
+    Ttau = np.zeros((n, 4)); Ttau[:, 0] = (4.0 * gamma ** 2 - 1.0) * eps / 3.0; Ttau[:, 1:3] = (4.0 * eps * gamma / 3.0)[:, None] * u
+    jB, jS, jQ = (np.zeros((n, 4)) for _ in range(3))
+    jB[:, 0], jS[:, 0], jQ[:, 0] = ic["rhoB"] * gamma, ic["rhoS"] * gamma, ic["rhoQ"] * gamma
+    path = tmp_path / "freezein.dat"
+    with open(path, "w") as f:
+        f.write("#0 0.1 0.1 0.1 0 -2.0 -2.0 -0.1\n# raw (un-diagonalized) contravariant T^{mu nu}\n")
+        rows = np.concatenate([ic["r"], np.zeros((n, 1)), Ttau, np.zeros((n, 6)), jB, jS, jQ], 1)
+        np.savetxt(f, rows, fmt="%.17g")
+    settings = charged_settings(dt=0.05, max_tau=1.07, IC_type="freezein", e_cutoff=0.05)
+    L = _lib()
+    out = tmp_path / "results"; out.mkdir()
+    s = dict(settings, freezein_input_file=str(path), results_directory=str(out))
+    keys = common.ref_module().SETTING_KEYS | {"results_directory", "freezein_input_file"}
+    kv = "\n".join("%s=%s" % (k, ("true" if v else "false") if isinstance(v, bool) else repr(v) if isinstance(v, float) else v)
+                   for k, v in s.items() if k in keys or k.startswith("kappa_")).encode()
+    rows_out = np.zeros((n, ROW))
+    n_out, t_out, steps = C.c_long(), C.c_double(), C.c_int()
+    err = C.create_string_buffer(512)
+    rc = L.dropin_bsqhydro_run(kv, n, C.byref(n_out), C.byref(t_out), rows_out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(steps), err, 512)
+    assert rc == 0, err.value.decode()
+    rows_out = rows_out[: n_out.value]
+    sim = common.ref_module().RefSim({k: v for k, v in settings.items() if k in common.ref_module().SETTING_KEYS or k.startswith("kappa_")})
+    sim.add_freezein(ic["r"], Ttau, jB, jS, jQ)
+    sim.initialize()
+    assert sim.n == n_out.value and 0 < sim.n <= n
+    # every cell of this file is above the cut-off in its rest frame: the matching keeps them all, on both sides
+    assert sim.n == int(np.sum(eps > settings["e_cutoff"])) == n
+    k = 0
+    while sim.t <= settings["max_tau"]:
+        sim.advance(settings["dt"], 2)
+        k += 1
+    assert steps.value == k
+    ref_rows = _ref_rows(sim)
+    assert np.array_equal(rows_out[:, 21], ref_rows[:, 21])
+    pmax = float(np.max(np.abs(ref_rows[:, 8])))
+    for name in ("r", "u", "T", "e", "p", "s", "rho", "sigma", "gamma", "extensive_s"):
+        lo, hi = COLS[name]
+        # the two sides stop the v-iteration at the same iterate, but their EoS roots differ within the 1e-10 root tolerance
+        assert common.rel_err(rows_out[:, lo:hi], ref_rows[:, lo:hi]) <= 1e-8, name
