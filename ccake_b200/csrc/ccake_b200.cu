@@ -400,10 +400,10 @@ int ensure_hitmask(ccb_ctx* ctx) {
   size_t free_b = 0, total_b = 0;
   CUDA_OK(cudaMemGetInfo(&free_b, &total_b));
   const size_t per_tile = sizeof(unsigned long long) * (size_t)ctx->cap;
-  size_t budget = free_b / 4;
-  if (budget > ((size_t)32 << 30)) budget = (size_t)32 << 30;
-  int64_t kmax = (int64_t)(budget / per_tile);
-  if (kmax > 1024) kmax = 1024;
+  // depth of the mask buffer: 8 GiB worth of tiles, but at least 48 tiles (a 3-D stencil at 64 .. 100 particles per cell needs 27 .. 43)
+  // when that is more, and never more than a quarter of the free memory or 1024 tiles
+  const int64_t k_quarter = (int64_t)((free_b / 4) / per_tile), k_8g = (int64_t)(((size_t)8 << 30) / per_tile);
+  int64_t kmax = std::min<int64_t>(std::min<int64_t>(1024, k_quarter), std::max<int64_t>(k_8g, 48));
   if (kmax < 4) { ctx->hit_off = true; return CCB_OK; }
   // a stage needs ceil(candidates / tile) tiles per task: 27 for a 3-D lattice at h = 2 d, ~140 for the 2-D h = 0.4 Gubser run
   if (cudaMalloc(&ctx->hitmask, per_tile * (size_t)kmax) != cudaSuccess) { cudaGetLastError(); ctx->hitmask = nullptr; ctx->hit_off = true; return CCB_OK; }
