@@ -49,8 +49,8 @@ cudaError_t launch_gather_fields<CCB_INST_D>(bool fact, const GatherShape& sh, c
                                              const GatherParams& gp) {
   constexpr int D = CCB_INST_D;
   if (gp.nbr_idx) return launch_shape<FieldsPolicy<D, false, true>, 8, 4>(sh, s, dv, g, gp);  // debug twin: neighbour ids (plain kernel)
-  if (D == 3 && fact) return launch_shape<FieldsPolicy<D, (D == 3)>, 12, 6>(sh, s, dv, g, gp);
-  return launch_shape<FieldsPolicy<D, false>, 12, 6>(sh, s, dv, g, gp);
+  if (D == 3 && fact) return launch_shape<FieldsPolicy<D, (D == 3)>, 16, 8>(sh, s, dv, g, gp);
+  return launch_shape<FieldsPolicy<D, false>, 16, 8>(sh, s, dv, g, gp);
 }
 
 template <>
