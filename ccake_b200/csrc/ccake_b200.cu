@@ -101,7 +101,7 @@ struct ccb_ctx {
   bool use_chain = false;    // phase 04 runs through the chain kernels (every eos_type but the closed-form conformal one)
   // launch shapes of the gradient / field gather. nt (targets = threads per task) is common to both: it is the chunk size of
   // the task list
-  ccb::GatherShape shape_grad{64, 64, 0}, shape_fields{64, 64, 0};
+  ccb::GatherShape shape_grad{64, 64}, shape_fields{64, 64};
   int sms = 148;
   // slab decomposition (nranks > 1): own cell columns [slab_lo, slab_hi) along x, neighbours rank -+ 1
   std::unique_ptr<ccb::Link> comm;
@@ -1150,7 +1150,6 @@ int ccb_create(ccb_ctx** out, const ccb_config* cfg) {
     if (const char* e = std::getenv("CCB_GATHER_NT")) { const int v = std::atoi(e); if (v == 64 || v == 128) ctx->shape_grad.nt = ctx->shape_fields.nt = v; }
     if (const char* e = std::getenv("CCB_GATHER_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_grad.tile = v; }
     if (const char* e = std::getenv("CCB_FIELDS_TILE")) { const int v = std::atoi(e); if (v == 32 || v == 64) ctx->shape_fields.tile = v; }
-    if (const char* e = std::getenv("CCB_GATHER_REGS")) ctx->shape_grad.regs = std::atoi(e) != 0;
     if (const char* e = std::getenv("CCB_HITMASK")) ctx->hit_off = std::atoi(e) == 0;
   }
   if (ctx->grid.ncells >= ((int64_t)1 << 31)) { ctx->err = "neighbour grid has more than 2^31 cells"; return CCB_ERR_INVALID; }

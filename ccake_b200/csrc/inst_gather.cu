@@ -26,21 +26,28 @@ cudaError_t launch(cudaStream_t s, const DeviceView& dv, const CellGrid& g, cons
   gather_kernel<P, NT, MINB, TILE><<<(unsigned)(most < grid ? most : grid), NT, 0, s>>>(dv, g, gp);
   return cudaGetLastError();
 }
-// GatherShape: targets per task (64 | 128), source records per shared-memory tile (32 | 64; tiles are double-buffered), and the
-// register budget of the gradient variants (regs = 0: 128 registers per thread, MINB CTAs per SM as given; regs = 1: one CTA per
-// SM fewer, i.e. 168 registers at 128 threads).
+// GatherShape: targets per task (64 | 128) and source records per shared-memory tile (32 | 64; tiles are double-buffered).
 template <class P, int MINB64, int MINB128>
 cudaError_t launch_shape(const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
   if (sh.tile == 32) return sh.nt == 128 ? launch<P, 128, MINB128, 32>(s, dv, g, gp) : launch<P, 64, MINB64, 32>(s, dv, g, gp);
   return sh.nt == 128 ? launch<P, 128, MINB128, 64>(s, dv, g, gp) : launch<P, 64, MINB64, 64>(s, dv, g, gp);
 }
+// Register budget of a gradient variant, by its accumulator count (measured on the five BASELINE configs, profiles/r02aa_*): the
+// variants with up to 30 fp64 accumulators (2-D all, 3-D without diffusion) run fastest at 102 registers = 10 CTAs of 64 threads per
+// SM (-1 .. -9 % against 128 registers), the 3-D shear + diffusion variants (37 | 43 accumulators) need their 128 registers (102: +60 %,
+// 85: +190 %, 168: +6 %).
+template <class P>
+cudaError_t launch_regs(const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
+  constexpr int M = P::NACC <= 30 ? 10 : 8;
+  return launch_shape<P, M, M / 2>(sh, s, dv, g, gp);
+}
 // a diffusion run launches both compile-time sparsity twins; the one that does not match DeviceView::qflag exits at once
 template <int D, bool S, bool F, bool X>
 cudaError_t launch_grad(const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g, const GatherParams& gp) {
-  if (!F) return sh.regs ? launch_shape<GradPolicy<D, S, false, X, false>, 6, 3>(sh, s, dv, g, gp) : launch_shape<GradPolicy<D, S, false, X, false>, 8, 4>(sh, s, dv, g, gp);
-  cudaError_t e = sh.regs ? launch_shape<GradPolicy<D, S, F, X, false>, 6, 3>(sh, s, dv, g, gp) : launch_shape<GradPolicy<D, S, F, X, false>, 8, 4>(sh, s, dv, g, gp);
+  if (!F) return launch_regs<GradPolicy<D, S, false, X, false>>(sh, s, dv, g, gp);
+  cudaError_t e = launch_regs<GradPolicy<D, S, F, X, false>>(sh, s, dv, g, gp);
   if (e != cudaSuccess) return e;
-  return sh.regs ? launch_shape<GradPolicy<D, S, F, X, true>, 6, 3>(sh, s, dv, g, gp) : launch_shape<GradPolicy<D, S, F, X, true>, 8, 4>(sh, s, dv, g, gp);
+  return launch_regs<GradPolicy<D, S, F, X, true>>(sh, s, dv, g, gp);
 }
 }  // namespace
 

@@ -8,9 +8,8 @@
 
 namespace ccb {
 
-// launch shape of a gather: nt = targets (= threads) per task (64 | 128), tile = source records per shared-memory tile (32 | 64),
-// regs = register budget of the gradient variants (0: 128 per thread; 1: 168 per thread, one CTA per SM fewer)
-struct GatherShape { int nt, tile, regs; };
+// launch shape of a gather: nt = targets (= threads) per task (64 | 128), tile = source records per shared-memory tile (32 | 64)
+struct GatherShape { int nt, tile; };
 template <int D> cudaError_t launch_gather_fields(bool fact, const GatherShape& sh, cudaStream_t s, const DeviceView& dv, const CellGrid& g,
                                                   const GatherParams& gp);
 template <int D> cudaError_t launch_gather_gradients(bool shear, bool diff, bool fact, const GatherShape& sh, cudaStream_t s, const DeviceView& dv,
