@@ -367,6 +367,9 @@ CCB_HD bool in_range(const double x[4], const double lo[4], const double hi[4]) 
 
 // Rootfinder::find_root (src/rootfinder.cpp:423-716): the seed, then the seed with T, muB, muS, muQ moved by
 // +-20 %, then the "mu = 0" seed. `x` holds the seed on entry and the root on success.
+// FIRST_ONLY: stop after the search from the seed itself (the fast path of phase 04: a particle that is on the table and stays on
+// it converges there; everything else is left to the full chain, which repeats this first search with the same outcome).
+template <bool FIRST_ONLY = false>
 CCB_HD bool find_root(const EosChain& ch, int k, bool energy, double t0_, double Bin, double Sin, double Qin, double x[4]) {
   double lo[4], hi[4];
   eos_bounds(ch, k, lo, hi);
@@ -398,6 +401,7 @@ CCB_HD bool find_root(const EosChain& ch, int k, bool energy, double t0_, double
   { CCB_UNROLL for (int d = 0; d < 4; ++d) y[d] = pos[d];                                      \
     if (newton_solve(ch, k, energy, mode, target, lo, hi, y)) { CCB_UNROLL for (int d = 0; d < 4; ++d) x[d] = y[d]; return true; } }
   CCB_TRY()
+  if (FIRST_ONLY) return false;
   const double base[4] = {pos[0], pos[1], pos[2], pos[3]};
   // Rootfinder::tbqs keeps the previous position when the proposed one is out of range (src/rootfinder.cpp:172-203)
   // (arrays are addressed with compile-time indices only -- a run-time index would move them to local memory for good)
