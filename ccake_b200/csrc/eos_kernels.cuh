@@ -9,8 +9,17 @@
 #include "local.cuh"
 #include "physics_eos_chain.cuh"
 
+// The kernels below inline the whole fall-back chain and take minutes each to compile; inst_eos.cu is therefore built as four
+// objects (-DCCB_EOS_PART=1..4: stage + fast path | initial location | host queries | pre-inverted tables and their generator) that
+// compile in parallel. Without the macro every kernel is visible (the host test harness, editors).
+#ifndef CCB_EOS_PART
+#define CCB_EOS_PART 0
+#endif
+#define CCB_EOS_HAS(part) (CCB_EOS_PART == 0 || CCB_EOS_PART == (part))
+
 namespace ccb {
 
+#if CCB_EOS_HAS(1)
 // (s, rhoB, rhoS, rhoQ) of the local rest frame (thermo columns 5..8, written by the field gather) -> thermo.
 // SPHWorkstation::locate_phase_diagram_point_sBSQ, src/sph_workstation.cpp:659-741
 // `todo` (nullable): per-particle flags of the fast path below; a particle it has already located is skipped.
@@ -57,6 +66,9 @@ __global__ void __launch_bounds__(128, MINB) eos_table_fast_kernel(DeviceView dv
   // eos_id stays 0
 }
 
+#endif  // part 1
+
+#if CCB_EOS_HAS(2)
 // Initial location from the IC densities (tmp columns: 0 e [GeV/fm^3] or s, 1 rhoB, 2 rhoS, 3 rhoQ).
 // SPHWorkstation::initialize_entropy_and_charge_densities -> locate_phase_diagram_point_{eBSQ,sBSQ}
 // (src/sph_workstation.cpp:253-320, 1791-1848): a particle without a solution is frozen out and located again
@@ -87,6 +99,9 @@ __global__ void __launch_bounds__(128) eos_chain_init_kernel(DeviceView dv, EosC
   dv.eos_id[i] = res.eos;
 }
 
+#endif  // part 2
+
+#if CCB_EOS_HAS(3)
 // ---- host-callable queries (C ABI: ccb_eos_full_thermo, ccb_eos_locate) -----------------------------------------------
 // EoS_base::get_full_thermo (include/eos_base.h:12-50) of chain member `member` at n points (T, muB, muQ, muS); a point
 // outside the member's domain gives a row of NaN. conf != nullptr: the closed-form conformal EoS of a conformal run.
@@ -137,6 +152,9 @@ __global__ void eos_locate_kernel(EosChain ch, ConformalParams conf, int use_cha
   eos_out[i] = eos;
 }
 
+#endif  // part 3
+
+#if CCB_EOS_HAS(4)
 // ---- pre-inverted equation of state (eos_preinverted.cuh) ---------------------------------------------------------------
 // Phase 04 with Settings::online_inverter_enabled = false: EoS_Interpolator::fill_thermodynamics (src/eos_interpolator.cpp:531-627).
 // Writes T, muB, muS, muQ, e, p, cs2, w = e + p and dw/d(s, B, S, Q); s and the charge densities stay what the field gather stored.
@@ -208,5 +226,7 @@ __global__ void __launch_bounds__(128) pre_generate_kernel(EosChain ch, Conforma
   for (int q = 0; q < PRE_NVAR; ++q) vars[(int64_t)q * total + k] = ok ? v[q] : nan("");
   eos_out[k] = eos;
 }
+
+#endif  // part 4
 
 }  // namespace ccb

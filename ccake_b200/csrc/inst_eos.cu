@@ -1,4 +1,4 @@
-// Tabulated-EoS kernels (not templated on dimension or metric): one object file.
+// Tabulated-EoS kernels (not templated on dimension or metric), built as four objects: -DCCB_EOS_PART=1..4 (eos_kernels.cuh).
 #include <cstdlib>
 
 #include "eos_kernels.cuh"
@@ -6,6 +6,7 @@
 
 namespace ccb {
 
+#if CCB_EOS_HAS(1)
 // phase 04 of a table run: the lean table-only search for the particles that stay on the table (todo != nullptr), then the full
 // chain for the particles it flagged. Measured at 7 989 930 particles (profiles/r02ac): full chain alone 7.80 ms, fast path at 168
 // registers 8.23 ms, at 128 registers (4 CTAs per SM, the default) 7.13 ms; CCB_EOS_FAST=0 runs the full chain alone.
@@ -23,11 +24,15 @@ cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const E
   }
   return cudaGetLastError();
 }
+#endif
+#if CCB_EOS_HAS(2)
 cudaError_t launch_eos_chain_init(cudaStream_t s, const DeviceView& dv, const EosChain& ch, const double* tmp, int input_as_entropy) {
   eos_chain_init_kernel<<<(unsigned)((dv.n + 127) / 128), 128, 0, s>>>(dv, ch, tmp, input_as_entropy);
   return cudaGetLastError();
 }
 
+#endif
+#if CCB_EOS_HAS(3)
 cudaError_t launch_eos_query(cudaStream_t s, const EosChain& ch, const ConformalParams* conf, int member, int64_t n, const double* pts, double* out) {
   ConformalParams c{};
   if (conf) c = *conf;
@@ -40,6 +45,8 @@ cudaError_t launch_eos_locate(cudaStream_t s, const EosChain& ch, const Conforma
   return cudaGetLastError();
 }
 
+#endif
+#if CCB_EOS_HAS(4)
 cudaError_t launch_pre_fill(cudaStream_t s, const DeviceView& dv, const PreTable& tb) {
   pre_fill_kernel<<<(unsigned)((dv.n + 127) / 128), 128, 0, s>>>(dv, tb);
   return cudaGetLastError();
@@ -55,4 +62,5 @@ cudaError_t launch_pre_generate(cudaStream_t s, const EosChain& ch, const Confor
   return cudaGetLastError();
 }
 
+#endif
 }  // namespace ccb
