@@ -863,8 +863,8 @@ int do_eos_local(ccb_ctx* ctx, int do_eos, int do_local) {
     if (!ctx->have_table) { ctx->err = "eos_type = table: no table loaded (ccb_set_eos_table / ccb_load_eos_table_dat)"; return CCB_ERR_STATE; }
     if (do_eos) {
       PhaseTimer pt(ctx, PH_THERMO);
-      LAUNCHER("eos_chain_stage_kernel", launch_eos_chain_stage(ctx->stream, ctx->dv, ctx->chain, ctx->task_pos));   // task_pos: free between the task-list build and the next one
-      ctx->launches++;
+      LAUNCHER("eos_chain_stage_kernel", launch_eos_chain_stage(ctx->stream, ctx->dv, ctx->chain, ctx->task_pos, ctx->d_stage));   // task_pos, d_stage: free during a stage
+      ctx->launches += 2;
     }
     if (do_local) {
       PhaseTimer pt(ctx, PH_LOCAL);

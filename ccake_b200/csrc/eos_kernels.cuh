@@ -40,14 +40,17 @@ __global__ void __launch_bounds__(128) eos_chain_stage_kernel(DeviceView dv, Eos
   dv.eos_id[i] = res.eos;
 }
 
-// Fast path of phase 04 on a table run: a particle that was on the table after the previous stage (eos_id = 0) almost always stays
-// there, and the full chain would locate it with its FIRST search -- Newton from the previous point on the table. This kernel does
-// exactly that search and nothing else (find_root<FIRST_ONLY>, then the member's acceptance test); without the seed cascade and the
-// three fall-back members in its body it runs at 128 registers with 256 B of stack where the full kernel needs 255 + 480 B, so 16
-// warps per SM run instead of 8 (-9 % on the 3+1D run, -23 % on the 2+1D table run; 168 registers measured slower than the full kernel). A particle it cannot finish (no convergence, acceptance test failed, not on the table) is flagged in `todo`
-// and done by eos_chain_stage_kernel, which repeats the same first search with the same outcome: results are identical either way.
+// Fast path of phase 04 on a table run, in two lean kernels. A particle that was on the table after the previous stage (eos_id = 0)
+// almost always stays there, and the full chain would locate it with its FIRST search -- Newton from the previous point on the table.
+//   eos_table_root_kernel     does exactly that search (find_root<FIRST_ONLY, TABLE>) and parks the root in a scratch column block;
+//   eos_table_epilogue_kernel evaluates the 17 table fields there, applies the member's acceptance test and stores the thermodynamics.
+// Whatever they cannot finish (no convergence, acceptance test failed, particle not on the table) is flagged in `todo` and done by
+// eos_chain_stage_kernel, which repeats the same first search with the same outcome: results are identical bit for bit. Why two
+// kernels: ncu put the one-kernel form (14 k instructions = 228 KB of code, profiles/r02af) at 5.7 warps stalled on instruction
+// fetch per issue; the search alone is 3.4 k instructions, the epilogue 4.9 k, each inside the instruction cache, and neither
+// carries the analytic members' code (TABLE). todo: 1 = full chain, 2 = root parked, 0 = done.
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) eos_table_fast_kernel(DeviceView dv, EosChain ch, uint32_t* __restrict__ todo) {
+__global__ void __launch_bounds__(128, MINB) eos_table_root_kernel(DeviceView dv, EosChain ch, uint32_t* __restrict__ todo, double* __restrict__ xs) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= dv.n) return;
   if (dv.eos_id[i] != 0 || ch.kind[0] != EOS_KIND_TABLE) { todo[i] = 1u; return; }
@@ -55,17 +58,24 @@ __global__ void __launch_bounds__(128, MINB) eos_table_fast_kernel(DeviceView dv
                S = col(dv.f[CCB_F_THERMO], dv.cap, 7, i), Q = col(dv.f[CCB_F_THERMO], dv.cap, 8, i);
   double x[4] = {col(dv.f[CCB_F_TSEED], dv.cap, 0, i), col(dv.f[CCB_F_TSEED], dv.cap, 1, i),
                  col(dv.f[CCB_F_TSEED], dv.cap, 3, i), col(dv.f[CCB_F_TSEED], dv.cap, 2, i)};
+  if (!find_root<true, true>(ch, 0, false, s, B, S, Q, x)) { todo[i] = 1u; return; }
+  todo[i] = 2u;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) xs[(int64_t)d * dv.cap + i] = x[d];   // the seed columns stay untouched: the full chain may still need them
+}
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) eos_table_epilogue_kernel(DeviceView dv, EosChain ch, uint32_t* __restrict__ todo, const double* __restrict__ xs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= dv.n || todo[i] != 2u) return;
+  const double x[4] = {xs[i], xs[dv.cap + i], xs[2 * dv.cap + i], xs[3 * dv.cap + i]};
   ChainResult res;
-  bool ok = find_root<true>(ch, 0, false, s, B, S, Q, x);
-  if (ok) { chain_evaluate(ch, 0, x, res); ok = chain_accepts(ch, 0, res); }
-  todo[i] = ok ? 0u : 1u;
-  if (!ok) return;
+  chain_evaluate<true>(ch, 0, x, res);
+  if (!chain_accepts(ch, 0, res)) { todo[i] = 1u; return; }
+  todo[i] = 0u;
   Thermo th;
   chain_thermo(ch, res, th);
-  store_thermo(dv, i, th);
-  // eos_id stays 0
+  store_thermo(dv, i, th);   // eos_id stays 0
 }
-
 #endif  // part 1
 
 #if CCB_EOS_HAS(2)

@@ -7,15 +7,15 @@
 namespace ccb {
 
 #if CCB_EOS_HAS(1)
-// phase 04 of a table run: the lean table-only search for the particles that stay on the table (todo != nullptr), then the full
-// chain for the particles it flagged. Measured at 7 989 930 particles (profiles/r02ac): full chain alone 7.80 ms, fast path at 168
-// registers 8.23 ms, at 128 registers (4 CTAs per SM, the default) 7.13 ms; CCB_EOS_FAST=0 runs the full chain alone.
-cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const EosChain& ch, uint32_t* todo) {
+// phase 04 of a table run: the two lean table-only kernels for the particles that stay on the table (todo, xs != nullptr), then the
+// full chain for the particles they flagged. CCB_EOS_FAST=0 runs the full chain alone.
+cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const EosChain& ch, uint32_t* todo, double* xs) {
   static int mode = -1;
-  if (mode < 0) { const char* e = std::getenv("CCB_EOS_FAST"); mode = e ? std::atoi(e) : 4; }
+  if (mode < 0) { const char* e = std::getenv("CCB_EOS_FAST"); mode = e ? std::atoi(e) : 1; }
   const unsigned grid = (unsigned)((dv.n + 127) / 128);
-  if (todo && mode != 0) {
-    eos_table_fast_kernel<4><<<grid, 128, 0, s>>>(dv, ch, todo);
+  if (todo && xs && mode != 0) {
+    eos_table_root_kernel<4><<<grid, 128, 0, s>>>(dv, ch, todo, xs);
+    eos_table_epilogue_kernel<4><<<grid, 128, 0, s>>>(dv, ch, todo, xs);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     eos_chain_stage_kernel<<<grid, 128, 0, s>>>(dv, ch, todo);

@@ -22,7 +22,7 @@ cudaError_t launch_init_particles(cudaStream_t s, const DeviceView& dv, const St
                                   int input_as_entropy, int input_initial_shear, int bulk_from_trace, double efcheck, int eos_done);
 struct EosChain;
 // tabulated EoS + fall-back chain (eos_kernels.cuh): phase 04 of a derivative evaluation, and the initial e|s -> (T, mu) location
-cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const EosChain& ch, uint32_t* todo);
+cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const EosChain& ch, uint32_t* todo, double* xs);
 cudaError_t launch_eos_chain_init(cudaStream_t s, const DeviceView& dv, const EosChain& ch, const double* tmp, int input_as_entropy);
 // host-callable EoS queries (ccb_eos_full_thermo, ccb_eos_locate)
 cudaError_t launch_eos_query(cudaStream_t s, const EosChain& ch, const ConformalParams* conf, int member, int64_t n, const double* pts, double* out);

@@ -284,8 +284,12 @@ CCB_HD bool chain_full_thermo(const EosChain& ch, int k, const double x[4], doub
 
 // Residual densities (s|e, B, S, Q) and Jacobian d(dens)/dx of member k; analytic members: from the Hessian
 // (d e / d x_j = sum_i x_i H_ij because dp/dx_j = n_j).
+// TABLE (here and below): member k is known to be the table at compile time (the fast path of phase 04), so the analytic members'
+// code -- most of the instructions of these functions -- is not generated.
+template <bool TABLE = false>
 CCB_HD bool chain_densities(const EosChain& ch, int k, bool energy, const double x[4], double val[4], double jac[4][4]) {
-  if (ch.kind[k] == EOS_KIND_TABLE) return table_densities(ch.table, energy ? ch.table.hot_e : ch.table.hot_s, x, val, jac);
+  if (TABLE || ch.kind[k] == EOS_KIND_TABLE) return table_densities(ch.table, energy ? ch.table.hot_e : ch.table.hot_s, x, val, jac);
+  if (TABLE) return false;
   double r[TH_N];
   chain_full_thermo(ch, k, x, r);
   // Hessian rows in x order (T, B, Q, S)
@@ -301,6 +305,7 @@ CCB_HD bool chain_densities(const EosChain& ch, int k, bool energy, const double
 
 // One run of the root search from x (Rootfinder::rootfinder4D, src/rootfinder.cpp:206-417).
 // mode: 0 full, 1 T-only, 2 baryon-only (the pinned potentials are driven to zero, :131-160).
+template <bool TABLE = false>
 CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const double target[4] /* s|e, B, S, Q */,
                          const double lo[4], const double hi[4], double x[4]) {
   double f[4], J[4][4], val[4], jac[4][4];
@@ -308,7 +313,7 @@ CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const
   int clamped = 0;
   bool have = false;  // val / jac already hold the evaluation at x (the accepted trial point of the previous iterate)
   for (int it = 0; it <= kNewtonMaxIter; ++it) {
-    if (!have && !chain_densities(ch, k, energy, x, val, jac)) return false;
+    if (!have && !chain_densities<TABLE>(ch, k, energy, x, val, jac)) return false;
     have = false;
     // residuals in the reference's order: (s, B, Q, S)
     f[0] = val[0] - target[0]; f[1] = val[1] - target[1]; f[2] = val[3] - target[3]; f[3] = val[2] - target[2];
@@ -340,7 +345,7 @@ CCB_HD bool newton_solve(const EosChain& ch, int k, bool energy, int mode, const
     bool accepted = false;
     for (int bt = 0; bt < 8; ++bt) {
       CCB_UNROLL for (int d = 0; d < 4; ++d) xt[d] = x[d] + scale * dx[d];
-      const bool ok = chain_densities(ch, k, energy, xt, v2, j2);
+      const bool ok = chain_densities<TABLE>(ch, k, energy, xt, v2, j2);
       if (ok) {
         double g[4] = {v2[0] - target[0], v2[1] - target[1], v2[3] - target[3], v2[2] - target[2]};
         if (mode == 1) { g[1] = xt[1]; g[2] = xt[2]; g[3] = xt[3]; }
@@ -369,13 +374,13 @@ CCB_HD bool in_range(const double x[4], const double lo[4], const double hi[4]) 
 // +-20 %, then the "mu = 0" seed. `x` holds the seed on entry and the root on success.
 // FIRST_ONLY: stop after the search from the seed itself (the fast path of phase 04: a particle that is on the table and stays on
 // it converges there; everything else is left to the full chain, which repeats this first search with the same outcome).
-template <bool FIRST_ONLY = false>
+template <bool FIRST_ONLY = false, bool TABLE = false>
 CCB_HD bool find_root(const EosChain& ch, int k, bool energy, double t0_, double Bin, double Sin, double Qin, double x[4]) {
   double lo[4], hi[4];
   eos_bounds(ch, k, lo, hi);
   const double target[4] = {t0_, Bin, Sin, Qin};
   // closed-form members
-  if (ch.kind[k] == EOS_KIND_CONFORMAL) {
+  if (!TABLE && ch.kind[k] == EOS_KIND_CONFORMAL) {
     const ConformalParams C{ch.conf_p.c, ch.conf_p.T0, ch.conf_p.muB0, ch.conf_p.muS0, ch.conf_p.muQ0};
     double T, muB, muS, muQ;
     const bool ok = energy ? conformal_invert_e(C, t0_, Bin, Sin, Qin, T, muB, muS, muQ) : conformal_invert_s(C, t0_, Bin, Sin, Qin, T, muB, muS, muQ);
@@ -383,7 +388,7 @@ CCB_HD bool find_root(const EosChain& ch, int k, bool energy, double t0_, double
     x[0] = T; x[1] = muB; x[2] = muQ; x[3] = muS;
     return in_range(x, lo, hi);
   }
-  if (ch.kind[k] == EOS_KIND_DIAGONAL) {
+  if (!TABLE && ch.kind[k] == EOS_KIND_DIAGONAL) {
     if (energy) diagonal_seed_e(ch.diag_p, t0_, Bin, Sin, Qin, x); else diagonal_seed_s(ch.diag_p, t0_, Bin, Sin, Qin, x);
     return in_range(x, lo, hi) && x[0] > 0.0;
   }
@@ -399,7 +404,7 @@ CCB_HD bool find_root(const EosChain& ch, int k, bool energy, double t0_, double
   double y[4];
 #define CCB_TRY()                                                                              \
   { CCB_UNROLL for (int d = 0; d < 4; ++d) y[d] = pos[d];                                      \
-    if (newton_solve(ch, k, energy, mode, target, lo, hi, y)) { CCB_UNROLL for (int d = 0; d < 4; ++d) x[d] = y[d]; return true; } }
+    if (newton_solve<TABLE>(ch, k, energy, mode, target, lo, hi, y)) { CCB_UNROLL for (int d = 0; d < 4; ++d) x[d] = y[d]; return true; } }
   CCB_TRY()
   if (FIRST_ONLY) return false;
   const double base[4] = {pos[0], pos[1], pos[2], pos[3]};
@@ -452,11 +457,12 @@ struct ChainResult {
 };
 
 // EquationOfState::evaluate_thermodynamics (src/eos.cpp:174-221)
+template <bool TABLE = false>
 CCB_HD void chain_evaluate(const EosChain& ch, int k, const double x[4], ChainResult& out) {
   CCB_UNROLL for (int d = 0; d < 4; ++d) out.x[d] = x[d];
-  chain_full_thermo(ch, k, x, out.r);
+  if (TABLE) table_full_thermo(ch.table, x, out.r); else chain_full_thermo(ch, k, x, out.r);
   out.chiBB0 = out.r[TH_B2];
-  if (ch.kind[k] == EOS_KIND_TABLE && (x[1] != 0.0 || x[2] != 0.0 || x[3] != 0.0)) {
+  if ((TABLE || ch.kind[k] == EOS_KIND_TABLE) && (x[1] != 0.0 || x[2] != 0.0 || x[3] != 0.0)) {
     const double x0[4] = {x[0], 0.0, 0.0, 0.0};
     out.chiBB0 = table_field(ch.table, x0, TH_B2);
   }
