@@ -14,7 +14,9 @@ cudaError_t launch_eos_chain_stage(cudaStream_t s, const DeviceView& dv, const E
   if (mode < 0) { const char* e = std::getenv("CCB_EOS_FAST"); mode = e ? std::atoi(e) : 1; }
   const unsigned grid = (unsigned)((dv.n + 127) / 128);
   if (todo && xs && mode != 0) {
-    eos_table_root_kernel<4><<<grid, 128, 0, s>>>(dv, ch, todo, xs);
+    // launch bounds measured at 2e6 particles (profiles/r02ah): search at 168 registers / 3 CTAs per SM 1.44 ms, at 128 / 4 1.61 ms,
+    // at 96 / 5 1.84 ms (the search spills below 168); epilogue at 128 / 4 1.61 ms, at 80 / 6 1.67 ms
+    eos_table_root_kernel<3><<<grid, 128, 0, s>>>(dv, ch, todo, xs);
     eos_table_epilogue_kernel<4><<<grid, 128, 0, s>>>(dv, ch, todo, xs);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
