@@ -58,6 +58,13 @@ assert n.item() == x.size and allids == list(range(x.size)), "slabs must tile th
 lo = torch.tensor([rg[rank][0]]); his = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
 dist.all_gather(his, torch.tensor([rg[rank][1]], dtype=torch.int64))
 if rank > 0: assert his[rank - 1].item() == rg[rank][0]
+# the strong-scaling bench also chooses the slab axis and a halo-aware cut from the IC: every rank must arrive at the same answer
+r3 = np.stack([x, rng.normal(0.0, 1.5, x.size), rng.uniform(-5.0, 5.0, x.size)], 1)
+ax, worst = slabs.best_axis(r3, [0.2, 0.2, 0.2], world, axes=[0, 2])
+rg2 = slabs.partition_columns(slabs.column_of(r3[:, ax], r3[:, ax].min() - 1e-9, 0.2, 80), 80, world, halo_cost=0.33)
+answers = [None] * world
+dist.all_gather_object(answers, (int(ax), round(float(worst), 12), rg2))
+assert all(a == answers[0] for a in answers), answers
 dist.destroy_process_group()
 print("OK", rank)
 """
