@@ -22,7 +22,7 @@ template <unsigned int D>
 class SystemState {
  public:
   SystemState() = delete;
-  SystemState(std::shared_ptr<Settings> settingsPtr_in) : settingsPtr(settingsPtr_in), device(std::make_shared<b200::Device>()) {}
+  SystemState(std::shared_ptr<Settings> settingsPtr_in) : device(std::make_shared<b200::Device>()), settingsPtr(settingsPtr_in) {}
   ~SystemState() {}
 
   double t = 0.0;
